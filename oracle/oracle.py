@@ -1,0 +1,277 @@
+"""ctypes front-end of ``oracle/sqlp_oracle.c`` (TEST INFRASTRUCTURE ONLY).
+
+The C file restates the reference's Julia hot path line by line (citations in its
+header).  This module only marshals numpy arrays into it.  Parity status: pinned on
+the reference's own lands-sized test vectors, unpinned beyond (no Julia in the image).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libsqlp_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (make -C oracle)."""
+    src = os.path.join(_HERE, "sqlp_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True,
+                       capture_output=True)
+    return _SO
+
+
+class _Problem(C.Structure):
+    _fields_ = [
+        ("m2", C.c_int64), ("n1", C.c_int64),
+        ("rbar", C.c_void_p),
+        ("T_colptr", C.c_void_p), ("T_rowval", C.c_void_p), ("T_nzval", C.c_void_p),
+        ("s", C.c_int64),
+        ("pos_row", C.c_void_p), ("pos_col", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_round_sig.restype = C.c_double
+        L.orc_round_sig.argtypes = [C.c_double]
+        L.orc_hash_dual_vector.restype = C.c_uint64
+        L.orc_hash_dual_vector.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_isequal.restype = C.c_int
+        L.orc_isequal.argtypes = [C.c_void_p, C.c_int64, C.c_uint64,
+                                  C.c_void_p, C.c_int64, C.c_uint64]
+        L.orc_pool_push.restype = C.c_int64
+        L.orc_pool_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_delta_coefficients.restype = None
+        L.orc_delta_coefficients.argtypes = [C.c_void_p] * 4
+        L.orc_eval_dual.restype = C.c_double
+        L.orc_eval_dual.argtypes = [C.c_void_p] * 4
+        L.orc_argmax_procedure.restype = None
+        L.orc_argmax_procedure.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+        L.orc_score_pair.restype = None
+        L.orc_score_pair.argtypes = [C.c_void_p] * 6
+        L.orc_build_sasa_cut.restype = C.c_int32
+        L.orc_build_sasa_cut.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        L.orc_bench_argmax.restype = C.c_int32
+        L.orc_bench_argmax.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32]
+        L.orc_max_threads.restype = C.c_int32
+        L.orc_u01.restype = C.c_double
+        L.orc_u01.argtypes = [C.c_uint64, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class Problem:
+    """Template coefficients + stochastic-position table of one epigraph
+    (``sdSubprobCoefficients``, subprob.jl:4-12, flattened)."""
+    m2: int
+    n1: int
+    rbar: np.ndarray            # dense [m2]
+    T_colptr: np.ndarray        # int64 [n1+1], 0-based CSC
+    T_rowval: np.ndarray        # int64 [nnz]
+    T_nzval: np.ndarray         # f64 [nnz]
+    pos_row: np.ndarray         # int32 [s]
+    pos_col: np.ndarray         # int32 [s]; -1 = RHS
+
+    def __post_init__(self):
+        self.rbar = _f64(self.rbar)
+        self.T_colptr = np.ascontiguousarray(self.T_colptr, dtype=np.int64)
+        self.T_rowval = np.ascontiguousarray(self.T_rowval, dtype=np.int64)
+        self.T_nzval = _f64(self.T_nzval)
+        self.pos_row = np.ascontiguousarray(self.pos_row, dtype=np.int32)
+        self.pos_col = np.ascontiguousarray(self.pos_col, dtype=np.int32)
+        assert self.rbar.shape == (self.m2,)
+        assert self.T_colptr.shape == (self.n1 + 1,)
+        self._c = _Problem(self.m2, self.n1, self.rbar.ctypes.data,
+                           self.T_colptr.ctypes.data, self.T_rowval.ctypes.data,
+                           self.T_nzval.ctypes.data, len(self.pos_row),
+                           self.pos_row.ctypes.data, self.pos_col.ctypes.data)
+
+    @property
+    def s(self) -> int:
+        return len(self.pos_row)
+
+    @property
+    def ref(self):
+        return C.byref(self._c)
+
+    def T_dense(self) -> np.ndarray:
+        T = np.zeros((self.m2, self.n1))
+        for j in range(self.n1):
+            for k in range(self.T_colptr[j], self.T_colptr[j + 1]):
+                T[self.T_rowval[k], j] = self.T_nzval[k]
+        return T
+
+
+# ---- A5 ---------------------------------------------------------------------------
+
+def round_sig(x: float) -> float:
+    return lib().orc_round_sig(float(x))
+
+
+def hash_dual_vector(v) -> int:
+    v = _f64(v)
+    return int(lib().orc_hash_dual_vector(_p(v), len(v)))
+
+
+def isequal(a, b) -> bool:
+    a, b = _f64(a), _f64(b)
+    return bool(lib().orc_isequal(_p(a), len(a), hash_dual_vector(a),
+                                  _p(b), len(b), hash_dual_vector(b)))
+
+
+class DualVertexSet:
+    """``sdDualVertexSet`` (dual_set.jl:69-127) over vectors of arbitrary length."""
+
+    def __init__(self, data=()):
+        self.data: list[np.ndarray] = []
+        for d in data:
+            self.push(d)
+
+    def push(self, v):
+        """Returns (inserted, 0-based index of v or of its first duplicate)."""
+        v = _f64(v).copy()
+        for k, w in enumerate(self.data):
+            if isequal(v, w):
+                return False, k
+        self.data.append(v)
+        return True, len(self.data) - 1
+
+    def __len__(self):
+        return len(self.data)
+
+    def __iter__(self):
+        return iter(self.data)
+
+    def matrix(self) -> np.ndarray:
+        return np.stack(self.data) if self.data else np.zeros((0, 0))
+
+
+def pool_push_many(m2: int, vectors: np.ndarray):
+    """Fixed-length pool: push every row of ``vectors``; returns (pool, inserted, index)."""
+    vectors = _f64(vectors).reshape(-1, m2)
+    n = len(vectors)
+    pool = np.zeros((max(n, 1), m2))
+    hashes = np.zeros(max(n, 1), dtype=np.uint64)
+    K = C.c_int64(0)
+    ins = np.zeros(n, dtype=np.int32)
+    idx = np.zeros(n, dtype=np.int64)
+    one = C.c_int32(0)
+    for i in range(n):
+        idx[i] = lib().orc_pool_push(_p(pool), _p(hashes), C.byref(K), len(pool), m2,
+                                     _p(vectors[i]), C.byref(one))
+        ins[i] = one.value
+    return pool[:K.value].copy(), ins, idx
+
+
+# ---- A1 / A7 / A2 / A3 --------------------------------------------------------------
+
+def delta_coefficients(P: Problem, values):
+    values = _f64(values)
+    drhs = np.zeros(P.m2)
+    dT = np.zeros(max(P.s, 1))
+    lib().orc_delta_coefficients(P.ref, _p(values), _p(drhs), _p(dT))
+    return drhs, dT[:P.s]
+
+
+def eval_dual(P: Problem, values, x, dual) -> float:
+    values, x, dual = _f64(values), _f64(x), _f64(dual)
+    return lib().orc_eval_dual(P.ref, _p(values), _p(x), _p(dual))
+
+
+def argmax_procedure(P: Problem, values, x, pool, want_second=False):
+    values = _f64(values).reshape(-1, max(P.s, 1)) if P.s else _f64(values)
+    N = len(values) if P.s else int(np.asarray(values).shape[0])
+    x, pool = _f64(x), _f64(pool).reshape(-1, P.m2)
+    mv = np.zeros(N)
+    mi = np.zeros(N, dtype=np.int64)
+    sec = np.zeros(N) if want_second else None
+    lib().orc_argmax_procedure(P.ref, N, _p(values), _p(x), _p(pool), len(pool),
+                               _p(mv), _p(mi), _p(sec) if want_second else None)
+    return (mv, mi, sec) if want_second else (mv, mi)
+
+
+def score_pair(P: Problem, values, x, vertex):
+    values, x, vertex = _f64(values), _f64(x), _f64(vertex)
+    s = C.c_double(0)
+    sl = C.c_longdouble(0)
+    lib().orc_score_pair(P.ref, _p(values), _p(x), _p(vertex), C.byref(s), C.byref(sl))
+    return s.value, sl.value
+
+
+def build_sasa_cut(P: Problem, values, weights, x, pool, total_weight=None):
+    """Returns dict(alpha, beta, weight_mark, val, max_val, max_idx, status)."""
+    values = _f64(values).reshape(-1, max(P.s, 1))
+    N = len(values)
+    weights = _f64(weights)
+    x, pool = _f64(x), _f64(pool).reshape(-1, P.m2)
+    if total_weight is None:
+        total_weight = 0.0
+        for w in weights:          # epigraph.jl:89 sequential accumulation
+            total_weight += float(w)
+    alpha = C.c_double(0)
+    wm = C.c_double(0)
+    val = C.c_double(0)
+    beta = np.zeros(P.n1)
+    mv = np.zeros(N)
+    mi = np.zeros(N, dtype=np.int64)
+    st = lib().orc_build_sasa_cut(P.ref, N, _p(values), _p(weights), float(total_weight),
+                                  _p(x), _p(pool), len(pool), C.byref(alpha), _p(beta),
+                                  C.byref(wm), C.byref(val), _p(mv), _p(mi))
+    return dict(alpha=alpha.value, beta=beta, weight_mark=wm.value, val=val.value,
+                max_val=mv, max_idx=mi, status=st)
+
+
+def bench_argmax(P: Problem, values, x, pool, threads=0, dot_kind=1):
+    values = _f64(values).reshape(-1, max(P.s, 1))
+    N = len(values)
+    x, pool = _f64(x), _f64(pool).reshape(-1, P.m2)
+    mv = np.zeros(N)
+    mi = np.zeros(N, dtype=np.int64)
+    used = lib().orc_bench_argmax(P.ref, N, _p(values), _p(x), _p(pool), len(pool),
+                                  _p(mv), _p(mi), threads, dot_kind)
+    return mv, mi, used
+
+
+def max_threads() -> int:
+    return lib().orc_max_threads()
+
+
+def u01(seed: int, idx) -> np.ndarray:
+    """Vectorised numpy twin of orc_u01 (splitmix64 counter generator)."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) ^ (idx * np.uint64(0x9E3779B97F4A7C15))
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)

@@ -1,0 +1,197 @@
+"""Pin the CPU oracle against the reference's own known answers for the path
+(SURVEY.md 8(c) G1-G6).  CPU only."""
+import numpy as np
+import pytest
+
+from tests.helpers import known_answers, load_instance, sample_instance_values, \
+    synthetic_problem, synthetic_values, synthetic_pool
+
+
+# ---- G1: test/dual_set_test.jl ------------------------------------------------------
+
+V1, V2, V3, V4, V5 = [1., 2, 3], [1.0000000001, 2, 3], [4., 5, 6], [4., 5, 6, 7], [3., 2, 1]
+
+
+def test_dedup_equality_cases(oracle):        # dual_set_test.jl:9-13
+    assert oracle.isequal(V1, V2)
+    assert oracle.isequal(V3, V3)
+    assert not oracle.isequal(V1, V3)
+    assert not oracle.isequal(V3, V4)          # length mismatch
+    assert not oracle.isequal(V5, V1)          # equal 1-norm hash, different elements
+
+
+def test_dedup_push_counts(oracle):           # dual_set_test.jl:16-33
+    dvs = oracle.DualVertexSet()
+    sizes = []
+    for v in (V1, V2, V3, V4, V5):
+        dvs.push(v)
+        sizes.append(len(dvs))
+    assert sizes == [1, 1, 2, 3, 4]
+    assert len(oracle.DualVertexSet([V1, V2, V3, V4, V5])) == 4
+    assert len(list(oracle.DualVertexSet([V1, V2, V3, V4, V5]))) == 4
+
+
+def test_round_is_16_significant_bits_ties_even(oracle):
+    assert oracle.round_sig(1 + 2.0 ** -16) == 1.0
+    assert oracle.round_sig(1 + 3 * 2.0 ** -16) == 1 + 2.0 ** -14
+    assert oracle.round_sig(0.0) == 0.0 and np.signbit(oracle.round_sig(-0.0))
+    assert np.isnan(oracle.round_sig(float("nan")))
+    assert oracle.round_sig(float("inf")) == float("inf")
+    assert oracle.round_sig(5e-324) == 5e-324              # scale overflows -> x itself
+    assert oracle.round_sig(12345678.9) == 12345600.0      # ulp(16 bits) at 2^23 is 256
+
+
+def test_hash_is_a_gate_not_a_prefilter(oracle):
+    e = float.fromhex("0x1.0000e66666666p+0")
+    assert all(oracle.round_sig(v) == 1.0 for v in (e, 1.0))
+    assert not oracle.isequal([1, 1, 1], [e, e, e])
+
+
+def test_nan_vertex_never_duplicate_and_signed_zero_equal(oracle):
+    dvs = oracle.DualVertexSet()
+    dvs.push([1.0, float("nan")])
+    dvs.push([1.0, float("nan")])
+    assert len(dvs) == 2
+    assert oracle.isequal([0.0, 1.0], [-0.0, 1.0])
+
+
+# ---- lands known answers: test/sd_test.jl, test/sgd_example.jl -------------------------
+
+def test_lands_lookups_and_delta():           # sd_test.jl:17-23, 36-41
+    ka = known_answers()
+    assert ka["row_lookup_S2C5_1based"] == 5 and ka["col_lookup_X2_1based"] == 2
+    P, z = load_instance("lands")
+    from oracle import oracle as O
+    # template instantiated at RHS=3 (sd_test.jl:36), scenario RHS=5 -> delta 2.0
+    rbar = z["rbar"].copy()
+    rbar[z["pos_row"][0]] = ka["delta_case"]["template_rhs"]
+    P3 = O.Problem(P.m2, P.n1, rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
+    drhs, dT = O.delta_coefficients(P3, [ka["delta_case"]["scenario_rhs"]])
+    assert drhs[4] == ka["delta_case"]["expect"]
+    assert dT.sum() == 0.0 and np.count_nonzero(drhs) == 1
+
+
+def test_lands_eval_dual_equals_lp_objective(oracle):     # sd_test.jl:45-65 (G4)
+    ka = known_answers()["eval_dual"]
+    P, _ = load_instance("lands")
+    for rhs, obj, dual in zip(ka["rhs"], ka["obj"], ka["dual"]):
+        assert oracle.eval_dual(P, [rhs], ka["x"], dual) == obj
+    assert ka["obj"] == [264.0, 177.0]
+
+
+def test_lands_argmax_equals_resolved_lp(oracle):         # sd_test.jl:69-94 (G4)
+    ka = known_answers()["argmax"]
+    P, _ = load_instance("lands")
+    pool = oracle.DualVertexSet(ka["pool"])
+    assert len(pool) == ka["pool_size_expected"] == 3
+    vals = np.asarray(ka["scen_rhs"]).reshape(-1, 1)
+    mv, mi = oracle.argmax_procedure(P, vals, ka["x2"], pool.matrix())
+    assert list(mv) == ka["lp_obj_at_x2"] == [281.0, 281.0, 191.0, 383.0]
+    assert (mi >= 0).all()
+
+
+def test_lands_subgradient(oracle):           # sd_test.jl:97-103, sgd_example.jl:22-28 (G2)
+    ka = known_answers()["subgradient"]
+    assert ka["dual"] == [-11.0, -6.0, -19.0, 0.0, 51.0, 33.0, 5.5]
+    P, _ = load_instance("lands")
+    cut = oracle.build_sasa_cut(P, [[ka["rhs"]]], [1.0], ka["x"], [ka["dual"]])
+    assert list(cut["beta"]) == ka["expect"]
+
+
+@pytest.mark.parametrize("second", ["my_dual_2_glpk_reconstructed", "my_dual_2_highs"])
+def test_lands_build_sasa_cut_closed_form(oracle, second):   # sd_test.jl:207-235 (G3)
+    ka = known_answers()["sasa"]
+    P, _ = load_instance("lands")
+    d1, d2 = np.asarray(ka["my_dual"]), np.asarray(ka[second])
+    x = np.asarray(ka["x"])
+    vals = np.asarray(ka["scen_rhs"]).reshape(-1, 1)
+    if second.endswith("reconstructed"):      # the scores quoted in sd_test.jl:216-222
+        q = ka["quoted_scores"]
+        assert [oracle.eval_dual(P, vals[0], x, d) for d in (d1, d2)] == q["scen3"]
+        assert [oracle.eval_dual(P, vals[1], x, d) for d in (d1, d2)] == q["scen7"]
+    cut = oracle.build_sasa_cut(P, vals, ka["weights"], x, np.stack([d1, d2]))
+    assert list(cut["max_idx"]) == [1, 0]
+    T = P.T_dense()
+    r1 = P.rbar.copy(); r1[4] = 3.0
+    r2 = P.rbar.copy(); r2[4] = 7.0
+    expected_alpha = 1.5 / 2.0 * (d2 @ r1) + 0.5 / 2.0 * (d1 @ r2)
+    expected_beta = 1.5 / 2.0 * (-T.T @ d2) + 0.5 / 2.0 * (-T.T @ d1)
+    assert cut["alpha"] == expected_alpha
+    assert np.array_equal(cut["beta"], expected_beta)
+    assert cut["weight_mark"] == ka["weight_mark"] == 2.0
+
+
+# ---- invariants at real shapes (G5, G6) ---------------------------------------------
+
+@pytest.mark.parametrize("name", ["lands", "baa99-20", "ssn", "storm"])
+def test_cut_value_invariant_and_template_shift(oracle, name):
+    P, z = load_instance(name)
+    N = 40
+    vals = sample_instance_values(z, N)
+    pool = z["pool"]
+    x = z["x_alt"]
+    w = 0.5 + oracle.u01(4, np.arange(N))
+    cut = oracle.build_sasa_cut(P, vals, w, x, pool)
+    assert cut["status"] == 0
+    scale = np.sum(w / w.sum() * np.abs(cut["max_val"])) + 1.0
+    # G5: alpha + beta.x == sum p_i maxval_i   (epigraph.jl:140-142)
+    assert abs(cut["alpha"] + cut["beta"] @ x - cut["val"]) <= 1e-10 * scale
+    # G6: deltas are relative to the frozen template, so shifting rbar changes nothing
+    rbar2 = P.rbar.copy()
+    rbar2[P.pos_row[P.pos_col < 0]] += 3.25
+    P2 = oracle.Problem(P.m2, P.n1, rbar2, P.T_colptr, P.T_rowval, P.T_nzval,
+                        P.pos_row, P.pos_col)
+    cut2 = oracle.build_sasa_cut(P2, vals, w, x, pool)
+    assert np.array_equal(cut2["max_idx"], cut["max_idx"])
+    assert abs(cut2["alpha"] - cut["alpha"]) <= 1e-10 * scale
+    assert np.allclose(cut2["beta"], cut["beta"], rtol=1e-12, atol=1e-10)
+
+
+def test_delta_T_path_matches_dense_numpy(oracle):
+    """dT != 0 (no shipped instance has it): oracle vs a dense numpy evaluation."""
+    P = synthetic_problem(m2=40, n1=12, s=14, n_T=6)
+    N, K = 25, 30
+    vals = synthetic_values(P, N)
+    pool = synthetic_pool(P.m2, K)
+    x = 10.0 * oracle.u01(3, np.arange(P.n1))
+    w = 0.5 + oracle.u01(4, np.arange(N))
+    cut = oracle.build_sasa_cut(P, vals, w, x, pool)
+    T = P.T_dense()
+    alpha = 0.0
+    beta = np.zeros(P.n1)
+    for i in range(N):
+        r = P.rbar.copy(); Ti = T.copy()
+        for e in range(P.s):
+            if P.pos_col[e] < 0:
+                r[P.pos_row[e]] = vals[i, e]
+            else:
+                Ti[P.pos_row[e], P.pos_col[e]] = vals[i, e]
+        scores = pool @ (r - Ti @ x)
+        k = int(np.argmax(scores))
+        assert k == cut["max_idx"][i]
+        assert abs(scores[k] - cut["max_val"][i]) <= 1e-9 * max(1, abs(scores[k]))
+        assert abs(oracle.eval_dual(P, vals[i], x, pool[k]) - scores[k]) <= 1e-9 * max(1, abs(scores[k]))
+        alpha += w[i] / w.sum() * (pool[k] @ r)
+        beta += -w[i] / w.sum() * (Ti.T @ pool[k])
+    assert abs(alpha - cut["alpha"]) <= 1e-10 * max(1, abs(alpha))
+    assert np.allclose(beta, cut["beta"], rtol=1e-10, atol=1e-8)
+
+
+def test_argmax_first_index_on_ties_and_no_argmax(oracle):
+    P, _ = load_instance("lands")
+    v = np.array([-4., -1, -12, 0, 44, 28, 5.5])
+    pool = np.stack([v, v.copy(), v + 1e-3])       # vertices 0 and 1 tie exactly
+    mv, mi = oracle.argmax_procedure(P, [[5.0], [3.0]], [3., 3, 3, 3], pool[:2])
+    assert list(mi) == [0, 0]                       # strict > keeps the first maximum
+    bad = np.full((2, 7), np.nan)
+    mv, mi = oracle.argmax_procedure(P, [[5.0]], [3., 3, 3, 3], bad)
+    assert mi[0] == -1 and mv[0] == -np.inf          # NaN never beats -Inf (subprob.jl:156)
+    cut = oracle.build_sasa_cut(P, [[5.0]], [1.0], [3., 3, 3, 3], bad)
+    assert cut["status"] == -1
+
+
+def test_counter_rng_twin(oracle):
+    idx = np.array([0, 1, 2, 12345678901], dtype=np.uint64)
+    a = oracle.u01(9, idx)
+    b = [oracle.lib().orc_u01(9, int(i)) for i in idx]
+    assert list(a) == b and (a >= 0).all() and (a < 1).all()
