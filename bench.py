@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- cut-formation throughput of the B200 path (BASELINE.json's metric).
+
+A *step* is the cut formation of one SD iteration (reference ``sd_iteration!``,
+algorithm.jl:45-55 and :79-85, without the LP/QP solves) on the storm shape
+(SURVEY.md 8(d) C4): for each of E = 4 weighted epigraphs append 1 scenario, push 2 dual
+vertices (one new, one duplicate), then build the candidate cut and the regenerated
+incumbent cut.  One *evaluation* is one score[k, i] at one x (subprob.jl:155-158), so a
+step performs  2 * K * N  evaluations over all epigraphs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N > 1: launched by torchrun)
+  python bench.py --impl reference ...     the reference's CPU loop (oracle restatement)
+
+Prints ONE JSON line (rank 0).  Workload is weak-scaled: every GPU holds --scen-per-gpu
+scenarios; the pool is replicated.  Inputs (the scenario store, ~0.94 GB per GPU) are
+larger than L2, so no explicit L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scenario_x_vertex_argmax_evals_per_sec"
+UNIT = "evals/s"
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak.json")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scen-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--vertices", type=int, default=16384)
+    ap.add_argument("--epigraphs", type=int, default=4)
+    ap.add_argument("--instance", default="storm")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- workload ---------------
+
+def load_instance(name):
+    z = dict(np.load(os.path.join(ROOT, "tests", "golden", "instances", f"{name}.npz")))
+    return z
+
+
+def u01(seed, idx):
+    idx = np.asarray(idx, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        zz = np.uint64(seed) ^ (idx * np.uint64(0x9E3779B97F4A7C15))
+        zz = zz + np.uint64(0x9E3779B97F4A7C15)
+        zz = (zz ^ (zz >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        zz = (zz ^ (zz >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        zz = zz ^ (zz >> np.uint64(31))
+    return (zz >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def make_pool(z, K, extra):
+    """K + extra vertices: the harvested real storm vertices first, then synthetic ones
+    pi_kj = scale * (2u - 1), distinct under the dedup rule."""
+    m2 = int(z["m2"])
+    real = z["pool"]
+    n_syn = K + extra - len(real)
+    scale = float(np.abs(real).max())
+    syn = scale * (2.0 * u01(2, np.arange(n_syn * m2, dtype=np.uint64)).reshape(n_syn, m2) - 1.0)
+    return np.vstack([real, syn])
+
+
+def sample_values(z, seed, g0, n):
+    """Host twin of the device sampler (sqlp_epi_sample_scenarios)."""
+    s = len(z["pos_row"])
+    g = np.arange(g0, g0 + n, dtype=np.uint64)
+    u = u01(seed, (g[:, None] * np.uint64(s) + np.arange(s, dtype=np.uint64)[None, :]))
+    idx = (u[:, :, None] >= z["out_cdf"][None, :, :]).sum(axis=2)
+    idx = np.minimum(idx, np.maximum(z["out_cnt"][None, :] - 1, 0))
+    return np.take_along_axis(np.broadcast_to(z["out_vals"], (n,) + z["out_vals"].shape),
+                              idx[:, :, None], 2)[:, :, 0].copy()
+
+
+# ---------------------------------------------------------------- clocks -----------------
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML during the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------- CPU reference arm -----
+
+def cpu_reference(z, pool, n_target_seconds, x2, threads=0):
+    """The reference's argmax loop (oracle restatement, reference loop structure, all host
+    cores, 8-accumulator dots) on a bounded prefix of the workload's scenarios."""
+    from oracle import oracle as O
+    P = O.Problem(int(z["m2"]), int(z["n1"]), z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"],
+                  z["pos_row"], z["pos_col"])
+    nthr = O.max_threads() if threads <= 0 else threads
+    probe = sample_values(z, 1, 0, 2 * nthr)
+    t0 = time.perf_counter()
+    O.bench_argmax(P, probe, x2[0], pool, threads=nthr)
+    dt = time.perf_counter() - t0
+    rate = len(probe) / dt                       # scenarios / s for one x
+    n = int(max(2 * nthr, min(20000, rate * n_target_seconds / 2)))
+    vals = sample_values(z, 1, 0, n)
+    t0 = time.perf_counter()
+    for x in x2:                                 # the reference runs candidate and incumbent
+        O.bench_argmax(P, vals, x, pool, threads=nthr)     # as two separate passes
+    dt = time.perf_counter() - t0
+    evals = 2.0 * n * len(pool)
+    return {"value": evals / dt, "unit": UNIT, "cores": nthr, "kind": "port",
+            "sample": f"first {n} scenarios x all {len(pool)} vertices x 2 points in {dt:.2f} s; "
+                      f"C restatement of the reference loop (not Julia), OpenMP over scenarios, "
+                      f"8-accumulator dots"}, dt, evals
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    z = load_instance(args.instance)
+    pool = make_pool(z, args.vertices, 0)
+    n1 = int(z["n1"])
+    x2 = [z["x_ev"], z["x_alt"]] if "x_ev" in z else [10 * u01(3, np.arange(n1)), 10 * u01(5, np.arange(n1))]
+    per_step = max(1.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference(z, pool, min(per_step, 2.0), x2)
+    t_tot, e_tot, base = 0.0, 0.0, None
+    for _ in range(args.steps):
+        base, dt, ev = cpu_reference(z, pool, per_step, x2)
+        t_tot += dt
+        e_tot += ev
+    val = e_tot / t_tot
+    base["value"] = val
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(args, z, args.gpus),
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, z, world):
+    return {"workload": f"{args.instance} shape: cut formation of one SD iteration "
+                        f"(append 1 scenario + 2 pool pushes per epigraph, candidate + incumbent cut)",
+            "instance": args.instance, "s": int(len(z["pos_row"])), "m2": int(z["m2"]), "n1": int(z["n1"]),
+            "K_vertices": args.vertices, "N_scenarios_per_gpu": args.scen_per_gpu,
+            "N_scenarios_total": args.scen_per_gpu * world, "epigraphs": args.epigraphs,
+            "weights": "0.5+u", "points_per_step": 2, "parallelism": f"scenario-shard x{world}",
+            "l2": "inputs larger than L2 (scenario store 8*s_pad*N bytes per GPU)"}
+
+
+# ---------------------------------------------------------------- our arm ----------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sqlp_b200 import twosd as T
+    from sqlp_b200 import _lib
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ids = [T.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = T.Context(local, rank, world, ids[0])
+    else:
+        ctx = T.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    L = _lib.lib()
+
+    z = load_instance(args.instance)
+    m2, n1, s = int(z["m2"]), int(z["n1"]), len(z["pos_row"])
+    E, K0 = args.epigraphs, args.vertices
+    n_steps = args.steps + args.warmup
+    total_steps = 2 * n_steps + 2            # device-resident leg + e2e leg (+ slack)
+    pool_all = make_pool(z, K0, E * total_steps)
+    x_c = np.ascontiguousarray(z["x_ev"])
+    x_i = np.ascontiguousarray(z["x_alt"])
+
+    coef = T.sdSubprobCoefficients.from_tables(z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"],
+                                               z["pos_row"], z["pos_col"])
+    dvs = T.sdDualVertexSet(ctx=ctx, m2=m2)
+    t_setup = time.perf_counter()
+    ins, _ = dvs.push_many(pool_all[:K0])
+    assert ins.all() and len(dvs) == K0, "workload vertices are not distinct under the dedup rule"
+    epis = []
+    n_epi_global = (args.scen_per_gpu * world) // E
+    for e in range(E):
+        epi = T.sdEpigraph(coef, 1.0 / E, 0.0, dvs)
+        epi.set_outcomes(z["out_vals"], z["out_cdf"], z["out_cnt"])
+        epi.sample_scenarios(n_epi_global, seed=101 + e, weight_seed=201 + e)
+        epis.append(epi)
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    # per-step inputs: E new scenarios, E new vertices + E duplicates, 2 points
+    def step_inputs(t):
+        g = n_epi_global + t
+        scen = np.stack([sample_values(z, 101 + e, g, 1)[0] for e in range(E)])      # [E, s]
+        newv = pool_all[K0 + t * E: K0 + (t + 1) * E]                                  # [E, m2]
+        dupv = pool_all[(7 * t + 3 * np.arange(E)) % K0]
+        verts = np.empty((2 * E, m2))
+        verts[0::2] = newv
+        verts[1::2] = dupv
+        return scen, verts
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tns = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    x2_dev = torch.from_numpy(np.concatenate([x_c, x_i])).to(dev)
+    out_dev = torch.zeros(E, 2, n1 + 2, dtype=torch.float64, device=dev)
+
+    # ---- leg 1: device-resident inputs, no host sync inside the timed region ----------------
+    staged = []
+    for t in range(n_steps):
+        scen, verts = step_inputs(t)
+        staged.append((torch.from_numpy(scen).to(dev), torch.from_numpy(verts).to(dev)))
+    torch.cuda.synchronize()
+
+    def dev_step(t):
+        scen_d, verts_d = staged[t]
+        for e, epi in enumerate(epis):
+            _lib.check(L.sqlp_epi_add_scenarios_dev(epi._h, 1, C.c_void_p(scen_d[e].data_ptr()), None))
+            _lib.check(L.sqlp_pool_push_dev(dvs._h, 2, C.c_void_p(verts_d[2 * e].data_ptr())))
+        for e, epi in enumerate(epis):
+            _lib.check(L.sqlp_epi_build_cuts2_dev(epi._h, C.c_void_p(x2_dev.data_ptr()),
+                                                  C.c_void_p(out_dev[e].data_ptr())))
+
+    for t in range(args.warmup):
+        dev_step(t)
+    barrier()
+    ctx.profile(True)
+    ctx.profile_read(reset=True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for t in range(args.warmup, n_steps):
+        dev_step(t)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.finish()
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = ctx.launch_count() - launches0
+    c_ms, c_launches, c_flops = ctx.profile_read(reset=True)
+    ctx.profile(False)
+    K_after = len(dvs)
+    assert K_after == K0 + E * n_steps, (K_after, K0, E, n_steps)
+    cut_check = out_dev.cpu().numpy()
+
+    # evaluations performed by global step t (K grows by E new vertices per step, N by E)
+    def evals_of(t):
+        return 2.0 * (K0 + E * (t + 1)) * ((n_epi_global + t + 1) * E)
+
+    evals_dev = sum(evals_of(t) for t in range(args.warmup, n_steps))
+    value = evals_dev / (ms_dev * 1e-3)
+
+    # ---- leg 2: end to end through the blocking host API (host buffers in, cuts out) -------
+    base_t = n_steps
+    host_in = []
+    for t in range(n_steps):
+        scen, verts = step_inputs(base_t + t)
+        host_in.append((torch.from_numpy(scen).pin_memory(), torch.from_numpy(verts).pin_memory()))
+    xc_p, xi_p = torch.from_numpy(x_c).pin_memory(), torch.from_numpy(x_i).pin_memory()
+    alpha = np.zeros((E, 2)); beta = np.zeros((E, 2, n1)); wm = np.zeros(E); val = np.zeros((E, 2))
+    handles = (C.c_void_p * E)(*[e._h for e in epis])
+
+    def e2e_step(t):
+        scen_p, verts_p = host_in[t]
+        for e, epi in enumerate(epis):
+            _lib.check(L.sqlp_epi_add_scenarios(epi._h, 1, C.c_void_p(scen_p[e].data_ptr()), None))
+        _lib.check(L.sqlp_pool_push_batch(dvs._h, 2 * E, C.c_void_p(verts_p.data_ptr()), None, None))
+        _lib.check(L.sqlp_cell_build_cuts2(E, handles, C.c_void_p(xc_p.data_ptr()),
+                                           C.c_void_p(xi_p.data_ptr()), alpha.ctypes.data_as(C.c_void_p),
+                                           beta.ctypes.data_as(C.c_void_p), wm.ctypes.data_as(C.c_void_p),
+                                           val.ctypes.data_as(C.c_void_p)))
+
+    for t in range(args.warmup):
+        e2e_step(t)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(args.warmup, n_steps):
+        e2e_step(t)
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    evals_e2e = sum(evals_of(base_t + t) for t in range(args.warmup, n_steps))
+    e2e_value = evals_e2e / (ms_e2e * 1e-3)
+    h2d = (E * s + 2 * E * m2 + 2 * n1) * 8
+    d2h = E * (2 * (n1 + 2) + 1) * 8 + 2 * E * 16
+
+    # sanity: G5 invariant alpha + beta.x == val on the last step's cuts
+    for e in range(E):
+        for xi_, x in enumerate((x_c, x_i)):
+            lhs = alpha[e, xi_] + beta[e, xi_] @ x
+            assert abs(lhs - val[e, xi_]) <= 1e-9 * (abs(alpha[e, xi_]) + np.abs(beta[e, xi_] * x).sum()), \
+                "cut invariant violated"
+    assert np.isfinite(cut_check).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak = None
+    peak_src = "unmeasured"
+    if os.path.exists(FP64_PEAK_FILE):
+        with open(FP64_PEAK_FILE) as fh:
+            pk = json.load(fh)
+        peak = pk["dfma"]["sustained_tflops"]
+        peak_src = "measured DFMA-chain microkernel, sustained (profiles/fp64_peak.json; MEASURED_PEAKS.json has no FP64 figure)"
+    achieved = c_flops / (c_ms * 1e-3) * 1e-12 if c_ms > 0 else None
+    roofline = {"bound": "fp64", "kernel": "k_contract_argmax<2>", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": (achieved / peak) if (achieved and peak) else None,
+                "traffic": None, "peak_source": peak_src,
+                "launches": c_launches, "avg_launch_ms": c_ms / max(1, c_launches),
+                "share_of_step": c_ms / ms_dev if ms_dev else None,
+                "note": "executed flops = 2*s*K*N per launch, counted once although the launch "
+                        "serves both points (candidate and incumbent share the contraction)"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (real storm template + outcome tables, counter-RNG scenarios, "
+                    "94 harvested + synthetic vertices)",
+            "config": workload_config(args, z, world),
+            "cut_formation_ms_per_sd_iter": ms_dev / max(1, args.steps),
+            "executed_tflops": c_flops / (ms_dev * 1e-3) * 1e-12,
+            "roofline": roofline, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / max(1, args.steps)},
+            "gpu_launches": launches, "setup_s": t_setup}
+    if not args.no_cpu_baseline and world == 1:
+        base, _, _ = cpu_reference(z, pool_all[:K0], args.cpu_seconds, [x_c, x_i])
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,190 @@
+/*
+ * sqlp_b200.h -- C ABI of libsqlp_b200.so: the argmax cut-formation path of the
+ * yhz0/SQLP `TwoSD` solver as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this
+ * path -- it is pure Julia -- so each entry point replaces a Julia METHOD, cited below
+ * as file:line in the reference checkout; the `ccall` stubs a maintainer would add are
+ * in INTEGRATION.md and julia/TwoSDB200.jl.
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 = SQLP_OK, < 0 = error; the message of
+ *     the calling thread's last error is sqlp_last_error().
+ *   - plain pointers and sizes only; the caller owns every buffer it passes; the library
+ *     copies inputs before returning and never retains a host pointer.
+ *   - indices are 0-based (the Julia shim adds 1); matrices named [a x b] are row-major
+ *     unless stated; Tbar is CSC as in SparseMatrixCSC but 0-based.
+ *   - blocking calls return after the context's stream has drained.  `_dev` variants
+ *     take DEVICE pointers, only enqueue work and do not synchronise.
+ *   - a handle is driven by one host thread at a time.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef SQLP_B200_H
+#define SQLP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQLP_API __attribute__((visibility("default")))
+
+typedef struct sqlp_ctx sqlp_ctx;   /* one GPU (+ its rank in a scenario-sharded job)   */
+typedef struct sqlp_pool sqlp_pool; /* sdDualVertexSet, dual_set.jl:69-78               */
+typedef struct sqlp_epi sqlp_epi;   /* the device half of sdEpigraph, epigraph.jl:17-45 */
+
+enum {
+    SQLP_OK = 0,
+    SQLP_E_INVALID = -1,     /* bad argument                                             */
+    SQLP_E_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...)      */
+    SQLP_E_UNSUPPORTED = -3, /* e.g. sense = MAX: the reference's MAX branch never
+                                selects (subprob.jl:159-161)                             */
+    SQLP_E_NO_ARGMAX = -4,   /* empty pool or all scores NaN/-Inf: the reference throws
+                                UndefRefError at epigraph.jl:140                         */
+    SQLP_E_NOMEM = -5,
+    SQLP_E_NCCL = -6,
+    SQLP_E_RANGE = -7        /* scenario / vertex index out of range                     */
+};
+
+enum { SQLP_MIN_SENSE = 0, SQLP_MAX_SENSE = 1 }; /* MOI.OptimizationSense */
+
+SQLP_API const char *sqlp_version(void);
+SQLP_API const char *sqlp_last_error(void);
+
+/* ---------------------------------------------------------------- context ---------- */
+
+/* One context per GPU.  `device` is the CUDA ordinal. */
+SQLP_API int32_t sqlp_ctx_create(int32_t device, sqlp_ctx **out);
+
+/* Scenario-sharded job, one process (or thread) per GPU.  `nccl_id` is the 128-byte
+ * ncclUniqueId produced by sqlp_nccl_unique_id() on rank 0 and handed to every rank by
+ * the host (MPI, torch.distributed, a file, ...).  Scenario g of an epigraph lives on
+ * rank (g / 128) % world.  The pool is replicated. */
+SQLP_API int32_t sqlp_nccl_unique_id(void *out128);
+SQLP_API int32_t sqlp_ctx_create_dist(int32_t device, int32_t rank, int32_t world,
+                                      const void *nccl_id, sqlp_ctx **out);
+SQLP_API int32_t sqlp_ctx_destroy(sqlp_ctx *ctx);
+
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the
+ * context's own.  NULL restores the context's stream. */
+SQLP_API int32_t sqlp_ctx_set_stream(sqlp_ctx *ctx, void *cuda_stream);
+SQLP_API int32_t sqlp_ctx_synchronize(sqlp_ctx *ctx);
+/* Number of kernels this context has launched so far. */
+SQLP_API int32_t sqlp_ctx_launch_count(sqlp_ctx *ctx, int64_t *n);
+/* CUDA-event stopwatch on the context's stream: start, stop (enqueue), elapsed (syncs). */
+SQLP_API int32_t sqlp_ctx_timer_start(sqlp_ctx *ctx);
+SQLP_API int32_t sqlp_ctx_timer_stop(sqlp_ctx *ctx);
+SQLP_API int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *ctx, double *ms);
+/* Accumulated device time (ms) and launch count of the contraction kernel since the last
+ * call with reset != 0; measured with CUDA events around each launch when enabled. */
+SQLP_API int32_t sqlp_ctx_profile(sqlp_ctx *ctx, int32_t enable);
+SQLP_API int32_t sqlp_ctx_profile_read(sqlp_ctx *ctx, int32_t reset, double *contract_ms,
+                                       int64_t *contract_launches, double *contract_flops);
+
+/* ---------------------------------------------------------------- dual-vertex pool -- */
+
+/* sdDualVertexSet() -- dual_set.jl:76-78.  All vertices have length m2. */
+SQLP_API int32_t sqlp_pool_create(sqlp_ctx *ctx, int64_t m2, sqlp_pool **out);
+SQLP_API int32_t sqlp_pool_destroy(sqlp_pool *pool);
+
+/* Base.push!(dvs, v) -- dual_set.jl:84-93, with the dedup rule of :24-53 reproduced bit
+ * for bit (16 significant BINARY digits, sequential 1-norm hash as a gate, first match
+ * wins, insertion order kept).  *index = slot of v or of the stored duplicate.
+ * In a sharded job rank 0's vector is broadcast (NCCL) and every rank reaches the same
+ * decision; `v` is ignored on the other ranks. */
+SQLP_API int32_t sqlp_pool_push(sqlp_pool *pool, const double *v, int32_t *inserted,
+                                int64_t *index);
+/* n pushes in order (each sees the ones before it); one synchronisation at the end. */
+SQLP_API int32_t sqlp_pool_push_batch(sqlp_pool *pool, int64_t n, const double *v /*[n x m2]*/,
+                                      int32_t *inserted /*[n] or NULL*/,
+                                      int64_t *index /*[n] or NULL*/);
+/* Enqueue n pushes of device-resident vectors; no synchronisation, no readback. */
+SQLP_API int32_t sqlp_pool_push_dev(sqlp_pool *pool, int64_t n, const double *d_v);
+/* length(dvs) -- dual_set.jl:109-111 */
+SQLP_API int32_t sqlp_pool_size(sqlp_pool *pool, int64_t *K);
+/* dvs.data[index].data -- the stored vector (the reference returns Refs to these). */
+SQLP_API int32_t sqlp_pool_get(sqlp_pool *pool, int64_t index, double *out /*[m2]*/);
+/* hash_dual_vector(v) as computed on the device -- dual_set.jl:46-53 (debug/test). */
+SQLP_API int32_t sqlp_pool_hash(sqlp_pool *pool, const double *v, uint64_t *hash);
+
+/* ---------------------------------------------------------------- epigraph ---------- */
+
+/* sdEpigraph(prob, w, lb) after extract_coefficients -- epigraph.jl:52-61,
+ * subprob.jl:15-69.  rbar as (index, value) pairs, Tbar as 0-based CSC [m2 x n1], and the
+ * stochastic-position table resolved once from the .sto file: element e perturbs
+ * (pos_row[e], pos_col[e]); pos_col[e] = -1 means the RHS column (subprob.jl:113).
+ * Positions must be distinct. */
+SQLP_API int32_t sqlp_epi_create(sqlp_ctx *ctx, sqlp_pool *pool, int64_t m2, int64_t n1,
+                                 int64_t r_nnz, const int64_t *r_idx, const double *r_val,
+                                 const int64_t *T_colptr, const int64_t *T_rowval,
+                                 const double *T_nzval, int64_t s, const int32_t *pos_row,
+                                 const int32_t *pos_col, sqlp_epi **out);
+SQLP_API int32_t sqlp_epi_destroy(sqlp_epi *epi);
+
+/* add_scenario!(epi, scenario, weight) -- epigraph.jl:81-96 -- for n_new scenarios, with
+ * delta_coefficients (subprob.jl:104-121) built on the device.  values[i][e] is the
+ * realised value of table element e; weights NULL means 1.0 (algorithm.jl:46).
+ * In a sharded job every rank passes the same arrays and keeps the scenarios it owns. */
+SQLP_API int32_t sqlp_epi_add_scenarios(sqlp_epi *epi, int64_t n_new,
+                                        const double *values /*[n_new x s]*/,
+                                        const double *weights /*[n_new] or NULL*/);
+SQLP_API int32_t sqlp_epi_add_scenarios_dev(sqlp_epi *epi, int64_t n_new, const double *d_values,
+                                            const double *weights_host /*[n_new] or NULL*/);
+
+/* Device-side sampling of INDEP DISCRETE elements (rand(sto), smps_sto.jl:113-149, with an
+ * explicit counter generator instead of a global RNG): outcome tables are rectangular
+ * [s x max_outcomes] with cnt[e] valid entries, cdf = running sum of probabilities.
+ * Scenario g (0-based ordinal in this epigraph) takes, for element e,
+ *   u = u01(seed, g*s + e),  value = vals[e][min(#{c : cdf[e][c] <= u}, cnt[e]-1)],
+ * and weight 1.0 (weight_seed = 0) or 0.5 + u01(weight_seed, g).  u01 is the splitmix64
+ * counter generator of SURVEY.md 8(d).  Each rank generates only the scenarios it owns. */
+SQLP_API int32_t sqlp_epi_set_outcomes(sqlp_epi *epi, int64_t max_outcomes, const double *vals,
+                                       const double *cdf, const int32_t *cnt);
+SQLP_API int32_t sqlp_epi_sample_scenarios(sqlp_epi *epi, int64_t n_new, uint64_t seed,
+                                           uint64_t weight_seed);
+
+/* Global scenario count, scenarios held by this rank, epi.total_scenario_weight. */
+SQLP_API int32_t sqlp_epi_counts(sqlp_epi *epi, int64_t *n_global, int64_t *n_local,
+                                 double *total_weight);
+
+/* delta_coefficients readback for LOCAL scenario i -- subprob.jl:104-121:
+ * delta_rhs dense [m2], delta_T one value per table element (0 for RHS elements). */
+SQLP_API int32_t sqlp_epi_delta(sqlp_epi *epi, int64_t local_scen, double *delta_rhs,
+                                double *delta_T);
+
+/* argmax_procedure(coef, delta_set, x, dual_vertices; sense) -- subprob.jl:141-169.
+ * max_val[i], max_idx[i] (pool slot, -1 if nothing beat -Inf) for this rank's scenarios
+ * in local order (n_local entries). */
+SQLP_API int32_t sqlp_epi_argmax(sqlp_epi *epi, const double *x /*[n1]*/, int32_t sense,
+                                 double *max_val, int64_t *max_idx);
+
+/* build_sasa_cut(epi, x, dual_vertices)::sdCut -- epigraph.jl:125-146.
+ * val (may be NULL) receives sum_i p_i max_val_i, the quantity of epigraph.jl:142. */
+SQLP_API int32_t sqlp_epi_build_cut(sqlp_epi *epi, const double *x, double *alpha,
+                                    double *beta /*[n1]*/, double *weight_mark, double *val);
+/* The candidate cut and the regenerated incumbent cut of one iteration
+ * (algorithm.jl:80 and :83) in one pass; when no random element touches Tbar the two
+ * share a single contraction.  beta is two contiguous n1-vectors. */
+SQLP_API int32_t sqlp_epi_build_cuts2(sqlp_epi *epi, const double *x_cand, const double *x_inc,
+                                      double alpha[2], double *beta /*[2 x n1]*/,
+                                      double *weight_mark, double *val /*[2] or NULL*/);
+/* Same for every epigraph of a cell (the loop of algorithm.jl:79-85), one
+ * synchronisation.  Outputs are [n_epi][2], [n_epi][2][n1], [n_epi]. */
+SQLP_API int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, const double *x_cand,
+                                       const double *x_inc, double *alpha, double *beta,
+                                       double *weight_mark, double *val /*or NULL*/);
+/* Enqueue only: d_x2 = [x_cand | x_inc] on the device, d_out = [2][n1 + 2] on the device
+ * holding (alpha, beta[n1], val) per x.  Errors such as a missing argmax surface at the
+ * next blocking call. */
+SQLP_API int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *epi, const double *d_x2, double *d_out);
+
+/* eval_dual(coef, delta, x, dual) -- subprob.jl:128-131 -- for LOCAL scenario `scen` and
+ * pool slot `vertex`, in the reference's operation order (debug / parity pin). */
+SQLP_API int32_t sqlp_eval_dual(sqlp_epi *epi, int64_t local_scen, int64_t vertex,
+                                const double *x, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQLP_B200_H */

@@ -68,7 +68,7 @@ def lib():
         L.orc_build_sasa_cut.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_void_p]
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bench_argmax.restype = C.c_int32
         L.orc_bench_argmax.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
@@ -227,7 +227,7 @@ def score_pair(P: Problem, values, x, vertex):
     return s.value, sl.value
 
 
-def build_sasa_cut(P: Problem, values, weights, x, pool, total_weight=None):
+def build_sasa_cut(P: Problem, values, weights, x, pool, total_weight=None, forced_idx=None):
     """Returns dict(alpha, beta, weight_mark, val, max_val, max_idx, status)."""
     values = _f64(values).reshape(-1, max(P.s, 1))
     N = len(values)
@@ -243,9 +243,11 @@ def build_sasa_cut(P: Problem, values, weights, x, pool, total_weight=None):
     beta = np.zeros(P.n1)
     mv = np.zeros(N)
     mi = np.zeros(N, dtype=np.int64)
+    fi = None if forced_idx is None else np.ascontiguousarray(forced_idx, dtype=np.int64)
     st = lib().orc_build_sasa_cut(P.ref, N, _p(values), _p(weights), float(total_weight),
                                   _p(x), _p(pool), len(pool), C.byref(alpha), _p(beta),
-                                  C.byref(wm), C.byref(val), _p(mv), _p(mi))
+                                  C.byref(wm), C.byref(val), _p(mv), _p(mi),
+                                  None if fi is None else _p(fi))
     return dict(alpha=alpha.value, beta=beta, weight_mark=wm.value, val=val.value,
                 max_val=mv, max_idx=mi, status=st)
 

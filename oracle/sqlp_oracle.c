@@ -365,13 +365,19 @@ ORC_API void orc_score_pair(const orc_problem *P, const double *values, const do
  * Outputs alpha, beta[n1], weight_mark, val (= sum p_i maxval_i, the dead variable of
  * :142, kept because alpha + beta.x == val is invariant G5), and optionally the
  * argmax results.  Returns 0, or -1 if some scenario had no argmax (UndefRefError in
- * the reference at :140). */
+ * the reference at :140).
+ * forced_idx (normally NULL): aggregate THESE vertices instead of the oracle's own argmax.
+ * Used by the parity tests after the device's selection passed the north-star rule
+ * (identical, or within the 1e-12 relative score gap): on exact or near ties two valid
+ * selections give different (alpha, beta) with the same alpha + beta.x, so coefficients
+ * are compared on the same selection. */
 ORC_API int32_t orc_build_sasa_cut(const orc_problem *P, int64_t N, const double *values,
                                    const double *weights, double total_weight,
                                    const double *x, const double *pool, int64_t K,
                                    double *alpha_out, double *beta_out,
                                    double *weight_mark, double *val_out,
-                                   double *max_val_out, int64_t *max_idx_out)
+                                   double *max_val_out, int64_t *max_idx_out,
+                                   const int64_t *forced_idx)
 {
     int64_t m2 = P->m2, n1 = P->n1;
     double *max_val = max_val_out ? max_val_out : malloc((size_t)(N ? N : 1) * sizeof(double));
@@ -387,8 +393,9 @@ ORC_API int32_t orc_build_sasa_cut(const orc_problem *P, int64_t N, const double
     int32_t status = 0;
 
     for (int64_t i = 0; i < N; ++i) {                            /* :134 */
-        if (max_idx[i] < 0) { status = -1; break; }
-        const double *dual = pool + max_idx[i] * m2;             /* :136 */
+        int64_t sel = forced_idx ? forced_idx[i] : max_idx[i];
+        if (sel < 0) { status = -1; break; }
+        const double *dual = pool + sel * m2;                    /* :136 */
         double p = weights[i] / total_weight;                    /* :138 */
         orc_delta_coefficients(P, values + i * P->s, drhs, dT);
 

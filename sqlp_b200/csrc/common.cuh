@@ -1,0 +1,73 @@
+// common.cuh -- shared device helpers for libsqlp_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define SQLP_TILE 128  // scenarios per tile == vertices per chunk
+#define SQLP_BK 8      // stochastic rows per pipeline slab (s is padded to a multiple)
+
+namespace sqlp {
+
+// Base.round(x; base=2, sigdigits=16) -- call sites dual_set.jl:32-33,51 of the reference.
+// hidigit = 1 + exponent(x); scale by 2^(16 - hidigit), round half to even, scale back.
+// All scalings are exact powers of two, so this is bit-identical to the CPU oracle.
+__device__ __forceinline__ double round_sig16(double x)
+{
+    if (!isfinite(x) || x == 0.0) return x;
+    int digits = 15 - ilogb(x);
+    double r;
+    if (digits >= 0) {
+        if (digits > 1023) return x;  // 2.0^digits = Inf -> NaN -> reference returns x
+        r = scalbn(rint(scalbn(x, digits)), -digits);
+    } else {
+        r = scalbn(rint(scalbn(x, digits)), -digits);
+    }
+    if (!isfinite(r)) return (digits > 0) ? x : copysign(0.0, x);
+    return r;
+}
+
+// splitmix64 counter generator of SURVEY.md 8(d); twin of orc_u01 in the oracle.
+__host__ __device__ __forceinline__ double u01(uint64_t seed, uint64_t idx)
+{
+    uint64_t z = seed ^ (idx * 0x9E3779B97F4A7C15ULL);
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Scenario g of an epigraph lives on rank (g / 128) % world, at this local slot.
+__host__ __device__ __forceinline__ int owner_of(int64_t g, int world)
+{
+    return (int)((g / SQLP_TILE) % world);
+}
+__host__ __device__ __forceinline__ int64_t local_of(int64_t g, int world)
+{
+    return (g / ((int64_t)SQLP_TILE * world)) * SQLP_TILE + g % SQLP_TILE;
+}
+// Number of scenarios with ordinal < n_global held by `rank`.
+__host__ __device__ __forceinline__ int64_t local_count(int64_t n_global, int rank, int world)
+{
+    int64_t full = n_global / SQLP_TILE;  // complete 128-blocks
+    int64_t rem = n_global % SQLP_TILE;
+    int64_t mine = full / world + ((full % world) > rank ? 1 : 0);
+    int64_t n = mine * SQLP_TILE;
+    if (rem && (int)(full % world) == rank) n += rem;
+    return n;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+}  // namespace sqlp

@@ -1,0 +1,148 @@
+// kernels_pool.cuh -- the device-resident dual-vertex pool (sdDualVertexSet).
+//
+// Reference behaviour reproduced bit for bit (src/sd_algorithm/dual_set.jl):
+//   hash_dual_vector :46-53   sequential 1-norm, rounded to 16 significant bits, as UInt64
+//   isequal          :24-40   same hash AND every element equal after rounding (fp !=)
+//   push!            :84-93   first match in insertion order wins, else append
+//
+// HBM layout: pi[cap][m2] row-major full vertices, hash[cap] uint64.  The pool size K
+// lives in device memory so pushes can be enqueued back to back without a host round trip.
+#pragma once
+#include "common.cuh"
+
+namespace sqlp {
+
+struct PushResult {
+    int64_t index;
+    int32_t inserted;
+    int32_t pad;
+};
+
+// Scratch shared by the two push kernels (one per pool).
+struct PushScratch {
+    unsigned long long hash;   // hash of the vector being pushed
+    int match;                 // lowest stored slot equal to it, INT_MAX if none
+    unsigned int done;         // blocks finished (last-block-commits pattern)
+};
+
+// Kernel 1: hash of the new vector (sequential order, one thread) and its rounded copy.
+__global__ void k_pool_prepare(const double *__restrict__ v, int m2, double *__restrict__ vr,
+                               PushScratch *__restrict__ sc)
+{
+    extern __shared__ double sh[];
+    for (int j = threadIdx.x; j < m2; j += blockDim.x) {
+        double x = v[j];
+        sh[j] = fabs(x);
+        vr[j] = round_sig16(x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mysum = 0.0;
+        for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, sh[j]);
+        sc->hash = (unsigned long long)__double_as_longlong(round_sig16(mysum));
+        sc->match = 0x7fffffff;
+        sc->done = 0u;
+    }
+}
+
+// Kernel 2: one warp per stored vertex (grid-stride); the last block to finish commits.
+__global__ void k_pool_find_commit(double *__restrict__ pi, unsigned long long *__restrict__ hash,
+                                   long long *__restrict__ d_K, int m2,
+                                   const double *__restrict__ v, const double *__restrict__ vr,
+                                   PushScratch *__restrict__ sc, PushResult *__restrict__ result)
+{
+    const long long K = *d_K;
+    const unsigned long long h = sc->hash;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * warps_per_block;
+
+    for (long long k = warp0; k < K; k += nwarps) {
+        if (hash[k] != h) continue;                       // :26 hash gate (warp-uniform)
+        const double *row = pi + k * (long long)m2;
+        bool same = true;
+        for (int j = lane; j < m2; j += 32) {
+            double r1 = vr[j];
+            double r2 = round_sig16(row[j]);
+            if (r1 != r2) same = false;                   // :34  NaN != NaN
+        }
+        same = __all_sync(0xffffffffu, same);
+        if (same && lane == 0) atomicMin(&sc->match, (int)k);
+    }
+
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(&sc->done, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int match = *((volatile int *)&sc->match);
+    if (match != 0x7fffffff) {
+        if (threadIdx.x == 0) {
+            result->index = match;
+            result->inserted = 0;
+        }
+        return;
+    }
+    double *dst = pi + K * (long long)m2;                 // :91 append
+    for (int j = threadIdx.x; j < m2; j += blockDim.x) dst[j] = v[j];
+    if (threadIdx.x == 0) {
+        hash[K] = h;
+        result->index = K;
+        result->inserted = 1;
+        __threadfence();
+        *d_K = K + 1;
+    }
+}
+
+// Stochastic-row view of the pool in the contraction's tile layout:
+//   piS[chunk][j][128]  with vertex k at (chunk = k / 128, column k % 128), j < s_pad.
+// Idempotent; run over [k_lo, *d_K) after pushes.
+__global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows,
+                            int n_rows, int s_pad, double *__restrict__ piS, long long k_lo,
+                            const long long *__restrict__ d_K)
+{
+    const long long K = *d_K;
+    const long long total = (K - k_lo) * n_rows;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        long long k = k_lo + t / n_rows;
+        int j = (int)(t % n_rows);
+        piS[((k >> 7) * s_pad + j) * SQLP_TILE + (k & 127)] = pi[k * m2 + s_rows[j]];
+    }
+}
+
+// Per-epigraph vertex tables: rt[k][0] = rho_k = pi_k . rbar (index order),
+// rt[k][1 + c] = tau_kc = sum over column c of Tbar (rows ascending) of T * pi_k[row]
+// -- the per-column gather of `(transfer)' * dual`, epigraph.jl:141.
+__global__ void k_epi_tables(const double *__restrict__ pi, int m2, const double *__restrict__ rbar,
+                             const long long *__restrict__ T_colptr, const int *__restrict__ T_rowval,
+                             const double *__restrict__ T_nzval, int n1, double *__restrict__ rt,
+                             long long k_lo, const long long *__restrict__ d_K)
+{
+    const long long K = *d_K;
+    const int RT = n1 + 1;
+    for (long long k = k_lo + blockIdx.x; k < K; k += gridDim.x) {
+        const double *row = pi + k * (long long)m2;
+        for (int c = threadIdx.x; c < RT; c += blockDim.x) {
+            double acc = 0.0;
+            if (c == 0) {
+                for (int j = 0; j < m2; ++j) {
+                    double r = rbar[j];
+                    if (r != 0.0) acc = __dadd_rn(acc, __dmul_rn(row[j], r));
+                }
+            } else {
+                for (long long q = T_colptr[c - 1]; q < T_colptr[c]; ++q)
+                    acc = __dadd_rn(acc, __dmul_rn(T_nzval[q], row[T_rowval[q]]));
+            }
+            rt[k * RT + c] = acc;
+        }
+    }
+}
+
+}  // namespace sqlp

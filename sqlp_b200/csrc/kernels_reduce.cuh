@@ -1,0 +1,238 @@
+// kernels_reduce.cuh -- bias vectors, the deterministic weighted cut reduction, eval_dual.
+//
+// Reference: build_sasa_cut, src/sd_algorithm/epigraph.jl:134-143
+//   p      = w_i / W
+//   alpha += p * dot(pi*, rbar + delta_rhs_i)
+//   beta  += -p * (Tbar + delta_T_i)' * pi*
+//   val   += p * max_val_i
+// Restated per scenario with the per-vertex tables rho_k = pi_k . rbar and
+// tau_k = Tbar' pi_k (kernels_pool.cuh):
+//   alpha_i = rho_k* + sum_{j in S} PiS[k*, j] * delta_rhs_i[j]
+//   beta_i  = tau_k* + sum_{T elements e} delta_T_ie * pi*[row_e]  (added to column col_e)
+// Accumulation is deterministic: one block per 128-scenario tile sums its scenarios in
+// index order, block partials are summed in block order by a fixed two-level pass, rank
+// partials (after the all-gather) in rank order.  No floating-point atomics anywhere.
+#pragma once
+#include "common.cuh"
+
+namespace sqlp {
+
+// base_x = rbar - Tbar * x   (subprob.jl:147), column-ordered scatter like SparseArrays.
+__global__ void k_base(const double *__restrict__ rbar, int m2, int n1,
+                       const long long *__restrict__ T_colptr, const int *__restrict__ T_rowval,
+                       const double *__restrict__ T_nzval, const double *__restrict__ x2,
+                       double *__restrict__ base)
+{
+    extern __shared__ double y[];           // [m2]
+    const double *x = x2 + (long long)blockIdx.x * n1;
+    for (int j = threadIdx.x; j < m2; j += blockDim.x) y[j] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < n1; ++c) {
+            const double xc = x[c];
+            for (long long q = T_colptr[c]; q < T_colptr[c + 1]; ++q)
+                y[T_rowval[q]] = __dadd_rn(y[T_rowval[q]], __dmul_rn(T_nzval[q], xc));
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m2; j += blockDim.x)
+        base[(long long)blockIdx.x * m2 + j] = __dsub_rn(rbar[j], y[j]);
+}
+
+// bias_x[k] = dot(pi_k, base_x)  (the first dot of subprob.jl:155), one warp per vertex,
+// lanes stride the row, fixed shuffle tree.  Slots K..kpad-1 get -inf so padded vertices
+// of the last chunk can never win.
+template <int NX>
+__global__ void k_bias(const double *__restrict__ pi, int m2, const double *__restrict__ base,
+                       const long long *__restrict__ d_K, long long kpad, double *__restrict__ bias,
+                       long long bias_stride)
+{
+    const long long K = *d_K;
+    const int lane = threadIdx.x & 31;
+    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= kpad) return;
+    if (k >= K) {
+        if (lane < NX) bias[lane * bias_stride + k] = -INFINITY;
+        return;
+    }
+    const double *row = pi + k * (long long)m2;
+    double s[NX];
+#pragma unroll
+    for (int x = 0; x < NX; ++x) s[x] = 0.0;
+    for (int j = lane; j < m2; j += 32) {
+        const double p = row[j];
+#pragma unroll
+        for (int x = 0; x < NX; ++x) s[x] = fma(p, base[(long long)x * m2 + j], s[x]);
+    }
+#pragma unroll
+    for (int x = 0; x < NX; ++x) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s[x] += __shfl_xor_sync(0xffffffffu, s[x], off);
+        if (lane == 0) bias[x * bias_stride + k] = s[x];
+    }
+}
+
+struct ReduceArgs {
+    const double *D;          // [ntiles][s_pad][128]  delta_rhs on S
+    const double *dT;         // [n_local][n_T] or null
+    const double *w;          // [n_local]
+    const double *PiS;        // [nchunks][s_pad][128]
+    const double *rt;         // [K][n1 + 1]  (rho, tau)
+    const double *best_val;   // [NX][out_stride]
+    const int *best_idx;      // [NX][out_stride]
+    long long out_stride;
+    long long n_local;
+    int s_pad, n_rows, n1;
+    double total_weight;
+    // delta_T scatter: elements sorted by first-stage column
+    int n_T;
+    const int *tc_col;        // [n_T] column, ascending
+    const int *tc_j;          // [n_T] row slot in S
+    const int *tc_slot;       // [n_T] slot in dT
+    double *partial;          // [ntiles][NX][n1 + 2]   (alpha, beta[n1], val)
+    int *flags;               // bit 0: some scenario had no argmax
+};
+
+template <int NX>
+__global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
+{
+    __shared__ double a_i[NX][SQLP_TILE];   // PiS[k*, :] . delta_rhs_i
+    __shared__ double p_i[SQLP_TILE];
+    __shared__ int k_i[NX][SQLP_TILE];
+    const long long tile = blockIdx.x;
+    const long long i0 = tile * SQLP_TILE;
+    const int cnt = (int)min((long long)SQLP_TILE, a.n_local - i0);
+    const double *Dt = a.D + tile * (long long)a.s_pad * SQLP_TILE;
+
+    // phase A: thread per (x, scenario)
+    for (int q = threadIdx.x; q < NX * SQLP_TILE; q += blockDim.x) {
+        const int x = q / SQLP_TILE, c = q % SQLP_TILE;
+        int k = -1;
+        double acc = 0.0;
+        if (c < cnt) {
+            k = a.best_idx[x * a.out_stride + i0 + c];
+            if (k < 0) {
+                atomicOr(a.flags, 1);
+            } else {
+                const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE + (k & 127);
+                for (int j = 0; j < a.n_rows; ++j)
+                    acc = fma(P[(long long)j * SQLP_TILE], Dt[(long long)j * SQLP_TILE + c], acc);
+            }
+            if (x == 0) p_i[c] = a.w[i0 + c] / a.total_weight;   // epigraph.jl:138
+        }
+        a_i[x][c] = acc;
+        k_i[x][c] = k;
+    }
+    __syncthreads();
+
+    // phase B: thread per (x, output column); scenarios in index order
+    const int NC = a.n1 + 2;
+    for (int q = threadIdx.x; q < NX * NC; q += blockDim.x) {
+        const int x = q / NC, col = q % NC;
+        double sum = 0.0;
+        int t0 = 0, t1 = 0;
+        if (col >= 1 && col <= a.n1 && a.n_T) {   // delta_T elements landing in this column
+            while (t0 < a.n_T && a.tc_col[t0] < col - 1) ++t0;
+            t1 = t0;
+            while (t1 < a.n_T && a.tc_col[t1] == col - 1) ++t1;
+        }
+        for (int c = 0; c < cnt; ++c) {
+            const int k = k_i[x][c];
+            if (k < 0) continue;
+            const double p = p_i[c];
+            double term;
+            if (col == 0) {
+                term = a.rt[(long long)k * (a.n1 + 1)] + a_i[x][c];           // :140
+                sum = fma(p, term, sum);
+            } else if (col <= a.n1) {
+                term = a.rt[(long long)k * (a.n1 + 1) + col];                 // :141
+                for (int t = t0; t < t1; ++t) {
+                    const double piv =
+                        a.PiS[((long long)(k >> 7) * a.s_pad + a.tc_j[t]) * SQLP_TILE + (k & 127)];
+                    term = fma(a.dT[(i0 + c) * (long long)a.n_T + a.tc_slot[t]], piv, term);
+                }
+                sum = fma(-p, term, sum);
+            } else {
+                sum = fma(p, a.best_val[x * a.out_stride + i0 + c], sum);     // :142
+            }
+        }
+        a.partial[(tile * NX + x) * NC + col] = sum;
+    }
+}
+
+// out[g][q] = sum over p in [g*group, min(n,(g+1)*group)) of in[p][q], in order.
+__global__ void k_sum_groups(const double *__restrict__ in, long long n, int group, int width,
+                             double *__restrict__ out)
+{
+    const long long g = blockIdx.x;
+    const long long p0 = g * group, p1 = min(n, p0 + group);
+    for (int q = threadIdx.x; q < width; q += blockDim.x) {
+        double s = 0.0;
+        for (long long p = p0; p < p1; ++p) s += in[p * width + q];
+        out[g * width + q] = s;
+    }
+}
+
+// eval_dual, subprob.jl:128-131, in the reference's operation order (single thread):
+//   dot(dual, (rbar + delta_rhs) - (Tbar + delta_T) * x)
+struct EvalArgs {
+    const double *pi_row;     // [m2]
+    const double *rbar;       // [m2]
+    const long long *T_colptr;
+    const int *T_rowval;
+    const double *T_nzval;
+    int m2, n1, s_pad, n_rows, n_T;
+    const int *s_rows;        // [n_rows] stage-2 row of slot j
+    const double *Dcol;       // D tile base + column
+    const double *dTrow;      // [n_T] or null
+    // delta_T elements sorted by (col, row): position in CSC order
+    const int *mc_col;
+    const int *mc_row;
+    const int *mc_slot;
+    const double *x;
+    double *out;
+    double *scratch;          // [2 * m2]
+};
+
+__global__ void k_eval_dual(EvalArgs a)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    double *y = a.scratch, *r = a.scratch + a.m2;
+    for (int j = 0; j < a.m2; ++j) { y[j] = 0.0; r[j] = a.rbar[j]; }
+    for (int j = 0; j < a.n_rows; ++j)
+        r[a.s_rows[j]] = __dadd_rn(a.rbar[a.s_rows[j]], a.Dcol[(long long)j * SQLP_TILE]);
+    int t = 0;
+    for (int c = 0; c < a.n1; ++c) {   // merged (Tbar + delta_T) * x, rows ascending per column
+        const double xc = a.x[c];
+        long long q = a.T_colptr[c], qe = a.T_colptr[c + 1];
+        while (t < a.n_T && a.mc_col[t] < c) ++t;
+        while (q < qe || (t < a.n_T && a.mc_col[t] == c)) {
+            const int rq = (q < qe) ? a.T_rowval[q] : 0x7fffffff;
+            const int rt = (t < a.n_T && a.mc_col[t] == c) ? a.mc_row[t] : 0x7fffffff;
+            if (rq < rt) {
+                y[rq] = __dadd_rn(y[rq], __dmul_rn(a.T_nzval[q], xc)); ++q;
+            } else if (rt < rq) {
+                y[rt] = __dadd_rn(y[rt], __dmul_rn(a.dTrow[a.mc_slot[t]], xc)); ++t;
+            } else {
+                y[rq] = __dadd_rn(y[rq], __dmul_rn(__dadd_rn(a.T_nzval[q], a.dTrow[a.mc_slot[t]]), xc));
+                ++q; ++t;
+            }
+        }
+    }
+    double s = 0.0;
+    for (int j = 0; j < a.m2; ++j) s = __dadd_rn(s, __dmul_rn(a.pi_row[j], __dsub_rn(r[j], y[j])));
+    *a.out = s;
+}
+
+// Rank-ordered sum of all-gathered partials: out[q] = sum_r in[r][q], r = 0..world-1.
+__global__ void k_rank_sum(const double *__restrict__ in, int world, int width,
+                           double *__restrict__ out)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= width) return;
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += in[(long long)r * width + q];
+    out[q] = s;
+}
+
+}  // namespace sqlp

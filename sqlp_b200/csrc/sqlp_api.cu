@@ -1,0 +1,1222 @@
+// sqlp_api.cu -- host side of libsqlp_b200.so: handles, memory, launches, NCCL plumbing.
+// The C ABI is declared in include/sqlp_b200.h; kernels live in the kernels_*.cuh files.
+// No CPU fallback: every compute entry point needs a CUDA device and fails otherwise.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sqlp_b200.h"
+#include "common.cuh"
+#include "kernels_contract.cuh"
+#include "kernels_delta.cuh"
+#include "kernels_pool.cuh"
+#include "kernels_reduce.cuh"
+
+namespace {
+
+using namespace sqlp;
+
+thread_local std::string g_err;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            throw Error(SQLP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)            \
+    do {                                    \
+        if (!(cond)) throw Error(code, msg); \
+    } while (0)
+
+template <class F>
+int32_t guard(F &&f)
+{
+    try {
+        f();
+        return SQLP_OK;
+    } catch (const Error &e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        g_err = "host allocation failed";
+        return SQLP_E_NOMEM;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return SQLP_E_INVALID;
+    }
+}
+
+// ---------------------------------------------------------------- NCCL (dlopen) --------
+// Only the scenario-sharded mode needs NCCL, so it is bound lazily; a single-GPU host never
+// loads it.  Types restated from nccl.h (2.x ABI).
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0 };
+enum { ncclFloat64_ = 8 };  // ncclDataType_t: ncclDouble
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+void load_nccl()
+{
+    if (g_nccl.h) return;
+    const char *env = getenv("SQLP_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    REQUIRE(h, SQLP_E_NCCL, "cannot dlopen libnccl.so.2 (set SQLP_NCCL_LIB)");
+    auto sym = [&](const char *s) {
+        void *p = dlsym(h, s);
+        REQUIRE(p, SQLP_E_NCCL, std::string("missing NCCL symbol ") + s);
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))sym("ncclBroadcast");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    g_nccl.h = h;
+}
+#define NK(call)                                                                            \
+    do {                                                                                    \
+        int r_ = (call);                                                                    \
+        if (r_ != ncclSuccess_)                                                             \
+            throw Error(SQLP_E_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------- device buffers -------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    // Grow to at least `need` bytes.  keep = bytes of existing content to preserve;
+    // the remainder is zero-filled.  All work is enqueued on `st`.
+    void ensure(size_t need, size_t keep, cudaStream_t st, bool zero = true)
+    {
+        if (need <= bytes) return;
+        size_t nb = std::max(need, bytes + bytes / 2);
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, nb);
+        if (e != cudaSuccess)
+            throw Error(SQLP_E_NOMEM, std::string("cudaMalloc(") + std::to_string(nb) +
+                                          "): " + cudaGetErrorString(e));
+        if (keep) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
+        if (zero && nb > keep) CK(cudaMemsetAsync((char *)np + keep, 0, nb - keep, st));
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        p = np;
+        bytes = nb;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class T>
+void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
+{
+    b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T), 0, st);
+    if (!v.empty())
+        CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- handles --------------
+struct sqlp_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    int64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    double prof_flops = 0.0;
+    bool smem_attr[3] = {false, false, false};
+    void bind() const { CK(cudaSetDevice(device)); }
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+    do {                                                                 \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        CK(cudaGetLastError());                                          \
+        ++(ctx)->launches;                                               \
+    } while (0)
+
+struct PoolView {   // the pool restricted to one set of stochastic rows, in tile layout
+    std::vector<int> rows;
+    int n_rows = 0, s_pad = 0;
+    DevBuf d_rows, d_piS;
+    int64_t synced_lo = 0;   // vertices < synced_lo are final in d_piS
+};
+
+struct sqlp_pool {
+    sqlp_ctx *ctx = nullptr;
+    int64_t m2 = 0;
+    int64_t cap = 0;        // vertex capacity (multiple of 128)
+    int64_t K = 0;          // confirmed size
+    int64_t pending = 0;    // enqueued pushes whose outcome the host has not read yet
+    DevBuf d_pi, d_hash, d_K, d_scratch, d_vnew, d_vr, d_results;
+    std::vector<PoolView *> views;
+    std::vector<sqlp_epi *> epis;
+    int64_t upper() const { return K + pending; }
+};
+
+struct sqlp_epi {
+    sqlp_ctx *ctx = nullptr;
+    sqlp_pool *pool = nullptr;
+    PoolView *view = nullptr;
+    int64_t m2 = 0, n1 = 0, s = 0;
+    int n_T = 0;
+    // template coefficients
+    std::vector<double> h_rbar;
+    std::vector<int64_t> h_colptr;
+    std::vector<int> h_rowval;
+    std::vector<double> h_nzval;
+    std::vector<int> h_pos_row, h_pos_col, h_elem_j, h_elem_t;
+    DevBuf d_rbar, d_colptr, d_rowval, d_nzval;
+    DevBuf d_elem_j, d_elem_t, d_elem_base;
+    DevBuf d_tj, d_tcol, d_tslot;         // T elements sorted by (row slot, col)  -> k_delta_x
+    DevBuf d_cc, d_cj, d_cslot;           // T elements sorted by col              -> reduce
+    DevBuf d_mcol, d_mrow, d_mslot;       // T elements sorted by (col, row)       -> eval_dual
+    DevBuf d_ovals, d_ocdf, d_ocnt;       // outcome tables
+    int mo = 0;
+    // scenario store
+    int64_t n_global = 0, n_local = 0, cap_tiles = 0;
+    double total_weight = 0.0;
+    DevBuf d_D, d_dT, d_w, d_Dx;
+    // per-vertex tables (rho, tau)
+    DevBuf d_rt;
+    int64_t rt_cap = 0, rt_synced_lo = 0;
+    // work buffers
+    DevBuf d_x2, d_base, d_bias, d_best_val, d_best_idx, d_partial, d_partial2, d_out, d_gather,
+        d_flags, d_stage, d_scratch;
+    int64_t bias_stride = 0, out_stride = 0;
+};
+
+namespace {
+
+cudaStream_t S(sqlp_ctx *c) { return c->stream; }
+
+int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+void pool_reserve(sqlp_pool *p, int64_t need)
+{
+    if (need <= p->cap) return;
+    sqlp_ctx *c = p->ctx;
+    int64_t ncap = std::max<int64_t>(round_up(need, SQLP_TILE), std::max<int64_t>(1024, p->cap * 2));
+    int64_t used = p->upper();
+    p->d_pi.ensure((size_t)ncap * p->m2 * 8, (size_t)used * p->m2 * 8, S(c));
+    p->d_hash.ensure((size_t)ncap * 8, (size_t)used * 8, S(c));
+    for (PoolView *v : p->views) {
+        size_t per_chunk = (size_t)v->s_pad * SQLP_TILE * 8;
+        v->d_piS.ensure((size_t)(ncap / SQLP_TILE) * per_chunk,
+                        (size_t)((used + SQLP_TILE - 1) / SQLP_TILE) * per_chunk, S(c));
+    }
+    for (sqlp_epi *e : p->epis) {
+        e->d_rt.ensure((size_t)ncap * (e->n1 + 1) * 8, (size_t)used * (e->n1 + 1) * 8, S(c));
+        e->rt_cap = ncap;
+    }
+    p->cap = ncap;
+}
+
+// Bring K up to date on the host (one small D2H + sync) if pushes are outstanding.
+void pool_confirm(sqlp_pool *p)
+{
+    if (!p->pending) return;
+    long long K = 0;
+    CK(cudaMemcpyAsync(&K, p->d_K.p, 8, cudaMemcpyDeviceToHost, S(p->ctx)));
+    CK(cudaStreamSynchronize(S(p->ctx)));
+    p->K = K;
+    p->pending = 0;
+}
+
+void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const double *v_dev)
+{
+    sqlp_ctx *c = p->ctx;
+    pool_reserve(p, p->upper() + n);
+    p->d_results.ensure((size_t)n * sizeof(PushResult), 0, S(c));
+    const double *src = v_dev;
+    if (!v_dev || c->world > 1) {
+        p->d_vnew.ensure((size_t)n * p->m2 * 8, 0, S(c));
+        if (v_host && (c->world == 1 || c->rank == 0))
+            CK(cudaMemcpyAsync(p->d_vnew.p, v_host, (size_t)n * p->m2 * 8, cudaMemcpyHostToDevice, S(c)));
+        else if (v_dev && (c->world == 1 || c->rank == 0))
+            CK(cudaMemcpyAsync(p->d_vnew.p, v_dev, (size_t)n * p->m2 * 8, cudaMemcpyDeviceToDevice, S(c)));
+        else
+            REQUIRE(c->world > 1 && c->rank != 0, SQLP_E_INVALID, "push: null vector");
+        if (c->world > 1)   // each new dual vertex is broadcast from rank 0 over NCCL/NVLink
+            NK(g_nccl.Broadcast(p->d_vnew.p, p->d_vnew.p, (size_t)n * p->m2, ncclFloat64_, 0,
+                                c->comm, S(c)));
+        src = p->d_vnew.as<double>();
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        LAUNCH(c, k_pool_prepare, 1, 256, (size_t)p->m2 * 8, src + i * p->m2, (int)p->m2,
+               p->d_vr.as<double>(), p->d_scratch.as<PushScratch>());
+        int64_t ku = p->upper() + i;
+        int grid = (int)std::min<int64_t>(std::max<int64_t>((ku + 7) / 8, 1), 4 * c->sm_count);
+        LAUNCH(c, k_pool_find_commit, grid, 256, 0, p->d_pi.as<double>(),
+               p->d_hash.as<unsigned long long>(), p->d_K.as<long long>(), (int)p->m2,
+               src + i * p->m2, p->d_vr.as<double>(), p->d_scratch.as<PushScratch>(),
+               p->d_results.as<PushResult>() + i);
+    }
+    p->pending += n;
+}
+
+// Bring a view / an epigraph's (rho, tau) tables up to the current pool contents.
+void view_sync(sqlp_pool *p, PoolView *v)
+{
+    sqlp_ctx *c = p->ctx;
+    int64_t hi = p->upper();
+    if (hi > v->synced_lo) {
+        int64_t work = (hi - v->synced_lo) * v->n_rows;
+        int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 8 * c->sm_count);
+        LAUNCH(c, k_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(),
+               v->n_rows, v->s_pad, v->d_piS.as<double>(), (long long)v->synced_lo,
+               p->d_K.as<long long>());
+    }
+    v->synced_lo = p->K;   // only confirmed vertices are final
+}
+
+void epi_tables_sync(sqlp_epi *e)
+{
+    sqlp_pool *p = e->pool;
+    sqlp_ctx *c = e->ctx;
+    int64_t hi = p->upper();
+    if (hi > e->rt_synced_lo) {
+        int grid = (int)std::min<int64_t>(hi - e->rt_synced_lo, 16 * c->sm_count);
+        LAUNCH(c, k_epi_tables, grid, 128, 0, p->d_pi.as<double>(), (int)p->m2, e->d_rbar.as<double>(),
+               e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
+               (int)e->n1, e->d_rt.as<double>(), (long long)e->rt_synced_lo, p->d_K.as<long long>());
+    }
+    e->rt_synced_lo = p->K;
+}
+
+DeltaTables delta_tables(sqlp_epi *e)
+{
+    DeltaTables tb;
+    tb.s = (int)e->s;
+    tb.n_T = e->n_T;
+    tb.elem_j = e->d_elem_j.as<int>();
+    tb.elem_t = e->d_elem_t.as<int>();
+    tb.elem_base = e->d_elem_base.as<double>();
+    tb.out_vals = e->d_ovals.as<double>();
+    tb.out_cdf = e->d_ocdf.as<double>();
+    tb.out_cnt = e->d_ocnt.as<int>();
+    tb.mo = e->mo;
+    return tb;
+}
+
+void epi_reserve_scenarios(sqlp_epi *e, int64_t n_local_new)
+{
+    sqlp_ctx *c = e->ctx;
+    int64_t tiles = (n_local_new + SQLP_TILE - 1) / SQLP_TILE;
+    if (tiles <= e->cap_tiles) return;
+    int64_t ncap = std::max<int64_t>(tiles, std::max<int64_t>(8, e->cap_tiles * 2));
+    int64_t used_tiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
+    size_t per_tile = (size_t)e->view->s_pad * SQLP_TILE * 8;
+    e->d_D.ensure(ncap * per_tile, used_tiles * per_tile, S(c));
+    e->d_w.ensure((size_t)ncap * SQLP_TILE * 8, (size_t)used_tiles * SQLP_TILE * 8, S(c));
+    if (e->n_T)
+        e->d_dT.ensure((size_t)ncap * SQLP_TILE * e->n_T * 8,
+                       (size_t)used_tiles * SQLP_TILE * e->n_T * 8, S(c));
+    e->cap_tiles = ncap;
+}
+
+// add_scenario! for a batch: values on host (v_host), on device (v_dev) or sampled.
+void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_dev,
+             const double *w_host, bool sample, uint64_t seed, uint64_t wseed)
+{
+    if (n_new <= 0) return;
+    sqlp_ctx *c = e->ctx;
+    const int64_t g0 = e->n_global;
+    const int64_t g1 = g0 + n_new;
+    const int64_t nl1 = local_count(g1, c->rank, c->world);
+    epi_reserve_scenarios(e, nl1);
+    // epigraph.jl:89  total_scenario_weight += weight, in scenario order
+    for (int64_t i = 0; i < n_new; ++i) {
+        double w = 1.0;
+        if (sample) { if (wseed) w = 0.5 + u01(wseed, (uint64_t)(g0 + i)); }
+        else if (w_host) w = w_host[i];
+        e->total_weight += w;
+    }
+    DeltaTables tb = delta_tables(e);
+    const int64_t piece = std::max<int64_t>(SQLP_TILE, ((int64_t)(64 << 20) / (8 * std::max<int64_t>(e->s, 1))) / SQLP_TILE * SQLP_TILE);
+    for (int64_t off = 0; off < n_new;) {
+        // cut pieces at 128-aligned global ordinals so a tile is never split mid-copy
+        int64_t end = std::min<int64_t>(n_new, ((g0 + off) / SQLP_TILE) * SQLP_TILE + piece - g0);
+        if (end <= off) end = std::min<int64_t>(n_new, off + piece);
+        const int64_t cnt = end - off;
+        const double *vals = nullptr, *wts = nullptr;
+        if (!sample) {
+            if (v_dev) {
+                vals = v_dev + off * e->s;
+            } else {
+                e->d_stage.ensure((size_t)cnt * (e->s + 1) * 8, 0, S(c), false);
+                if (e->s)
+                    CK(cudaMemcpyAsync(e->d_stage.p, v_host + off * e->s, (size_t)cnt * e->s * 8,
+                                       cudaMemcpyHostToDevice, S(c)));
+                vals = e->d_stage.as<double>();
+            }
+            if (w_host) {
+                if (v_dev) e->d_stage.ensure((size_t)cnt * (e->s + 1) * 8, 0, S(c), false);
+                double *dw = e->d_stage.as<double>() + (v_dev ? 0 : cnt * e->s);
+                CK(cudaMemcpyAsync(dw, w_host + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, S(c)));
+                wts = dw;
+            }
+        }
+        const int64_t gs = g0 + off;
+        const int blocks = (int)((gs + cnt - 1) / SQLP_TILE - gs / SQLP_TILE + 1);
+        if (sample)
+            LAUNCH(c, k_delta_build<true>, blocks, 256, 0, tb, vals, (long long)gs, (long long)cnt,
+                   c->rank, c->world, e->view->s_pad, e->d_D.as<double>(), e->d_dT.as<double>(),
+                   e->d_w.as<double>(), wts, (unsigned long long)seed, (unsigned long long)wseed);
+        else
+            LAUNCH(c, k_delta_build<false>, blocks, 256, 0, tb, vals, (long long)gs, (long long)cnt,
+                   c->rank, c->world, e->view->s_pad, e->d_D.as<double>(), e->d_dT.as<double>(),
+                   e->d_w.as<double>(), wts, 0ull, 0ull);
+        if (!sample && !v_dev) CK(cudaStreamSynchronize(S(c)));   // staging buffer is reused
+        off = end;
+    }
+    e->n_global = g1;
+    e->n_local = nl1;
+}
+
+template <int NX>
+void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
+{
+    sqlp_ctx *c = e->ctx;
+    size_t smem = ContractSmem<NX>::bytes();
+    if (!c->smem_attr[NX]) {   // per device, so per context
+        CK(cudaFuncSetAttribute(k_contract_argmax<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+        c->smem_attr[NX] = true;
+    }
+    ContractArgs a;
+    a.D = D;
+    a.PiS = e->view->d_piS.as<double>();
+    a.bias = bias;
+    a.bias_stride = e->bias_stride;
+    a.d_K = e->pool->d_K.as<long long>();
+    a.s_pad = e->view->s_pad;
+    a.ntiles = (int)((e->n_local + SQLP_TILE - 1) / SQLP_TILE);
+    a.n_local = e->n_local;
+    a.best_val = bv;
+    a.best_idx = bi;
+    a.out_stride = e->out_stride;
+    int grid = std::min(a.ntiles, c->sm_count);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        if (c->prof_used == c->prof_events.size()) {
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            c->prof_events.push_back({e0, e1});
+        }
+        e0 = c->prof_events[c->prof_used].first;
+        e1 = c->prof_events[c->prof_used].second;
+        ++c->prof_used;
+        c->prof_flops += 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local;
+        CK(cudaEventRecord(e0, S(c)));
+    }
+    LAUNCH(c, k_contract_argmax<NX>, grid, SQLP_CT_THREADS, smem, a);
+    if (c->profile) CK(cudaEventRecord(e1, S(c)));
+}
+
+// Everything of build_sasa_cut for NX points, enqueued on the stream.  x on host or device.
+// Result lands in e->d_out as [NX][n1 + 2] = (alpha, beta[n1], val).
+void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x_dev, bool want_cut)
+{
+    sqlp_ctx *c = e->ctx;
+    sqlp_pool *p = e->pool;
+    const int n1 = (int)e->n1, m2 = (int)e->m2;
+    const int NC = n1 + 2;
+    e->d_x2.ensure((size_t)2 * std::max(n1, 1) * 8, 0, S(c));
+    e->d_out.ensure((size_t)2 * NC * 8, 0, S(c));
+    e->d_flags.ensure(16, 0, S(c));
+    if (x_host)
+        CK(cudaMemcpyAsync(e->d_x2.p, x_host, (size_t)NX * n1 * 8, cudaMemcpyHostToDevice, S(c)));
+    else
+        CK(cudaMemcpyAsync(e->d_x2.p, x_dev, (size_t)NX * n1 * 8, cudaMemcpyDeviceToDevice, S(c)));
+    CK(cudaMemsetAsync(e->d_flags.p, 0, 4, S(c)));
+    CK(cudaMemsetAsync(e->d_out.p, 0, (size_t)2 * NC * 8, S(c)));
+
+    view_sync(p, e->view);
+    if (want_cut) epi_tables_sync(e);
+
+    const int64_t ku = p->upper();
+    const int64_t kpad = round_up(std::max<int64_t>(ku, 1), SQLP_TILE);
+    if (kpad > e->bias_stride) {
+        e->bias_stride = round_up(kpad * 2, SQLP_TILE);
+        e->d_bias.ensure((size_t)2 * e->bias_stride * 8, 0, S(c), false);
+    }
+    const int64_t ntiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
+    if (ntiles * SQLP_TILE > e->out_stride) {
+        e->out_stride = round_up(ntiles * SQLP_TILE * 2, SQLP_TILE);
+        e->d_best_val.ensure((size_t)2 * e->out_stride * 8, 0, S(c), false);
+        e->d_best_idx.ensure((size_t)2 * e->out_stride * 4, 0, S(c), false);
+    }
+    e->d_base.ensure((size_t)2 * m2 * 8, 0, S(c));
+
+    if (ntiles > 0) {
+        LAUNCH(c, k_base, NX, 128, (size_t)m2 * 8, e->d_rbar.as<double>(), m2, n1,
+               e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
+               e->d_x2.as<double>(), e->d_base.as<double>());
+        int bgrid = (int)((kpad + 7) / 8);
+        if (NX == 2)
+            LAUNCH(c, k_bias<2>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
+                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
+                   (long long)e->bias_stride);
+        else
+            LAUNCH(c, k_bias<1>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
+                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
+                   (long long)e->bias_stride);
+
+        if (e->n_T == 0) {
+            if (NX == 2)
+                launch_contract<2>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
+                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
+            else
+                launch_contract<1>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
+                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
+        } else {
+            // some element perturbs Tbar: d(x) = delta_rhs - delta_T x is rebuilt per point
+            size_t bytes = (size_t)ntiles * e->view->s_pad * SQLP_TILE * 8;
+            e->d_Dx.ensure(bytes, 0, S(c), false);
+            TransferList tl{e->n_T, e->d_tj.as<int>(), e->d_tcol.as<int>(), e->d_tslot.as<int>()};
+            for (int x = 0; x < NX; ++x) {
+                CK(cudaMemcpyAsync(e->d_Dx.p, e->d_D.p, bytes, cudaMemcpyDeviceToDevice, S(c)));
+                LAUNCH(c, k_delta_x, (int)((e->n_local + 255) / 256), 256, 0, tl,
+                       e->d_x2.as<double>() + (size_t)x * n1, (long long)e->n_local, e->view->s_pad,
+                       e->d_D.as<double>(), e->d_dT.as<double>(), e->d_Dx.as<double>());
+                launch_contract<1>(e, e->d_Dx.as<double>(), e->d_bias.as<double>() + x * e->bias_stride,
+                                   e->d_best_val.as<double>() + x * e->out_stride,
+                                   e->d_best_idx.as<int>() + x * e->out_stride);
+            }
+        }
+    }
+    if (!want_cut) return;
+
+    const int width = NX * NC;
+    if (ntiles > 0) {
+        e->d_partial.ensure((size_t)ntiles * width * 8, 0, S(c), false);
+        ReduceArgs r;
+        r.D = e->d_D.as<double>();
+        r.dT = e->d_dT.as<double>();
+        r.w = e->d_w.as<double>();
+        r.PiS = e->view->d_piS.as<double>();
+        r.rt = e->d_rt.as<double>();
+        r.best_val = e->d_best_val.as<double>();
+        r.best_idx = e->d_best_idx.as<int>();
+        r.out_stride = e->out_stride;
+        r.n_local = e->n_local;
+        r.s_pad = e->view->s_pad;
+        r.n_rows = e->view->n_rows;
+        r.n1 = n1;
+        r.total_weight = e->total_weight;
+        r.n_T = e->n_T;
+        r.tc_col = e->d_cc.as<int>();
+        r.tc_j = e->d_cj.as<int>();
+        r.tc_slot = e->d_cslot.as<int>();
+        r.partial = e->d_partial.as<double>();
+        r.flags = e->d_flags.as<int>();
+        if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, 0, r);
+        else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, 0, r);
+        const int group = 64;
+        int64_t ng = (ntiles + group - 1) / group;
+        e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
+        LAUNCH(c, k_sum_groups, (int)ng, 256, 0, e->d_partial.as<double>(), (long long)ntiles, group,
+               width, e->d_partial2.as<double>());
+        LAUNCH(c, k_sum_groups, 1, 256, 0, e->d_partial2.as<double>(), (long long)ng, (int)ng, width,
+               e->d_out.as<double>());
+    }
+    if (c->world > 1) {
+        // per-epigraph partials are all-gathered and summed in fixed rank order
+        e->d_gather.ensure((size_t)c->world * width * 8, 0, S(c));
+        NK(g_nccl.AllGather(e->d_out.p, e->d_gather.p, (size_t)width, ncclFloat64_, c->comm, S(c)));
+        LAUNCH(c, k_rank_sum, (width + 127) / 128, 128, 0, e->d_gather.as<double>(), c->world, width,
+               e->d_out.as<double>());
+    }
+}
+
+struct CutHost {
+    std::vector<double> out;
+    int flags = 0;
+};
+
+void epi_cuts_fetch(sqlp_epi *e, int NX, CutHost &h)
+{
+    const int NC = (int)e->n1 + 2;
+    h.out.resize((size_t)NX * NC);
+    CK(cudaMemcpyAsync(h.out.data(), e->d_out.p, (size_t)NX * NC * 8, cudaMemcpyDeviceToHost, S(e->ctx)));
+    CK(cudaMemcpyAsync(&h.flags, e->d_flags.p, 4, cudaMemcpyDeviceToHost, S(e->ctx)));
+}
+
+void check_sense(int32_t sense)
+{
+    REQUIRE(sense == SQLP_MIN_SENSE || sense == SQLP_MAX_SENSE, SQLP_E_INVALID, "bad sense");
+    REQUIRE(sense == SQLP_MIN_SENSE, SQLP_E_UNSUPPORTED,
+            "MAX_SENSE is unsupported: the reference's MAX branch never selects a vertex");
+}
+
+}  // namespace
+
+// ================================================================ C ABI =================
+extern "C" {
+
+const char *sqlp_version(void) { return "sqlp_b200 0.1 (sm_100a)"; }
+const char *sqlp_last_error(void) { return g_err.c_str(); }
+
+static void ctx_init(sqlp_ctx *c, int32_t device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Error(SQLP_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                     " (libsqlp_b200 has no CPU fallback)");
+    REQUIRE(device >= 0 && device < n, SQLP_E_INVALID, "device ordinal out of range");
+    c->device = device;
+    c->bind();
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CK(cudaEventCreate(&c->t0));
+    CK(cudaEventCreate(&c->t1));
+}
+
+int32_t sqlp_ctx_create(int32_t device, sqlp_ctx **out)
+{
+    return guard([&] {
+        REQUIRE(out, SQLP_E_INVALID, "null out");
+        sqlp_ctx *c = new sqlp_ctx();
+        try { ctx_init(c, device); } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+int32_t sqlp_nccl_unique_id(void *out128)
+{
+    return guard([&] {
+        REQUIRE(out128, SQLP_E_INVALID, "null out");
+        load_nccl();
+        ncclUniqueId id;
+        NK(g_nccl.GetUniqueId(&id));
+        memcpy(out128, &id, sizeof id);
+    });
+}
+
+int32_t sqlp_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const void *nccl_id,
+                             sqlp_ctx **out)
+{
+    return guard([&] {
+        REQUIRE(out && nccl_id, SQLP_E_INVALID, "null argument");
+        REQUIRE(world >= 1 && rank >= 0 && rank < world, SQLP_E_INVALID, "bad rank/world");
+        sqlp_ctx *c = new sqlp_ctx();
+        try {
+            ctx_init(c, device);
+            c->rank = rank;
+            c->world = world;
+            if (world > 1) {
+                load_nccl();
+                ncclUniqueId id;
+                memcpy(&id, nccl_id, sizeof id);
+                NK(g_nccl.CommInitRank(&c->comm, world, id, rank));
+            }
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+int32_t sqlp_ctx_destroy(sqlp_ctx *c)
+{
+    return guard([&] {
+        if (!c) return;
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        if (c->comm) g_nccl.CommDestroy(c->comm);
+        for (auto &pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        if (c->t0) cudaEventDestroy(c->t0);
+        if (c->t1) cudaEventDestroy(c->t1);
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        delete c;
+    });
+}
+
+int32_t sqlp_ctx_set_stream(sqlp_ctx *c, void *stream)
+{
+    return guard([&] {
+        REQUIRE(c, SQLP_E_INVALID, "null ctx");
+        c->bind();
+        CK(cudaStreamSynchronize(c->stream));
+        c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    });
+}
+
+int32_t sqlp_ctx_synchronize(sqlp_ctx *c)
+{
+    return guard([&] {
+        REQUIRE(c, SQLP_E_INVALID, "null ctx");
+        c->bind();
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t sqlp_ctx_launch_count(sqlp_ctx *c, int64_t *n)
+{
+    return guard([&] {
+        REQUIRE(c && n, SQLP_E_INVALID, "null argument");
+        *n = c->launches;
+    });
+}
+
+int32_t sqlp_ctx_timer_start(sqlp_ctx *c)
+{
+    return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->bind(); CK(cudaEventRecord(c->t0, c->stream)); });
+}
+int32_t sqlp_ctx_timer_stop(sqlp_ctx *c)
+{
+    return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->bind(); CK(cudaEventRecord(c->t1, c->stream)); });
+}
+int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *c, double *ms)
+{
+    return guard([&] {
+        REQUIRE(c && ms, SQLP_E_INVALID, "null argument");
+        c->bind();
+        CK(cudaEventSynchronize(c->t1));
+        float f = 0;
+        CK(cudaEventElapsedTime(&f, c->t0, c->t1));
+        *ms = f;
+    });
+}
+
+int32_t sqlp_ctx_profile(sqlp_ctx *c, int32_t enable)
+{
+    return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->profile = enable != 0; });
+}
+
+int32_t sqlp_ctx_profile_read(sqlp_ctx *c, int32_t reset, double *ms, int64_t *launches, double *flops)
+{
+    return guard([&] {
+        REQUIRE(c, SQLP_E_INVALID, "null ctx");
+        c->bind();
+        CK(cudaStreamSynchronize(c->stream));
+        double total = 0;
+        for (size_t i = 0; i < c->prof_used; ++i) {
+            float f = 0;
+            CK(cudaEventElapsedTime(&f, c->prof_events[i].first, c->prof_events[i].second));
+            total += f;
+        }
+        if (ms) *ms = total;
+        if (launches) *launches = (int64_t)c->prof_used;
+        if (flops) *flops = c->prof_flops;
+        if (reset) { c->prof_used = 0; c->prof_flops = 0; }
+    });
+}
+
+// ---------------------------------------------------------------- pool -------------------
+int32_t sqlp_pool_create(sqlp_ctx *c, int64_t m2, sqlp_pool **out)
+{
+    return guard([&] {
+        REQUIRE(c && out, SQLP_E_INVALID, "null argument");
+        REQUIRE(m2 >= 1 && m2 < (1 << 24), SQLP_E_INVALID, "bad m2");
+        c->bind();
+        sqlp_pool *p = new sqlp_pool();
+        try {
+            p->ctx = c;
+            p->m2 = m2;
+            p->d_K.ensure(8, 0, S(c));
+            p->d_scratch.ensure(sizeof(PushScratch), 0, S(c));
+            p->d_vr.ensure((size_t)m2 * 8, 0, S(c));
+            pool_reserve(p, 1024);
+            CK(cudaStreamSynchronize(S(c)));
+        } catch (...) { delete p; throw; }
+        *out = p;
+    });
+}
+
+int32_t sqlp_pool_destroy(sqlp_pool *p)
+{
+    return guard([&] {
+        if (!p) return;
+        cudaSetDevice(p->ctx->device);
+        cudaStreamSynchronize(p->ctx->stream);
+        for (PoolView *v : p->views) delete v;
+        delete p;
+    });
+}
+
+int32_t sqlp_pool_push_batch(sqlp_pool *p, int64_t n, const double *v, int32_t *inserted, int64_t *index)
+{
+    return guard([&] {
+        REQUIRE(p, SQLP_E_INVALID, "null pool");
+        REQUIRE(n >= 0, SQLP_E_INVALID, "negative count");
+        if (n == 0) return;
+        sqlp_ctx *c = p->ctx;
+        REQUIRE(v || (c->world > 1 && c->rank != 0), SQLP_E_INVALID, "null vector");
+        c->bind();
+        pool_push_enqueue(p, n, v, nullptr);
+        std::vector<PushResult> res((size_t)n);
+        CK(cudaMemcpyAsync(res.data(), p->d_results.p, (size_t)n * sizeof(PushResult),
+                           cudaMemcpyDeviceToHost, S(c)));
+        pool_confirm(p);
+        for (int64_t i = 0; i < n; ++i) {
+            if (inserted) inserted[i] = res[i].inserted;
+            if (index) index[i] = res[i].index;
+        }
+    });
+}
+
+int32_t sqlp_pool_push(sqlp_pool *p, const double *v, int32_t *inserted, int64_t *index)
+{
+    return sqlp_pool_push_batch(p, 1, v, inserted, index);
+}
+
+int32_t sqlp_pool_push_dev(sqlp_pool *p, int64_t n, const double *d_v)
+{
+    return guard([&] {
+        REQUIRE(p, SQLP_E_INVALID, "null pool");
+        REQUIRE(n >= 0, SQLP_E_INVALID, "negative count");
+        if (n == 0) return;
+        REQUIRE(d_v || (p->ctx->world > 1 && p->ctx->rank != 0), SQLP_E_INVALID, "null vector");
+        p->ctx->bind();
+        pool_push_enqueue(p, n, nullptr, d_v);
+    });
+}
+
+int32_t sqlp_pool_size(sqlp_pool *p, int64_t *K)
+{
+    return guard([&] {
+        REQUIRE(p && K, SQLP_E_INVALID, "null argument");
+        p->ctx->bind();
+        pool_confirm(p);
+        *K = p->K;
+    });
+}
+
+int32_t sqlp_pool_get(sqlp_pool *p, int64_t index, double *out)
+{
+    return guard([&] {
+        REQUIRE(p && out, SQLP_E_INVALID, "null argument");
+        p->ctx->bind();
+        pool_confirm(p);
+        REQUIRE(index >= 0 && index < p->K, SQLP_E_RANGE, "vertex index out of range");
+        CK(cudaMemcpyAsync(out, p->d_pi.as<double>() + index * p->m2, (size_t)p->m2 * 8,
+                           cudaMemcpyDeviceToHost, S(p->ctx)));
+        CK(cudaStreamSynchronize(S(p->ctx)));
+    });
+}
+
+int32_t sqlp_pool_hash(sqlp_pool *p, const double *v, uint64_t *hash)
+{
+    return guard([&] {
+        REQUIRE(p && v && hash, SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = p->ctx;
+        c->bind();
+        p->d_vnew.ensure((size_t)p->m2 * 8, 0, S(c));
+        CK(cudaMemcpyAsync(p->d_vnew.p, v, (size_t)p->m2 * 8, cudaMemcpyHostToDevice, S(c)));
+        LAUNCH(c, k_pool_prepare, 1, 256, (size_t)p->m2 * 8, p->d_vnew.as<double>(), (int)p->m2,
+               p->d_vr.as<double>(), p->d_scratch.as<PushScratch>());
+        PushScratch sc;
+        CK(cudaMemcpyAsync(&sc, p->d_scratch.p, sizeof sc, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        *hash = sc.hash;
+    });
+}
+
+// ---------------------------------------------------------------- epigraph ---------------
+int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64_t r_nnz,
+                        const int64_t *r_idx, const double *r_val, const int64_t *T_colptr,
+                        const int64_t *T_rowval, const double *T_nzval, int64_t s,
+                        const int32_t *pos_row, const int32_t *pos_col, sqlp_epi **out)
+{
+    return guard([&] {
+        REQUIRE(c && p && out, SQLP_E_INVALID, "null argument");
+        REQUIRE(p->ctx == c, SQLP_E_INVALID, "pool belongs to another context");
+        REQUIRE(m2 == p->m2, SQLP_E_INVALID, "m2 differs from the pool's vertex length");
+        REQUIRE(n1 >= 0 && s >= 0 && r_nnz >= 0, SQLP_E_INVALID, "negative size");
+        REQUIRE(T_colptr || n1 == 0, SQLP_E_INVALID, "null T_colptr");
+        c->bind();
+        sqlp_epi *e = new sqlp_epi();
+        try {
+            e->ctx = c; e->pool = p; e->m2 = m2; e->n1 = n1; e->s = s;
+            e->h_rbar.assign((size_t)m2, 0.0);
+            for (int64_t q = 0; q < r_nnz; ++q) {
+                REQUIRE(r_idx[q] >= 0 && r_idx[q] < m2, SQLP_E_RANGE, "rbar index out of range");
+                e->h_rbar[(size_t)r_idx[q]] = r_val[q];
+            }
+            e->h_colptr.assign((size_t)n1 + 1, 0);
+            for (int64_t j = 0; j <= n1 && n1 > 0; ++j) e->h_colptr[(size_t)j] = T_colptr[j];
+            int64_t nnz = n1 > 0 ? T_colptr[n1] : 0;
+            REQUIRE(nnz >= 0, SQLP_E_INVALID, "bad T_colptr");
+            e->h_rowval.resize((size_t)nnz);
+            e->h_nzval.resize((size_t)nnz);
+            for (int64_t j = 0; j < n1; ++j) {
+                REQUIRE(T_colptr[j] <= T_colptr[j + 1], SQLP_E_INVALID, "T_colptr not monotone");
+                for (int64_t q = T_colptr[j]; q < T_colptr[j + 1]; ++q) {
+                    REQUIRE(T_rowval[q] >= 0 && T_rowval[q] < m2, SQLP_E_RANGE, "T row out of range");
+                    REQUIRE(q == T_colptr[j] || T_rowval[q] > T_rowval[q - 1], SQLP_E_INVALID,
+                            "T rows must ascend within a column");
+                    e->h_rowval[(size_t)q] = (int)T_rowval[q];
+                    e->h_nzval[(size_t)q] = T_nzval[q];
+                }
+            }
+            auto T_at = [&](int row, int col) {
+                for (int64_t q = e->h_colptr[col]; q < e->h_colptr[col + 1]; ++q)
+                    if (e->h_rowval[(size_t)q] == row) return e->h_nzval[(size_t)q];
+                return 0.0;
+            };
+            // stochastic rows S = sorted distinct rows of the position table
+            std::vector<int> rows;
+            for (int64_t q = 0; q < s; ++q) {
+                REQUIRE(pos_row[q] >= 0 && pos_row[q] < m2, SQLP_E_RANGE, "position row out of range");
+                REQUIRE(pos_col[q] >= -1 && pos_col[q] < n1, SQLP_E_RANGE, "position column out of range");
+                for (int64_t r = 0; r < q; ++r)
+                    REQUIRE(pos_row[r] != pos_row[q] || pos_col[r] != pos_col[q], SQLP_E_INVALID,
+                            "duplicate stochastic position");
+                rows.push_back(pos_row[q]);
+            }
+            std::sort(rows.begin(), rows.end());
+            rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+            // share the pool view with any epigraph that has the same row set
+            for (PoolView *v : p->views)
+                if (v->rows == rows) e->view = v;
+            if (!e->view) {
+                PoolView *v = new PoolView();
+                v->rows = rows;
+                v->n_rows = (int)rows.size();
+                v->s_pad = (int)std::max<int64_t>(SQLP_BK, round_up(v->n_rows, SQLP_BK));
+                upload(v->d_rows, rows, S(c));
+                size_t per_chunk = (size_t)v->s_pad * SQLP_TILE * 8;
+                v->d_piS.ensure((size_t)(p->cap / SQLP_TILE) * per_chunk, 0, S(c));
+                p->views.push_back(v);
+                e->view = v;
+            }
+            std::vector<double> base((size_t)s);
+            e->h_pos_row.assign(pos_row, pos_row + s);
+            e->h_pos_col.assign(pos_col, pos_col + s);
+            e->h_elem_j.resize((size_t)s);
+            e->h_elem_t.resize((size_t)s);
+            struct TE { int j, col, row, slot; };
+            std::vector<TE> te;
+            for (int64_t q = 0; q < s; ++q) {
+                int j = (int)(std::lower_bound(rows.begin(), rows.end(), pos_row[q]) - rows.begin());
+                e->h_elem_j[(size_t)q] = j;
+                if (pos_col[q] < 0) {
+                    e->h_elem_t[(size_t)q] = -1;
+                    base[(size_t)q] = e->h_rbar[(size_t)pos_row[q]];
+                } else {
+                    e->h_elem_t[(size_t)q] = e->n_T;
+                    base[(size_t)q] = T_at(pos_row[q], pos_col[q]);
+                    te.push_back({j, pos_col[q], pos_row[q], e->n_T});
+                    ++e->n_T;
+                }
+            }
+            upload(e->d_rbar, e->h_rbar, S(c));
+            upload(e->d_colptr, e->h_colptr, S(c));
+            upload(e->d_rowval, e->h_rowval, S(c));
+            upload(e->d_nzval, e->h_nzval, S(c));
+            upload(e->d_elem_j, e->h_elem_j, S(c));
+            upload(e->d_elem_t, e->h_elem_t, S(c));
+            upload(e->d_elem_base, base, S(c));
+            auto up3 = [&](std::vector<TE> v, DevBuf &a, DevBuf &b, DevBuf &d, int key) {
+                std::sort(v.begin(), v.end(), [&](const TE &x, const TE &y) {
+                    if (key == 0) return x.j != y.j ? x.j < y.j : x.col < y.col;      // (row slot, col)
+                    if (key == 1) return x.col != y.col ? x.col < y.col : x.row < y.row;  // (col, row)
+                    return x.col != y.col ? x.col < y.col : x.row < y.row;
+                });
+                std::vector<int> A, B, D;
+                for (auto &t : v) {
+                    A.push_back(key == 0 ? t.j : t.col);
+                    B.push_back(key == 0 ? t.col : (key == 1 ? t.j : t.row));
+                    D.push_back(t.slot);
+                }
+                upload(a, A, S(c)); upload(b, B, S(c)); upload(d, D, S(c));
+            };
+            up3(te, e->d_tj, e->d_tcol, e->d_tslot, 0);
+            up3(te, e->d_cc, e->d_cj, e->d_cslot, 1);
+            up3(te, e->d_mcol, e->d_mrow, e->d_mslot, 2);
+            e->d_rt.ensure((size_t)p->cap * (n1 + 1) * 8, 0, S(c));
+            e->rt_cap = p->cap;
+            e->d_scratch.ensure((size_t)(2 * m2 + 2) * 8, 0, S(c));
+            CK(cudaStreamSynchronize(S(c)));
+            p->epis.push_back(e);
+        } catch (...) { delete e; throw; }
+        *out = e;
+    });
+}
+
+int32_t sqlp_epi_destroy(sqlp_epi *e)
+{
+    return guard([&] {
+        if (!e) return;
+        cudaSetDevice(e->ctx->device);
+        cudaStreamSynchronize(e->ctx->stream);
+        auto &v = e->pool->epis;
+        v.erase(std::remove(v.begin(), v.end(), e), v.end());
+        delete e;
+    });
+}
+
+int32_t sqlp_epi_add_scenarios(sqlp_epi *e, int64_t n_new, const double *values, const double *weights)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
+        REQUIRE(values || n_new == 0 || e->s == 0, SQLP_E_INVALID, "null values");
+        e->ctx->bind();
+        epi_add(e, n_new, values, nullptr, weights, false, 0, 0);
+        CK(cudaStreamSynchronize(S(e->ctx)));
+    });
+}
+
+int32_t sqlp_epi_add_scenarios_dev(sqlp_epi *e, int64_t n_new, const double *d_values,
+                                   const double *weights_host)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
+        REQUIRE(d_values || n_new == 0 || e->s == 0, SQLP_E_INVALID, "null values");
+        e->ctx->bind();
+        epi_add(e, n_new, nullptr, d_values, weights_host, false, 0, 0);
+    });
+}
+
+int32_t sqlp_epi_set_outcomes(sqlp_epi *e, int64_t mo, const double *vals, const double *cdf,
+                              const int32_t *cnt)
+{
+    return guard([&] {
+        REQUIRE(e && vals && cdf && cnt, SQLP_E_INVALID, "null argument");
+        REQUIRE(mo >= 1, SQLP_E_INVALID, "max_outcomes < 1");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        for (int64_t q = 0; q < e->s; ++q)
+            REQUIRE(cnt[q] >= 1 && cnt[q] <= mo, SQLP_E_INVALID, "outcome count out of range");
+        std::vector<double> v(vals, vals + e->s * mo), f(cdf, cdf + e->s * mo);
+        std::vector<int> n(cnt, cnt + e->s);
+        upload(e->d_ovals, v, S(c));
+        upload(e->d_ocdf, f, S(c));
+        upload(e->d_ocnt, n, S(c));
+        e->mo = (int)mo;
+        CK(cudaStreamSynchronize(S(c)));
+    });
+}
+
+int32_t sqlp_epi_sample_scenarios(sqlp_epi *e, int64_t n_new, uint64_t seed, uint64_t weight_seed)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
+        REQUIRE(e->mo > 0 || e->s == 0, SQLP_E_INVALID, "call sqlp_epi_set_outcomes first");
+        e->ctx->bind();
+        epi_add(e, n_new, nullptr, nullptr, nullptr, true, seed, weight_seed);
+    });
+}
+
+int32_t sqlp_epi_counts(sqlp_epi *e, int64_t *n_global, int64_t *n_local, double *total_weight)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        if (n_global) *n_global = e->n_global;
+        if (n_local) *n_local = e->n_local;
+        if (total_weight) *total_weight = e->total_weight;
+    });
+}
+
+int32_t sqlp_epi_delta(sqlp_epi *e, int64_t i, double *delta_rhs, double *delta_T)
+{
+    return guard([&] {
+        REQUIRE(e && delta_rhs, SQLP_E_INVALID, "null argument");
+        REQUIRE(i >= 0 && i < e->n_local, SQLP_E_RANGE, "scenario index out of range");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        PoolView *v = e->view;
+        std::vector<double> col((size_t)std::max(v->n_rows, 1)), trow((size_t)std::max(e->n_T, 1));
+        const double *src = e->d_D.as<double>() + (i >> 7) * (int64_t)v->s_pad * SQLP_TILE + (i & 127);
+        if (v->n_rows)
+            CK(cudaMemcpy2DAsync(col.data(), 8, src, SQLP_TILE * 8, 8, (size_t)v->n_rows,
+                                 cudaMemcpyDeviceToHost, S(c)));
+        if (e->n_T)
+            CK(cudaMemcpyAsync(trow.data(), e->d_dT.as<double>() + i * e->n_T, (size_t)e->n_T * 8,
+                               cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        for (int64_t r = 0; r < e->m2; ++r) delta_rhs[r] = 0.0;
+        for (int64_t q = 0; q < e->s; ++q) {
+            if (e->h_elem_t[(size_t)q] < 0) {
+                delta_rhs[e->h_pos_row[(size_t)q]] = col[(size_t)e->h_elem_j[(size_t)q]];
+                if (delta_T) delta_T[q] = 0.0;
+            } else if (delta_T) {
+                delta_T[q] = trow[(size_t)e->h_elem_t[(size_t)q]];
+            }
+        }
+    });
+}
+
+int32_t sqlp_epi_argmax(sqlp_epi *e, const double *x, int32_t sense, double *max_val, int64_t *max_idx)
+{
+    return guard([&] {
+        REQUIRE(e && (x || e->n1 == 0), SQLP_E_INVALID, "null argument");
+        check_sense(sense);
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        if (e->n_local == 0) return;
+        REQUIRE(max_val && max_idx, SQLP_E_INVALID, "null output");
+        epi_cuts_enqueue(e, 1, x, nullptr, false);
+        std::vector<int> idx((size_t)e->n_local);
+        CK(cudaMemcpyAsync(max_val, e->d_best_val.p, (size_t)e->n_local * 8, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaMemcpyAsync(idx.data(), e->d_best_idx.p, (size_t)e->n_local * 4, cudaMemcpyDeviceToHost, S(c)));
+        pool_confirm(e->pool);
+        CK(cudaStreamSynchronize(S(c)));
+        for (int64_t i = 0; i < e->n_local; ++i) max_idx[i] = idx[(size_t)i];
+    });
+}
+
+static void finish_cut(sqlp_epi *e, int NX, const CutHost &h, double *alpha, double *beta,
+                       double *weight_mark, double *val)
+{
+    const int n1 = (int)e->n1, NC = n1 + 2;
+    REQUIRE(!(h.flags & 1), SQLP_E_NO_ARGMAX,
+            "no dual vertex beat -Inf for some scenario (empty pool or all scores NaN/-Inf)");
+    for (int x = 0; x < NX; ++x) {
+        alpha[x] = h.out[(size_t)x * NC];
+        for (int j = 0; j < n1; ++j) beta[(size_t)x * n1 + j] = h.out[(size_t)x * NC + 1 + j];
+        if (val) val[x] = h.out[(size_t)x * NC + n1 + 1];
+    }
+    if (weight_mark) *weight_mark = e->total_weight;   // epigraph.jl:145
+}
+
+int32_t sqlp_epi_build_cut(sqlp_epi *e, const double *x, double *alpha, double *beta,
+                           double *weight_mark, double *val)
+{
+    return guard([&] {
+        REQUIRE(e && alpha && (beta || e->n1 == 0) && (x || e->n1 == 0), SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        epi_cuts_enqueue(e, 1, x, nullptr, true);
+        CutHost h;
+        epi_cuts_fetch(e, 1, h);
+        pool_confirm(e->pool);
+        CK(cudaStreamSynchronize(S(c)));
+        finish_cut(e, 1, h, alpha, beta, weight_mark, val);
+    });
+}
+
+int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, const double *x_cand,
+                              const double *x_inc, double *alpha, double *beta, double *weight_mark,
+                              double *val)
+{
+    return guard([&] {
+        REQUIRE(n_epi >= 0 && (epi || n_epi == 0), SQLP_E_INVALID, "bad epigraph list");
+        if (n_epi == 0) return;
+        REQUIRE(alpha && weight_mark, SQLP_E_INVALID, "null output");
+        sqlp_ctx *c = epi[0]->ctx;
+        c->bind();
+        std::vector<CutHost> h((size_t)n_epi);
+        std::vector<double> x2;
+        for (int i = 0; i < n_epi; ++i) {
+            sqlp_epi *e = epi[i];
+            REQUIRE(e && e->ctx == c, SQLP_E_INVALID, "epigraphs must share one context");
+            REQUIRE((x_cand && x_inc && beta) || e->n1 == 0, SQLP_E_INVALID, "null argument");
+            x2.assign((size_t)2 * e->n1, 0.0);
+            for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
+            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true);
+            epi_cuts_fetch(e, 2, h[(size_t)i]);   // x2 is pageable: staged before the call returns
+        }
+        for (int i = 0; i < n_epi; ++i) pool_confirm(epi[i]->pool);
+        CK(cudaStreamSynchronize(S(c)));
+        int64_t boff = 0;
+        for (int i = 0; i < n_epi; ++i) {
+            sqlp_epi *e = epi[i];
+            finish_cut(e, 2, h[(size_t)i], alpha + 2 * i, beta + boff, weight_mark + i,
+                       val ? val + 2 * i : nullptr);
+            boff += 2 * e->n1;
+        }
+    });
+}
+
+int32_t sqlp_epi_build_cuts2(sqlp_epi *e, const double *x_cand, const double *x_inc, double alpha[2],
+                             double *beta, double *weight_mark, double *val)
+{
+    double wm = 0;
+    int32_t st = sqlp_cell_build_cuts2(1, &e, x_cand, x_inc, alpha, beta, &wm, val);
+    if (st == SQLP_OK && weight_mark) *weight_mark = wm;
+    return st;
+}
+
+int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *e, const double *d_x2, double *d_out)
+{
+    return guard([&] {
+        REQUIRE(e && d_out && (d_x2 || e->n1 == 0), SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        epi_cuts_enqueue(e, 2, nullptr, d_x2, true);
+        CK(cudaMemcpyAsync(d_out, e->d_out.p, (size_t)2 * (e->n1 + 2) * 8, cudaMemcpyDeviceToDevice, S(c)));
+    });
+}
+
+int32_t sqlp_eval_dual(sqlp_epi *e, int64_t i, int64_t vertex, const double *x, double *out)
+{
+    return guard([&] {
+        REQUIRE(e && out && (x || e->n1 == 0), SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = e->ctx;
+        sqlp_pool *p = e->pool;
+        c->bind();
+        pool_confirm(p);
+        REQUIRE(i >= 0 && i < e->n_local, SQLP_E_RANGE, "scenario index out of range");
+        REQUIRE(vertex >= 0 && vertex < p->K, SQLP_E_RANGE, "vertex index out of range");
+        e->d_x2.ensure((size_t)2 * std::max<int64_t>(e->n1, 1) * 8, 0, S(c));
+        if (e->n1) CK(cudaMemcpyAsync(e->d_x2.p, x, (size_t)e->n1 * 8, cudaMemcpyHostToDevice, S(c)));
+        EvalArgs a;
+        a.pi_row = p->d_pi.as<double>() + vertex * p->m2;
+        a.rbar = e->d_rbar.as<double>();
+        a.T_colptr = e->d_colptr.as<long long>();
+        a.T_rowval = e->d_rowval.as<int>();
+        a.T_nzval = e->d_nzval.as<double>();
+        a.m2 = (int)e->m2; a.n1 = (int)e->n1; a.s_pad = e->view->s_pad; a.n_rows = e->view->n_rows;
+        a.n_T = e->n_T;
+        a.s_rows = e->view->d_rows.as<int>();
+        a.Dcol = e->d_D.as<double>() + (i >> 7) * (int64_t)e->view->s_pad * SQLP_TILE + (i & 127);
+        a.dTrow = e->n_T ? e->d_dT.as<double>() + i * e->n_T : nullptr;
+        a.mc_col = e->d_mcol.as<int>(); a.mc_row = e->d_mrow.as<int>(); a.mc_slot = e->d_mslot.as<int>();
+        a.x = e->d_x2.as<double>();
+        a.scratch = e->d_scratch.as<double>();
+        a.out = e->d_scratch.as<double>() + 2 * e->m2;
+        LAUNCH(c, k_eval_dual, 1, 32, 0, a);
+        CK(cudaMemcpyAsync(out, a.out, 8, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// fp64_peak.cu -- measures the FP64 roofline denominators MEASURED_PEAKS.json lacks:
+//   (a) register-resident DFMA chains, (b) mma.sync.m8n8k4.f64 (DMMA) chains,
+//   (c) cuBLAS DGEMM 8192^3; each as a burst (best of 10) and sustained (~4 s back to back).
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o fp64_peak fp64_peak.cu -lcublas
+// Prints one JSON object.
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int CHAINS = 16;     // independent accumulators per thread
+constexpr int ITERS = 4096;
+
+__global__ void __launch_bounds__(256) k_dfma(double *out, double a, double b)
+{
+    double acc[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) acc[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+constexpr int MMA_CHAINS = 8;
+__global__ void __launch_bounds__(256) k_dmma(double *out, double a, double b)
+{
+    double c0[MMA_CHAINS], c1[MMA_CHAINS];
+#pragma unroll
+    for (int i = 0; i < MMA_CHAINS; ++i) { c0[i] = threadIdx.x * 1e-9; c1[i] = i; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < MMA_CHAINS; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < MMA_CHAINS; ++i) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// m16n8k16 f64 (sm_90+ shape): A 16x16 (8 regs/thread), B 16x8 (4 regs), C 16x8 (4 regs)
+__global__ void __launch_bounds__(256) k_dmma16(double *out, double a, double b)
+{
+    double c[MMA_CHAINS][4];
+#pragma unroll
+    for (int i = 0; i < MMA_CHAINS; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[i][q] = threadIdx.x * 1e-9 + q;
+    for (int it = 0; it < ITERS / 4; ++it) {
+#pragma unroll
+        for (int i = 0; i < MMA_CHAINS; ++i)
+            asm volatile(
+                "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, "
+                "{%4,%4,%4,%4,%4,%4,%4,%4}, {%5,%5,%5,%5}, {%0,%1,%2,%3};\n"
+                : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < MMA_CHAINS; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <class F>
+void measure(const char *name, double flops_per_launch, F launch, bool last = false)
+{
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int i = 0; i < 10; ++i) {
+        CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    int reps = (int)(4000.0f / best) + 1;
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) launch();
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float tot; CK(cudaEventElapsedTime(&tot, e0, e1));
+    printf(" \"%s\": {\"burst_tflops\": %.2f, \"sustained_tflops\": %.2f, \"burst_ms\": %.4f, \"sustained_s\": %.2f}%s\n",
+           name, flops_per_launch / best * 1e-9, flops_per_launch * reps / tot * 1e-9, best, tot * 1e-3,
+           last ? "" : ",");
+}
+
+int main()
+{
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int sms = p.multiProcessorCount;
+    int grid = sms * 8;   // 8 CTAs x 256 threads = 64 warps per SM
+    double *out; CK(cudaMalloc(&out, (size_t)grid * 256 * 8));
+    printf("{\n \"gpu\": \"%s\", \"sms\": %d, \"clock_mhz\": %d,\n", p.name, sms, p.clockRate / 1000);
+    measure("dfma", 2.0 * CHAINS * ITERS * 256.0 * grid, [&] { k_dfma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
+    measure("dmma_m8n8k4", 2.0 * 256 * MMA_CHAINS * ITERS * 8.0 * grid, [&] { k_dmma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
+    measure("dmma_m16n8k16", 2.0 * 16 * 8 * 16 * MMA_CHAINS * (ITERS / 4) * 8.0 * grid, [&] { k_dmma16<<<grid, 256>>>(out, 1.0000001, 1e-9); });
+    CK(cudaGetLastError());
+    {
+        const int n = 8192;
+        double *A, *B, *C;
+        CK(cudaMalloc(&A, (size_t)n * n * 8)); CK(cudaMalloc(&B, (size_t)n * n * 8)); CK(cudaMalloc(&C, (size_t)n * n * 8));
+        CK(cudaMemset(A, 0, (size_t)n * n * 8)); CK(cudaMemset(B, 0, (size_t)n * n * 8));
+        cublasHandle_t h; cublasCreate(&h);
+        double one = 1.0, zero = 0.0;
+        measure("cublas_dgemm_8192", 2.0 * n * (double)n * n, [&] {
+            cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, A, n, B, n, &zero, C, n); }, true);
+    }
+    printf("}\n");
+    return 0;
+}
