@@ -218,7 +218,8 @@ def run_ours(args):
         ctx = T.Context(local, rank, world, ids[0])
     else:
         ctx = T.Context(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)     # a real (non-NULL) stream shared with the library
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     L = _lib.lib()
 

@@ -9,6 +9,20 @@
 
 namespace sqlp {
 
+// Fragment-major tile layout shared by the scenario store D and the pool view PiS.
+// A tile holds 128 columns (scenarios or vertices) x s_pad row slots.  Slots are grouped by
+// four (one k-step of mma.sync.m8n8k4.f64) and columns by sixteen; inside a (group, column
+// pair-block) cell the 64 doubles are ordered [lane][h] so that lane t of a warp finds the
+// two m8n8k4 operand fragments of column blocks 2P and 2P+1,
+//     element (column (2P + h) * 8 + t / 4, slot 4g + t % 4),
+// in ONE 16-byte word at ((g * 8 + P) * 32 + t) * 2.  A warp-wide LDS.128 therefore reads
+// 512 contiguous bytes (conflict free) and yields two fragments per lane, and every 8-slot
+// pipeline slab of a tile is one contiguous 8 KB block in HBM.
+__host__ __device__ __forceinline__ long long tile_off(int c, int j)
+{
+    return ((((long long)(j >> 2) * 8 + (c >> 4)) * 32 + (c & 7) * 4 + (j & 3)) << 1) + ((c >> 3) & 1);
+}
+
 // Base.round(x; base=2, sigdigits=16) -- call sites dual_set.jl:32-33,51 of the reference.
 // hidigit = 1 + exponent(x); scale by 2^(16 - hidigit), round half to even, scale back.
 // All scalings are exact powers of two, so this is bit-identical to the CPU oracle.

@@ -10,18 +10,23 @@
 // incumbent points (NX = 2) share ONE contraction and differ only in the bias.
 //
 // Shape: a [N x s] by [s x K] GEMM in fp64 whose [N x K] result never leaves registers.
-//   CTA tile 128 scenarios x 128 vertices, 256 threads, 8 x 8 accumulators per thread,
-//   operands streamed L2 -> shared memory in 8-row slabs by a 4-stage cp.async pipeline
-//   that runs continuously across slabs, vertex chunks and scenario tiles.  Both operands
-//   are stored in HBM already in [tile][j][128] order (kernels_delta.cuh, kernels_pool.cuh),
-//   so every slab is one contiguous 8 KB block and every shared-memory read in the inner
-//   loop is a conflict-free, broadcast LDS.128.
+//   fp64 has no tcgen05 path (the 5th-gen tensor cores stop at tf32), so the math runs on
+//   the FP64 tensor pipe through mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Measured on this
+//   pool's B200 (profiles/fp64_peak.json): DMMA 37.0 TFLOP/s, DFMA chain 36.7, but an 8x8
+//   register-tiled DFMA loop tops out near 31 (three 64-bit sources per DFMA exceed the
+//   register-file read bandwidth), and the first version of this kernel, built on DFMA,
+//   reached 21.4.  DMMA reads 4 register pairs per 256 MACs instead of 3 per MAC.
+//   CTA tile 128 scenarios x 128 vertices, 256 threads = 2 x 4 warps, warp tile 64 x 32 =
+//   8 x 4 m8n8 accumulator blocks (128 registers).  Both operands live in HBM in the
+//   fragment-major tile layout of common.cuh, so (a) every 8-slot pipeline slab is one
+//   contiguous 8 KB block, streamed L2 -> shared memory by a 4-stage cp.async pipeline that
+//   runs continuously across slabs, vertex chunks and scenario tiles, and (b) one
+//   conflict-free LDS.128 hands each lane two operand fragments: 6 LDS.128 per 32 DMMA.
 //   After the last slab of a vertex chunk the epilogue adds the bias and folds the 64
 //   scores of each thread into per-thread running (max, argmax); after the last chunk of a
 //   scenario tile the 16 threads that share a scenario row merge with warp shuffles and
 //   one shared-memory pass, comparing on (value desc, index asc) so the first index wins.
-//   fp64 has no tcgen05 path (the 5th-gen tensor cores stop at tf32); the roofline is the
-//   DFMA pipe: 2 * s flop per (scenario, vertex) evaluation.
+//   Roofline: 2 * s flop per (scenario, vertex) evaluation against the measured FP64 peak.
 #pragma once
 #include "common.cuh"
 
@@ -42,8 +47,8 @@ struct ContractSmem {
 };
 
 struct ContractArgs {
-    const double *D;        // [ntiles][s_pad][128] scenario deltas on the stochastic rows
-    const double *PiS;      // [nchunks][s_pad][128] pool restricted to the stochastic rows
+    const double *D;        // [ntiles] fragment-major tiles: scenario deltas on the stochastic rows
+    const double *PiS;      // [nchunks] fragment-major tiles: pool restricted to those rows
     const double *bias;     // [NX][bias_stride]; -inf for k >= K
     long long bias_stride;
     const long long *d_K;   // pool size (device resident)
@@ -71,9 +76,11 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int wy = warp >> 2, wx = warp & 3;   // warp grid 2 (scenarios) x 4 (vertices)
-    const int ly = lane >> 2, lx = lane & 3;   // lane grid 8 x 4
-    const int a_off = wy * 64 + ly * 2;        // + n * 16, n = 0..3  (two scenarios each)
-    const int b_off = wx * 32 + lx * 2;        // + m * 8,  m = 0..3  (two vertices each)
+    const int ly = lane >> 2, lx = lane & 3;   // m8n8k4 C fragment: row ly, columns 2 lx + {0, 1}
+    // fragment-major cell [g][P][lane][h]: the A cells of this warp are P = 4 wy .. 4 wy + 3
+    // (scenario blocks mi = 0..7), the B cells P = 2 wx, 2 wx + 1 (vertex blocks ni = 0..3)
+    const int a_off = (wy * 4) * 64 + lane * 2;
+    const int b_off = (wx * 2) * 64 + lane * 2;
 
     const long long K = *a.d_K;
     const int nchunks = (int)((K + SQLP_TILE - 1) / SQLP_TILE);
@@ -129,13 +136,13 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
         cp_async_commit();
     };
 
-    double acc[8][8];
+    double acc[8][4][2];   // [mi][ni][h]: scenario wy*64 + mi*8 + ly, vertex wx*32 + ni*8 + 2 lx + h
     double best[NX][8];
     int bidx[NX][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
 #pragma unroll
         for (int x = 0; x < NX; ++x) { best[x][r] = -INFINITY; bidx[x][r] = -1; }
     }
@@ -153,46 +160,51 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
         const double *As = st + a_off;
         const double *Bs = st + slab_doubles + b_off;
 #pragma unroll
-        for (int j = 0; j < SQLP_BK; ++j) {
-            double2 av[4], bv[4];
+        for (int g = 0; g < SQLP_BK / 4; ++g) {
+            double2 av[4], bv[2];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                av[n] = *reinterpret_cast<const double2 *>(As + j * SQLP_TILE + n * 16);
-                bv[n] = *reinterpret_cast<const double2 *>(Bs + j * SQLP_TILE + n * 8);
-            }
+            for (int q = 0; q < 4; ++q)
+                av[q] = *reinterpret_cast<const double2 *>(As + g * 512 + q * 64);
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            for (int q = 0; q < 2; ++q)
+                bv[q] = *reinterpret_cast<const double2 *>(Bs + g * 512 + q * 64);
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    acc[2 * n][2 * m] = fma(av[n].x, bv[m].x, acc[2 * n][2 * m]);
-                    acc[2 * n][2 * m + 1] = fma(av[n].x, bv[m].y, acc[2 * n][2 * m + 1]);
-                    acc[2 * n + 1][2 * m] = fma(av[n].y, bv[m].x, acc[2 * n + 1][2 * m]);
-                    acc[2 * n + 1][2 * m + 1] = fma(av[n].y, bv[m].y, acc[2 * n + 1][2 * m + 1]);
+            for (int mi = 0; mi < 8; ++mi) {
+                const double af = (mi & 1) ? av[mi >> 1].y : av[mi >> 1].x;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double bf = (ni & 1) ? bv[ni >> 1].y : bv[ni >> 1].x;
+                    asm volatile(
+                        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                        : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                        : "d"(af), "d"(bf));
                 }
             }
         }
 
         if (slab == nslab - 1) {
             // ---- chunk epilogue: bias add + running argmax (vertex index ascending) ----
-            const double *bs = st + 2 * slab_doubles + b_off;
-            const int kbase = chunk * SQLP_TILE + b_off;
+            const double *bs = st + 2 * slab_doubles + wx * 32 + lx * 2;
+            const int kbase = chunk * SQLP_TILE + wx * 32 + lx * 2;
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
-                double bb[8];
+                double2 bb[4];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    double2 q = *reinterpret_cast<const double2 *>(bs + x * SQLP_TILE + m * 8);
-                    bb[2 * m] = q.x;
-                    bb[2 * m + 1] = q.y;
-                }
+                for (int ni = 0; ni < 4; ++ni)
+                    bb[ni] = *reinterpret_cast<const double2 *>(bs + x * SQLP_TILE + ni * 8);
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        double v = acc[r][c] + bb[c];
-                        if (v > best[x][r]) {   // strict: first maximum wins (subprob.jl:156)
-                            best[x][r] = v;
-                            bidx[x][r] = kbase + (c >> 1) * 8 + (c & 1);
+                    for (int ni = 0; ni < 4; ++ni) {   // vertex index ascending in (ni, h)
+                        double v0 = acc[r][ni][0] + bb[ni].x;
+                        if (v0 > best[x][r]) {   // strict: first maximum wins (subprob.jl:156)
+                            best[x][r] = v0;
+                            bidx[x][r] = kbase + ni * 8;
+                        }
+                        double v1 = acc[r][ni][1] + bb[ni].y;
+                        if (v1 > best[x][r]) {
+                            best[x][r] = v1;
+                            bidx[x][r] = kbase + ni * 8 + 1;
                         }
                     }
                 }
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+                for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
 
             if (chunk == nchunks - 1) {
                 // ---- tile epilogue: merge the 16 threads sharing each scenario row ----
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
                             if (better(ov, oi, v, i)) { v = ov; i = oi; }
                         }
                         if (lx == 0) {
-                            int row = a_off + (r >> 1) * 16 + (r & 1);
+                            int row = wy * 64 + r * 8 + ly;
                             red_val[(x * 4 + wx) * SQLP_TILE + row] = v;
                             red_idx[(x * 4 + wx) * SQLP_TILE + row] = i;
                         }

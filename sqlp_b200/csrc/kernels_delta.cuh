@@ -5,15 +5,16 @@
 // delta_T[row, col] = val - Tbar[row, col] otherwise.
 //
 // HBM layout of the scenario store (per epigraph, per rank):
-//   D[tile][j][128]   x-independent part  d = delta_rhs restricted to the stochastic rows
-//                     S (j indexes S, padded with zero rows to s_pad), scenario i at
-//                     (tile = i / 128, column i % 128).  This is exactly the operand tile
-//                     the contraction streams, so it is written once and never reshaped.
-//   dT[i][n_T]        row-major delta_T values (only when some element perturbs Tbar).
-//   w[i]              scenario weights.
+//   D[tile]   x-independent part  d = delta_rhs restricted to the stochastic rows S (slot j
+//             indexes S, padded with zero slots to s_pad); scenario i is column i % 128 of
+//             tile i / 128, stored in the fragment-major order of common.cuh tile_off.
+//             This is exactly the operand tile the contraction streams, so it is written
+//             once and never reshaped.
+//   dT[i][n_T]  row-major delta_T values (only when some element perturbs Tbar).
+//   w[i]        scenario weights.
 // One CUDA block per 128-aligned block of global scenario ordinals: realised values are
-// read coalesced along the element axis, transposed through shared memory and written
-// coalesced along the scenario axis.
+// read coalesced along the element axis, staged in shared memory, and written out as the
+// contiguous 4 KB (4 slots x 128 columns) cells of the tile layout.
 #pragma once
 #include "common.cuh"
 
@@ -22,8 +23,9 @@ namespace sqlp {
 struct DeltaTables {
     int s;                    // random elements
     int n_T;                  // of which perturb Tbar
-    const int *elem_j;        // [s] row slot in S of element e
-    const int *elem_t;        // [s] slot in dT of element e, -1 for RHS elements
+    int n_rows;               // stochastic row slots
+    const int *slot_elem;     // [n_rows] RHS element of slot j, -1 if only T elements touch it
+    const int *t_elem;        // [n_T] element of dT slot t
     const double *elem_base;  // [s] rbar[row] or Tbar[row, col] of element e
     // optional outcome tables for device-side sampling
     const double *out_vals;   // [s][mo]
@@ -32,7 +34,23 @@ struct DeltaTables {
     int mo;
 };
 
-#define SQLP_DELTA_SLAB 32
+#define SQLP_DELTA_SLAB 32   // slots staged per pass (8 k-groups)
+
+template <bool SAMPLE>
+__device__ __forceinline__ double realised_value(const DeltaTables &tb, const double *values,
+                                                 long long g, long long g0, int e,
+                                                 unsigned long long seed)
+{
+    if (SAMPLE) {
+        double u = u01(seed, (unsigned long long)g * tb.s + e);
+        const double *cdf = tb.out_cdf + (long long)e * tb.mo;
+        int idx = 0;
+        for (int q = 0; q < tb.mo; ++q) idx += (u >= cdf[q]) ? 1 : 0;
+        idx = min(idx, max(tb.out_cnt[e] - 1, 0));
+        return tb.out_vals[(long long)e * tb.mo + idx];
+    }
+    return values[(g - g0) * tb.s + e];
+}
 
 // SAMPLE = false: values[i_batch][e] given.  SAMPLE = true: drawn from the outcome tables.
 template <bool SAMPLE>
@@ -64,38 +82,33 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
         w[ltile * SQLP_TILE + c] = wt;
     }
 
-    for (int e0 = 0; e0 < tb.s; e0 += SQLP_DELTA_SLAB) {
-        const int ne = min(SQLP_DELTA_SLAB, tb.s - e0);
-        // phase 1: one warp per scenario, lanes along the element axis (coalesced reads)
+    // delta_T values, row-major per scenario (rare path)
+    for (int q = threadIdx.x; q < (c1 - c0) * tb.n_T; q += blockDim.x) {
+        const int c = c0 + q / tb.n_T, t = q % tb.n_T, e = tb.t_elem[t];
+        const double val = realised_value<SAMPLE>(tb, values, gb0 + c, g0, e, seed);
+        dT[(ltile * SQLP_TILE + c) * (long long)tb.n_T + t] = __dsub_rn(val, tb.elem_base[e]);   // :117
+    }
+
+    for (int j0 = 0; j0 < tb.n_rows; j0 += SQLP_DELTA_SLAB) {
+        // phase 1: one warp per scenario, lanes along the slot axis (coalesced reads)
         for (int c = c0 + warp; c < c1; c += nwarp) {
-            if (lane < ne) {
-                const int e = e0 + lane;
-                const long long g = gb0 + c;
-                double val;
-                if (SAMPLE) {
-                    double u = u01(seed, (unsigned long long)g * tb.s + e);
-                    const double *cdf = tb.out_cdf + (long long)e * tb.mo;
-                    int idx = 0;
-                    for (int q = 0; q < tb.mo; ++q) idx += (u >= cdf[q]) ? 1 : 0;
-                    idx = min(idx, max(tb.out_cnt[e] - 1, 0));
-                    val = tb.out_vals[(long long)e * tb.mo + idx];
-                } else {
-                    val = values[(g - g0) * tb.s + e];
-                }
-                sh[lane][c] = __dsub_rn(val, tb.elem_base[e]);   // :114 / :117
-            }
+            const int j = j0 + lane;
+            const int e = (j < tb.n_rows) ? tb.slot_elem[j] : -1;
+            double d = 0.0;
+            if (e >= 0)
+                d = __dsub_rn(realised_value<SAMPLE>(tb, values, gb0 + c, g0, e, seed),
+                              tb.elem_base[e]);                                                   // :114
+            sh[lane][c] = d;
         }
         __syncthreads();
-        // phase 2: one warp per element, lanes along the scenario axis (coalesced writes)
-        for (int q = warp; q < ne; q += nwarp) {
-            const int e = e0 + q;
-            const int t = tb.elem_t[e];
-            for (int c = c0 + lane; c < c1; c += 32) {
-                if (t < 0)
-                    Dt[(long long)tb.elem_j[e] * SQLP_TILE + c] = sh[q][c];
-                else
-                    dT[(ltile * SQLP_TILE + c) * (long long)tb.n_T + t] = sh[q][c];
-            }
+        // phase 2: each k-group (4 slots x 128 columns) is 512 contiguous doubles of the tile
+        const int ngroups = min(SQLP_DELTA_SLAB / 4, (s_pad - j0) / 4);
+        for (int q = threadIdx.x; q < ngroups * 512; q += blockDim.x) {
+            const int gq = q >> 9, o = q & 511;
+            const int P = o >> 6, t = (o & 63) >> 1, h = o & 1;
+            const int c = (2 * P + h) * 8 + (t >> 2);
+            if (c >= c0 && c < c1)
+                Dt[(long long)(j0 / 4 + gq) * 512 + o] = sh[gq * 4 + (t & 3)][c];
         }
         __syncthreads();
     }
@@ -117,10 +130,8 @@ __global__ void k_delta_x(TransferList tl, const double *__restrict__ x, long lo
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local) return;
-    const long long tile = i >> 7;
+    const long long tbase = (i >> 7) * (long long)s_pad * SQLP_TILE;
     const int c = (int)(i & 127);
-    const double *Dt = D + tile * (long long)s_pad * SQLP_TILE + c;
-    double *Xt = Dx + tile * (long long)s_pad * SQLP_TILE + c;
     const double *row = dT + i * (long long)tl.n_T;
     int q = 0;
     while (q < tl.n_T) {
@@ -130,8 +141,16 @@ __global__ void k_delta_x(TransferList tl, const double *__restrict__ x, long lo
             acc = __dadd_rn(acc, __dmul_rn(row[tl.t_slot[q]], x[tl.t_col[q]]));
             ++q;
         }
-        Xt[(long long)j * SQLP_TILE] = __dsub_rn(Dt[(long long)j * SQLP_TILE], acc);
+        const long long o = tbase + tile_off(c, j);
+        Dx[o] = __dsub_rn(D[o], acc);
     }
+}
+
+// One scenario's column of D gathered into a dense [n_rows] vector (delta readback).
+__global__ void k_gather_column(const double *__restrict__ Dtile, int c, int n_rows,
+                                double *__restrict__ out)
+{
+    for (int j = threadIdx.x; j < n_rows; j += blockDim.x) out[j] = Dtile[tile_off(c, j)];
 }
 
 }  // namespace sqlp

@@ -100,8 +100,8 @@ __global__ void k_pool_find_commit(double *__restrict__ pi, unsigned long long *
     }
 }
 
-// Stochastic-row view of the pool in the contraction's tile layout:
-//   piS[chunk][j][128]  with vertex k at (chunk = k / 128, column k % 128), j < s_pad.
+// Stochastic-row view of the pool in the contraction's fragment-major tile layout
+// (common.cuh tile_off): vertex k is column k % 128 of tile k / 128, slot j < s_pad.
 // Idempotent; run over [k_lo, *d_K) after pushes.
 __global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows,
                             int n_rows, int s_pad, double *__restrict__ piS, long long k_lo,
@@ -113,7 +113,7 @@ __global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__
          t += (long long)gridDim.x * blockDim.x) {
         long long k = k_lo + t / n_rows;
         int j = (int)(t % n_rows);
-        piS[((k >> 7) * s_pad + j) * SQLP_TILE + (k & 127)] = pi[k * m2 + s_rows[j]];
+        piS[(k >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(k & 127), j)] = pi[k * m2 + s_rows[j]];
     }
 }
 

@@ -73,10 +73,10 @@ __global__ void k_bias(const double *__restrict__ pi, int m2, const double *__re
 }
 
 struct ReduceArgs {
-    const double *D;          // [ntiles][s_pad][128]  delta_rhs on S
+    const double *D;          // [ntiles] fragment-major tiles: delta_rhs on S
     const double *dT;         // [n_local][n_T] or null
     const double *w;          // [n_local]
-    const double *PiS;        // [nchunks][s_pad][128]
+    const double *PiS;        // [nchunks] fragment-major tiles
     const double *rt;         // [K][n1 + 1]  (rho, tau)
     const double *best_val;   // [NX][out_stride]
     const int *best_idx;      // [NX][out_stride]
@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             if (k < 0) {
                 atomicOr(a.flags, 1);
             } else {
-                const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE + (k & 127);
+                const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE;
                 for (int j = 0; j < a.n_rows; ++j)
-                    acc = fma(P[(long long)j * SQLP_TILE], Dt[(long long)j * SQLP_TILE + c], acc);
+                    acc = fma(P[tile_off(k & 127, j)], Dt[tile_off(c, j)], acc);
             }
             if (x == 0) p_i[c] = a.w[i0 + c] / a.total_weight;   // epigraph.jl:138
         }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
                 term = a.rt[(long long)k * (a.n1 + 1) + col];                 // :141
                 for (int t = t0; t < t1; ++t) {
                     const double piv =
-                        a.PiS[((long long)(k >> 7) * a.s_pad + a.tc_j[t]) * SQLP_TILE + (k & 127)];
+                        a.PiS[(long long)(k >> 7) * a.s_pad * SQLP_TILE + tile_off(k & 127, a.tc_j[t])];
                     term = fma(a.dT[(i0 + c) * (long long)a.n_T + a.tc_slot[t]], piv, term);
                 }
                 sum = fma(-p, term, sum);
@@ -183,7 +183,8 @@ struct EvalArgs {
     const double *T_nzval;
     int m2, n1, s_pad, n_rows, n_T;
     const int *s_rows;        // [n_rows] stage-2 row of slot j
-    const double *Dcol;       // D tile base + column
+    const double *Dtile;      // base of the scenario's D tile
+    int dcol;                 // its column in the tile
     const double *dTrow;      // [n_T] or null
     // delta_T elements sorted by (col, row): position in CSC order
     const int *mc_col;
@@ -200,7 +201,7 @@ __global__ void k_eval_dual(EvalArgs a)
     double *y = a.scratch, *r = a.scratch + a.m2;
     for (int j = 0; j < a.m2; ++j) { y[j] = 0.0; r[j] = a.rbar[j]; }
     for (int j = 0; j < a.n_rows; ++j)
-        r[a.s_rows[j]] = __dadd_rn(a.rbar[a.s_rows[j]], a.Dcol[(long long)j * SQLP_TILE]);
+        r[a.s_rows[j]] = __dadd_rn(a.rbar[a.s_rows[j]], a.Dtile[tile_off(a.dcol, j)]);
     int t = 0;
     for (int c = 0; c < a.n1; ++c) {   // merged (Tbar + delta_T) * x, rows ascending per column
         const double xc = a.x[c];

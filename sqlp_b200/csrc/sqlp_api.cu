@@ -207,7 +207,7 @@ struct sqlp_epi {
     std::vector<double> h_nzval;
     std::vector<int> h_pos_row, h_pos_col, h_elem_j, h_elem_t;
     DevBuf d_rbar, d_colptr, d_rowval, d_nzval;
-    DevBuf d_elem_j, d_elem_t, d_elem_base;
+    DevBuf d_slot_elem, d_t_elem, d_elem_base;
     DevBuf d_tj, d_tcol, d_tslot;         // T elements sorted by (row slot, col)  -> k_delta_x
     DevBuf d_cc, d_cj, d_cslot;           // T elements sorted by col              -> reduce
     DevBuf d_mcol, d_mrow, d_mslot;       // T elements sorted by (col, row)       -> eval_dual
@@ -329,8 +329,9 @@ DeltaTables delta_tables(sqlp_epi *e)
     DeltaTables tb;
     tb.s = (int)e->s;
     tb.n_T = e->n_T;
-    tb.elem_j = e->d_elem_j.as<int>();
-    tb.elem_t = e->d_elem_t.as<int>();
+    tb.n_rows = e->view->n_rows;
+    tb.slot_elem = e->d_slot_elem.as<int>();
+    tb.t_elem = e->d_t_elem.as<int>();
     tb.elem_base = e->d_elem_base.as<double>();
     tb.out_vals = e->d_ovals.as<double>();
     tb.out_cdf = e->d_ocdf.as<double>();
@@ -948,8 +949,13 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
             upload(e->d_colptr, e->h_colptr, S(c));
             upload(e->d_rowval, e->h_rowval, S(c));
             upload(e->d_nzval, e->h_nzval, S(c));
-            upload(e->d_elem_j, e->h_elem_j, S(c));
-            upload(e->d_elem_t, e->h_elem_t, S(c));
+            std::vector<int> slot_elem(rows.size(), -1), t_elem;
+            for (int64_t q = 0; q < s; ++q) {
+                if (pos_col[q] < 0) slot_elem[(size_t)e->h_elem_j[(size_t)q]] = (int)q;
+                else t_elem.push_back((int)q);
+            }
+            upload(e->d_slot_elem, slot_elem, S(c));
+            upload(e->d_t_elem, t_elem, S(c));
             upload(e->d_elem_base, base, S(c));
             auto up3 = [&](std::vector<TE> v, DevBuf &a, DevBuf &b, DevBuf &d, int key) {
                 std::sort(v.begin(), v.end(), [&](const TE &x, const TE &y) {
@@ -970,7 +976,7 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
             up3(te, e->d_mcol, e->d_mrow, e->d_mslot, 2);
             e->d_rt.ensure((size_t)p->cap * (n1 + 1) * 8, 0, S(c));
             e->rt_cap = p->cap;
-            e->d_scratch.ensure((size_t)(2 * m2 + 2) * 8, 0, S(c));
+            e->d_scratch.ensure((size_t)(2 * m2 + 2 + rows.size() + 1) * 8, 0, S(c));
             CK(cudaStreamSynchronize(S(c)));
             p->epis.push_back(e);
         } catch (...) { delete e; throw; }
@@ -1064,10 +1070,13 @@ int32_t sqlp_epi_delta(sqlp_epi *e, int64_t i, double *delta_rhs, double *delta_
         c->bind();
         PoolView *v = e->view;
         std::vector<double> col((size_t)std::max(v->n_rows, 1)), trow((size_t)std::max(e->n_T, 1));
-        const double *src = e->d_D.as<double>() + (i >> 7) * (int64_t)v->s_pad * SQLP_TILE + (i & 127);
-        if (v->n_rows)
-            CK(cudaMemcpy2DAsync(col.data(), 8, src, SQLP_TILE * 8, 8, (size_t)v->n_rows,
-                                 cudaMemcpyDeviceToHost, S(c)));
+        const double *src = e->d_D.as<double>() + (i >> 7) * (int64_t)v->s_pad * SQLP_TILE;
+        if (v->n_rows) {
+            e->d_scratch.ensure((size_t)(2 * e->m2 + 2 + v->n_rows) * 8, 0, S(c));
+            double *tmp = e->d_scratch.as<double>() + 2 * e->m2 + 2;
+            LAUNCH(c, k_gather_column, 1, 128, 0, src, (int)(i & 127), v->n_rows, tmp);
+            CK(cudaMemcpyAsync(col.data(), tmp, (size_t)v->n_rows * 8, cudaMemcpyDeviceToHost, S(c)));
+        }
         if (e->n_T)
             CK(cudaMemcpyAsync(trow.data(), e->d_dT.as<double>() + i * e->n_T, (size_t)e->n_T * 8,
                                cudaMemcpyDeviceToHost, S(c)));
@@ -1207,7 +1216,8 @@ int32_t sqlp_eval_dual(sqlp_epi *e, int64_t i, int64_t vertex, const double *x, 
         a.m2 = (int)e->m2; a.n1 = (int)e->n1; a.s_pad = e->view->s_pad; a.n_rows = e->view->n_rows;
         a.n_T = e->n_T;
         a.s_rows = e->view->d_rows.as<int>();
-        a.Dcol = e->d_D.as<double>() + (i >> 7) * (int64_t)e->view->s_pad * SQLP_TILE + (i & 127);
+        a.Dtile = e->d_D.as<double>() + (i >> 7) * (int64_t)e->view->s_pad * SQLP_TILE;
+        a.dcol = (int)(i & 127);
         a.dTrow = e->n_T ? e->d_dT.as<double>() + i * e->n_T : nullptr;
         a.mc_col = e->d_mcol.as<int>(); a.mc_row = e->d_mrow.as<int>(); a.mc_slot = e->d_mslot.as<int>();
         a.x = e->d_x2.as<double>();

@@ -30,6 +30,42 @@ __global__ void __launch_bounds__(256) k_dfma(double *out, double a, double b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// 8x8 register tile, three distinct 64-bit sources per DFMA (the shape of a register-tiled
+// GEMM inner loop): tests whether register-file bandwidth, not the FP64 pipe, is the limit.
+template <bool SNAKE>
+__global__ void __launch_bounds__(256) k_dfma_tile(double *out, const double *in)
+{
+    double a[8], b[8], acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = in[threadIdx.x % 32 + i]; b[i] = in[64 + threadIdx.x % 16 + i]; }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = r + c;
+    for (int it = 0; it < ITERS / 4; ++it) {
+        if (SNAKE) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = (r & 1) ? 7 - cc : cc;
+                    asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc[r][c]) : "d"(a[r]), "d"(b[c]));
+                }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s += acc[r][c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 constexpr int MMA_CHAINS = 8;
 __global__ void __launch_bounds__(256) k_dmma(double *out, double a, double b)
 {
@@ -101,6 +137,12 @@ int main()
     double *out; CK(cudaMalloc(&out, (size_t)grid * 256 * 8));
     printf("{\n \"gpu\": \"%s\", \"sms\": %d, \"clock_mhz\": %d,\n", p.name, sms, p.clockRate / 1000);
     measure("dfma", 2.0 * CHAINS * ITERS * 256.0 * grid, [&] { k_dfma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
+    {
+        double *in; CK(cudaMalloc(&in, 1024)); CK(cudaMemset(in, 0, 1024));
+        int g1 = sms;   // 1 CTA x 8 warps per SM, like the contraction kernel
+        measure("dfma_tile8x8_compiler_order_8warps", 2.0 * 64 * (ITERS / 4) * 256.0 * g1, [&] { k_dfma_tile<false><<<g1, 256>>>(out, in); });
+        measure("dfma_tile8x8_snake_order_8warps", 2.0 * 64 * (ITERS / 4) * 256.0 * g1, [&] { k_dfma_tile<true><<<g1, 256>>>(out, in); });
+    }
     measure("dmma_m8n8k4", 2.0 * 256 * MMA_CHAINS * ITERS * 8.0 * grid, [&] { k_dmma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
     measure("dmma_m16n8k16", 2.0 * 16 * 8 * 16 * MMA_CHAINS * (ITERS / 4) * 8.0 * grid, [&] { k_dmma16<<<grid, 256>>>(out, 1.0000001, 1e-9); });
     CK(cudaGetLastError());
