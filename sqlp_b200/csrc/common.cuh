@@ -72,16 +72,53 @@ __host__ __device__ __forceinline__ int64_t local_count(int64_t n_global, int ra
     return n;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+// ---- mbarrier + bulk async copy (TMA 1-D, SASS UBLKCP) -------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
 {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+    return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar),
+                 "r"(bytes)
+                 : "memory");
+}
+// Wait for the phase with the given parity to complete.  A pipeline bug would otherwise hang
+// the GPU, so the spin is bounded (about two seconds) and traps instead.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// global -> shared bulk copy; completion is signalled on `bar` as `bytes` of transaction.
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
 }
 
 }  // namespace sqlp

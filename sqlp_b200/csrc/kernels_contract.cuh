@@ -16,12 +16,21 @@
 //   register-tiled DFMA loop tops out near 31 (three 64-bit sources per DFMA exceed the
 //   register-file read bandwidth), and the first version of this kernel, built on DFMA,
 //   reached 21.4.  DMMA reads 4 register pairs per 256 MACs instead of 3 per MAC.
-//   CTA tile 128 scenarios x 128 vertices, 256 threads = 2 x 4 warps, warp tile 64 x 32 =
-//   8 x 4 m8n8 accumulator blocks (128 registers).  Both operands live in HBM in the
+//   CTA tile 64 scenarios x 128 vertices, 128 threads = 4 warps side by side along the
+//   vertex axis, warp tile 64 x 32 = 8 x 4 m8n8 accumulator blocks (128 registers); two
+//   CTAs per SM, i.e. two warps from DIFFERENT CTAs on every sub-partition.  Both operands live in HBM in the
 //   fragment-major tile layout of common.cuh, so (a) every 8-slot pipeline slab is one
-//   contiguous 8 KB block, streamed L2 -> shared memory by a 4-stage cp.async pipeline that
-//   runs continuously across slabs, vertex chunks and scenario tiles, and (b) one
-//   conflict-free LDS.128 hands each lane two operand fragments: 6 LDS.128 per 32 DMMA.
+//   contiguous 8 KB block, moved L2 -> shared memory by ONE bulk async copy (TMA 1-D,
+//   cp.async.bulk, SASS UBLKCP) per operand, and (b) one conflict-free LDS.128 hands each
+//   lane two operand fragments: 6 LDS.128 per 32 DMMA.
+//   Pipeline: SQLP_CT_STAGES stages guarded by full/empty mbarriers, running continuously
+//   across slabs, vertex chunks and scenario half-tiles; no CTA-wide barrier in the steady
+//   state.  ptxas spaces a warp's DMMAs 16 cycles apart, exactly the pipe's rate, so ONE
+//   warp can saturate its sub-partition's FP64 tensor pipe; the second warp there belongs to
+//   the other resident CTA, whose phase is unrelated, so it feeds the pipe while the first is
+//   in its epilogue or waiting on a load (two warps of one CTA share the pipe fairly and
+//   would reach their epilogues together).  The copy for item L is issued by lane 0 of warp
+//   L % 4 once every warp has released the stage's previous contents.
 //   After the last slab of a vertex chunk the epilogue adds the bias and folds the 64
 //   scores of each thread into per-thread running (max, argmax); after the last chunk of a
 //   scenario tile the 16 threads that share a scenario row merge with warp shuffles and
@@ -32,17 +41,22 @@
 
 namespace sqlp {
 
-#define SQLP_CT_THREADS 256
-#define SQLP_CT_STAGES 4
+#define SQLP_CT_THREADS 128
+#define SQLP_CT_ROWS 64      // scenarios per CTA tile (half of a 128-column D tile)
+#define SQLP_CT_STAGES 7
+#define SQLP_CT_PREFETCH 3   // copies run this many items ahead; STAGES - PREFETCH - 1 items of slack
+                            // between the fastest and the slowest warp before a copy has to wait
 
 template <int NX>
 struct ContractSmem {
-    static constexpr int kStageDoubles = 2 * SQLP_BK * SQLP_TILE + NX * SQLP_TILE;
-    static constexpr int kRedDoubles = 4 * SQLP_TILE * NX;  // merge buffers (value)
+    static constexpr int kADoubles = SQLP_BK * SQLP_CT_ROWS;   // 64 scenarios x 8 slots
+    static constexpr int kBDoubles = SQLP_BK * SQLP_TILE;      // 128 vertices x 8 slots
+    static constexpr int kStageDoubles = kADoubles + kBDoubles + NX * SQLP_TILE;
+    static constexpr int kRedDoubles = 4 * SQLP_CT_ROWS * NX;  // merge buffers (value)
     static constexpr size_t bytes()
     {
         return sizeof(double) * (SQLP_CT_STAGES * kStageDoubles + kRedDoubles) +
-               sizeof(int) * (4 * SQLP_TILE * NX);
+               sizeof(int) * (4 * SQLP_CT_ROWS * NX) + sizeof(unsigned long long) * 2 * SQLP_CT_STAGES;
     }
 };
 
@@ -66,37 +80,40 @@ __device__ __forceinline__ bool better(double ov, int oi, double v, int i)
 }
 
 template <int NX>
-__global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(ContractArgs a)
+__global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(ContractArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);
     double *red_val = stages + SQLP_CT_STAGES * ContractSmem<NX>::kStageDoubles;
     int *red_idx = reinterpret_cast<int *>(red_val + ContractSmem<NX>::kRedDoubles);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(red_idx + 4 * SQLP_CT_ROWS * NX);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + SQLP_CT_STAGES);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wy = warp >> 2, wx = warp & 3;   // warp grid 2 (scenarios) x 4 (vertices)
+    const int wx = warp;                       // 4 warps along the vertex axis
     const int ly = lane >> 2, lx = lane & 3;   // m8n8k4 C fragment: row ly, columns 2 lx + {0, 1}
-    // fragment-major cell [g][P][lane][h]: the A cells of this warp are P = 4 wy .. 4 wy + 3
-    // (scenario blocks mi = 0..7), the B cells P = 2 wx, 2 wx + 1 (vertex blocks ni = 0..3)
-    const int a_off = (wy * 4) * 64 + lane * 2;
+    // fragment-major cell [g][P][lane][h]: the staged A half-tile holds 4 cells per k-group
+    // (scenario blocks mi = 0..7), the B cells of this warp are P = 2 wx, 2 wx + 1 (ni = 0..3)
+    const int a_off = lane * 2;
     const int b_off = (wx * 2) * 64 + lane * 2;
 
     const long long K = *a.d_K;
     const int nchunks = (int)((K + SQLP_TILE - 1) / SQLP_TILE);
     const int nslab = a.s_pad / SQLP_BK;
-    const int my_tiles = (a.ntiles > (int)blockIdx.x)
-                             ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+    const int nunits = 2 * a.ntiles;           // work unit = one 64-scenario half-tile
+    const int my_tiles = (nunits > (int)blockIdx.x)
+                             ? (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
                              : 0;
 
     if (nchunks == 0) {  // empty pool: nothing beats -Inf (subprob.jl:151)
         for (int t = 0; t < my_tiles; ++t) {
-            long long tile = blockIdx.x + (long long)t * gridDim.x;
-            for (int q = tid; q < SQLP_TILE * NX; q += SQLP_CT_THREADS) {
-                long long i = tile * SQLP_TILE + (q % SQLP_TILE);
+            long long unit = blockIdx.x + (long long)t * gridDim.x;
+            for (int q = tid; q < SQLP_CT_ROWS * NX; q += SQLP_CT_THREADS) {
+                long long i = unit * SQLP_CT_ROWS + (q % SQLP_CT_ROWS);
                 if (i < a.n_local) {
-                    a.best_val[(q / SQLP_TILE) * a.out_stride + i] = -INFINITY;
-                    a.best_idx[(q / SQLP_TILE) * a.out_stride + i] = -1;
+                    a.best_val[(q / SQLP_CT_ROWS) * a.out_stride + i] = -INFINITY;
+                    a.best_idx[(q / SQLP_CT_ROWS) * a.out_stride + i] = -1;
                 }
             }
         }
@@ -107,36 +124,48 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
     const size_t slab_doubles = (size_t)SQLP_BK * SQLP_TILE;
     const size_t tile_doubles = (size_t)a.s_pad * SQLP_TILE;
 
-    // producer cursor
-    int ld_slab = 0, ld_chunk = 0, ld_t = 0;
-    long long ld_it = 0;
-    auto issue_load = [&]() {
-        if (ld_it < total) {
-            double *st = stages + (ld_it % SQLP_CT_STAGES) * ContractSmem<NX>::kStageDoubles;
-            const long long tile = blockIdx.x + (long long)ld_t * gridDim.x;
-            const double *gA = a.D + tile * tile_doubles + ld_slab * slab_doubles;
-            const double *gB = a.PiS + (size_t)ld_chunk * tile_doubles + ld_slab * slab_doubles;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {   // 512 16-byte pieces per operand, 256 threads
-                int piece = tid + q * SQLP_CT_THREADS;
-                cp_async16(st + piece * 2, gA + piece * 2);
-                cp_async16(st + slab_doubles + piece * 2, gB + piece * 2);
-            }
-            if (ld_slab == nslab - 1 && tid < NX * SQLP_TILE / 2) {
-                int x = tid / (SQLP_TILE / 2), p = tid % (SQLP_TILE / 2);
-                cp_async16(st + 2 * slab_doubles + x * SQLP_TILE + p * 2,
-                           a.bias + x * a.bias_stride + (size_t)ld_chunk * SQLP_TILE + p * 2);
-            }
-            if (++ld_slab == nslab) {
-                ld_slab = 0;
-                if (++ld_chunk == nchunks) { ld_chunk = 0; ++ld_t; }
-            }
+    if (tid == 0) {
+        for (int q = 0; q < SQLP_CT_STAGES; ++q) {
+            mbar_init(full0 + 8 * q, 1);                       // one arrive.expect_tx per fill
+            mbar_init(empty0 + 8 * q, SQLP_CT_THREADS / 32);   // one arrive per consumer warp
         }
-        ++ld_it;
-        cp_async_commit();
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // Issue the bulk copies of item L (only the elected lane of the duty warp calls this).
+    auto issue_load = [&](long long L) {
+        const int stage = (int)(L % SQLP_CT_STAGES);
+        const long long fill = L / SQLP_CT_STAGES;
+        if (fill > 0) mbar_wait(empty0 + 8 * stage, (unsigned)((fill - 1) & 1));
+        const int l_slab = (int)(L % nslab);
+        const long long r = L / nslab;
+        const int l_chunk = (int)(r % nchunks);
+        const long long unit = blockIdx.x + (r / nchunks) * gridDim.x;
+        const long long tile = unit >> 1;
+        const int half = (int)(unit & 1);
+        double *st = stages + stage * ContractSmem<NX>::kStageDoubles;
+        const unsigned bar = full0 + 8 * stage;
+        const bool last = (l_slab == nslab - 1);
+        constexpr unsigned a_bytes = ContractSmem<NX>::kADoubles * 8, b_bytes = ContractSmem<NX>::kBDoubles * 8;
+        mbar_arrive_expect_tx(bar, a_bytes + b_bytes + (last ? NX * SQLP_TILE * 8 : 0));
+        // A: per k-group, the 4 cells (256 doubles) of this half of the 128-column D tile
+#pragma unroll
+        for (int g = 0; g < SQLP_BK / 4; ++g)
+            bulk_g2s(smem_u32(st + g * 256),
+                     a.D + tile * tile_doubles + (size_t)(l_slab * (SQLP_BK / 4) + g) * 512 + half * 256,
+                     256 * 8, bar);
+        bulk_g2s(smem_u32(st + ContractSmem<NX>::kADoubles),
+                 a.PiS + (size_t)l_chunk * tile_doubles + l_slab * slab_doubles, b_bytes, bar);
+        if (last) {
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+                bulk_g2s(smem_u32(st + ContractSmem<NX>::kADoubles + ContractSmem<NX>::kBDoubles + x * SQLP_TILE),
+                         a.bias + x * a.bias_stride + (size_t)l_chunk * SQLP_TILE, SQLP_TILE * 8, bar);
+        }
     };
 
-    double acc[8][4][2];   // [mi][ni][h]: scenario wy*64 + mi*8 + ly, vertex wx*32 + ni*8 + 2 lx + h
+    double acc[8][4][2];   // [mi][ni][h]: scenario mi*8 + ly of the half-tile, vertex wx*32 + ni*8 + 2 lx + h
     double best[NX][8];
     int bidx[NX][8];
 #pragma unroll
@@ -147,24 +176,27 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
         for (int x = 0; x < NX; ++x) { best[x][r] = -INFINITY; bidx[x][r] = -1; }
     }
 
-#pragma unroll
-    for (int p = 0; p < SQLP_CT_STAGES - 1; ++p) issue_load();
+    for (long long L = 0; L < SQLP_CT_PREFETCH && L < total; ++L)
+        if (lane == 0 && warp == (int)(L % (SQLP_CT_THREADS / 32))) issue_load(L);
 
     int slab = 0, chunk = 0, t = 0;
     for (long long it = 0; it < total; ++it) {
-        cp_async_wait<SQLP_CT_STAGES - 2>();
-        __syncthreads();
-        issue_load();
+        {
+            const long long L = it + SQLP_CT_PREFETCH;
+            if (L < total && lane == 0 && warp == (int)(L % (SQLP_CT_THREADS / 32))) issue_load(L);
+        }
+        const int stage = (int)(it % SQLP_CT_STAGES);
+        mbar_wait(full0 + 8 * stage, (unsigned)((it / SQLP_CT_STAGES) & 1));
 
-        const double *st = stages + (it % SQLP_CT_STAGES) * ContractSmem<NX>::kStageDoubles;
+        const double *st = stages + stage * ContractSmem<NX>::kStageDoubles;
         const double *As = st + a_off;
-        const double *Bs = st + slab_doubles + b_off;
+        const double *Bs = st + ContractSmem<NX>::kADoubles + b_off;
 #pragma unroll
         for (int g = 0; g < SQLP_BK / 4; ++g) {
             double2 av[4], bv[2];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                av[q] = *reinterpret_cast<const double2 *>(As + g * 512 + q * 64);
+                av[q] = *reinterpret_cast<const double2 *>(As + g * 256 + q * 64);
 #pragma unroll
             for (int q = 0; q < 2; ++q)
                 bv[q] = *reinterpret_cast<const double2 *>(Bs + g * 512 + q * 64);
@@ -184,7 +216,7 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
 
         if (slab == nslab - 1) {
             // ---- chunk epilogue: bias add + running argmax (vertex index ascending) ----
-            const double *bs = st + 2 * slab_doubles + wx * 32 + lx * 2;
+            const double *bs = st + ContractSmem<NX>::kADoubles + ContractSmem<NX>::kBDoubles + wx * 32 + lx * 2;
             const int kbase = chunk * SQLP_TILE + wx * 32 + lx * 2;
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
@@ -229,41 +261,43 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 1) k_contract_argmax(Contract
                             if (better(ov, oi, v, i)) { v = ov; i = oi; }
                         }
                         if (lx == 0) {
-                            int row = wy * 64 + r * 8 + ly;
-                            red_val[(x * 4 + wx) * SQLP_TILE + row] = v;
-                            red_idx[(x * 4 + wx) * SQLP_TILE + row] = i;
+                            int row = r * 8 + ly;
+                            red_val[(x * 4 + wx) * SQLP_CT_ROWS + row] = v;
+                            red_idx[(x * 4 + wx) * SQLP_CT_ROWS + row] = i;
                         }
                         best[x][r] = -INFINITY;
                         bidx[x][r] = -1;
                     }
                 }
                 __syncthreads();
-                const long long tile = blockIdx.x + (long long)t * gridDim.x;
-                for (int q = tid; q < SQLP_TILE * NX; q += SQLP_CT_THREADS) {
-                    const int x = q / SQLP_TILE, row = q % SQLP_TILE;
-                    double v = red_val[(x * 4) * SQLP_TILE + row];
-                    int i = red_idx[(x * 4) * SQLP_TILE + row];
+                const long long unit = blockIdx.x + (long long)t * gridDim.x;
+                for (int q = tid; q < SQLP_CT_ROWS * NX; q += SQLP_CT_THREADS) {
+                    const int x = q / SQLP_CT_ROWS, row = q % SQLP_CT_ROWS;
+                    double v = red_val[(x * 4) * SQLP_CT_ROWS + row];
+                    int i = red_idx[(x * 4) * SQLP_CT_ROWS + row];
 #pragma unroll
                     for (int w = 1; w < 4; ++w) {
-                        double ov = red_val[(x * 4 + w) * SQLP_TILE + row];
-                        int oi = red_idx[(x * 4 + w) * SQLP_TILE + row];
+                        double ov = red_val[(x * 4 + w) * SQLP_CT_ROWS + row];
+                        int oi = red_idx[(x * 4 + w) * SQLP_CT_ROWS + row];
                         if (better(ov, oi, v, i)) { v = ov; i = oi; }
                     }
-                    const long long sc = tile * SQLP_TILE + row;
+                    const long long sc = unit * SQLP_CT_ROWS + row;
                     if (sc < a.n_local) {
                         a.best_val[x * a.out_stride + sc] = v;
                         a.best_idx[x * a.out_stride + sc] = i;
                     }
                 }
-                // red_* is next written after at least one more __syncthreads (top of loop)
+                __syncthreads();   // red_* may be rewritten at the next tile's end
             }
         }
+        // this warp is done with the stage (operands and, on a chunk's last slab, the bias)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * stage);
         if (++slab == nslab) {
             slab = 0;
             if (++chunk == nchunks) { chunk = 0; ++t; }
         }
     }
-    cp_async_wait<0>();
 }
 
 }  // namespace sqlp

@@ -437,7 +437,7 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.best_val = bv;
     a.best_idx = bi;
     a.out_stride = e->out_stride;
-    int grid = std::min(a.ntiles, c->sm_count);
+    int grid = std::min(2 * a.ntiles, 2 * c->sm_count);   // half-tile units, two CTAs per SM
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         if (c->prof_used == c->prof_events.size()) {
