@@ -112,11 +112,22 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         else if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// Non-blocking probe of the same condition.
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // global -> shared bulk copy; completion is signalled on `bar` as `bytes` of transaction.
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+        "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }

@@ -42,21 +42,29 @@
 namespace sqlp {
 
 #define SQLP_CT_THREADS 128
-#define SQLP_CT_ROWS 64      // scenarios per CTA tile (half of a 128-column D tile)
-#define SQLP_CT_STAGES 7
-#define SQLP_CT_PREFETCH 3   // copies run this many items ahead; STAGES - PREFETCH - 1 items of slack
-                            // between the fastest and the slowest warp before a copy has to wait
 
-template <int NX>
-struct ContractSmem {
-    static constexpr int kADoubles = SQLP_BK * SQLP_CT_ROWS;   // 64 scenarios x 8 slots
-    static constexpr int kBDoubles = SQLP_BK * SQLP_TILE;      // 128 vertices x 8 slots
+// Compile-time shape of one contraction variant.
+//   MI      m8n8 blocks per warp along the scenario axis: the CTA tile is (8 MI) scenarios x
+//           128 vertices (4 warps side by side along the vertex axis, warp tile 8 MI x 32)
+//   STAGES  pipeline stages; PREFETCH  how many items ahead the copies run.  The fastest warp
+//           may lead the slowest by STAGES - PREFETCH - 1 items before a copy has to wait.
+//   CTAS    resident CTAs per SM the register budget is set for
+//   KG      k-groups (of 4 row slots) per pipeline item; the last item of a chunk may be
+//           shorter (s_pad is a multiple of 8, so every item holds an even number of groups)
+template <int NX_, int MI_, int STAGES_, int PREFETCH_, int CTAS_, int KG_>
+struct ContractCfg {
+    static constexpr int NX = NX_, MI = MI_, STAGES = STAGES_, PREFETCH = PREFETCH_, CTAS = CTAS_, KG = KG_;
+    static constexpr int ROWS = 8 * MI;                         // scenarios per work unit
+    static constexpr int UNITS_PER_TILE = SQLP_TILE / ROWS;
+    static constexpr int kAGroup = MI * 32;                     // doubles of A per k-group
+    static constexpr int kADoubles = KG * kAGroup;
+    static constexpr int kBDoubles = KG * 512;
     static constexpr int kStageDoubles = kADoubles + kBDoubles + NX * SQLP_TILE;
-    static constexpr int kRedDoubles = 4 * SQLP_CT_ROWS * NX;  // merge buffers (value)
-    static constexpr size_t bytes()
+    static constexpr int kRedDoubles = 4 * ROWS * NX;
+    static constexpr size_t smem_bytes()
     {
-        return sizeof(double) * (SQLP_CT_STAGES * kStageDoubles + kRedDoubles) +
-               sizeof(int) * (4 * SQLP_CT_ROWS * NX) + sizeof(unsigned long long) * 2 * SQLP_CT_STAGES;
+        return sizeof(double) * (STAGES * kStageDoubles + kRedDoubles) + sizeof(int) * (4 * ROWS * NX) +
+               sizeof(unsigned long long) * 2 * STAGES;
     }
 };
 
@@ -79,53 +87,51 @@ __device__ __forceinline__ bool better(double ov, int oi, double v, int i)
     return (ov > v) || (ov == v && (unsigned)oi < (unsigned)i);
 }
 
-template <int NX>
-__global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(ContractArgs a)
+template <class C>
+__global__ void __launch_bounds__(SQLP_CT_THREADS, C::CTAS) k_contract_argmax(ContractArgs a)
 {
+    constexpr int NX = C::NX, MI = C::MI, S = C::STAGES, ROWS = C::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);
-    double *red_val = stages + SQLP_CT_STAGES * ContractSmem<NX>::kStageDoubles;
-    int *red_idx = reinterpret_cast<int *>(red_val + ContractSmem<NX>::kRedDoubles);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(red_idx + 4 * SQLP_CT_ROWS * NX);
-    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + SQLP_CT_STAGES);
+    double *red_val = stages + S * C::kStageDoubles;
+    int *red_idx = reinterpret_cast<int *>(red_val + C::kRedDoubles);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(red_idx + 4 * ROWS * NX);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int wx = warp;                       // 4 warps along the vertex axis
+    const int lane = tid & 31, wx = tid >> 5;  // 4 warps along the vertex axis
     const int ly = lane >> 2, lx = lane & 3;   // m8n8k4 C fragment: row ly, columns 2 lx + {0, 1}
-    // fragment-major cell [g][P][lane][h]: the staged A half-tile holds 4 cells per k-group
-    // (scenario blocks mi = 0..7), the B cells of this warp are P = 2 wx, 2 wx + 1 (ni = 0..3)
+    // fragment-major cell [g][P][lane][h]: the staged A sub-tile holds MI / 2 cells per k-group
+    // (scenario blocks mi = 0..MI-1), the B cells of this warp are P = 2 wx, 2 wx + 1 (ni = 0..3)
     const int a_off = lane * 2;
     const int b_off = (wx * 2) * 64 + lane * 2;
 
     const long long K = *a.d_K;
     const int nchunks = (int)((K + SQLP_TILE - 1) / SQLP_TILE);
-    const int nslab = a.s_pad / SQLP_BK;
-    const int nunits = 2 * a.ntiles;           // work unit = one 64-scenario half-tile
-    const int my_tiles = (nunits > (int)blockIdx.x)
-                             ? (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
-                             : 0;
+    const int ngroups = a.s_pad / 4;
+    const int nslab = (ngroups + C::KG - 1) / C::KG;
+    const long long nunits = (long long)C::UNITS_PER_TILE * a.ntiles;
+    const long long my_units = (nunits > blockIdx.x) ? (nunits - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (nchunks == 0) {  // empty pool: nothing beats -Inf (subprob.jl:151)
-        for (int t = 0; t < my_tiles; ++t) {
-            long long unit = blockIdx.x + (long long)t * gridDim.x;
-            for (int q = tid; q < SQLP_CT_ROWS * NX; q += SQLP_CT_THREADS) {
-                long long i = unit * SQLP_CT_ROWS + (q % SQLP_CT_ROWS);
+        for (long long t = 0; t < my_units; ++t) {
+            const long long unit = blockIdx.x + t * gridDim.x;
+            for (int q = tid; q < ROWS * NX; q += SQLP_CT_THREADS) {
+                const long long i = unit * ROWS + (q % ROWS);
                 if (i < a.n_local) {
-                    a.best_val[(q / SQLP_CT_ROWS) * a.out_stride + i] = -INFINITY;
-                    a.best_idx[(q / SQLP_CT_ROWS) * a.out_stride + i] = -1;
+                    a.best_val[(q / ROWS) * a.out_stride + i] = -INFINITY;
+                    a.best_idx[(q / ROWS) * a.out_stride + i] = -1;
                 }
             }
         }
         return;
     }
 
-    const long long total = (long long)my_tiles * nchunks * nslab;
-    const size_t slab_doubles = (size_t)SQLP_BK * SQLP_TILE;
+    const long long total = my_units * nchunks * nslab;
     const size_t tile_doubles = (size_t)a.s_pad * SQLP_TILE;
 
     if (tid == 0) {
-        for (int q = 0; q < SQLP_CT_STAGES; ++q) {
+        for (int q = 0; q < S; ++q) {
             mbar_init(full0 + 8 * q, 1);                       // one arrive.expect_tx per fill
             mbar_init(empty0 + 8 * q, SQLP_CT_THREADS / 32);   // one arrive per consumer warp
         }
@@ -133,75 +139,88 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(Contract
     }
     __syncthreads();
 
-    // Issue the bulk copies of item L (only the elected lane of the duty warp calls this).
-    auto issue_load = [&](long long L) {
-        const int stage = (int)(L % SQLP_CT_STAGES);
-        const long long fill = L / SQLP_CT_STAGES;
-        if (fill > 0) mbar_wait(empty0 + 8 * stage, (unsigned)((fill - 1) & 1));
-        const int l_slab = (int)(L % nslab);
-        const long long r = L / nslab;
-        const int l_chunk = (int)(r % nchunks);
-        const long long unit = blockIdx.x + (r / nchunks) * gridDim.x;
-        const long long tile = unit >> 1;
-        const int half = (int)(unit & 1);
-        double *st = stages + stage * ContractSmem<NX>::kStageDoubles;
-        const unsigned bar = full0 + 8 * stage;
-        const bool last = (l_slab == nslab - 1);
-        constexpr unsigned a_bytes = ContractSmem<NX>::kADoubles * 8, b_bytes = ContractSmem<NX>::kBDoubles * 8;
-        mbar_arrive_expect_tx(bar, a_bytes + b_bytes + (last ? NX * SQLP_TILE * 8 : 0));
-        // A: per k-group, the 4 cells (256 doubles) of this half of the 128-column D tile
+    // ---- producer cursor: item pL lands in stage p_stage; every thread advances it the same
+    // way (no divisions in the loop), lane 0 of warp pL % 4 issues the copies.
+    long long pL = 0, p_unit = blockIdx.x;
+    int p_stage = 0, p_slab = 0, p_chunk = 0, p_duty = 0;
+    unsigned p_par = 0;   // parity of pL / S
+    auto produce = [&]() {
+        if (pL >= total) return;
+        if (wx == p_duty && lane == 0) {
+            if (pL >= S) mbar_wait(empty0 + 8 * p_stage, p_par ^ 1u);   // previous contents released
+            const long long tile = p_unit / C::UNITS_PER_TILE;
+            const int sub = (int)(p_unit % C::UNITS_PER_TILE);
+            double *st = stages + p_stage * C::kStageDoubles;
+            const unsigned bar = full0 + 8 * p_stage;
+            const bool last = (p_slab == nslab - 1);
+            const int pg = min(C::KG, ngroups - p_slab * C::KG);   // k-groups in this item
+            mbar_arrive_expect_tx(bar, (pg * (C::kAGroup + 512) + (last ? NX * SQLP_TILE : 0)) * 8);
+            const double *gA = a.D + tile * tile_doubles + (size_t)p_slab * (C::KG * 512) + sub * C::kAGroup;
+            for (int g = 0; g < pg; ++g)   // per k-group, this unit's cells of the D tile
+                bulk_g2s(smem_u32(st + g * C::kAGroup), gA + g * 512, C::kAGroup * 8, bar);
+            bulk_g2s(smem_u32(st + C::kADoubles),
+                     a.PiS + (size_t)p_chunk * tile_doubles + (size_t)p_slab * (C::KG * 512), pg * 512 * 8, bar);
+            if (last) {
 #pragma unroll
-        for (int g = 0; g < SQLP_BK / 4; ++g)
-            bulk_g2s(smem_u32(st + g * 256),
-                     a.D + tile * tile_doubles + (size_t)(l_slab * (SQLP_BK / 4) + g) * 512 + half * 256,
-                     256 * 8, bar);
-        bulk_g2s(smem_u32(st + ContractSmem<NX>::kADoubles),
-                 a.PiS + (size_t)l_chunk * tile_doubles + l_slab * slab_doubles, b_bytes, bar);
-        if (last) {
-#pragma unroll
-            for (int x = 0; x < NX; ++x)
-                bulk_g2s(smem_u32(st + ContractSmem<NX>::kADoubles + ContractSmem<NX>::kBDoubles + x * SQLP_TILE),
-                         a.bias + x * a.bias_stride + (size_t)l_chunk * SQLP_TILE, SQLP_TILE * 8, bar);
+                for (int x = 0; x < NX; ++x)
+                    bulk_g2s(smem_u32(st + C::kADoubles + C::kBDoubles + x * SQLP_TILE),
+                             a.bias + x * a.bias_stride + (size_t)p_chunk * SQLP_TILE, SQLP_TILE * 8, bar);
+            }
         }
+        if (++p_slab == nslab) {
+            p_slab = 0;
+            if (++p_chunk == nchunks) { p_chunk = 0; p_unit += gridDim.x; }
+        }
+        if (++p_stage == S) { p_stage = 0; p_par ^= 1u; }
+        p_duty = (p_duty + 1) & 3;
+        ++pL;
     };
 
-    double acc[8][4][2];   // [mi][ni][h]: scenario mi*8 + ly of the half-tile, vertex wx*32 + ni*8 + 2 lx + h
-    double best[NX][8];
-    int bidx[NX][8];
+    double acc[MI][4][2];   // [mi][ni][h]: scenario mi*8 + ly of the unit, vertex wx*32 + ni*8 + 2 lx + h
+    double best[NX][MI];
+    int bidx[NX][MI];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < MI; ++r) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
 #pragma unroll
         for (int x = 0; x < NX; ++x) { best[x][r] = -INFINITY; bidx[x][r] = -1; }
     }
 
-    for (long long L = 0; L < SQLP_CT_PREFETCH && L < total; ++L)
-        if (lane == 0 && warp == (int)(L % (SQLP_CT_THREADS / 32))) issue_load(L);
+#pragma unroll 1
+    for (int q = 0; q < C::PREFETCH; ++q) produce();
 
-    int slab = 0, chunk = 0, t = 0;
+    int slab = 0, chunk = 0, stage = 0;
+    unsigned par = 0;
+    long long unit = blockIdx.x;
+    bool ready = false;   // item `it` already known to have landed (probed during item it - 1)
+#pragma unroll 1
     for (long long it = 0; it < total; ++it) {
-        {
-            const long long L = it + SQLP_CT_PREFETCH;
-            if (L < total && lane == 0 && warp == (int)(L % (SQLP_CT_THREADS / 32))) issue_load(L);
-        }
-        const int stage = (int)(it % SQLP_CT_STAGES);
-        mbar_wait(full0 + 8 * stage, (unsigned)((it / SQLP_CT_STAGES) & 1));
+        produce();
+        if (!ready) mbar_wait(full0 + 8 * stage, par);
+        // probe the next item now; the answer comes back while this item's DMMAs run
+        const int nstage = (stage + 1 == S) ? 0 : stage + 1;
+        const unsigned npar = (stage + 1 == S) ? par ^ 1u : par;
+        ready = mbar_test(full0 + 8 * nstage, npar);
 
-        const double *st = stages + stage * ContractSmem<NX>::kStageDoubles;
+        const double *st = stages + stage * C::kStageDoubles;
         const double *As = st + a_off;
-        const double *Bs = st + ContractSmem<NX>::kADoubles + b_off;
+        const double *Bs = st + C::kADoubles + b_off;
+        const int ng = min(C::KG, ngroups - slab * C::KG);
+#pragma unroll 1
+        for (int g0 = 0; g0 < ng; g0 += 2) {
 #pragma unroll
-        for (int g = 0; g < SQLP_BK / 4; ++g) {
-            double2 av[4], bv[2];
+        for (int gg = 0; gg < 2; ++gg) {
+            const int g = g0 + gg;
+            double2 av[MI / 2], bv[2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                av[q] = *reinterpret_cast<const double2 *>(As + g * 256 + q * 64);
+            for (int q = 0; q < MI / 2; ++q)
+                av[q] = *reinterpret_cast<const double2 *>(As + g * C::kAGroup + q * 64);
 #pragma unroll
             for (int q = 0; q < 2; ++q)
                 bv[q] = *reinterpret_cast<const double2 *>(Bs + g * 512 + q * 64);
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) {
+            for (int mi = 0; mi < MI; ++mi) {
                 const double af = (mi & 1) ? av[mi >> 1].y : av[mi >> 1].x;
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
@@ -213,10 +232,11 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(Contract
                 }
             }
         }
+        }
 
         if (slab == nslab - 1) {
             // ---- chunk epilogue: bias add + running argmax (vertex index ascending) ----
-            const double *bs = st + ContractSmem<NX>::kADoubles + ContractSmem<NX>::kBDoubles + wx * 32 + lx * 2;
+            const double *bs = st + C::kADoubles + C::kBDoubles + wx * 32 + lx * 2;
             const int kbase = chunk * SQLP_TILE + wx * 32 + lx * 2;
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(Contract
                 for (int ni = 0; ni < 4; ++ni)
                     bb[ni] = *reinterpret_cast<const double2 *>(bs + x * SQLP_TILE + ni * 8);
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < MI; ++r) {
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) {   // vertex index ascending in (ni, h)
                         double v0 = acc[r][ni][0] + bb[ni].x;
@@ -242,16 +262,16 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(Contract
                 }
             }
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < MI; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
 
             if (chunk == nchunks - 1) {
-                // ---- tile epilogue: merge the 16 threads sharing each scenario row ----
+                // ---- unit epilogue: merge the 16 threads sharing each scenario row ----
 #pragma unroll
                 for (int x = 0; x < NX; ++x) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
+                    for (int r = 0; r < MI; ++r) {
                         double v = best[x][r];
                         int i = bidx[x][r];
 #pragma unroll
@@ -261,41 +281,41 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, 2) k_contract_argmax(Contract
                             if (better(ov, oi, v, i)) { v = ov; i = oi; }
                         }
                         if (lx == 0) {
-                            int row = r * 8 + ly;
-                            red_val[(x * 4 + wx) * SQLP_CT_ROWS + row] = v;
-                            red_idx[(x * 4 + wx) * SQLP_CT_ROWS + row] = i;
+                            const int row = r * 8 + ly;
+                            red_val[(x * 4 + wx) * ROWS + row] = v;
+                            red_idx[(x * 4 + wx) * ROWS + row] = i;
                         }
                         best[x][r] = -INFINITY;
                         bidx[x][r] = -1;
                     }
                 }
                 __syncthreads();
-                const long long unit = blockIdx.x + (long long)t * gridDim.x;
-                for (int q = tid; q < SQLP_CT_ROWS * NX; q += SQLP_CT_THREADS) {
-                    const int x = q / SQLP_CT_ROWS, row = q % SQLP_CT_ROWS;
-                    double v = red_val[(x * 4) * SQLP_CT_ROWS + row];
-                    int i = red_idx[(x * 4) * SQLP_CT_ROWS + row];
+                for (int q = tid; q < ROWS * NX; q += SQLP_CT_THREADS) {
+                    const int x = q / ROWS, row = q % ROWS;
+                    double v = red_val[(x * 4) * ROWS + row];
+                    int i = red_idx[(x * 4) * ROWS + row];
 #pragma unroll
                     for (int w = 1; w < 4; ++w) {
-                        double ov = red_val[(x * 4 + w) * SQLP_CT_ROWS + row];
-                        int oi = red_idx[(x * 4 + w) * SQLP_CT_ROWS + row];
+                        double ov = red_val[(x * 4 + w) * ROWS + row];
+                        int oi = red_idx[(x * 4 + w) * ROWS + row];
                         if (better(ov, oi, v, i)) { v = ov; i = oi; }
                     }
-                    const long long sc = unit * SQLP_CT_ROWS + row;
+                    const long long sc = unit * ROWS + row;
                     if (sc < a.n_local) {
                         a.best_val[x * a.out_stride + sc] = v;
                         a.best_idx[x * a.out_stride + sc] = i;
                     }
                 }
-                __syncthreads();   // red_* may be rewritten at the next tile's end
+                __syncthreads();   // red_* may be rewritten at the next unit's end
             }
         }
         // this warp is done with the stage (operands and, on a chunk's last slab, the bias)
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+        if (++stage == S) { stage = 0; par ^= 1u; }
         if (++slab == nslab) {
             slab = 0;
-            if (++chunk == nchunks) { chunk = 0; ++t; }
+            if (++chunk == nchunks) { chunk = 0; unit += gridDim.x; }
         }
     }
 }

@@ -13,6 +13,16 @@
 
 #include "../../include/sqlp_b200.h"
 #include "common.cuh"
+// contraction variant (overridable with -D for experiments)
+#ifndef SQLP_VARIANT_MI
+#define SQLP_VARIANT_MI 8
+#define SQLP_VARIANT_STAGES 7
+#define SQLP_VARIANT_PREFETCH 3
+#define SQLP_VARIANT_CTAS 2
+#endif
+#ifndef SQLP_VARIANT_KG
+#define SQLP_VARIANT_KG 2
+#endif
 #include "kernels_contract.cuh"
 #include "kernels_delta.cuh"
 #include "kernels_pool.cuh"
@@ -415,13 +425,19 @@ void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_d
     e->n_local = nl1;
 }
 
+// The contraction variant used in production (see DESIGN.md for the measurements behind it).
+template <int NX>
+using ContractVariant = ContractCfg<NX, SQLP_VARIANT_MI, SQLP_VARIANT_STAGES, SQLP_VARIANT_PREFETCH, SQLP_VARIANT_CTAS,
+                                    SQLP_VARIANT_KG>;
+
 template <int NX>
 void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
 {
+    using Cfg = ContractVariant<NX>;
     sqlp_ctx *c = e->ctx;
-    size_t smem = ContractSmem<NX>::bytes();
+    size_t smem = Cfg::smem_bytes();
     if (!c->smem_attr[NX]) {   // per device, so per context
-        CK(cudaFuncSetAttribute(k_contract_argmax<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CK(cudaFuncSetAttribute(k_contract_argmax<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
         c->smem_attr[NX] = true;
     }
@@ -437,7 +453,8 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.best_val = bv;
     a.best_idx = bi;
     a.out_stride = e->out_stride;
-    int grid = std::min(2 * a.ntiles, 2 * c->sm_count);   // half-tile units, two CTAs per SM
+    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+    int grid = (int)std::min<long long>(nunits, (long long)Cfg::CTAS * c->sm_count);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         if (c->prof_used == c->prof_events.size()) {
@@ -451,7 +468,7 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
         c->prof_flops += 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local;
         CK(cudaEventRecord(e0, S(c)));
     }
-    LAUNCH(c, k_contract_argmax<NX>, grid, SQLP_CT_THREADS, smem, a);
+    LAUNCH(c, k_contract_argmax<Cfg>, grid, SQLP_CT_THREADS, smem, a);
     if (c->profile) CK(cudaEventRecord(e1, S(c)));
 }
 

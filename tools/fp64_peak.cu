@@ -84,6 +84,30 @@ __global__ void __launch_bounds__(256) k_dmma(double *out, double a, double b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// 32 independent m8n8k4 accumulator blocks per warp (the contraction's warp tile), issued
+// back to back: what the FP64 tensor pipe sustains at 1, 2 or 4 warps per sub-partition.
+template <int THR>
+__global__ void __launch_bounds__(THR) k_dmma_tile(double *out, const double *in)
+{
+    double c[32][2], a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = in[threadIdx.x % 32 + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = in[64 + threadIdx.x % 16 + i];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { c[i][0] = i; c[i][1] = threadIdx.x; }
+    for (int it = 0; it < ITERS / 4; ++it) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a[i >> 2]), "d"(b[i & 3]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // m16n8k16 f64 (sm_90+ shape): A 16x16 (8 regs/thread), B 16x8 (4 regs), C 16x8 (4 regs)
 __global__ void __launch_bounds__(256) k_dmma16(double *out, double a, double b)
 {
@@ -142,6 +166,12 @@ int main()
         int g1 = sms;   // 1 CTA x 8 warps per SM, like the contraction kernel
         measure("dfma_tile8x8_compiler_order_8warps", 2.0 * 64 * (ITERS / 4) * 256.0 * g1, [&] { k_dfma_tile<false><<<g1, 256>>>(out, in); });
         measure("dfma_tile8x8_snake_order_8warps", 2.0 * 64 * (ITERS / 4) * 256.0 * g1, [&] { k_dfma_tile<true><<<g1, 256>>>(out, in); });
+    }
+    {
+        double *in; CK(cudaMalloc(&in, 1024)); CK(cudaMemset(in, 0, 1024));
+        const double f = 2.0 * 256 * 32 * (ITERS / 4) * sms;
+        measure("dmma_tile32_1warp_per_subpartition", f * 4, [&] { k_dmma_tile<128><<<sms, 128>>>(out, in); });
+        measure("dmma_tile32_2warp_per_subpartition", f * 8, [&] { k_dmma_tile<256><<<sms, 256>>>(out, in); });
     }
     measure("dmma_m8n8k4", 2.0 * 256 * MMA_CHAINS * ITERS * 8.0 * grid, [&] { k_dmma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
     measure("dmma_m16n8k16", 2.0 * 16 * 8 * 16 * MMA_CHAINS * (ITERS / 4) * 8.0 * grid, [&] { k_dmma16<<<grid, 256>>>(out, 1.0000001, 1e-9); });
