@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, C::CTAS) k_contract_argmax(Co
             // ---- chunk epilogue: bias add + running argmax (vertex index ascending) ----
             const double *bs = st + C::kADoubles + C::kBDoubles + wx * 32 + lx * 2;
             const int kbase = chunk * SQLP_TILE + wx * 32 + lx * 2;
+#ifndef SQLP_EXPERIMENT_NO_EPILOGUE
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
                 double2 bb[4];
@@ -261,6 +262,18 @@ __global__ void __launch_bounds__(SQLP_CT_THREADS, C::CTAS) k_contract_argmax(Co
                     }
                 }
             }
+#else
+            if (chunk == nchunks - 1) {   // experiment: epilogue cost ceiling (results are wrong)
+#pragma unroll
+                for (int r = 0; r < MI; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int x = 0; x < NX; ++x)
+                            if (acc[r][c][0] + acc[r][c][1] > best[x][r]) { best[x][r] = acc[r][c][0]; bidx[x][r] = kbase + c; }
+                    }
+            }
+#endif
 #pragma unroll
             for (int r = 0; r < MI; ++r)
 #pragma unroll

@@ -16,12 +16,12 @@
 // contraction variant (overridable with -D for experiments)
 #ifndef SQLP_VARIANT_MI
 #define SQLP_VARIANT_MI 8
-#define SQLP_VARIANT_STAGES 7
-#define SQLP_VARIANT_PREFETCH 3
+#define SQLP_VARIANT_STAGES 4
+#define SQLP_VARIANT_PREFETCH 2
 #define SQLP_VARIANT_CTAS 2
 #endif
 #ifndef SQLP_VARIANT_KG
-#define SQLP_VARIANT_KG 2
+#define SQLP_VARIANT_KG 4
 #endif
 #include "kernels_contract.cuh"
 #include "kernels_delta.cuh"

@@ -1,0 +1,88 @@
+"""Scenario-sharded path on 2 GPUs (skipped on a single-GPU box): NCCL vertex broadcast and
+partial all-gather inside the library, host plumbing through torch.distributed (gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from sqlp_b200 import dist as D, twosd as T
+        from tests.helpers import check_argmax_parity, load_instance, sample_instance_values
+        ctx = D.init_context()
+        assert (ctx.rank, ctx.world) == (rank, world)
+        P, z = load_instance("storm")
+        N = 1500
+        vals = sample_instance_values(z, N)
+        w = 0.5 + O.u01(4, np.arange(N))
+        pool = z["pool"]
+        coef = T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval,
+                                                   P.pos_row, P.pos_col)
+        dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+        # only rank 0's vectors count: the others push garbage of the right shape
+        src = pool if rank == 0 else np.full_like(pool, 7.0)
+        ins, idx = dvs.push_many(np.vstack([src, src[:3]]))
+        assert ins.sum() == len(pool) and len(dvs) == len(pool)
+        assert np.array_equal(np.stack(list(dvs)), pool)
+        epi = T.sdEpigraph(coef, 1.0, 0.0, dvs)
+        epi.add_scenarios(vals, w)                     # SPMD: same arrays on every rank
+        ng, nl, tw = epi.counts()
+        assert ng == N and nl == D.local_count(N, rank, world)
+        xs = (z["x_ev"], z["x_alt"])
+        (cand, inc), val = epi.build_cuts2(*xs, with_val=True)
+        ok = True
+        for x, cut in zip(xs, (cand, inc)):
+            mv, mi = epi.argmax(x)                      # this rank's scenarios, local order
+            gmv = D.gather_scenario_results(mv, N)
+            gmi = D.gather_scenario_results(mi, N)
+            check_argmax_parity(P, vals, x, pool, gmv, gmi)
+            ref = O.build_sasa_cut(P, vals, w, x, pool, forced_idx=gmi)
+            ok &= abs(cut.alpha - ref["alpha"]) <= 1e-10 * abs(ref["alpha"])
+            ok &= bool(np.allclose(cut.beta, ref["beta"], rtol=1e-10, atol=1e-6))
+            ok &= cut.weight_mark == ref["weight_mark"]
+        # sharded device sampling generates the same scenarios as one GPU would
+        epi2 = T.sdEpigraph(coef, 1.0, 0.0, dvs)
+        epi2.set_outcomes(z["out_vals"], z["out_cdf"], z["out_cnt"])
+        epi2.sample_scenarios(N, seed=1, weight_seed=4)
+        c2 = epi2.build_cut(xs[1])
+        ok &= abs(c2.alpha - inc.alpha) <= 1e-12 * abs(inc.alpha)
+        ok &= bool(np.allclose(c2.beta, inc.beta, rtol=1e-12, atol=1e-9))
+        again = epi.build_cuts2(*xs)[1]                 # run-to-run bitwise identical
+        ok &= again.alpha == inc.alpha and np.array_equal(again.beta, inc.beta)
+        q.put((rank, bool(ok), np.concatenate([[cand.alpha, inc.alpha], cand.beta, inc.beta]).tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_sharded_cuts():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2] == res[1][2]        # fixed rank-order sum: identical bits on every rank
