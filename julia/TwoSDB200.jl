@@ -1,0 +1,159 @@
+# TwoSDB200.jl -- reroutes TwoSD's argmax cut formation to libsqlp_b200.so (B200, sm_100a).
+#
+# UNRUN: Julia is not available in the build image.  This file is the reference-side binding a
+# maintainer would add; `sqlp_b200/twosd.py` is its executable twin and is what the parity tests
+# drive.  Usage, after `include("src/TwoSD.jl")`:
+#
+#     include("julia/TwoSDB200.jl"); using .TwoSDB200
+#     TwoSDB200.enable!(TwoSD; lib = "/path/to/libsqlp_b200.so", device = 0)
+#
+# `enable!` overrides five methods of TwoSD, keeping their signatures and return types
+# (SURVEY.md 8(b)):
+#     sdEpigraph(prob, w, lb)                  src/sd_algorithm/epigraph.jl:52-61
+#     add_scenario!(epi, scenario, weight)     src/sd_algorithm/epigraph.jl:81-96
+#     Base.push!(dvs::sdDualVertexSet, v)      src/sd_algorithm/dual_set.jl:84-93
+#     argmax_procedure(coef, deltas, x, dvs)   src/sd_algorithm/subprob.jl:141-169
+#     build_sasa_cut(epi, x, dvs)::sdCut       src/sd_algorithm/epigraph.jl:125-146
+# Host-side lists (scenario_list, scenario_weight, dvs.data) are still maintained so the rest of
+# TwoSD (sd_iteration!, check_improvement, sync_cuts!) runs unchanged.
+module TwoSDB200
+
+using SparseArrays
+
+const LIB = Ref{String}("libsqlp_b200.so")
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+struct DeviceState
+    pool::Ptr{Cvoid}
+end
+const POOLS = IdDict{Any,Ptr{Cvoid}}()        # sdDualVertexSet => sqlp_pool*
+const EPIS = IdDict{Any,Ptr{Cvoid}}()         # sdEpigraph      => sqlp_epi*
+const DELTA_OWNER = IdDict{Any,Any}()         # epi.scenario_delta => epi
+const TABLES = IdDict{Any,Vector{Any}}()      # sdSubprobCoefficients => position table
+
+function check(status::Int32)
+    status == 0 && return
+    msg = unsafe_string(ccall((:sqlp_last_error, LIB[]), Cstring, ()))
+    status == -4 && throw(UndefRefError())                      # what the reference throws
+    error("libsqlp_b200 [$status]: $msg")
+end
+
+function context()
+    if CTX[] == C_NULL
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:sqlp_ctx_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), Int32(DEVICE[]), out))
+        CTX[] = out[]
+    end
+    return CTX[]
+end
+const DEVICE = Ref{Int}(0)
+
+function pool_of(dvs, m2::Int)
+    get!(POOLS, dvs) do
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:sqlp_pool_create, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
+                    context(), m2, out))
+        # replay vertices that were pushed before the pool existed
+        for dv in dvs.data
+            ins = Ref{Int32}(0); idx = Ref{Int64}(0)
+            check(ccall((:sqlp_pool_push, LIB[]), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}, Ref{Int64}), out[], dv.data, ins, idx))
+        end
+        out[]
+    end
+end
+
+"Position table (row, col | -1) of the instance's random elements, fixed once from `sto`."
+function position_table(T, coef, sto)
+    rows = Int32[]; cols = Int32[]; order = Any[]
+    for (pos, _) in sto.indep                       # Dict order is hash order: freeze it here
+        push!(order, pos)
+        push!(rows, Int32(coef.row_lookup[pos.row_name] - 1))
+        push!(cols, (pos.col_name == "RHS" || pos.col_name == "rhs") ? Int32(-1) :
+                    Int32(coef.col_lookup[pos.col_name] - 1))
+    end
+    return order, rows, cols
+end
+
+function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, sto = nothing)
+    LIB[] = lib; DEVICE[] = device
+    sto === nothing && error("pass the spStoType so the position table can be resolved once")
+
+    # --- sdEpigraph(prob, w, lb): also create the device epigraph --------------------------------
+    @eval T function bind_device!(epi::sdEpigraph, dvs::sdDualVertexSet)
+        coef = epi.subproblem_coef
+        order, rows, cols = $position_table($T, coef, $sto)
+        $TABLES[coef] = order
+        r = coef.rhs; Tm = coef.transfer
+        ridx = Int64.(r.nzind .- 1); rval = Float64.(r.nzval)
+        colptr = Int64.(Tm.colptr .- 1); rowval = Int64.(Tm.rowval .- 1); nzval = Float64.(Tm.nzval)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        $check(ccall((:sqlp_epi_create, $LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64},
+             Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+            $context(), $pool_of(dvs, length(r)), length(r), size(Tm, 2), length(ridx), ridx, rval,
+            colptr, rowval, nzval, length(rows), rows, cols, out))
+        $EPIS[epi] = out[]
+        $DELTA_OWNER[epi.scenario_delta] = epi
+        finalizer(e -> ccall((:sqlp_epi_destroy, $LIB[]), Int32, (Ptr{Cvoid},), $EPIS[e]), epi)
+        return epi
+    end
+
+    # --- add_scenario!(epi, scenario, weight) -- epigraph.jl:81-96 --------------------------------
+    @eval T function add_scenario!(epi::sdEpigraph, scenario::spSmpsScenario, weight::Float64 = 1.0)
+        push!(epi.scenario_list, scenario)
+        push!(epi.scenario_weight, weight)
+        epi.total_scenario_weight += weight
+        lookup = Dict(p => v for (p, v) in scenario)
+        vals = Float64[lookup[p] for p in $TABLES[epi.subproblem_coef]]
+        $check(ccall((:sqlp_epi_add_scenarios, $LIB[]), Int32,
+                     (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), $EPIS[epi], 1, vals, [weight]))
+        return
+    end
+
+    # --- Base.push!(dvs, v) -- dual_set.jl:84-93 (returns the set) --------------------------------
+    @eval T function Base.push!(dvs::sdDualVertexSet, new_vec::Vector{Float64})
+        ins = Ref{Int32}(0); idx = Ref{Int64}(0)
+        $check(ccall((:sqlp_pool_push, $LIB[]), Int32,
+                     (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}, Ref{Int64}),
+                     $pool_of(dvs, length(new_vec)), new_vec, ins, idx))
+        ins[] == 1 && push!(dvs.data, sdDualVertex(new_vec))   # keeps dvs.data in device order
+        return dvs
+    end
+
+    # --- argmax_procedure(coef, delta_set, x, dvs; sense) -- subprob.jl:141-169 -------------------
+    @eval T function argmax_procedure(coef::sdSubprobCoefficients, delta_set::Vector{sdDeltaCoefficients},
+            x::Vector{Float64}, dual_vertices::sdDualVertexSet;
+            sense::MOI.OptimizationSense = MIN_SENSE)
+        epi = $DELTA_OWNER[delta_set]
+        n = length(epi.scenario_list)
+        max_val = Vector{Float64}(undef, n); max_idx = Vector{Int64}(undef, n)
+        $check(ccall((:sqlp_epi_argmax, $LIB[]), Int32,
+                     (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Int64}),
+                     $EPIS[epi], x, sense == MIN_SENSE ? Int32(0) : Int32(1), max_val, max_idx))
+        any(<(0), max_idx) && throw(UndefRefError())
+        max_arg = Ref{Vector{Float64}}[Ref(dual_vertices.data[k + 1].data) for k in max_idx]
+        return max_val, max_arg
+    end
+
+    # --- build_sasa_cut(epi, x, dvs)::sdCut -- epigraph.jl:125-146 --------------------------------
+    @eval T function build_sasa_cut(epi::sdEpigraph, x::Vector{Float64}, dual_vertices::sdDualVertexSet)::sdCut
+        alpha = Ref{Float64}(0); wm = Ref{Float64}(0); beta = zeros(length(x))
+        $check(ccall((:sqlp_epi_build_cut, $LIB[]), Int32,
+                     (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                     $EPIS[epi], x, alpha, beta, wm, C_NULL))
+        return sdCut(alpha[], beta, wm[])
+    end
+
+    # --- both cuts of one iteration (algorithm.jl:80,83) in one pass ------------------------------
+    @eval T function build_two_cuts(epi::sdEpigraph, x_cand::Vector{Float64}, x_inc::Vector{Float64})
+        alpha = zeros(2); beta = zeros(length(x_cand), 2); wm = Ref{Float64}(0)
+        $check(ccall((:sqlp_epi_build_cuts2, $LIB[]), Int32,
+                     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                     $EPIS[epi], x_cand, x_inc, alpha, beta, wm, C_NULL))
+        return sdCut(alpha[1], beta[:, 1], wm[]), sdCut(alpha[2], beta[:, 2], wm[])
+    end
+    return nothing
+end
+
+end # module
