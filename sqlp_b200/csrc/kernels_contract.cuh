@@ -80,6 +80,10 @@ struct ContractArgs {
     double *best_val;       // [NX][out_stride]
     int *best_idx;          // [NX][out_stride]
     long long out_stride;
+    // resident variant only (kernels_contract_res.cuh)
+    int nstages, prefetch;  // pool-ring depth and how many items ahead the copies run
+    double *piece_val;      // [grid][2][NX][ROWS] partial results of units cut by a span boundary
+    int *piece_idx;
 };
 
 __device__ __forceinline__ bool better(double ov, int oi, double v, int i)

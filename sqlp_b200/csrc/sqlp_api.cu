@@ -23,7 +23,15 @@
 #ifndef SQLP_VARIANT_KG
 #define SQLP_VARIANT_KG 4
 #endif
+// resident variant (production): warp rows, m8n8 blocks per warp, k-groups per item, CTAs per SM
+#ifndef SQLP_RES_WR
+#define SQLP_RES_WR 1
+#define SQLP_RES_MI 8
+#define SQLP_RES_KG 2
+#define SQLP_RES_CTAS 2
+#endif
 #include "kernels_contract.cuh"
+#include "kernels_contract_res.cuh"
 #include "kernels_delta.cuh"
 #include "kernels_pool.cuh"
 #include "kernels_reduce.cuh"
@@ -175,6 +183,12 @@ struct sqlp_ctx {
     size_t prof_used = 0;
     double prof_flops = 0.0;
     bool smem_attr[3] = {false, false, false};
+    // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
+    int contract_mode = 0;        // 0 = automatic, 1 = streaming kernel only, 2 = resident only
+    int contract_grid = 0;        // > 0: force this many CTAs (tests of the span split)
+    int smem_per_sm = 0, smem_optin = 0;
+    int res_smem_set[3] = {0, 0, 0};
+    DevBuf d_piece_val, d_piece_idx;
     void bind() const { CK(cudaSetDevice(device)); }
 };
 
@@ -431,16 +445,74 @@ using ContractVariant = ContractCfg<NX, SQLP_VARIANT_MI, SQLP_VARIANT_STAGES, SQ
                                     SQLP_VARIANT_KG>;
 
 template <int NX>
+using ResidentVariant = ResidentCfg<NX, SQLP_RES_WR, SQLP_RES_MI, SQLP_RES_KG, SQLP_RES_CTAS>;
+
+struct ProfScope {   // CUDA events around the contraction launch(es) when profiling is on
+    sqlp_ctx *c;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(sqlp_ctx *c_, double flops) : c(c_)
+    {
+        if (!c->profile) return;
+        if (c->prof_used == c->prof_events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->prof_events.push_back({a, b});
+        }
+        cudaEvent_t e0 = c->prof_events[c->prof_used].first;
+        e1 = c->prof_events[c->prof_used].second;
+        ++c->prof_used;
+        c->prof_flops += flops;
+        CK(cudaEventRecord(e0, c->stream));
+    }
+    void stop() { if (e1) CK(cudaEventRecord(e1, c->stream)); }
+};
+
+// Resident-scenario kernel: returns false when one unit of scenarios plus a two-stage pool
+// ring does not fit in shared memory (very wide stochastic row sets).
+template <int NX>
+bool launch_contract_resident(sqlp_epi *e, ContractArgs &a)
+{
+    using Cfg = ResidentVariant<NX>;
+    sqlp_ctx *c = e->ctx;
+    const size_t fixed = Cfg::fixed_bytes(a.s_pad), stage = Cfg::stage_bytes();
+    int ctas = Cfg::CTAS;
+    size_t budget = 0;
+    int stages = 0;
+    for (; ctas >= 1; --ctas) {
+        budget = std::min<size_t>((size_t)c->smem_optin, ((size_t)c->smem_per_sm - 1024u * ctas) / ctas);
+        stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
+        if (stages >= 2) break;
+    }
+    if (stages < 2) return false;
+    const size_t smem = fixed + stage * stages;
+    if (c->res_smem_set[NX] < (int)smem) {
+        CK(cudaFuncSetAttribute(k_contract_resident<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->res_smem_set[NX] = (int)smem;
+    }
+    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+    const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;   // host upper bound
+    int grid = ctas * c->sm_count;
+    if (c->contract_grid > 0) grid = c->contract_grid;
+    grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>(nunits * nchunks_ub, nunits)));
+    const size_t pieces = (size_t)grid * 2 * NX * Cfg::ROWS;
+    c->d_piece_val.ensure(pieces * 8, 0, S(c), false);
+    c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
+    a.nstages = stages;
+    a.prefetch = std::max(1, stages - 2);
+    a.piece_val = c->d_piece_val.as<double>();
+    a.piece_idx = c->d_piece_idx.as<int>();
+    LAUNCH(c, k_contract_resident<Cfg>, grid, Cfg::THREADS, smem, a);
+    auto fixup = k_argmax_fixup<Cfg::ROWS, NX>;
+    LAUNCH(c, fixup, grid, 128, 0, a, grid);
+    return true;
+}
+
+template <int NX>
 void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
 {
     using Cfg = ContractVariant<NX>;
     sqlp_ctx *c = e->ctx;
-    size_t smem = Cfg::smem_bytes();
-    if (!c->smem_attr[NX]) {   // per device, so per context
-        CK(cudaFuncSetAttribute(k_contract_argmax<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-        c->smem_attr[NX] = true;
-    }
     ContractArgs a;
     a.D = D;
     a.PiS = e->view->d_piS.as<double>();
@@ -453,23 +525,25 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.best_val = bv;
     a.best_idx = bi;
     a.out_stride = e->out_stride;
-    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
-    int grid = (int)std::min<long long>(nunits, (long long)Cfg::CTAS * c->sm_count);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->profile) {
-        if (c->prof_used == c->prof_events.size()) {
-            CK(cudaEventCreate(&e0));
-            CK(cudaEventCreate(&e1));
-            c->prof_events.push_back({e0, e1});
+    a.nstages = a.prefetch = 0;
+    a.piece_val = nullptr;
+    a.piece_idx = nullptr;
+    ProfScope prof(c, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
+    bool done = false;
+    if (c->contract_mode != 1) done = launch_contract_resident<NX>(e, a);
+    REQUIRE(done || c->contract_mode != 2, SQLP_E_UNSUPPORTED, "resident contraction does not fit");
+    if (!done) {   // streaming kernel: both operands flow through the ring
+        size_t smem = Cfg::smem_bytes();
+        if (!c->smem_attr[NX]) {   // per device, so per context
+            CK(cudaFuncSetAttribute(k_contract_argmax<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+            c->smem_attr[NX] = true;
         }
-        e0 = c->prof_events[c->prof_used].first;
-        e1 = c->prof_events[c->prof_used].second;
-        ++c->prof_used;
-        c->prof_flops += 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local;
-        CK(cudaEventRecord(e0, S(c)));
+        const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+        int grid = (int)std::min<long long>(nunits, (long long)Cfg::CTAS * c->sm_count);
+        LAUNCH(c, k_contract_argmax<Cfg>, grid, SQLP_CT_THREADS, smem, a);
     }
-    LAUNCH(c, k_contract_argmax<Cfg>, grid, SQLP_CT_THREADS, smem, a);
-    if (c->profile) CK(cudaEventRecord(e1, S(c)));
+    prof.stop();
 }
 
 // Everything of build_sasa_cut for NX points, enqueued on the stream.  x on host or device.
@@ -629,6 +703,13 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char *m = getenv("SQLP_CONTRACT")) {   // experiments / tests of the fallback
+        if (!strcmp(m, "stream")) c->contract_mode = 1;
+        else if (!strcmp(m, "resident")) c->contract_mode = 2;
+    }
+    if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreate(&c->t0));
