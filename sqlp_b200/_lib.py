@@ -13,7 +13,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "libsqlp_b200.so")
+SO_PATH = os.environ.get("SQLP_B200_LIB") or os.path.join(_HERE, "libsqlp_b200.so")   # override: kernel-variant sweeps
 SRC = os.path.join(_HERE, "csrc", "sqlp_api.cu")
 HEADER = os.path.join(ROOT, "include", "sqlp_b200.h")
 

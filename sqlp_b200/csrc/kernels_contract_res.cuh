@@ -27,6 +27,7 @@ namespace sqlp {
 
 #define SQLP_RES_MAX_STAGES 8
 
+
 //   WR   warp rows: the CTA is WR x 4 warps, warp tile (8 MI) scenarios x 32 vertices
 //   MI   m8n8 blocks per warp along the scenario axis (even)
 //   KG   k-groups (of 4 row slots) per pipeline item
@@ -176,6 +177,26 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(Contr
         }
     };
 
+    // Bias add + running argmax of one 8-scenario row block (vertex index ascending in (ni, h)).
+    auto epilogue_row = [&](int r, const double *bs, int kbase) {
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const double2 bb = *reinterpret_cast<const double2 *>(bs + x * SQLP_TILE + ni * 8);
+                double v0 = acc[r][ni][0] + bb.x;
+                if (v0 > best[x][r]) {   // strict: first maximum wins (subprob.jl:156)
+                    best[x][r] = v0;
+                    bidx[x][r] = kbase + ni * 8;
+                }
+                double v1 = acc[r][ni][1] + bb.y;
+                if (v1 > best[x][r]) {
+                    best[x][r] = v1;
+                    bidx[x][r] = kbase + ni * 8 + 1;
+                }
+            }
+        }
+    };
     int stage = 0;
     unsigned par = 0, uphase = 0;
     bool ready = false;   // the current item is already known to have landed
@@ -226,28 +247,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(Contr
                     const double *bs = st + C::KG * 512 + wx * 32 + lx * 2;
                     const int kbase = chunk * SQLP_TILE + wx * 32 + lx * 2;
 #pragma unroll
-                    for (int x = 0; x < NX; ++x) {
-                        double2 bb[4];
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni)
-                            bb[ni] = *reinterpret_cast<const double2 *>(bs + x * SQLP_TILE + ni * 8);
-#pragma unroll
-                        for (int r = 0; r < MI; ++r) {
-#pragma unroll
-                            for (int ni = 0; ni < 4; ++ni) {   // vertex index ascending in (ni, h)
-                                double v0 = acc[r][ni][0] + bb[ni].x;
-                                if (v0 > best[x][r]) {   // strict: first maximum wins (subprob.jl:156)
-                                    best[x][r] = v0;
-                                    bidx[x][r] = kbase + ni * 8;
-                                }
-                                double v1 = acc[r][ni][1] + bb[ni].y;
-                                if (v1 > best[x][r]) {
-                                    best[x][r] = v1;
-                                    bidx[x][r] = kbase + ni * 8 + 1;
-                                }
-                            }
-                        }
-                    }
+                    for (int r = 0; r < MI; ++r) epilogue_row(r, bs, kbase);
 #pragma unroll
                     for (int r = 0; r < MI; ++r)
 #pragma unroll

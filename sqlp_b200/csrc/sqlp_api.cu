@@ -25,10 +25,10 @@
 #endif
 // resident variant (production): warp rows, m8n8 blocks per warp, k-groups per item, CTAs per SM
 #ifndef SQLP_RES_WR
-#define SQLP_RES_WR 1
+#define SQLP_RES_WR 2
 #define SQLP_RES_MI 8
-#define SQLP_RES_KG 2
-#define SQLP_RES_CTAS 2
+#define SQLP_RES_KG 6
+#define SQLP_RES_CTAS 1
 #endif
 #include "kernels_contract.cuh"
 #include "kernels_contract_res.cuh"
@@ -186,6 +186,7 @@ struct sqlp_ctx {
     // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
     int contract_mode = 0;        // 0 = automatic, 1 = streaming kernel only, 2 = resident only
     int contract_grid = 0;        // > 0: force this many CTAs (tests of the span split)
+    int contract_prefetch = 0;    // > 0: items the copies run ahead (tuning knob, environment)
     int smem_per_sm = 0, smem_optin = 0;
     int res_smem_set[3] = {0, 0, 0};
     DevBuf d_piece_val, d_piece_idx;
@@ -500,6 +501,7 @@ bool launch_contract_resident(sqlp_epi *e, ContractArgs &a)
     c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
     a.nstages = stages;
     a.prefetch = std::max(1, stages - 2);
+    if (c->contract_prefetch > 0) a.prefetch = std::min(c->contract_prefetch, stages - 1);
     a.piece_val = c->d_piece_val.as<double>();
     a.piece_idx = c->d_piece_idx.as<int>();
     LAUNCH(c, k_contract_resident<Cfg>, grid, Cfg::THREADS, smem, a);
@@ -710,6 +712,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
         else if (!strcmp(m, "resident")) c->contract_mode = 2;
     }
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
+    if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreate(&c->t0));
