@@ -54,8 +54,26 @@ def parse():
 # ---------------------------------------------------------------- workload ---------------
 
 def load_instance(name):
+    if name.startswith("synth"):
+        return synthetic_instance(int(name[5:] or 128))
     z = dict(np.load(os.path.join(ROOT, "tests", "golden", "instances", f"{name}.npz")))
     return z
+
+
+def synthetic_instance(s):
+    """The storm-shaped synthetic template of SURVEY.md 8(d) C5: m2 = 4 s rows of which the first s
+    are stochastic (RHS only), n1 = s, Tbar = one -1 per first-stage column on rows s..2s-1,
+    rbar_j = 100 + 400 u(6, j) on the stochastic rows, five equiprobable outcomes rbar_j * {0.8..1.2}."""
+    m2, n1 = 4 * s, s
+    rbar = np.zeros(m2)
+    rbar[:s] = 100.0 + 400.0 * u01(6, np.arange(s))
+    fac = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    return {"m2": np.int64(m2), "n1": np.int64(n1), "rbar": rbar,
+            "T_colptr": np.arange(n1 + 1, dtype=np.int64), "T_rowval": np.arange(s, 2 * s, dtype=np.int64),
+            "T_nzval": -np.ones(n1), "pos_row": np.arange(s, dtype=np.int32),
+            "pos_col": -np.ones(s, dtype=np.int32), "out_vals": rbar[:s, None] * fac[None, :],
+            "out_cdf": np.tile(np.cumsum(np.full(5, 0.2)), (s, 1)), "out_cnt": np.full(s, 5, dtype=np.int32),
+            "pool": np.zeros((0, m2)), "x_ev": 10.0 * u01(3, np.arange(n1)), "x_alt": 10.0 * u01(5, np.arange(n1))}
 
 
 def u01(seed, idx):
@@ -75,7 +93,7 @@ def make_pool(z, K, extra):
     m2 = int(z["m2"])
     real = z["pool"]
     n_syn = K + extra - len(real)
-    scale = float(np.abs(real).max())
+    scale = float(np.abs(real).max()) if len(real) else 1000.0
     syn = scale * (2.0 * u01(2, np.arange(n_syn * m2, dtype=np.uint64)).reshape(n_syn, m2) - 1.0)
     return np.vstack([real, syn])
 
