@@ -81,6 +81,10 @@ SQLP_API int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *ctx, double *ms);
 SQLP_API int32_t sqlp_ctx_profile(sqlp_ctx *ctx, int32_t enable);
 SQLP_API int32_t sqlp_ctx_profile_read(sqlp_ctx *ctx, int32_t reset, double *contract_ms,
                                        int64_t *contract_launches, double *contract_flops);
+/* The same for every kernel class, arrays of 5: 0 contraction (work = flops), 1 delta build,
+ * 2 cut reduction, 3 pool push, 4 bias vectors (work = algorithmic bytes). */
+SQLP_API int32_t sqlp_ctx_profile_classes(sqlp_ctx *ctx, int32_t reset, double *ms /*[5]*/,
+                                          int64_t *launches /*[5]*/, double *work /*[5]*/);
 
 /* ---------------------------------------------------------------- dual-vertex pool -- */
 

@@ -5,6 +5,13 @@
 #include <stdint.h>
 
 #define SQLP_TILE 128  // scenarios per tile == vertices per chunk
+// kernel classes of the built-in profiler (sqlp_ctx_profile_classes)
+#define SQLP_PROF_CONTRACT 0
+#define SQLP_PROF_DELTA 1
+#define SQLP_PROF_REDUCE 2
+#define SQLP_PROF_POOL 3
+#define SQLP_PROF_BIAS 4
+#define SQLP_PROF_CLASSES 5
 #define SQLP_BK 8      // stochastic rows per pipeline slab (s is padded to a multiple)
 
 namespace sqlp {

@@ -60,7 +60,7 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(ContractArgs a)
 {
     constexpr int NX = C::NX, MI = C::MI, ROWS = C::ROWS, WARPS = C::WARPS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ngroups = a.s_pad / 4;
     const int S = a.nstages;
     double *Ares = reinterpret_cast<double *>(smem_raw);

@@ -12,9 +12,9 @@
 //             once and never reshaped.
 //   dT[i][n_T]  row-major delta_T values (only when some element perturbs Tbar).
 //   w[i]        scenario weights.
-// One CUDA block per 128-aligned block of global scenario ordinals: realised values are
-// read coalesced along the element axis, staged in shared memory, and written out as the
-// contiguous 4 KB (4 slots x 128 columns) cells of the tile layout.
+// One CUDA block per 64-scenario half of a 128-aligned block of global scenario ordinals:
+// realised values are read coalesced along the element axis, staged in shared memory, and
+// written out as the contiguous 2 KB (4 slots x 64 columns) half cells of the tile layout.
 #pragma once
 #include "common.cuh"
 
@@ -34,7 +34,17 @@ struct DeltaTables {
     int mo;
 };
 
-#define SQLP_DELTA_SLAB 32   // slots staged per pass (8 k-groups)
+#define SQLP_DELTA_COLS 64      // scenarios per block (half a tile)
+#define SQLP_DELTA_SLAB 128     // row slots staged per pass
+#define SQLP_DELTA_THREADS 512
+
+// Row stride (doubles) of the staging buffer sh[column][slot]: >= slab and = 4 (mod 16), so that
+// phase 1 (lanes along the slot axis) and phase 2 (lanes over 4 slots x 8 columns that are 0..3
+// and 8..11 apart) both touch 16 distinct 8-byte bank pairs per half-warp.
+__host__ __device__ __forceinline__ int delta_stride(int slab)
+{
+    return ((slab + 11) / 16) * 16 + 4;
+}
 
 template <bool SAMPLE>
 __device__ __forceinline__ double realised_value(const DeltaTables &tb, const double *values,
@@ -53,22 +63,31 @@ __device__ __forceinline__ double realised_value(const DeltaTables &tb, const do
 }
 
 // SAMPLE = false: values[i_batch][e] given.  SAMPLE = true: drawn from the outcome tables.
+// One block per 64-scenario half of a 128-aligned block of global ordinals.  Phase 1: one warp
+// per scenario, lanes along the slot axis, so the realised values (contiguous per scenario) are
+// read in 256-byte runs and all of a block's loads are in flight at once.  Phase 2: the half
+// tile's part of every k-group (4 slots x 64 columns = 2 KB contiguous) is written in order.
 template <bool SAMPLE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SQLP_DELTA_THREADS)
 k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, long long n_new,
               int rank, int world, int s_pad, double *__restrict__ D, double *__restrict__ dT,
               double *__restrict__ w, const double *__restrict__ w_batch, unsigned long long seed,
               unsigned long long wseed)
 {
-    __shared__ double sh[SQLP_DELTA_SLAB][SQLP_TILE + 1];
-    const long long gblock = g0 / SQLP_TILE + blockIdx.x;   // global 128-block
+    extern __shared__ __align__(16) double sh[];   // [SQLP_DELTA_COLS][stride]
+    const long long gblock = g0 / SQLP_TILE + (blockIdx.x >> 1);   // global 128-block
     if ((int)(gblock % world) != rank) return;
+    const int half = blockIdx.x & 1;
     const long long gb0 = gblock * SQLP_TILE;
-    const long long lo = max(gb0, g0), hi = min(gb0 + SQLP_TILE, g0 + n_new);
+    const long long lo = max(gb0 + half * SQLP_DELTA_COLS, g0);
+    const long long hi = min(gb0 + (half + 1) * SQLP_DELTA_COLS, g0 + n_new);
+    if (lo >= hi) return;
     const int c0 = (int)(lo - gb0), c1 = (int)(hi - gb0);   // columns [c0, c1) of the tile
+    const int cb = half * SQLP_DELTA_COLS;
     const long long ltile = gblock / world;                  // local tile index
     double *Dt = D + ltile * (long long)s_pad * SQLP_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int slab = min(s_pad, SQLP_DELTA_SLAB), stride = delta_stride(slab);
 
     // weights
     for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
@@ -89,26 +108,53 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
         dT[(ltile * SQLP_TILE + c) * (long long)tb.n_T + t] = __dsub_rn(val, tb.elem_base[e]);   // :117
     }
 
-    for (int j0 = 0; j0 < tb.n_rows; j0 += SQLP_DELTA_SLAB) {
-        // phase 1: one warp per scenario, lanes along the slot axis (coalesced reads)
-        for (int c = c0 + warp; c < c1; c += nwarp) {
-            const int j = j0 + lane;
-            const int e = (j < tb.n_rows) ? tb.slot_elem[j] : -1;
-            double d = 0.0;
-            if (e >= 0)
-                d = __dsub_rn(realised_value<SAMPLE>(tb, values, gb0 + c, g0, e, seed),
-                              tb.elem_base[e]);                                                   // :114
-            sh[lane][c] = d;
+    for (int j0 = 0; j0 < s_pad; j0 += slab) {
+        const int jn = min(slab, s_pad - j0);   // slots of this pass (a multiple of 4)
+        // phase 1: the element and template value of a lane's slots do not depend on the scenario
+        int el[SQLP_DELTA_SLAB / 32];
+        double eb[SQLP_DELTA_SLAB / 32];
+#pragma unroll
+        for (int k = 0; k < SQLP_DELTA_SLAB / 32; ++k) {
+            const int j = j0 + lane + 32 * k;
+            el[k] = (lane + 32 * k < jn && j < tb.n_rows) ? tb.slot_elem[j] : -1;
+            eb[k] = (el[k] >= 0) ? tb.elem_base[el[k]] : 0.0;
+        }
+        // every load of the block (64 scenarios x up to 128 slots over 16 warps) is issued before
+        // the first use: 16 independent 8-byte loads per lane
+        constexpr int CPW = SQLP_DELTA_COLS / (SQLP_DELTA_THREADS / 32);   // scenarios per warp
+        double v[CPW][SQLP_DELTA_SLAB / 32];
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+            const int c = cb + warp + i * (SQLP_DELTA_THREADS / 32);
+#pragma unroll
+            for (int k = 0; k < SQLP_DELTA_SLAB / 32; ++k)
+                v[i][k] = (el[k] >= 0 && c >= c0 && c < c1)
+                              ? realised_value<SAMPLE>(tb, values, gb0 + c, g0, el[k], seed) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+            double *row = sh + (warp + i * (SQLP_DELTA_THREADS / 32)) * stride;
+#pragma unroll
+            for (int k = 0; k < SQLP_DELTA_SLAB / 32; ++k)
+                if (lane + 32 * k < jn) row[lane + 32 * k] = (el[k] >= 0) ? __dsub_rn(v[i][k], eb[k]) : 0.0;   // :114
         }
         __syncthreads();
-        // phase 2: each k-group (4 slots x 128 columns) is 512 contiguous doubles of the tile
-        const int ngroups = min(SQLP_DELTA_SLAB / 4, (s_pad - j0) / 4);
-        for (int q = threadIdx.x; q < ngroups * 512; q += blockDim.x) {
-            const int gq = q >> 9, o = q & 511;
-            const int P = o >> 6, t = (o & 63) >> 1, h = o & 1;
-            const int c = (2 * P + h) * 8 + (t >> 2);
-            if (c >= c0 && c < c1)
-                Dt[(long long)(j0 / 4 + gq) * 512 + o] = sh[gq * 4 + (t & 3)][c];
+        // phase 2: offset o of a k-group's 512 doubles is cell P = o / 64, lane t = (o % 64) / 2,
+        // h = o % 2, i.e. column (2 P + h) * 8 + t / 4 and slot t % 4 (common.cuh tile_off); the two
+        // columns of a pair (h = 0, 1) are one 16-byte store
+        const bool whole = (c0 == cb && c1 == cb + SQLP_DELTA_COLS);
+        for (int q = threadIdx.x; q < (jn / 4) * 128; q += blockDim.x) {
+            const int gq = q >> 7, o = cb * 4 + 2 * (q & 127);
+            const int P = o >> 6, t = (o & 63) >> 1;
+            const int c = (2 * P) * 8 + (t >> 2);            // h = 0 column; h = 1 is c + 8
+            const double *src = sh + (c - cb) * stride + gq * 4 + (t & 3);
+            double *dst = Dt + (long long)(j0 / 4 + gq) * 512 + o;
+            if (whole) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(src[0], src[8 * stride]);
+            } else {
+                if (c >= c0 && c < c1) dst[0] = src[0];
+                if (c + 8 >= c0 && c + 8 < c1) dst[1] = src[8 * stride];
+            }
         }
         __syncthreads();
     }

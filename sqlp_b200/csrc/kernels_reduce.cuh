@@ -17,26 +17,21 @@
 
 namespace sqlp {
 
-// base_x = rbar - Tbar * x   (subprob.jl:147), column-ordered scatter like SparseArrays.
+// base_x = rbar - Tbar * x   (subprob.jl:147).  SparseArrays' CSC product adds the entries of a
+// row in column order starting from zero; a CSR copy of Tbar (columns ascending within a row)
+// lets one thread per row do exactly that sum, so every row is bit-identical to the reference
+// and no thread walks the whole matrix.  blockIdx.y selects the point.
 __global__ void k_base(const double *__restrict__ rbar, int m2, int n1,
-                       const long long *__restrict__ T_colptr, const int *__restrict__ T_rowval,
-                       const double *__restrict__ T_nzval, const double *__restrict__ x2,
+                       const int *__restrict__ R_ptr, const int *__restrict__ R_col,
+                       const double *__restrict__ R_val, const double *__restrict__ x2,
                        double *__restrict__ base)
 {
-    extern __shared__ double y[];           // [m2]
-    const double *x = x2 + (long long)blockIdx.x * n1;
-    for (int j = threadIdx.x; j < m2; j += blockDim.x) y[j] = 0.0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < n1; ++c) {
-            const double xc = x[c];
-            for (long long q = T_colptr[c]; q < T_colptr[c + 1]; ++q)
-                y[T_rowval[q]] = __dadd_rn(y[T_rowval[q]], __dmul_rn(T_nzval[q], xc));
-        }
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < m2; j += blockDim.x)
-        base[(long long)blockIdx.x * m2 + j] = __dsub_rn(rbar[j], y[j]);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m2) return;
+    const double *x = x2 + (long long)blockIdx.y * n1;
+    double y = 0.0;
+    for (int q = R_ptr[j]; q < R_ptr[j + 1]; ++q) y = __dadd_rn(y, __dmul_rn(R_val[q], x[R_col[q]]));
+    base[(long long)blockIdx.y * m2 + j] = __dsub_rn(rbar[j], y);
 }
 
 // bias_x[k] = dot(pi_k, base_x)  (the first dot of subprob.jl:155), one warp per vertex,
@@ -114,9 +109,22 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             if (k < 0) {
                 atomicOr(a.flags, 1);
             } else {
-                const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE;
-                for (int j = 0; j < a.n_rows; ++j)
-                    acc = fma(P[tile_off(k & 127, j)], Dt[tile_off(c, j)], acc);
+                // slots in order; a k-group (4 slots) is 512 doubles further in both tiles and its
+                // four slots sit 2 doubles apart, so the walk needs no index arithmetic.  Pad slots
+                // are zero in both operands and add nothing.
+                const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE + tile_off(k & 127, 0);
+                const double *Dc = Dt + tile_off(c, 0);
+                const int ng = a.s_pad / 4;   // even: s_pad is a multiple of 8
+                for (int g = 0; g < ng; g += 2, P += 1024, Dc += 1024) {
+                    double pv[8], dv[8];   // sixteen loads in flight, then the ordered chain
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        pv[u] = P[(u >> 2) * 512 + (u & 3) * 2];
+                        dv[u] = Dc[(u >> 2) * 512 + (u & 3) * 2];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = fma(pv[u], dv[u], acc);
+                }
             }
             if (x == 0) p_i[c] = a.w[i0 + c] / a.total_weight;   // epigraph.jl:138
         }
@@ -125,8 +133,11 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
     }
     __syncthreads();
 
-    // phase B: thread per (x, output column); scenarios in index order
+    // phase B: thread per (x, output column); scenarios in index order.  The table rows of eight
+    // scenarios are fetched before they are used, so the gathers overlap instead of queueing
+    // behind one another; the additions keep the scenario order.
     const int NC = a.n1 + 2;
+    const long long RT = a.n1 + 1;
     for (int q = threadIdx.x; q < NX * NC; q += blockDim.x) {
         const int x = q / NC, col = q % NC;
         double sum = 0.0;
@@ -136,24 +147,35 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             t1 = t0;
             while (t1 < a.n_T && a.tc_col[t1] == col - 1) ++t1;
         }
-        for (int c = 0; c < cnt; ++c) {
-            const int k = k_i[x][c];
-            if (k < 0) continue;
-            const double p = p_i[c];
-            double term;
-            if (col == 0) {
-                term = a.rt[(long long)k * (a.n1 + 1)] + a_i[x][c];           // :140
-                sum = fma(p, term, sum);
-            } else if (col <= a.n1) {
-                term = a.rt[(long long)k * (a.n1 + 1) + col];                 // :141
-                for (int t = t0; t < t1; ++t) {
-                    const double piv =
-                        a.PiS[(long long)(k >> 7) * a.s_pad * SQLP_TILE + tile_off(k & 127, a.tc_j[t])];
-                    term = fma(a.dT[(i0 + c) * (long long)a.n_T + a.tc_slot[t]], piv, term);
+        const bool is_val = (col == NC - 1);
+        const double *src = is_val ? a.best_val + x * a.out_stride + i0 : a.rt + col;
+        for (int cb = 0; cb < cnt; cb += 8) {
+            int kk[8];
+            double tv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = cb + u;
+                kk[u] = (c < cnt) ? k_i[x][c] : -1;
+                tv[u] = (kk[u] >= 0) ? (is_val ? src[c] : src[(long long)kk[u] * RT]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = cb + u, k = kk[u];
+                if (k < 0) continue;
+                const double p = p_i[c];
+                double term = tv[u];
+                if (col == 0) {
+                    sum = fma(p, term + a_i[x][c], sum);                              // :140
+                } else if (!is_val) {
+                    for (int t = t0; t < t1; ++t) {                                   // :141
+                        const double piv =
+                            a.PiS[(long long)(k >> 7) * a.s_pad * SQLP_TILE + tile_off(k & 127, a.tc_j[t])];
+                        term = fma(a.dT[(i0 + c) * (long long)a.n_T + a.tc_slot[t]], piv, term);
+                    }
+                    sum = fma(-p, term, sum);
+                } else {
+                    sum = fma(p, term, sum);                                          // :142
                 }
-                sum = fma(-p, term, sum);
-            } else {
-                sum = fma(p, a.best_val[x * a.out_stride + i0 + c], sum);     // :142
             }
         }
         a.partial[(tile * NX + x) * NC + col] = sum;

@@ -179,15 +179,17 @@ struct sqlp_ctx {
     int64_t launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    struct ProfEvent { cudaEvent_t e0, e1; int cls; };
+    std::vector<ProfEvent> prof_events;
     size_t prof_used = 0;
-    double prof_flops = 0.0;
+    double prof_work[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};   // flops (contraction) or algorithmic bytes
     bool smem_attr[3] = {false, false, false};
     // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
     int contract_mode = 0;        // 0 = automatic, 1 = streaming kernel only, 2 = resident only
     int contract_grid = 0;        // > 0: force this many CTAs (tests of the span split)
     int contract_prefetch = 0;    // > 0: items the copies run ahead (tuning knob, environment)
     int smem_per_sm = 0, smem_optin = 0;
+    bool delta_smem_set = false;
     int res_smem_set[3] = {0, 0, 0};
     DevBuf d_piece_val, d_piece_idx;
     void bind() const { CK(cudaSetDevice(device)); }
@@ -232,6 +234,7 @@ struct sqlp_epi {
     std::vector<double> h_nzval;
     std::vector<int> h_pos_row, h_pos_col, h_elem_j, h_elem_t;
     DevBuf d_rbar, d_colptr, d_rowval, d_nzval;
+    DevBuf d_rptr, d_rcol, d_rval;        // CSR copy of Tbar (columns ascending per row) -> k_base
     DevBuf d_slot_elem, d_t_elem, d_elem_base;
     DevBuf d_tj, d_tcol, d_tslot;         // T elements sorted by (row slot, col)  -> k_delta_x
     DevBuf d_cc, d_cj, d_cslot;           // T elements sorted by col              -> reduce
@@ -254,6 +257,29 @@ struct sqlp_epi {
 namespace {
 
 cudaStream_t S(sqlp_ctx *c) { return c->stream; }
+
+struct ProfScope {   // CUDA events around the launch(es) of one kernel class when profiling is on
+    sqlp_ctx *c;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(sqlp_ctx *c_, int cls, double work) : c(c_)
+    {
+        if (!c->profile) return;
+        if (c->prof_used == c->prof_events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->prof_events.push_back({a, b, cls});
+        }
+        sqlp_ctx::ProfEvent &pe = c->prof_events[c->prof_used++];
+        pe.cls = cls;
+        e1 = pe.e1;
+        c->prof_work[cls] += work;
+        CK(cudaEventRecord(pe.e0, c->stream));
+    }
+    void stop() { if (e1) CK(cudaEventRecord(e1, c->stream)); e1 = nullptr; }
+    ~ProfScope() { if (e1) cudaEventRecord(e1, c->stream); }
+};
+
 
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
@@ -307,6 +333,8 @@ void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const doub
                                 c->comm, S(c)));
         src = p->d_vnew.as<double>();
     }
+    // algorithmic bytes: the hash scan (8 K per push) + the pushed vector in and, if new, out
+    ProfScope prof(c, SQLP_PROF_POOL, (double)n * (8.0 * (double)p->upper() + 16.0 * (double)p->m2));
     for (int64_t i = 0; i < n; ++i) {
         LAUNCH(c, k_pool_prepare, 1, 256, (size_t)p->m2 * 8, src + i * p->m2, (int)p->m2,
                p->d_vr.as<double>(), p->d_scratch.as<PushScratch>());
@@ -399,7 +427,12 @@ void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_d
         e->total_weight += w;
     }
     DeltaTables tb = delta_tables(e);
-    const int64_t piece = std::max<int64_t>(SQLP_TILE, ((int64_t)(64 << 20) / (8 * std::max<int64_t>(e->s, 1))) / SQLP_TILE * SQLP_TILE);
+    // algorithmic bytes: 8 s in + 8 s out per scenario (sampled: out only), this rank's share
+    ProfScope prof(c, SQLP_PROF_DELTA, (double)(nl1 - e->n_local) * e->s * (sample ? 8.0 : 16.0));
+    // host values go through a 64 MB staging buffer piece by piece; device-resident or sampled
+    // values need no staging, so the whole batch is one launch
+    const int64_t piece = (sample || v_dev) ? std::max<int64_t>(SQLP_TILE, (n_new / SQLP_TILE + 2) * SQLP_TILE)
+        : std::max<int64_t>(SQLP_TILE, ((int64_t)(64 << 20) / (8 * std::max<int64_t>(e->s, 1))) / SQLP_TILE * SQLP_TILE);
     for (int64_t off = 0; off < n_new;) {
         // cut pieces at 128-aligned global ordinals so a tile is never split mid-copy
         int64_t end = std::min<int64_t>(n_new, ((g0 + off) / SQLP_TILE) * SQLP_TILE + piece - g0);
@@ -417,22 +450,31 @@ void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_d
                 vals = e->d_stage.as<double>();
             }
             if (w_host) {
-                if (v_dev) e->d_stage.ensure((size_t)cnt * (e->s + 1) * 8, 0, S(c), false);
+                if (v_dev) e->d_stage.ensure((size_t)cnt * 8, 0, S(c), false);   // weights only
                 double *dw = e->d_stage.as<double>() + (v_dev ? 0 : cnt * e->s);
                 CK(cudaMemcpyAsync(dw, w_host + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, S(c)));
                 wts = dw;
             }
         }
         const int64_t gs = g0 + off;
-        const int blocks = (int)((gs + cnt - 1) / SQLP_TILE - gs / SQLP_TILE + 1);
+        const int blocks = 2 * (int)((gs + cnt - 1) / SQLP_TILE - gs / SQLP_TILE + 1);   // half tiles
+        const int slab = std::min(e->view->s_pad, SQLP_DELTA_SLAB);
+        const size_t dsmem = (size_t)SQLP_DELTA_COLS * delta_stride(slab) * 8;
+        if (!c->delta_smem_set) {
+            const int mx = SQLP_DELTA_COLS * delta_stride(SQLP_DELTA_SLAB) * 8;
+            CK(cudaFuncSetAttribute(k_delta_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            CK(cudaFuncSetAttribute(k_delta_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            c->delta_smem_set = true;
+        }
         if (sample)
-            LAUNCH(c, k_delta_build<true>, blocks, 256, 0, tb, vals, (long long)gs, (long long)cnt,
-                   c->rank, c->world, e->view->s_pad, e->d_D.as<double>(), e->d_dT.as<double>(),
-                   e->d_w.as<double>(), wts, (unsigned long long)seed, (unsigned long long)wseed);
+            LAUNCH(c, k_delta_build<true>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
+                   (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
+                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, (unsigned long long)seed,
+                   (unsigned long long)wseed);
         else
-            LAUNCH(c, k_delta_build<false>, blocks, 256, 0, tb, vals, (long long)gs, (long long)cnt,
-                   c->rank, c->world, e->view->s_pad, e->d_D.as<double>(), e->d_dT.as<double>(),
-                   e->d_w.as<double>(), wts, 0ull, 0ull);
+            LAUNCH(c, k_delta_build<false>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
+                   (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
+                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, 0ull, 0ull);
         if (!sample && !v_dev) CK(cudaStreamSynchronize(S(c)));   // staging buffer is reused
         off = end;
     }
@@ -447,27 +489,6 @@ using ContractVariant = ContractCfg<NX, SQLP_VARIANT_MI, SQLP_VARIANT_STAGES, SQ
 
 template <int NX>
 using ResidentVariant = ResidentCfg<NX, SQLP_RES_WR, SQLP_RES_MI, SQLP_RES_KG, SQLP_RES_CTAS>;
-
-struct ProfScope {   // CUDA events around the contraction launch(es) when profiling is on
-    sqlp_ctx *c;
-    cudaEvent_t e1 = nullptr;
-    ProfScope(sqlp_ctx *c_, double flops) : c(c_)
-    {
-        if (!c->profile) return;
-        if (c->prof_used == c->prof_events.size()) {
-            cudaEvent_t a = nullptr, b = nullptr;
-            CK(cudaEventCreate(&a));
-            CK(cudaEventCreate(&b));
-            c->prof_events.push_back({a, b});
-        }
-        cudaEvent_t e0 = c->prof_events[c->prof_used].first;
-        e1 = c->prof_events[c->prof_used].second;
-        ++c->prof_used;
-        c->prof_flops += flops;
-        CK(cudaEventRecord(e0, c->stream));
-    }
-    void stop() { if (e1) CK(cudaEventRecord(e1, c->stream)); }
-};
 
 // Resident-scenario kernel: returns false when one unit of scenarios plus a two-stage pool
 // ring does not fit in shared memory (very wide stochastic row sets).
@@ -530,7 +551,7 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.nstages = a.prefetch = 0;
     a.piece_val = nullptr;
     a.piece_idx = nullptr;
-    ProfScope prof(c, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
+    ProfScope prof(c, SQLP_PROF_CONTRACT, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
     bool done = false;
     if (c->contract_mode != 1) done = launch_contract_resident<NX>(e, a);
     REQUIRE(done || c->contract_mode != 2, SQLP_E_UNSUPPORTED, "resident contraction does not fit");
@@ -584,8 +605,9 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
     e->d_base.ensure((size_t)2 * m2 * 8, 0, S(c));
 
     if (ntiles > 0) {
-        LAUNCH(c, k_base, NX, 128, (size_t)m2 * 8, e->d_rbar.as<double>(), m2, n1,
-               e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
+        ProfScope prof_bias(c, SQLP_PROF_BIAS, 8.0 * (double)ku * m2 + 8.0 * NX * (double)ku);
+        LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
+               e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
                e->d_x2.as<double>(), e->d_base.as<double>());
         int bgrid = (int)((kpad + 7) / 8);
         if (NX == 2)
@@ -596,6 +618,8 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
             LAUNCH(c, k_bias<1>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
                    p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
                    (long long)e->bias_stride);
+
+        prof_bias.stop();
 
         if (e->n_T == 0) {
             if (NX == 2)
@@ -645,6 +669,10 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         r.tc_slot = e->d_cslot.as<int>();
         r.partial = e->d_partial.as<double>();
         r.flags = e->d_flags.as<int>();
+        // algorithmic bytes: per point N (idx + weight + winning dot) + the (rho, tau)
+        // table + the cut; the implementation also re-reads D (8 s_pad N) to recompute the winning dot
+        ProfScope prof_red(c, SQLP_PROF_REDUCE,
+                           NX * (24.0 * (double)e->n_local + 8.0 * (double)ku * (n1 + 1) + 8.0 * (n1 + 1)));
         if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, 0, r);
         else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, 0, r);
         const int group = 64;
@@ -654,6 +682,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
                width, e->d_partial2.as<double>());
         LAUNCH(c, k_sum_groups, 1, 256, 0, e->d_partial2.as<double>(), (long long)ng, (int)ng, width,
                e->d_out.as<double>());
+        prof_red.stop();
     }
     if (c->world > 1) {
         // per-epigraph partials are all-gathered and summed in fixed rank order
@@ -769,7 +798,7 @@ int32_t sqlp_ctx_destroy(sqlp_ctx *c)
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         if (c->comm) g_nccl.CommDestroy(c->comm);
-        for (auto &pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        for (auto &pr : c->prof_events) { cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1); }
         if (c->t0) cudaEventDestroy(c->t0);
         if (c->t1) cudaEventDestroy(c->t1);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -829,23 +858,42 @@ int32_t sqlp_ctx_profile(sqlp_ctx *c, int32_t enable)
     return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->profile = enable != 0; });
 }
 
-int32_t sqlp_ctx_profile_read(sqlp_ctx *c, int32_t reset, double *ms, int64_t *launches, double *flops)
+int32_t sqlp_ctx_profile_classes(sqlp_ctx *c, int32_t reset, double *ms, int64_t *launches, double *work)
 {
     return guard([&] {
         REQUIRE(c, SQLP_E_INVALID, "null ctx");
         c->bind();
         CK(cudaStreamSynchronize(c->stream));
-        double total = 0;
+        double t[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};
+        int64_t n[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};
         for (size_t i = 0; i < c->prof_used; ++i) {
             float f = 0;
-            CK(cudaEventElapsedTime(&f, c->prof_events[i].first, c->prof_events[i].second));
-            total += f;
+            CK(cudaEventElapsedTime(&f, c->prof_events[i].e0, c->prof_events[i].e1));
+            t[c->prof_events[i].cls] += f;
+            ++n[c->prof_events[i].cls];
         }
-        if (ms) *ms = total;
-        if (launches) *launches = (int64_t)c->prof_used;
-        if (flops) *flops = c->prof_flops;
-        if (reset) { c->prof_used = 0; c->prof_flops = 0; }
+        for (int k = 0; k < SQLP_PROF_CLASSES; ++k) {
+            if (ms) ms[k] = t[k];
+            if (launches) launches[k] = n[k];
+            if (work) work[k] = c->prof_work[k];
+        }
+        if (reset) {
+            c->prof_used = 0;
+            for (double &w : c->prof_work) w = 0;
+        }
     });
+}
+
+int32_t sqlp_ctx_profile_read(sqlp_ctx *c, int32_t reset, double *ms, int64_t *launches, double *flops)
+{
+    double t[SQLP_PROF_CLASSES], w[SQLP_PROF_CLASSES];
+    int64_t n[SQLP_PROF_CLASSES];
+    int32_t rc = sqlp_ctx_profile_classes(c, reset, t, n, w);
+    if (rc != SQLP_OK) return rc;
+    if (ms) *ms = t[SQLP_PROF_CONTRACT];
+    if (launches) *launches = n[SQLP_PROF_CONTRACT];
+    if (flops) *flops = w[SQLP_PROF_CONTRACT];
+    return SQLP_OK;
 }
 
 // ---------------------------------------------------------------- pool -------------------
@@ -1050,6 +1098,22 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
             upload(e->d_colptr, e->h_colptr, S(c));
             upload(e->d_rowval, e->h_rowval, S(c));
             upload(e->d_nzval, e->h_nzval, S(c));
+            {   // CSR copy: walking the columns in order keeps each row's entries column-ascending
+                std::vector<int> rptr((size_t)m2 + 1, 0), rcol((size_t)nnz);
+                std::vector<double> rval((size_t)nnz);
+                for (int64_t q = 0; q < nnz; ++q) ++rptr[(size_t)e->h_rowval[(size_t)q] + 1];
+                for (int64_t j = 0; j < m2; ++j) rptr[(size_t)j + 1] += rptr[(size_t)j];
+                std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+                for (int64_t col = 0; col < n1; ++col)
+                    for (int64_t q = e->h_colptr[(size_t)col]; q < e->h_colptr[(size_t)col + 1]; ++q) {
+                        int at = fill[(size_t)e->h_rowval[(size_t)q]]++;
+                        rcol[(size_t)at] = (int)col;
+                        rval[(size_t)at] = e->h_nzval[(size_t)q];
+                    }
+                upload(e->d_rptr, rptr, S(c));
+                upload(e->d_rcol, rcol, S(c));
+                upload(e->d_rval, rval, S(c));
+            }
             std::vector<int> slot_elem(rows.size(), -1), t_elem;
             for (int64_t q = 0; q < s; ++q) {
                 if (pos_col[q] < 0) slot_elem[(size_t)e->h_elem_j[(size_t)q]] = (int)q;

@@ -93,6 +93,16 @@ class Context:
         check(_lib.lib().sqlp_ctx_profile_read(self._h, int(reset), C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
 
+    PROFILE_CLASSES = ("contract", "delta", "reduce", "pool", "bias")
+
+    def profile_classes(self, reset=True):
+        """{class: (device ms, event scopes, work)}; work = flops for the contraction, algorithmic bytes else."""
+        import numpy as np
+        ms, n, wk = np.zeros(5), np.zeros(5, dtype=np.int64), np.zeros(5)
+        check(_lib.lib().sqlp_ctx_profile_classes(self._h, int(reset), ms.ctypes.data_as(C.c_void_p),
+                                                  n.ctypes.data_as(C.c_void_p), wk.ctypes.data_as(C.c_void_p)))
+        return {k: (float(ms[i]), int(n[i]), float(wk[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
+
     def close(self):
         if self._h:
             _lib.lib().sqlp_ctx_destroy(self._h)
