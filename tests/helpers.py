@@ -114,3 +114,79 @@ def check_argmax_parity(P, values, x, pool, got_val, got_idx, rel_gap=1e-12, val
     err = np.max(np.abs(np.asarray(got_val) - ov) / scale) if len(ov) else 0.0
     assert err <= val_rtol, f"max relative max_val error {err:g}"
     return exempt
+
+
+# ---------------------------------------------------------------- SD-loop harness --------
+
+def load_full_instance(name):
+    """First-stage rows + second-stage LP data of a small instance (tools/make_golden.py --full)."""
+    return dict(np.load(os.path.join(GOLDEN, "instances", f"{name}_full.npz")))
+
+
+class OracleEpigraph:
+    """The epigraph interface ``sqlp_b200.sd.sd_iteration_`` drives, answered by the CPU oracle:
+    test infrastructure for the host logic (``-m "not gpu"``) and the lock-step checker of
+    the GPU run.  Shares an ``O.DualVertexSet`` with the cell."""
+
+    class _Coef:
+        def __init__(self, s):
+            self.s = s
+
+        def scenario_values(self, scen):
+            return np.asarray(scen, dtype=np.float64).reshape(self.s)
+
+    def __init__(self, P, objective_weight, lower_bound, dual_vertices):
+        self.P, self.objective_weight, self.lower_bound = P, float(objective_weight), float(lower_bound)
+        self.dual_vertices = dual_vertices
+        self.subproblem_coef = self._Coef(P.s)
+        self.values, self.weights = [], []
+        self.cuts, self.incumbent_cut = [], None
+
+    @property
+    def total_scenario_weight(self):
+        tw = 0.0
+        for w in self.weights:       # epigraph.jl:89, in scenario order
+            tw += w
+        return tw
+
+    def add_scenarios(self, values, weights=None):
+        values = np.asarray(values, dtype=np.float64).reshape(-1, self.P.s)
+        for i, v in enumerate(values):
+            self.values.append(v.copy())
+            self.weights.append(1.0 if weights is None else float(weights[i]))
+
+    def build_cut(self, x, forced_idx=None):
+        from sqlp_b200.twosd import sdCut
+        r = O.build_sasa_cut(self.P, np.asarray(self.values), np.asarray(self.weights), x,
+                             self.dual_vertices.matrix(), forced_idx=forced_idx)
+        return sdCut(r["alpha"], r["beta"], r["weight_mark"])
+
+    def build_cuts2(self, x_cand, x_inc):
+        return self.build_cut(x_cand), self.build_cut(x_inc)
+
+
+class OraclePool(O.DualVertexSet):
+    """``push`` with the product pool's return convention (inserted, slot)."""
+
+    def push(self, v):
+        before = len(self)
+        super().push(np.asarray(v, dtype=np.float64))
+        return len(self) > before, None
+
+
+def make_cell(zf, dual_vertices, make_epigraph, x0, n_epi=1, lower_bound=0.0):
+    """A cell over the full-instance fixture ``zf`` with ``n_epi`` equally weighted epigraphs."""
+    from sqlp_b200 import sd
+    fs = sd.FirstStage(zf["x_cost"], zf["A1"], zf["row_lower"], zf["row_upper"], zf["x_lower"], zf["x_upper"])
+    cell = sd.sdCell(fs, dual_vertices)
+    for _ in range(n_epi):
+        sd.bind_epigraph_(cell, make_epigraph(1.0 / n_epi, lower_bound))
+    cell.x_candidate[:] = x0
+    cell.x_incumbent[:] = x0
+    T = np.zeros((int(zf["m2"]), int(zf["n1"])))
+    for j in range(int(zf["n1"])):
+        for q in range(zf["T_colptr"][j], zf["T_colptr"][j + 1]):
+            T[zf["T_rowval"][q], j] = zf["T_nzval"][q]
+    lp = sd.Stage2LP(zf["W"], zf["cost"], zf["y_lower"], zf["y_upper"], zf["directions"], zf["rbar"], T,
+                     zf["pos_row"], zf["pos_col"])
+    return cell, lp

@@ -247,8 +247,37 @@ def glpk_like_vertex(st, x, rhs, s2c5):
     return res.x
 
 
+def make_full_instance(name):
+    """Everything a host SD loop needs (first-stage rows, second-stage LP data) for a small
+    instance: tests/golden/instances/<name>_full.npz (config C1, tests/test_sd_loop*.py)."""
+    cor, tim, sto, st = load(name)
+    r2 = len(cor.row_names) - st.m2
+    A1 = np.zeros((r2 - 1, st.n1))
+    for (i, j), v in cor.entries.items():
+        if 1 <= i < r2 and j < st.n1:
+            A1[i - 1, j] = v
+        assert not (1 <= i < r2 and j >= st.n1), "first-stage row touches a second-stage column"
+    dirs1 = cor.directions[1:r2]
+    b1 = cor.rhs[1:r2]
+    lo = np.array([b if d in "GE" else -np.inf for d, b in zip(dirs1, b1)])
+    up = np.array([b if d in "LE" else np.inf for d, b in zip(dirs1, b1)])
+    vals, cdf, cnt = discrete_tables(sto)
+    out = dict(n1=st.n1, m2=st.m2, n2=st.n2, rbar=st.rbar, T_colptr=st.T_colptr, T_rowval=st.T_rowval,
+               T_nzval=st.T_nzval, pos_row=st.pos_row, pos_col=st.pos_col, x_lower=st.x_lower,
+               x_upper=st.x_upper, x_cost=st.x_cost, A1=A1, row_lower=lo, row_upper=up, W=st.W,
+               cost=st.cost, y_lower=st.y_lower, y_upper=st.y_upper,
+               directions=np.array(st.directions), out_vals=vals, out_cdf=cdf, out_cnt=cnt,
+               probs=np.array([p[1] for p in sto.params]))
+    np.savez_compressed(os.path.join(OUT, "instances", f"{name}_full.npz"), **out)
+    print(f"{name}_full: first stage {A1.shape}, second stage W {st.W.shape}")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--full":
+        for nm in sys.argv[2:]:
+            make_full_instance(nm)
+        sys.exit(0)
     lands_known_answers()
     make_instance("lands", 12)
     make_instance("baa99-20", 96)
