@@ -419,3 +419,54 @@ def test_storm_shape_properties_at_scale(T, oracle):
     assert np.mean(mi2 == mi) > 0.9999
     c2 = epi2.build_cut(xs[1])
     assert abs(c2.alpha - inc.alpha) <= 1e-9 * abs(inc.alpha)
+
+
+# ---- contraction plans: the even split of (unit, chunk) work and the streaming fallback ----
+
+@pytest.mark.parametrize("plan", ["grid1", "grid3", "grid7", "grid50", "grid1000", "stream"])
+@pytest.mark.parametrize("N,K,s", [(1000, 300, 13), (700, 1500, 117), (129, 127, 20), (3000, 129, 86)])
+def test_contraction_plans(T, oracle, monkeypatch, plan, N, K, s):
+    """Forced grid sizes cut the units at many different places (one CTA doing everything,
+    several CTAs per unit, more CTAs than chunk-units); every plan must give the oracle's argmax
+    and, bit for bit, the values and indices of the default plan."""
+    base_ctx = T.default_context()           # created without overrides
+    if plan == "stream":
+        monkeypatch.setenv("SQLP_CONTRACT", "stream")
+    else:
+        monkeypatch.setenv("SQLP_CONTRACT_GRID", plan[4:])
+    forced_ctx = T.Context(0)                # reads the overrides at creation
+    monkeypatch.delenv("SQLP_CONTRACT", raising=False)
+    monkeypatch.delenv("SQLP_CONTRACT_GRID", raising=False)
+    P = synthetic_problem(m2=s + 30, n1=11, s=s, first_stoch_row=5)
+    vals = synthetic_values(P, N)
+    pool = synthetic_pool(P.m2, K)
+    x2 = [10.0 * oracle.u01(3, np.arange(P.n1)), 10.0 * oracle.u01(5, np.arange(P.n1))]
+    out = []
+    for ctx in (forced_ctx, base_ctx):       # the forced plan, then the default one
+        dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+        dvs.push_many(pool)
+        epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+        epi.add_scenarios(vals)
+        res = [epi.argmax(x) for x in x2]
+        (c0, c1), val = epi.build_cuts2(x2[0], x2[1], with_val=True)
+        out.append((res, c0, c1))
+        for x, (mv, mi) in zip(x2, res):
+            check_argmax_parity(P, vals, x, pool, mv, mi)
+    (ra, a0, a1), (rb, b0, b1) = out
+    for (mva, mia), (mvb, mib) in zip(ra, rb):
+        assert (mia == mib).all() and (mva == mvb).all()
+    assert a0.alpha == b0.alpha and (a0.beta == b0.beta).all() and a1.alpha == b1.alpha
+
+
+@pytest.mark.parametrize("s", [256, 400])
+def test_wide_row_sets_use_the_streaming_kernel(T, oracle, s):
+    """One unit of scenarios no longer fits in shared memory: the streaming kernel takes over."""
+    P = synthetic_problem(m2=s + 30, n1=11, s=s, first_stoch_row=7)
+    N, K = 200, 140
+    vals = synthetic_values(P, N)
+    pool = synthetic_pool(P.m2, K)
+    dvs, epi = make_epi(T, P, pool, vals)
+    x = 10.0 * oracle.u01(3, np.arange(P.n1))
+    mv, mi = epi.argmax(x)
+    check_argmax_parity(P, vals, x, pool, mv, mi)
+    check_cut(oracle, P, vals, np.ones(N), x, pool, epi.build_cut(x))
