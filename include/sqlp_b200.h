@@ -145,6 +145,13 @@ SQLP_API int32_t sqlp_epi_add_scenarios_dev(sqlp_epi *epi, int64_t n_new, const 
  * counter generator of SURVEY.md 8(d).  Each rank generates only the scenarios it owns. */
 SQLP_API int32_t sqlp_epi_set_outcomes(sqlp_epi *epi, int64_t max_outcomes, const double *vals,
                                        const double *cdf, const int32_t *cnt);
+/* Continuous INDEP elements (smps_sto.jl:118-127): kind[e] = 0 DISCRETE (outcome tables above),
+ * 1 NORMAL(mean = a, variance = b), 2 UNIFORM(left = a, right = b).  A continuous element takes
+ *   uo = (top 53 bits of the same counter stream + 1/2) / 2^53  in (0, 1),
+ *   value = a + sqrt(b) * Phi^-1(uo)   |   a + (b - a) * uo      (one fma each).
+ * Optional: without this call every element is DISCRETE. */
+SQLP_API int32_t sqlp_epi_set_distributions(sqlp_epi *epi, const int32_t *kind /*[s]*/,
+                                            const double *par_a /*[s]*/, const double *par_b /*[s]*/);
 SQLP_API int32_t sqlp_epi_sample_scenarios(sqlp_epi *epi, int64_t n_new, uint64_t seed,
                                            uint64_t weight_seed);
 

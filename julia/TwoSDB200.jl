@@ -153,6 +153,34 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
                      $EPIS[epi], x_cand, x_inc, alpha, beta, wm, C_NULL))
         return sdCut(alpha[1], beta[:, 1], wm[]), sdCut(alpha[2], beta[:, 2], wm[])
     end
+    # --- rand(sto) on the device for a batch (smps_sto.jl:113-149; SURVEY.md 8(f) N2) -------------
+    # Outcome tables / distribution parameters are uploaded once, in position-table order; the
+    # scenarios never visit the host, so the host-side scenario_list is NOT extended here.
+    @eval T function sample_scenarios!(epi::sdEpigraph, n_new::Int, seed::UInt64; weight_seed::UInt64 = UInt64(0))
+        order = $TABLES[epi.subproblem_coef]
+        s = length(order)
+        dists = [$sto.indep[p] for p in order]
+        kind = Int32[d isa spSmpsDiscreteDistribution ? 0 : d isa spSmpsNormalDistribution ? 1 : 2 for d in dists]
+        a = Float64[k == 1 ? d.mean : k == 2 ? d.left : 0.0 for (k, d) in zip(kind, dists)]
+        b = Float64[k == 1 ? d.variance : k == 2 ? d.right : 0.0 for (k, d) in zip(kind, dists)]
+        mo = max(1, maximum(k == 0 ? length(d.value) : 1 for (k, d) in zip(kind, dists)))
+        vals = zeros(mo, s); cdf = ones(mo, s); cnt = ones(Int32, s)      # column-major = [s][mo] row-major
+        for (e, (k, d)) in enumerate(zip(kind, dists))
+            k == 0 || continue
+            cnt[e] = length(d.value); vals[1:cnt[e], e] = d.value; cdf[1:cnt[e], e] = cumsum(d.probability)
+        end
+        $check(ccall((:sqlp_epi_set_outcomes, $LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                     $EPIS[epi], mo, vals, cdf, cnt))
+        $check(ccall((:sqlp_epi_set_distributions, $LIB[]), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                     $EPIS[epi], kind, a, b))
+        $check(ccall((:sqlp_epi_sample_scenarios, $LIB[]), Int32, (Ptr{Cvoid}, Int64, UInt64, UInt64),
+                     $EPIS[epi], n_new, seed, weight_seed))
+        tw = Ref{Float64}(0)
+        $check(ccall((:sqlp_epi_counts, $LIB[]), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Float64}),
+                     $EPIS[epi], C_NULL, C_NULL, tw))
+        epi.total_scenario_weight = tw[]
+        return
+    end
     return nothing
 end
 

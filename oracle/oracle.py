@@ -277,3 +277,40 @@ def u01(seed: int, idx) -> np.ndarray:
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
     return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def u01_open(seed: int, idx) -> np.ndarray:
+    """Open-interval twin of the device's u01_open: (top 53 bits + 1/2) / 2^53."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) ^ (idx * np.uint64(0x9E3779B97F4A7C15))
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def sample_twin(seed: int, g0: int, n: int, kind, par_a, par_b, out_vals=None, out_cdf=None, out_cnt=None):
+    """Host twin of sqlp_epi_sample_scenarios for scenarios g0 .. g0+n-1 (values [n, s]): the
+    reference's rand(sto) (smps_sto.jl:113-149) with the counter generator in place of the global
+    RNG.  DISCRETE: inverse CDF on u01; NORMAL(mean, variance): mean + sqrt(variance) * Phi^-1(u);
+    UNIFORM(left, right): left + (right - left) * u, u from u01_open.  Phi^-1 is scipy's ndtri, so
+    NORMAL values agree with the device's normcdfinv to rounding, not bit for bit."""
+    from scipy.special import ndtri
+    kind = np.asarray(kind)
+    s = len(kind)
+    g = np.arange(g0, g0 + n, dtype=np.uint64)
+    ctr = g[:, None] * np.uint64(s) + np.arange(s, dtype=np.uint64)[None, :]
+    u, uo = u01(seed, ctr), u01_open(seed, ctr)
+    out = np.empty((n, s))
+    for e in range(s):
+        if kind[e] == 0:
+            idx = (u[:, e, None] >= np.asarray(out_cdf)[e][None, :]).sum(axis=1)
+            idx = np.minimum(idx, max(int(out_cnt[e]) - 1, 0))
+            out[:, e] = np.asarray(out_vals)[e][idx]
+        elif kind[e] == 1:
+            out[:, e] = par_a[e] + np.sqrt(par_b[e]) * ndtri(uo[:, e])
+        else:
+            out[:, e] = par_a[e] + (par_b[e] - par_a[e]) * uo[:, e]
+    return out

@@ -87,6 +87,7 @@ SIGNATURES = {
     "sqlp_epi_add_scenarios": [_vp, _i64, _vp, _vp],
     "sqlp_epi_add_scenarios_dev": [_vp, _i64, _vp, _vp],
     "sqlp_epi_set_outcomes": [_vp, _i64, _vp, _vp, _vp],
+    "sqlp_epi_set_distributions": [_vp, _vp, _vp, _vp],
     "sqlp_epi_sample_scenarios": [_vp, _i64, _u64, _u64],
     "sqlp_epi_counts": [_vp, _P(_i64), _P(_i64), _P(_f64)],
     "sqlp_epi_delta": [_vp, _i64, _vp, _vp],

@@ -59,6 +59,18 @@ __host__ __device__ __forceinline__ double u01(uint64_t seed, uint64_t idx)
     return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// The same stream mapped into the OPEN interval: (top 53 bits + 1/2) / 2^53 (exact in fp64 up to
+// the final rounding), for inverse-CDF sampling of continuous distributions.
+__host__ __device__ __forceinline__ double u01_open(uint64_t seed, uint64_t idx)
+{
+    uint64_t z = seed ^ (idx * 0x9E3779B97F4A7C15ULL);
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
 // Scenario g of an epigraph lives on rank (g / 128) % world, at this local slot.
 __host__ __device__ __forceinline__ int owner_of(int64_t g, int world)
 {

@@ -32,6 +32,11 @@ struct DeltaTables {
     const double *out_cdf;    // [s][mo]
     const int *out_cnt;       // [s]
     int mo;
+    // optional continuous elements: kind 0 DISCRETE (tables above), 1 NORMAL(mean, variance),
+    // 2 UNIFORM(left, right) -- smps_sto.jl:113-127; null = every element is discrete
+    const int *kind;          // [s]
+    const double *par_a;      // [s] mean | left
+    const double *par_b;      // [s] variance | right
 };
 
 #define SQLP_DELTA_COLS 64      // scenarios per block (half a tile)
@@ -52,6 +57,13 @@ __device__ __forceinline__ double realised_value(const DeltaTables &tb, const do
                                                  unsigned long long seed)
 {
     if (SAMPLE) {
+        const int kind = tb.kind ? tb.kind[e] : 0;
+        if (kind != 0) {
+            // open-interval uniform (z + 1/2) / 2^53 so that the normal quantile stays finite
+            const double uo = u01_open(seed, (unsigned long long)g * tb.s + e);
+            if (kind == 1) return fma(sqrt(tb.par_b[e]), normcdfinv(uo), tb.par_a[e]);
+            return fma(tb.par_b[e] - tb.par_a[e], uo, tb.par_a[e]);
+        }
         double u = u01(seed, (unsigned long long)g * tb.s + e);
         const double *cdf = tb.out_cdf + (long long)e * tb.mo;
         int idx = 0;

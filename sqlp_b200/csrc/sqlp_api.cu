@@ -241,6 +241,8 @@ struct sqlp_epi {
     DevBuf d_mcol, d_mrow, d_mslot;       // T elements sorted by (col, row)       -> eval_dual
     DevBuf d_ovals, d_ocdf, d_ocnt;       // outcome tables
     int mo = 0;
+    DevBuf d_kind, d_par_a, d_par_b;      // continuous elements (NORMAL / UNIFORM)
+    bool has_kinds = false, all_continuous = false;
     // scenario store
     int64_t n_global = 0, n_local = 0, cap_tiles = 0;
     double total_weight = 0.0;
@@ -390,6 +392,9 @@ DeltaTables delta_tables(sqlp_epi *e)
     tb.out_cdf = e->d_ocdf.as<double>();
     tb.out_cnt = e->d_ocnt.as<int>();
     tb.mo = e->mo;
+    tb.kind = e->has_kinds ? e->d_kind.as<int>() : nullptr;
+    tb.par_a = e->d_par_a.as<double>();
+    tb.par_b = e->d_par_b.as<double>();
     return tb;
 }
 
@@ -1205,12 +1210,37 @@ int32_t sqlp_epi_set_outcomes(sqlp_epi *e, int64_t mo, const double *vals, const
     });
 }
 
+int32_t sqlp_epi_set_distributions(sqlp_epi *e, const int32_t *kind, const double *par_a,
+                                   const double *par_b)
+{
+    return guard([&] {
+        REQUIRE(e && kind && par_a && par_b, SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        bool all = true;
+        for (int64_t q = 0; q < e->s; ++q) {
+            REQUIRE(kind[q] >= 0 && kind[q] <= 2, SQLP_E_INVALID, "distribution kind must be 0, 1 or 2");
+            REQUIRE(kind[q] != 1 || par_b[q] >= 0.0, SQLP_E_INVALID, "negative variance");
+            all = all && kind[q] != 0;
+        }
+        std::vector<int> k(kind, kind + e->s);
+        std::vector<double> a(par_a, par_a + e->s), b(par_b, par_b + e->s);
+        upload(e->d_kind, k, S(c));
+        upload(e->d_par_a, a, S(c));
+        upload(e->d_par_b, b, S(c));
+        e->has_kinds = true;
+        e->all_continuous = all;
+        CK(cudaStreamSynchronize(S(c)));
+    });
+}
+
 int32_t sqlp_epi_sample_scenarios(sqlp_epi *e, int64_t n_new, uint64_t seed, uint64_t weight_seed)
 {
     return guard([&] {
         REQUIRE(e, SQLP_E_INVALID, "null epigraph");
         REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
-        REQUIRE(e->mo > 0 || e->s == 0, SQLP_E_INVALID, "call sqlp_epi_set_outcomes first");
+        REQUIRE(e->mo > 0 || e->s == 0 || e->all_continuous, SQLP_E_INVALID,
+                "call sqlp_epi_set_outcomes (and sqlp_epi_set_distributions) first");
         e->ctx->bind();
         epi_add(e, n_new, nullptr, nullptr, nullptr, true, seed, weight_seed);
     });

@@ -330,6 +330,11 @@ class sdEpigraph:
         cnt = np.ascontiguousarray(cnt, dtype=np.int32)
         check(_lib.lib().sqlp_epi_set_outcomes(self._h, vals.shape[1], _ptr(vals), _ptr(cdf), _ptr(cnt)))
 
+    def set_distributions(self, kind, par_a, par_b):
+        """kind[e]: 0 DISCRETE (outcome tables), 1 NORMAL(mean, variance), 2 UNIFORM(left, right)."""
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        check(_lib.lib().sqlp_epi_set_distributions(self._h, _ptr(kind), _ptr(_f64(par_a)), _ptr(_f64(par_b))))
+
     def sample_scenarios(self, n_new, seed, weight_seed=0):
         check(_lib.lib().sqlp_epi_sample_scenarios(self._h, int(n_new), int(seed), int(weight_seed)))
 

@@ -371,6 +371,44 @@ def test_device_sampling_matches_host_sampling(T, oracle):
     check_cut(oracle, P, vals, w, x, z["pool"], epi.build_cut(x), epi=epi)
 
 
+def test_device_sampling_of_normal_and_uniform_elements(T, oracle):
+    """INDEP NORMAL / UNIFORM elements (smps_sto.jl:118-127; transship is all NORMAL) mixed with
+    DISCRETE ones: the device draws agree with the host twin to rounding (the normal quantile is
+    normcdfinv on the device, scipy's ndtri on the host), the moments are right, and the cut built
+    from the device's scenarios matches the oracle fed the twin's values."""
+    P = synthetic_problem(m2=70, n1=12, s=24)
+    s, N = P.s, 1000
+    kind = np.arange(s) % 3
+    base = P.rbar[P.pos_row]
+    par_a = np.where(kind == 1, base, 0.8 * base)                 # mean | left
+    par_b = np.where(kind == 1, (0.1 * base) ** 2, 1.2 * base)    # variance | right
+    mo = 5
+    out_vals = base[:, None] * np.array([0.8, 0.9, 1.0, 1.1, 1.2])[None, :]
+    out_cdf = np.tile(np.array([0.1, 0.3, 0.6, 0.8, 1.0]), (s, 1))
+    out_cnt = np.full(s, mo, dtype=np.int32)
+    pool = synthetic_pool(P.m2, 200)
+    dvs, epi = make_epi(T, P, pool, [])
+    epi.set_outcomes(out_vals, out_cdf, out_cnt)
+    epi.set_distributions(kind, par_a, par_b)
+    epi.sample_scenarios(N, seed=33)
+    twin = oracle.sample_twin(33, 0, N, kind, par_a, par_b, out_vals, out_cdf, out_cnt)
+    got = np.array([epi.delta(i).delta_rhs[P.pos_row] + base for i in range(0, N, 7)])
+    ref = twin[::7]
+    assert np.array_equal(got[:, kind == 0], ref[:, kind == 0])                  # discrete: exact
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-12
+    z = (twin[:, kind == 1] - par_a[kind == 1]) / np.sqrt(par_b[kind == 1])
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1.0) < 0.05
+    uu = (twin[:, kind == 2] - par_a[kind == 2]) / (par_b - par_a)[kind == 2]
+    assert 0.0 < uu.min() and uu.max() < 1.0 and abs(uu.mean() - 0.5) < 0.02
+    x = 10.0 * oracle.u01(3, np.arange(P.n1))
+    check_cut(oracle, P, twin, np.ones(N), x, pool, epi.build_cut(x), epi=epi)
+    # an all-continuous table needs no outcome tables
+    dvs2, epi2 = make_epi(T, P, pool, [])
+    epi2.set_distributions(np.full(s, 2), par_a, par_b)
+    epi2.sample_scenarios(10, seed=5)
+    assert epi2.counts()[0] == 10
+
+
 def test_multi_epigraph_cell_call(T, oracle):
     """E = 4 weighted epigraphs sharing one pool, one library call."""
     P, z = load_instance("storm")
