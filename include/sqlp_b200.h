@@ -190,6 +190,46 @@ SQLP_API int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, cons
  * next blocking call. */
 SQLP_API int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *epi, const double *d_x2, double *d_out);
 
+/* ---------------------------------------------------------------- cut list (next rows N1, N3) --- */
+
+/* The epigraph's cuts kept on the device, so that the cuts the reduction just produced reach the
+ * incumbent test and the master without a round trip each.  A cut is (alpha, beta[n1], weight_mark),
+ * never scaled (sdCut, epigraph.jl:5-12).  In a sharded job every rank holds the same list. */
+
+/* epi.objective_weight, epi.lower_bound -- epigraph.jl:27-31 (defaults 1.0, 0.0). */
+SQLP_API int32_t sqlp_epi_set_weights(sqlp_epi *epi, double objective_weight, double lower_bound);
+/* push!(epi.cuts, sdCut(alpha, beta, weight_mark)) with host values. */
+SQLP_API int32_t sqlp_epi_cuts_push(sqlp_epi *epi, double alpha, const double *beta, double weight_mark);
+/* epi.incumbent_cut = sdCut(...); beta = NULL means `nothing`. */
+SQLP_API int32_t sqlp_epi_cuts_set_incumbent(sqlp_epi *epi, double alpha, const double *beta,
+                                             double weight_mark);
+/* algorithm.jl:76-84 after a cut formation: snapshot the list (sdEpigraphInfo, f_{k-1}), then
+ * push!(epi.cuts, candidate cut) and, if with_incumbent, epi.incumbent_cut = incumbent cut -- both
+ * taken on the device from the last sqlp_epi_build_cuts2 / sqlp_cell_build_cuts2 /
+ * sqlp_epi_build_cut result, with weight_mark = total_scenario_weight. */
+SQLP_API int32_t sqlp_epi_cuts_commit(sqlp_epi *epi, int32_t with_incumbent);
+/* deleteat!(epi.cuts, idx) -- algorithm.jl:69; idx ascending, 0-based. */
+SQLP_API int32_t sqlp_epi_cuts_delete(sqlp_epi *epi, int64_t n, const int64_t *idx);
+SQLP_API int32_t sqlp_epi_cuts_count(sqlp_epi *epi, int64_t *n_cuts, int32_t *has_incumbent);
+/* Read one cut back; index -1 is the incumbent cut. */
+SQLP_API int32_t sqlp_epi_cuts_get(sqlp_epi *epi, int64_t index, double *alpha, double *beta /*[n1]*/,
+                                   double *weight_mark);
+/* evaluate_epigraph(epi | info, x) including the epigraph's weight -- epigraph.jl:177-220.
+ * which = 0: the current list; 1: the snapshot taken by the last commit. */
+SQLP_API int32_t sqlp_epi_evaluate(sqlp_epi *epi, const double *x /*[n1]*/, int32_t which, double *out);
+/* The rows sync_cuts! adds to the master (cell.jl:163-202, add_cut_to_master! epigraph.jl:101-117):
+ * rows[j] = (discount alpha + (1 - discount) lb, discount beta[n1]), discount = weight_mark /
+ * total_scenario_weight, the incumbent cut last and undiscounted; one dense [n_rows x (1 + n1)]
+ * block in one copy.  rows = NULL only returns the count. */
+SQLP_API int32_t sqlp_epi_master_rows(sqlp_epi *epi, double *rows, int64_t *n_rows);
+/* check_improvement(f_last, f_current, x_cand, x_inc, ...) -- improvement.jl:19-49 -- over the
+ * epigraphs of a cell; cost[n1] is the linear first-stage objective (cell.objf_original),
+ * q_factor the reference's INCUMBENT_SELECTION_Q = 0.2.  out4 = {candidate_estimation,
+ * incumbent_estimation, required_improvement, is_improved (0 | 1)}. */
+SQLP_API int32_t sqlp_cell_check_improvement(int32_t n_epi, sqlp_epi *const *epi, const double *x_cand,
+                                             const double *x_inc, const double *cost, double q_factor,
+                                             double *out4);
+
 /* eval_dual(coef, delta, x, dual) -- subprob.jl:128-131 -- for LOCAL scenario `scen` and
  * pool slot `vertex`, in the reference's operation order (debug / parity pin). */
 SQLP_API int32_t sqlp_eval_dual(sqlp_epi *epi, int64_t local_scen, int64_t vertex,

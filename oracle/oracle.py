@@ -314,3 +314,51 @@ def sample_twin(seed: int, g0: int, n: int, kind, par_a, par_b, out_vals=None, o
         else:
             out[:, e] = par_a[e] + (par_b[e] - par_a[e]) * uo[:, e]
     return out
+
+
+# ---------------------------------------------------------------- cut list (N1 / N3) -----
+# Plain-Python restatement of the reference's cut bookkeeping; a cut is (alpha, beta, weight_mark).
+
+def cut_evaluate(cuts, incumbent, x, total_weight, lower_bound, objective_weight=1.0):
+    """evaluate_epigraph, src/sd_algorithm/epigraph.jl:177-220 (MIN sense): pointwise max of the
+    lower bound, the discounted cuts and the undiscounted incumbent cut, times the epigraph's weight."""
+    x = np.asarray(x, dtype=np.float64)
+    best = lower_bound
+    for alpha, beta, wm in cuts:
+        discount = wm / total_weight
+        val = discount * (alpha + float(np.dot(np.asarray(beta, dtype=np.float64), x))) + (1 - discount) * lower_bound
+        if val > best:
+            best = val
+    if incumbent is not None:
+        alpha, beta, _ = incumbent
+        val = alpha + float(np.dot(np.asarray(beta, dtype=np.float64), x))
+        if val > best:
+            best = val
+    return objective_weight * best
+
+
+def cut_master_rows(cuts, incumbent, total_weight, lower_bound):
+    """sync_cuts!, src/sd_algorithm/cell.jl:163-202 with add_cut_to_master!, epigraph.jl:101-117:
+    rows (discount alpha + (1 - discount) lb, discount beta), the incumbent cut last with discount 1."""
+    rows = []
+    for alpha, beta, wm in cuts:
+        discount = wm / total_weight
+        rows.append(np.concatenate([[discount * alpha + (1 - discount) * lower_bound],
+                                    discount * np.asarray(beta, dtype=np.float64)]))
+    if incumbent is not None:
+        alpha, beta, _ = incumbent
+        rows.append(np.concatenate([[1.0 * alpha + (1 - 1.0) * lower_bound], 1.0 * np.asarray(beta, dtype=np.float64)]))
+    n1 = len(cuts[0][1]) if cuts else (len(incumbent[1]) if incumbent is not None else 0)
+    return np.asarray(rows).reshape(len(rows), 1 + n1)
+
+
+def cut_check_improvement(last, current, x_cand, x_inc, cost, q=0.2):
+    """check_improvement, src/sd_algorithm/improvement.jl:19-49.  ``last`` / ``current`` are lists of
+    (cuts, incumbent, total_weight, lower_bound, objective_weight), one per epigraph."""
+    f = lambda x: float(np.dot(np.asarray(cost, dtype=np.float64), np.asarray(x, dtype=np.float64)))
+    multi = lambda es, x: sum(cut_evaluate(c, i, x, tw, lb, w) for c, i, tw, lb, w in es)
+    f_cand, f_inc = f(x_cand), f(x_inc)
+    cand = multi(current, x_cand) + f_cand
+    inc = multi(current, x_inc) + f_inc
+    required = q * ((multi(last, x_cand) + f_cand) - (multi(last, x_inc) + f_inc))
+    return cand, inc, required, cand < inc + required

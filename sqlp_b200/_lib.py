@@ -97,6 +97,16 @@ SIGNATURES = {
     "sqlp_cell_build_cuts2": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "sqlp_epi_build_cuts2_dev": [_vp, _vp, _vp],
     "sqlp_eval_dual": [_vp, _i64, _i64, _vp, _P(_f64)],
+    "sqlp_epi_set_weights": [_vp, _f64, _f64],
+    "sqlp_epi_cuts_push": [_vp, _f64, _vp, _f64],
+    "sqlp_epi_cuts_set_incumbent": [_vp, _f64, _vp, _f64],
+    "sqlp_epi_cuts_commit": [_vp, _i32],
+    "sqlp_epi_cuts_delete": [_vp, _i64, _vp],
+    "sqlp_epi_cuts_count": [_vp, _P(_i64), _P(_i32)],
+    "sqlp_epi_cuts_get": [_vp, _i64, _P(_f64), _vp, _P(_f64)],
+    "sqlp_epi_evaluate": [_vp, _vp, _i32, _P(_f64)],
+    "sqlp_epi_master_rows": [_vp, _vp, _P(_i64)],
+    "sqlp_cell_check_improvement": [_i32, _vp, _vp, _vp, _vp, _f64, _vp],
 }
 _RESTYPE = {"sqlp_version": C.c_char_p, "sqlp_last_error": C.c_char_p}
 

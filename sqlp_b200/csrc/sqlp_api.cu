@@ -35,6 +35,7 @@
 #include "kernels_delta.cuh"
 #include "kernels_pool.cuh"
 #include "kernels_reduce.cuh"
+#include "kernels_cuts.cuh"
 
 namespace {
 
@@ -254,6 +255,12 @@ struct sqlp_epi {
     DevBuf d_x2, d_base, d_bias, d_best_val, d_best_idx, d_partial, d_partial2, d_out, d_gather,
         d_flags, d_stage, d_scratch;
     int64_t bias_stride = 0, out_stride = 0;
+    // the cut list on the device (kernels_cuts.cuh): rows (alpha, beta[n1], weight_mark)
+    double objective_weight = 1.0, lower_bound = 0.0;
+    DevBuf d_cuts, d_cuts_tmp, d_inc, d_prev_inc, d_keep, d_eval, d_rows;
+    int64_t n_cuts = 0, cuts_cap = 0, n_last = 0;
+    bool has_inc = false, has_prev_inc = false;
+    int last_nx = 0;   // points of the last cut formation whose result is still in d_out
 };
 
 namespace {
@@ -650,6 +657,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         }
     }
     if (!want_cut) return;
+    e->last_nx = NX;
 
     const int width = NX * NC;
     if (ntiles > 0) {
@@ -709,6 +717,37 @@ void epi_cuts_fetch(sqlp_epi *e, int NX, CutHost &h)
     h.out.resize((size_t)NX * NC);
     CK(cudaMemcpyAsync(h.out.data(), e->d_out.p, (size_t)NX * NC * 8, cudaMemcpyDeviceToHost, S(e->ctx)));
     CK(cudaMemcpyAsync(&h.flags, e->d_flags.p, 4, cudaMemcpyDeviceToHost, S(e->ctx)));
+}
+
+// ---- device cut list -------------------------------------------------------------------------
+void cuts_reserve(sqlp_epi *e, int64_t need)
+{
+    if (need <= e->cuts_cap) return;
+    const size_t RS = (size_t)e->n1 + 2;
+    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(64, e->cuts_cap * 2));
+    e->d_cuts.ensure((size_t)ncap * RS * 8, (size_t)e->n_cuts * RS * 8, S(e->ctx));
+    e->d_inc.ensure(RS * 8, 0, S(e->ctx));
+    e->d_prev_inc.ensure(RS * 8, 0, S(e->ctx));
+    e->cuts_cap = ncap;
+}
+
+CutList cut_list(sqlp_epi *e, bool last)
+{
+    CutList L;
+    L.cuts = e->d_cuts.as<double>();
+    L.n = (int)(last ? e->n_last : e->n_cuts);
+    L.inc = last ? (e->has_prev_inc ? e->d_prev_inc.as<double>() : nullptr)
+                 : (e->has_inc ? e->d_inc.as<double>() : nullptr);
+    return L;
+}
+
+// est[0 .. nlists * NX): weighted value of the current (and snapshot) approximation at NX device points
+void cuts_evaluate_enqueue(sqlp_epi *e, const double *d_x, int NX, int nlists, double *d_est)
+{
+    sqlp_ctx *c = e->ctx;
+    cuts_reserve(e, 1);
+    LAUNCH(c, k_cuts_evaluate, 1, 256, 0, cut_list(e, false), cut_list(e, true), nlists, d_x, NX, (int)e->n1,
+           e->total_weight, e->lower_bound, e->objective_weight, d_est);
 }
 
 void check_sense(int32_t sense)
@@ -1387,6 +1426,204 @@ int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *e, const double *d_x2, double *d_out)
         c->bind();
         epi_cuts_enqueue(e, 2, nullptr, d_x2, true);
         CK(cudaMemcpyAsync(d_out, e->d_out.p, (size_t)2 * (e->n1 + 2) * 8, cudaMemcpyDeviceToDevice, S(c)));
+    });
+}
+
+// ---------------------------------------------------------------- cut list (N1 / N3) ----
+int32_t sqlp_epi_set_weights(sqlp_epi *e, double objective_weight, double lower_bound)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        e->objective_weight = objective_weight;
+        e->lower_bound = lower_bound;
+    });
+}
+
+int32_t sqlp_epi_cuts_push(sqlp_epi *e, double alpha, const double *beta, double weight_mark)
+{
+    return guard([&] {
+        REQUIRE(e && (beta || e->n1 == 0), SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        const size_t RS = (size_t)e->n1 + 2;
+        cuts_reserve(e, e->n_cuts + 1);
+        std::vector<double> row(RS);
+        row[0] = alpha;
+        for (int64_t j = 0; j < e->n1; ++j) row[(size_t)j + 1] = beta[j];
+        row[RS - 1] = weight_mark;
+        CK(cudaMemcpyAsync(e->d_cuts.as<double>() + (size_t)e->n_cuts * RS, row.data(), RS * 8,
+                           cudaMemcpyHostToDevice, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        ++e->n_cuts;
+    });
+}
+
+int32_t sqlp_epi_cuts_set_incumbent(sqlp_epi *e, double alpha, const double *beta, double weight_mark)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        if (!beta && e->n1 > 0) { e->has_inc = false; return; }   // incumbent_cut = nothing
+        const size_t RS = (size_t)e->n1 + 2;
+        cuts_reserve(e, 1);
+        std::vector<double> row(RS);
+        row[0] = alpha;
+        for (int64_t j = 0; j < e->n1; ++j) row[(size_t)j + 1] = beta[j];
+        row[RS - 1] = weight_mark;
+        CK(cudaMemcpyAsync(e->d_inc.p, row.data(), RS * 8, cudaMemcpyHostToDevice, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        e->has_inc = true;
+    });
+}
+
+int32_t sqlp_epi_cuts_commit(sqlp_epi *e, int32_t with_incumbent)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        REQUIRE(e->last_nx >= 1, SQLP_E_INVALID, "no cut has been formed since the last commit");
+        REQUIRE(!with_incumbent || e->last_nx == 2, SQLP_E_INVALID,
+                "the incumbent cut needs sqlp_epi_build_cuts2 / sqlp_cell_build_cuts2");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        const size_t RS = (size_t)e->n1 + 2;
+        cuts_reserve(e, e->n_cuts + 1);
+        // snapshot f_{k-1} = the list before the new cuts (algorithm.jl:76, sdEpigraphInfo)
+        e->n_last = e->n_cuts;
+        e->has_prev_inc = e->has_inc;
+        if (e->has_inc)
+            CK(cudaMemcpyAsync(e->d_prev_inc.p, e->d_inc.p, RS * 8, cudaMemcpyDeviceToDevice, S(c)));
+        LAUNCH(c, k_cut_store, 1, 128, 0, e->d_out.as<double>(), e->total_weight, (int)e->n1,
+               e->d_cuts.as<double>() + (size_t)e->n_cuts * RS);                    // push!(epi.cuts, new_cut)
+        ++e->n_cuts;
+        if (with_incumbent) {                                                       // epi.incumbent_cut = ...
+            LAUNCH(c, k_cut_store, 1, 128, 0, e->d_out.as<double>() + RS, e->total_weight, (int)e->n1,
+                   e->d_inc.as<double>());
+            e->has_inc = true;
+        }
+        e->last_nx = 0;
+    });
+}
+
+int32_t sqlp_epi_cuts_delete(sqlp_epi *e, int64_t n, const int64_t *idx)
+{
+    return guard([&] {
+        REQUIRE(e && (idx || n == 0) && n >= 0, SQLP_E_INVALID, "bad argument");
+        if (n == 0) return;
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        std::vector<char> drop((size_t)e->n_cuts, 0);
+        for (int64_t q = 0; q < n; ++q) {
+            REQUIRE(idx[q] >= 0 && idx[q] < e->n_cuts, SQLP_E_RANGE, "cut index out of range");
+            REQUIRE(q == 0 || idx[q] > idx[q - 1], SQLP_E_INVALID, "indices must ascend (deleteat!)");
+            drop[(size_t)idx[q]] = 1;
+        }
+        std::vector<int> keep;
+        for (int64_t j = 0; j < e->n_cuts; ++j) if (!drop[(size_t)j]) keep.push_back((int)j);
+        const int RS = (int)e->n1 + 2;
+        if (!keep.empty()) {
+            upload(e->d_keep, keep, S(c));
+            e->d_cuts_tmp.ensure(keep.size() * RS * 8, 0, S(c), false);
+            LAUNCH(c, k_cuts_gather, (int)((keep.size() * RS + 255) / 256), 256, 0, e->d_cuts.as<double>(),
+                   e->d_keep.as<int>(), (int)keep.size(), RS, e->d_cuts_tmp.as<double>());
+            CK(cudaMemcpyAsync(e->d_cuts.p, e->d_cuts_tmp.p, keep.size() * RS * 8, cudaMemcpyDeviceToDevice, S(c)));
+        }
+        CK(cudaStreamSynchronize(S(c)));   // `keep` is read by the upload
+        e->n_cuts = (int64_t)keep.size();
+        e->n_last = std::min(e->n_last, e->n_cuts);
+    });
+}
+
+int32_t sqlp_epi_cuts_count(sqlp_epi *e, int64_t *n_cuts, int32_t *has_incumbent)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        if (n_cuts) *n_cuts = e->n_cuts;
+        if (has_incumbent) *has_incumbent = e->has_inc ? 1 : 0;
+    });
+}
+
+int32_t sqlp_epi_cuts_get(sqlp_epi *e, int64_t index, double *alpha, double *beta, double *weight_mark)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        REQUIRE(index >= -1 && index < e->n_cuts, SQLP_E_RANGE, "cut index out of range");
+        REQUIRE(index >= 0 || e->has_inc, SQLP_E_RANGE, "there is no incumbent cut");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        const size_t RS = (size_t)e->n1 + 2;
+        std::vector<double> row(RS);
+        const double *src = index < 0 ? e->d_inc.as<double>() : e->d_cuts.as<double>() + (size_t)index * RS;
+        CK(cudaMemcpyAsync(row.data(), src, RS * 8, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        if (alpha) *alpha = row[0];
+        if (beta) for (int64_t j = 0; j < e->n1; ++j) beta[j] = row[(size_t)j + 1];
+        if (weight_mark) *weight_mark = row[RS - 1];
+    });
+}
+
+int32_t sqlp_epi_evaluate(sqlp_epi *e, const double *x, int32_t which, double *out)
+{
+    return guard([&] {
+        REQUIRE(e && out && (x || e->n1 == 0), SQLP_E_INVALID, "null argument");
+        REQUIRE(which == 0 || which == 1, SQLP_E_INVALID, "which must be 0 (current) or 1 (snapshot)");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        e->d_x2.ensure((size_t)2 * std::max<int64_t>(e->n1, 1) * 8, 0, S(c));
+        e->d_eval.ensure(64, 0, S(c));
+        CK(cudaMemcpyAsync(e->d_x2.p, x, (size_t)e->n1 * 8, cudaMemcpyHostToDevice, S(c)));
+        cuts_evaluate_enqueue(e, e->d_x2.as<double>(), 1, 2, e->d_eval.as<double>());
+        double h[2];
+        CK(cudaMemcpyAsync(h, e->d_eval.p, 16, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        *out = h[which];
+    });
+}
+
+int32_t sqlp_epi_master_rows(sqlp_epi *e, double *rows, int64_t *n_rows)
+{
+    return guard([&] {
+        REQUIRE(e && n_rows, SQLP_E_INVALID, "null argument");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        const int64_t nr = e->n_cuts + (e->has_inc ? 1 : 0);
+        *n_rows = nr;
+        if (!rows || nr == 0) return;
+        const size_t RW = (size_t)e->n1 + 1;
+        cuts_reserve(e, 1);
+        e->d_rows.ensure((size_t)nr * RW * 8, 0, S(c), false);
+        LAUNCH(c, k_cuts_master_rows, (int)std::min<size_t>((nr * RW + 255) / 256, 1024), 256, 0, cut_list(e, false),
+               (int)e->n1, e->total_weight, e->lower_bound, e->d_rows.as<double>());
+        CK(cudaMemcpyAsync(rows, e->d_rows.p, (size_t)nr * RW * 8, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+    });
+}
+
+int32_t sqlp_cell_check_improvement(int32_t n_epi, sqlp_epi *const *epi, const double *x_cand,
+                                    const double *x_inc, const double *cost, double q_factor, double *out4)
+{
+    return guard([&] {
+        REQUIRE(n_epi >= 1 && epi && x_cand && x_inc && cost && out4, SQLP_E_INVALID, "null argument");
+        sqlp_epi *e0 = epi[0];
+        sqlp_ctx *c = e0->ctx;
+        c->bind();
+        const int64_t n1 = e0->n1;
+        for (int32_t i = 0; i < n_epi; ++i)
+            REQUIRE(epi[i] && epi[i]->ctx == c && epi[i]->n1 == n1, SQLP_E_INVALID,
+                    "the epigraphs of a cell share a context and a first stage");
+        // x2 = [cand | inc], cost, est[n_epi][4], out[4] in one scratch buffer of the first epigraph
+        const size_t need = (size_t)(3 * std::max<int64_t>(n1, 1) + 4 * n_epi + 4) * 8;
+        e0->d_eval.ensure(need, 0, S(c));
+        double *d_x2 = e0->d_eval.as<double>(), *d_cost = d_x2 + 2 * n1, *d_est = d_cost + n1,
+               *d_out = d_est + 4 * n_epi;
+        CK(cudaMemcpyAsync(d_x2, x_cand, (size_t)n1 * 8, cudaMemcpyHostToDevice, S(c)));
+        CK(cudaMemcpyAsync(d_x2 + n1, x_inc, (size_t)n1 * 8, cudaMemcpyHostToDevice, S(c)));
+        CK(cudaMemcpyAsync(d_cost, cost, (size_t)n1 * 8, cudaMemcpyHostToDevice, S(c)));
+        for (int32_t i = 0; i < n_epi; ++i)
+            cuts_evaluate_enqueue(epi[i], d_x2, 2, 2, d_est + 4 * i);   // {cur@cand, cur@inc, last@cand, last@inc}
+        LAUNCH(c, k_improvement, 1, 32, 0, d_est, (int)n_epi, d_cost, d_x2, (int)n1, q_factor, d_out);
+        CK(cudaMemcpyAsync(out4, d_out, 32, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
     });
 }
 

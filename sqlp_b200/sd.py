@@ -234,6 +234,9 @@ class sdCell:
     incumbent_cut_dual: list = field(default_factory=list)
     cut_rows: list = field(default_factory=list)           # per epigraph: [n_rows, 1 + n1] block
     master_objective: float = float("nan")
+    # keep the cut lists on the device as well (sqlp_epi_cuts_*): the incumbent test and the master
+    # rows then come from the library (rows N1 / N3); the host lists are still maintained
+    device_cuts: bool = False
 
     def __post_init__(self):
         n1 = len(self.first_stage.cost)
@@ -261,6 +264,9 @@ def sync_cuts(cell: sdCell):
     not discounted."""
     n1 = len(cell.first_stage.cost)
     for i, epi in enumerate(cell.epi):
+        if cell.device_cuts:
+            cell.cut_rows[i] = epi.master_rows()
+            continue
         rows = []
         tw = epi.total_scenario_weight
         for cut in epi.cuts:
@@ -365,6 +371,8 @@ def sd_iteration_(cell: sdCell, scenario_list, solve_subproblem, update_incumben
             duals = cell.cut_duals[i]
             assert len(duals) == len(epi.cuts)
             keep = [j for j in range(len(epi.cuts)) if not abs(duals[j]) < CUT_REMOVE_TOLERANCE]
+            if cell.device_cuts and len(keep) < len(epi.cuts):
+                epi.cuts_delete([j for j in range(len(epi.cuts)) if j not in set(keep)])
             epi.cuts[:] = [epi.cuts[j] for j in keep]
     epi_info_last = [sdEpigraphInfo.of(epi) for epi in cell.epi]
     # the hot path: candidate cut + regenerated incumbent cut (algorithm.jl:79-85)
@@ -376,10 +384,17 @@ def sd_iteration_(cell: sdCell, scenario_list, solve_subproblem, update_incumben
         else:
             new_cut = epi.build_cut(cell.x_candidate)
             epi.cuts.append(new_cut)
+        if cell.device_cuts:
+            epi.cuts_commit(update_incumbent_cut)
         if on_cuts is not None:
             on_cuts(i, new_cut, epi.incumbent_cut)
-    cell.improvement_info = check_improvement(epi_info_last, cell.epi, cell.x_candidate,
-                                              cell.x_incumbent, cell.objf_original)
+    if cell.device_cuts:
+        from .twosd import check_improvement_device
+        cell.improvement_info = sdImprovementInfo(*check_improvement_device(
+            cell.epi, cell.x_candidate, cell.x_incumbent, cell.first_stage.cost, INCUMBENT_SELECTION_Q))
+    else:
+        cell.improvement_info = check_improvement(epi_info_last, cell.epi, cell.x_candidate,
+                                                  cell.x_incumbent, cell.objf_original)
     rho = quad_scalar_schedule(cell)
     if cell.improvement_info.is_improved:
         cell.x_incumbent[:] = cell.x_candidate

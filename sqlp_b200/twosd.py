@@ -316,6 +316,7 @@ class sdEpigraph:
             _ptr(coef.T_colptr), _ptr(coef.T_rowval), _ptr(coef.T_nzval), self.s,
             _ptr(pos_row), _ptr(pos_col), C.byref(self._h)))
         self.scenario_delta = _DeviceDeltaSet(self)
+        check(_lib.lib().sqlp_epi_set_weights(self._h, self.objective_weight, self.lower_bound))
 
     # -- scenario store ---------------------------------------------------------------
     def add_scenarios(self, values, weights=None):
@@ -388,6 +389,56 @@ class sdEpigraph:
                                               C.byref(wm), _ptr(val)))
         cuts = (sdCut(alpha[0], beta[0].copy(), wm.value), sdCut(alpha[1], beta[1].copy(), wm.value))
         return (cuts, val) if with_val else cuts
+
+    # -- the cut list on the device -----------------------------------
+    def cuts_push(self, cut: sdCut):
+        check(_lib.lib().sqlp_epi_cuts_push(self._h, float(cut.alpha), _ptr(_f64(cut.beta)), float(cut.weight_mark)))
+
+    def cuts_set_incumbent(self, cut: sdCut | None):
+        if cut is None:
+            check(_lib.lib().sqlp_epi_cuts_set_incumbent(self._h, 0.0, None, 0.0))
+        else:
+            check(_lib.lib().sqlp_epi_cuts_set_incumbent(self._h, float(cut.alpha), _ptr(_f64(cut.beta)),
+                                                         float(cut.weight_mark)))
+
+    def cuts_commit(self, with_incumbent=True):
+        """After a cut formation: snapshot the list, push the candidate cut and (optionally) replace
+        the incumbent cut, all on the device (algorithm.jl:76-84)."""
+        check(_lib.lib().sqlp_epi_cuts_commit(self._h, int(bool(with_incumbent))))
+
+    def cuts_delete(self, idx):
+        idx = np.ascontiguousarray(sorted(int(i) for i in idx), dtype=np.int64)
+        check(_lib.lib().sqlp_epi_cuts_delete(self._h, len(idx), _ptr(idx)))
+
+    def cuts_count(self):
+        n, inc = C.c_int64(), C.c_int32()
+        check(_lib.lib().sqlp_epi_cuts_count(self._h, C.byref(n), C.byref(inc)))
+        return n.value, bool(inc.value)
+
+    def cuts_get(self, index: int) -> sdCut:
+        """Cut ``index`` of the device list; -1 is the incumbent cut."""
+        a, wm = C.c_double(), C.c_double()
+        beta = np.zeros(self.subproblem_coef.n1)
+        check(_lib.lib().sqlp_epi_cuts_get(self._h, int(index), C.byref(a), _ptr(beta), C.byref(wm)))
+        return sdCut(a.value, beta, wm.value)
+
+    def evaluate(self, x, snapshot=False) -> float:
+        """``evaluate_epigraph(epi, x)`` on the device list (``snapshot``: the list as it was before
+        the last commit, i.e. the reference's ``sdEpigraphInfo`` f_{k-1})."""
+        x = _f64(x)
+        self._check_x(x)
+        out = C.c_double()
+        check(_lib.lib().sqlp_epi_evaluate(self._h, _ptr(x), int(bool(snapshot)), C.byref(out)))
+        return out.value
+
+    def master_rows(self) -> np.ndarray:
+        """The dense ``[n_rows, 1 + n1]`` block ``sync_cuts!`` adds to the master."""
+        n = C.c_int64()
+        check(_lib.lib().sqlp_epi_master_rows(self._h, None, C.byref(n)))
+        rows = np.zeros((n.value, self.subproblem_coef.n1 + 1))
+        if n.value:
+            check(_lib.lib().sqlp_epi_master_rows(self._h, _ptr(rows), C.byref(n)))
+        return rows
 
     def eval_dual(self, local_scen, vertex, x):
         x = _f64(x)
@@ -513,3 +564,15 @@ def build_cuts_at_candidate_and_incumbent(epis, x_candidate, x_incumbent):
         e.incumbent_cut = inc
         out.append((cand, inc))
     return out
+
+
+def check_improvement_device(epis, x_candidate, x_incumbent, cost, q_factor=0.2):
+    """``check_improvement`` (improvement.jl:19-49) on the device cut lists of a cell's epigraphs.
+    Returns (candidate_estimation, incumbent_estimation, required_improvement, is_improved)."""
+    epis = list(epis)
+    E = len(epis)
+    handles = (C.c_void_p * E)(*[e._h for e in epis])
+    out = np.zeros(4)
+    check(_lib.lib().sqlp_cell_check_improvement(E, handles, _ptr(_f64(x_candidate)), _ptr(_f64(x_incumbent)),
+                                                 _ptr(_f64(cost)), float(q_factor), _ptr(out)))
+    return float(out[0]), float(out[1]), float(out[2]), bool(out[3])

@@ -15,14 +15,16 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("n_epi,schedule", [(1, "constant"), (2, "adaptive")])
-def test_lands_sd_run_matches_oracle_every_iteration(n_epi, schedule):
+@pytest.mark.parametrize("n_epi,schedule,device_cuts", [(1, "constant", False), (2, "adaptive", False),
+                                                        (2, "constant", True)])
+def test_lands_sd_run_matches_oracle_every_iteration(n_epi, schedule, device_cuts):
     from sqlp_b200 import twosd as T
     zf = load_full_instance("lands")
     P, z = load_instance("lands")
     coef = T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
     dvs = T.sdDualVertexSet(m2=P.m2)
     cell, lp = make_cell(zf, dvs, lambda w, lb: T.sdEpigraph(coef, w, lb, dvs), np.full(4, 3.0), n_epi=n_epi)
+    cell.device_cuts = device_cuts             # cut lists, incumbent test and master rows on the device
     shadow = O.DualVertexSet()                 # the oracle's pool, fed the same vertices
     seen = [[] for _ in range(n_epi)]          # scenarios of each epigraph so far
     vals = sample_instance_values(zf, 200 * n_epi, seed=42)
@@ -60,6 +62,14 @@ def test_lands_sd_run_matches_oracle_every_iteration(n_epi, schedule):
         k0 = len(dvs)
         sd.sd_iteration_(cell, scen, solve, quad_scalar_schedule=sched, on_cuts=on_cuts)
         assert len(dvs) == len(shadow)         # same dedup decisions, vertex for vertex
+        if device_cuts:                        # the device's master rows are the host formula's bits
+            for i, epi in enumerate(cell.epi):
+                tw = epi.total_scenario_weight
+                ref = O.cut_master_rows([(c.alpha, c.beta, c.weight_mark) for c in epi.cuts],
+                                        (epi.incumbent_cut.alpha, epi.incumbent_cut.beta, epi.incumbent_cut.weight_mark),
+                                        tw, epi.lower_bound)
+                assert np.array_equal(cell.cut_rows[i], ref)
+                assert epi.cuts_count() == (len(epi.cuts), True)
     for k in range(len(shadow)):
         assert (dvs[k] == shadow.matrix()[k]).all()
     assert checked["cuts"] == 2 * n_epi * iters
