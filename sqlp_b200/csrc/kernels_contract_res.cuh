@@ -197,25 +197,31 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(Contr
             }
         }
     };
+    // One 2..4 KB bulk copy per k-group brings a unit's scenarios into shared memory.
+    auto load_unit = [&](long long u) {
+        if (warp == 0) {
+            if (lane == 0) mbar_arrive_expect_tx(afull, (unsigned)(ngroups * C::kAGroup * 8));
+            __syncwarp();
+            const double *src = a.D + (size_t)(u / C::UNITS_PER_TILE) * tile_doubles +
+                                (size_t)(u % C::UNITS_PER_TILE) * C::kAGroup;
+            for (int g = lane; g < ngroups; g += 32)
+                bulk_g2s(smem_u32(Ares + (size_t)g * C::kAGroup), src + (size_t)g * 512, C::kAGroup * 8, afull);
+        }
+    };
+
     int stage = 0;
     unsigned par = 0, uphase = 0;
     bool ready = false;   // the current item is already known to have landed
     long long unit = L0 / nchunks;
     int c_begin = (int)(L0 - unit * nchunks);
     int rem = (int)(L1 - L0);   // chunk-units left in the span
+    load_unit(unit);
 #pragma unroll 1
     while (rem > 0) {
         const int c_end = min(nchunks, c_begin + rem);
 
-        // ---- the unit's scenarios become resident: one 2..4 KB bulk copy per k-group
-        if (warp == 0) {
-            if (lane == 0) mbar_arrive_expect_tx(afull, (unsigned)(ngroups * C::kAGroup * 8));
-            __syncwarp();
-            const double *src = a.D + (size_t)(unit / C::UNITS_PER_TILE) * tile_doubles +
-                                (size_t)(unit % C::UNITS_PER_TILE) * C::kAGroup;
-            for (int g = lane; g < ngroups; g += 32)
-                bulk_g2s(smem_u32(Ares + (size_t)g * C::kAGroup), src + (size_t)g * 512, C::kAGroup * 8, afull);
-        }
+        // ---- the unit's scenarios become resident (the copies were issued by load_unit below:
+        // before the loop for the first unit, during the previous unit's epilogue otherwise)
         mbar_wait(afull, uphase);
         uphase ^= 1u;
 
@@ -283,6 +289,9 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(Contr
             }
         }
         __syncthreads();
+        // every warp is past its last read of the resident scenarios: the next unit's copies run
+        // under the merge below
+        if (rem > c_end - c_begin) load_unit(unit + 1);
         const bool complete = (c_begin == 0 && c_end == nchunks);
         for (int q = tid; q < ROWS * NX; q += C::THREADS) {
             const int x = q / ROWS, row = q % ROWS;
