@@ -80,7 +80,7 @@ __device__ __forceinline__ double realised_value(const DeltaTables &tb, const do
 // read in 256-byte runs and all of a block's loads are in flight at once.  Phase 2: the half
 // tile's part of every k-group (4 slots x 64 columns = 2 KB contiguous) is written in order.
 template <bool SAMPLE>
-__global__ void __launch_bounds__(SQLP_DELTA_THREADS)
+__global__ void __launch_bounds__(SQLP_DELTA_THREADS, 2)
 k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, long long n_new,
               int rank, int world, int s_pad, double *__restrict__ D, double *__restrict__ dT,
               double *__restrict__ w, const double *__restrict__ w_batch, unsigned long long seed,
@@ -134,6 +134,23 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
         // every load of the block (64 scenarios x up to 128 slots over 16 warps) is issued before
         // the first use: 16 independent 8-byte loads per lane
         constexpr int CPW = SQLP_DELTA_COLS / (SQLP_DELTA_THREADS / 32);   // scenarios per warp
+        if (SAMPLE) {
+            // drawn values need no loads in flight: one scenario at a time keeps the registers (and
+            // with them the resident blocks per SM) for the generator
+#pragma unroll 1
+            for (int i = 0; i < CPW; ++i) {
+                const int c = cb + warp + i * (SQLP_DELTA_THREADS / 32);
+                double *row = sh + (warp + i * (SQLP_DELTA_THREADS / 32)) * stride;
+#pragma unroll
+                for (int k = 0; k < SQLP_DELTA_SLAB / 32; ++k) {
+                    if (lane + 32 * k >= jn) continue;
+                    double d = 0.0;
+                    if (el[k] >= 0 && c >= c0 && c < c1)
+                        d = __dsub_rn(realised_value<true>(tb, values, gb0 + c, g0, el[k], seed), eb[k]);   // :114
+                    row[lane + 32 * k] = d;
+                }
+            }
+        } else {
         double v[CPW][SQLP_DELTA_SLAB / 32];
 #pragma unroll
         for (int i = 0; i < CPW; ++i) {
@@ -149,6 +166,7 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
 #pragma unroll
             for (int k = 0; k < SQLP_DELTA_SLAB / 32; ++k)
                 if (lane + 32 * k < jn) row[lane + 32 * k] = (el[k] >= 0) ? __dsub_rn(v[i][k], eb[k]) : 0.0;   // :114
+        }
         }
         __syncthreads();
         // phase 2: offset o of a k-group's 512 doubles is cell P = o / 64, lane t = (o % 64) / 2,
