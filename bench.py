@@ -423,7 +423,7 @@ def run_ours(args):
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         traffic_src = tj["source"]
     roofline = {"bound": "tensor", "pipe": "fp64 tensor (DMMA, mma.sync.m8n8k4.f64; tcgen05 has no fp64)",
-                "kernel": "k_contract_resident<NX=2> + k_argmax_fixup", "achieved": achieved, "peak": peak,
+                "kernel": "k_contract_ws<NX=2> + k_argmax_fixup", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": (achieved / peak) if (achieved and peak) else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "launches": c_launches, "avg_launch_ms": c_ms / max(1, c_launches),

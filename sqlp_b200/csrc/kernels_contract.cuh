@@ -82,6 +82,7 @@ struct ContractArgs {
     long long out_stride;
     // resident variant only (kernels_contract_res.cuh)
     int nstages, prefetch;  // pool-ring depth and how many items ahead the copies run
+    int lag_ns;             // warp-specialised variant: start-up delay of the second row group
     double *piece_val;      // [grid][2][NX][ROWS] partial results of units cut by a span boundary
     int *piece_idx;
 };

@@ -26,6 +26,9 @@
 namespace sqlp {
 
 #define SQLP_RES_MAX_STAGES 8
+#ifndef SQLP_RES_UNROLL   // k-groups per trip of the DMMA loop (fragment loads are pipelined inside a trip)
+#define SQLP_RES_UNROLL 2
+#endif
 
 
 //   WR   warp rows: the CTA is WR x 4 warps, warp tile (8 MI) scenarios x 32 vertices
@@ -242,11 +245,13 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(Contr
                 const int ng = min(C::KG, ngroups - slab * C::KG);
                 int g = 0;
 #pragma unroll 1
-                for (; g + 1 < ng; g += 2) {
-                    mma_group(As + g * C::kAGroup, Bs + g * 512);
-                    mma_group(As + (g + 1) * C::kAGroup, Bs + (g + 1) * 512);
+                for (; g + SQLP_RES_UNROLL <= ng; g += SQLP_RES_UNROLL) {
+#pragma unroll
+                    for (int u = 0; u < SQLP_RES_UNROLL; ++u)
+                        mma_group(As + (g + u) * C::kAGroup, Bs + (g + u) * 512);
                 }
-                if (g < ng) mma_group(As + g * C::kAGroup, Bs + g * 512);
+#pragma unroll 1
+                for (; g < ng; ++g) mma_group(As + g * C::kAGroup, Bs + g * 512);
 
                 if (slab == nslab - 1) {
                     // ---- chunk epilogue: bias add + running argmax (vertex index ascending) ----

@@ -32,6 +32,10 @@
 #endif
 #include "kernels_contract.cuh"
 #include "kernels_contract_res.cuh"
+#ifndef SQLP_WS_KG
+#define SQLP_WS_KG 6
+#endif
+#include "kernels_contract_ws.cuh"
 #include "kernels_delta.cuh"
 #include "kernels_pool.cuh"
 #include "kernels_reduce.cuh"
@@ -186,7 +190,9 @@ struct sqlp_ctx {
     double prof_work[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};   // flops (contraction) or algorithmic bytes
     bool smem_attr[3] = {false, false, false};
     // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
-    int contract_mode = 0;        // 0 = automatic, 1 = streaming kernel only, 2 = resident only
+    int contract_mode = 0;        // 0 = automatic, 1 = streaming only, 2 = resident (or streaming), 3 = warp-specialised first
+    int contract_lag_ns = 2000;
+    int ws_smem_set[3] = {0, 0, 0};
     int contract_grid = 0;        // > 0: force this many CTAs (tests of the span split)
     int contract_prefetch = 0;    // > 0: items the copies run ahead (tuning knob, environment)
     int smem_per_sm = 0, smem_optin = 0;
@@ -543,6 +549,39 @@ bool launch_contract_resident(sqlp_epi *e, ContractArgs &a)
     return true;
 }
 
+// Warp-specialised kernel (one CTA per SM, producer warp + two consumer row groups).
+template <int NX>
+bool launch_contract_ws(sqlp_epi *e, ContractArgs &a)
+{
+    using Cfg = WsCfg<NX, SQLP_WS_KG>;
+    sqlp_ctx *c = e->ctx;
+    const size_t fixed = Cfg::fixed_bytes(a.s_pad), stage = Cfg::stage_bytes();
+    const size_t budget = std::min<size_t>((size_t)c->smem_optin, (size_t)c->smem_per_sm - 1024u);
+    const int stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
+    if (stages < 3) return false;
+    const size_t smem = fixed + stage * stages;
+    if (c->ws_smem_set[NX] < (int)smem) {
+        CK(cudaFuncSetAttribute(k_contract_ws<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->ws_smem_set[NX] = (int)smem;
+    }
+    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+    const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;
+    int grid = c->contract_grid > 0 ? c->contract_grid : c->sm_count;
+    grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>(nunits * nchunks_ub, nunits)));
+    const size_t pieces = (size_t)grid * 2 * NX * Cfg::ROWS;
+    c->d_piece_val.ensure(pieces * 8, 0, S(c), false);
+    c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
+    a.nstages = stages;
+    a.prefetch = 0;
+    a.lag_ns = c->contract_lag_ns;
+    a.piece_val = c->d_piece_val.as<double>();
+    a.piece_idx = c->d_piece_idx.as<int>();
+    LAUNCH(c, k_contract_ws<Cfg>, grid, SQLP_WS_THREADS, smem, a);
+    auto fixup = k_argmax_fixup<Cfg::ROWS, NX>;
+    LAUNCH(c, fixup, grid, 128, 0, a, grid);
+    return true;
+}
+
 template <int NX>
 void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
 {
@@ -560,13 +599,15 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.best_val = bv;
     a.best_idx = bi;
     a.out_stride = e->out_stride;
-    a.nstages = a.prefetch = 0;
+    a.nstages = a.prefetch = a.lag_ns = 0;
     a.piece_val = nullptr;
     a.piece_idx = nullptr;
     ProfScope prof(c, SQLP_PROF_CONTRACT, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
     bool done = false;
-    if (c->contract_mode != 1) done = launch_contract_resident<NX>(e, a);
-    REQUIRE(done || c->contract_mode != 2, SQLP_E_UNSUPPORTED, "resident contraction does not fit");
+    // automatic: warp-specialised -> resident (fewer ring stages suffice) -> streaming (any s_pad)
+    if (c->contract_mode == 0 || c->contract_mode == 3) done = launch_contract_ws<NX>(e, a);
+    if (!done && c->contract_mode != 1) done = launch_contract_resident<NX>(e, a);
+
     if (!done) {   // streaming kernel: both operands flow through the ring
         size_t smem = Cfg::smem_bytes();
         if (!c->smem_attr[NX]) {   // per device, so per context
@@ -783,9 +824,11 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     if (const char *m = getenv("SQLP_CONTRACT")) {   // experiments / tests of the fallback
         if (!strcmp(m, "stream")) c->contract_mode = 1;
         else if (!strcmp(m, "resident")) c->contract_mode = 2;
+        else if (!strcmp(m, "ws")) c->contract_mode = 3;
     }
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
+    if (const char *g = getenv("SQLP_CONTRACT_LAG_NS")) c->contract_lag_ns = atoi(g);
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreate(&c->t0));

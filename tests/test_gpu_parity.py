@@ -461,15 +461,16 @@ def test_storm_shape_properties_at_scale(T, oracle):
 
 # ---- contraction plans: the even split of (unit, chunk) work and the streaming fallback ----
 
-@pytest.mark.parametrize("plan", ["grid1", "grid3", "grid7", "grid50", "grid1000", "stream"])
+@pytest.mark.parametrize("plan", ["grid1", "grid3", "grid7", "grid50", "grid1000", "stream", "resident"])
 @pytest.mark.parametrize("N,K,s", [(1000, 300, 13), (700, 1500, 117), (129, 127, 20), (3000, 129, 86)])
 def test_contraction_plans(T, oracle, monkeypatch, plan, N, K, s):
     """Forced grid sizes cut the units at many different places (one CTA doing everything,
-    several CTAs per unit, more CTAs than chunk-units); every plan must give the oracle's argmax
-    and, bit for bit, the values and indices of the default plan."""
+    several CTAs per unit, more CTAs than chunk-units) and the two fallback kernels replace the
+    warp-specialised one; every plan must give the oracle's argmax and, bit for bit, the values
+    and indices of the default plan."""
     base_ctx = T.default_context()           # created without overrides
-    if plan == "stream":
-        monkeypatch.setenv("SQLP_CONTRACT", "stream")
+    if plan in ("stream", "resident"):
+        monkeypatch.setenv("SQLP_CONTRACT", plan)
     else:
         monkeypatch.setenv("SQLP_CONTRACT_GRID", plan[4:])
     forced_ctx = T.Context(0)                # reads the overrides at creation

@@ -108,6 +108,48 @@ __global__ void __launch_bounds__(THR) k_dmma_tile(double *out, const double *in
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The same warp tile with its operand fragments re-read from shared memory for every k-group
+// (4 + 2 LDS.128 per 32 DMMA, the contraction's inner loop without barriers or epilogue): the
+// ceiling of a DMMA stream that is fed through the load/store unit.
+template <int THR>
+__global__ void __launch_bounds__(THR) k_dmma_tile_lds(double *out, const double *in)
+{
+    __shared__ __align__(16) double sA[4 * 256], sB[4 * 512];   // 4 k-groups of A (2 KB each) and B (4 KB each)
+    for (int i = threadIdx.x; i < 4 * 256; i += THR) sA[i] = in[i % 96];
+    for (int i = threadIdx.x; i < 4 * 512; i += THR) sB[i] = in[i % 96];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wx = (threadIdx.x >> 5) & 3;
+    double c[32][2];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { c[i][0] = i; c[i][1] = threadIdx.x; }
+    for (int it = 0; it < ITERS / 4; it += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int g = (it + u) & 3;
+            const double *Ag = sA + g * 256 + lane * 2, *Bg = sB + g * 512 + wx * 128 + lane * 2;
+            double2 av[4], bv[2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) av[q] = *reinterpret_cast<const double2 *>(Ag + q * 64);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) bv[q] = *reinterpret_cast<const double2 *>(Bg + q * 64);
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) {
+                const double af = (mi & 1) ? av[mi >> 1].y : av[mi >> 1].x;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double bf = (ni & 1) ? bv[ni >> 1].y : bv[ni >> 1].x;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(c[mi * 4 + ni][0]), "+d"(c[mi * 4 + ni][1]) : "d"(af), "d"(bf));
+                }
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // m16n8k16 f64 (sm_90+ shape): A 16x16 (8 regs/thread), B 16x8 (4 regs), C 16x8 (4 regs)
 __global__ void __launch_bounds__(256) k_dmma16(double *out, double a, double b)
 {
@@ -172,6 +214,10 @@ int main()
         const double f = 2.0 * 256 * 32 * (ITERS / 4) * sms;
         measure("dmma_tile32_1warp_per_subpartition", f * 4, [&] { k_dmma_tile<128><<<sms, 128>>>(out, in); });
         measure("dmma_tile32_2warp_per_subpartition", f * 8, [&] { k_dmma_tile<256><<<sms, 256>>>(out, in); });
+        CK(cudaFuncSetAttribute(k_dmma_tile_lds<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 0));
+        measure("dmma_tile32_lds_fed_1warp_per_subpartition", f * 4, [&] { k_dmma_tile_lds<128><<<sms, 128>>>(out, in); });
+        measure("dmma_tile32_lds_fed_2warp_per_subpartition", f * 8, [&] { k_dmma_tile_lds<256><<<sms, 256>>>(out, in); });
+        measure("dmma_tile32_lds_fed_4warp_per_subpartition", f * 16, [&] { k_dmma_tile_lds<512><<<sms, 512>>>(out, in); });
     }
     measure("dmma_m8n8k4", 2.0 * 256 * MMA_CHAINS * ITERS * 8.0 * grid, [&] { k_dmma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
     measure("dmma_m16n8k16", 2.0 * 16 * 8 * 16 * MMA_CHAINS * (ITERS / 4) * 8.0 * grid, [&] { k_dmma16<<<grid, 256>>>(out, 1.0000001, 1e-9); });

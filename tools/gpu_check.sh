@@ -15,4 +15,6 @@ run grid3 SQLP_CONTRACT_GRID=3
 run grid50 SQLP_CONTRACT_GRID=50
 run grid1000 SQLP_CONTRACT_GRID=1000
 run stream SQLP_CONTRACT=stream
+run resident SQLP_CONTRACT=resident
+run resident_grid7 SQLP_CONTRACT=resident SQLP_CONTRACT_GRID=7
 exit $rc
