@@ -98,7 +98,7 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
     const int cb = half * SQLP_DELTA_COLS;
     const long long ltile = gblock / world;                  // local tile index
     double *Dt = D + ltile * (long long)s_pad * SQLP_TILE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slab = min(s_pad, SQLP_DELTA_SLAB), stride = delta_stride(slab);
 
     // weights
