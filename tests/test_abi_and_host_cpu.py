@@ -112,3 +112,22 @@ def test_committed_fixtures_match_the_reference_data():
         assert (st.n1, st.m2, len(st.pos_row)) == dims == (P.n1, P.m2, P.s)
         assert np.array_equal(st.rbar, P.rbar) and np.array_equal(st.T_nzval, P.T_nzval)
         assert np.array_equal(st.pos_row, P.pos_row)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours) prints one JSON line with
+    the agreed keys; a tiny workload keeps this in seconds."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(_lib.ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--vertices", "128", "--scen-per-gpu", "2000", "--epigraphs", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "evals/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]

@@ -509,3 +509,44 @@ def test_wide_row_sets_use_the_streaming_kernel(T, oracle, s):
     mv, mi = epi.argmax(x)
     check_argmax_parity(P, vals, x, pool, mv, mi)
     check_cut(oracle, P, vals, np.ones(N), x, pool, epi.build_cut(x))
+
+
+def test_scenario_permutation_changes_cuts_only_at_rounding_level(T, oracle):
+    """the cut is a weighted sum over scenarios, so a permutation of the scenarios
+    (with their weights) permutes the argmax and moves (alpha, beta) by rounding only."""
+    P, z = load_instance("ssn")
+    N = 700
+    vals = sample_instance_values(z, N, seed=3)
+    w = 0.5 + oracle.u01(4, np.arange(N))
+    perm = np.argsort(oracle.u01(11, np.arange(N)))
+    x = z["x_alt"]
+    _, e1 = make_epi(T, P, z["pool"], vals, w)
+    _, e2 = make_epi(T, P, z["pool"], vals[perm], w[perm])
+    (mv1, mi1), (mv2, mi2) = e1.argmax(x), e2.argmax(x)
+    assert np.array_equal(mi1[perm], mi2) and np.array_equal(mv1[perm], mv2)      # bit for bit
+    c1, c2 = e1.build_cut(x), e2.build_cut(x)
+    assert abs(c1.alpha - c2.alpha) <= 1e-12 * max(1.0, abs(c1.alpha))
+    assert np.max(np.abs(c1.beta - c2.beta)) <= 1e-12 * max(1.0, np.abs(c1.beta).max())
+    assert abs(e1.total_scenario_weight - e2.total_scenario_weight) <= 1e-12 * e1.total_scenario_weight
+
+
+def test_device_profiler_classes(T, oracle):
+    """sqlp_ctx_profile_classes: every kernel class reports its scopes, device time and algorithmic work."""
+    P, z = load_instance("storm")
+    ctx = T.Context(0)
+    dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+    epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+    ctx.profile(True)
+    ctx.profile_classes(reset=True)
+    dvs.push_many(z["pool"])
+    N = 300
+    epi.add_scenarios(sample_instance_values(z, N))
+    epi.build_cuts2(z["x_ev"], z["x_alt"])
+    prof = ctx.profile_classes(reset=True)
+    ctx.profile(False)
+    K, s = len(z["pool"]), P.s
+    assert prof["contract"][1] == 1 and prof["contract"][2] == 2.0 * s * K * N
+    assert prof["delta"][1] == 1 and prof["delta"][2] == 16.0 * s * N
+    assert prof["reduce"][1] == 1 and prof["pool"][1] == 1 and prof["bias"][1] == 1
+    assert all(prof[k][0] > 0 for k in prof)
+    assert ctx.profile_classes()["contract"][1] == 0         # reset
