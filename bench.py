@@ -159,7 +159,10 @@ def cpu_reference(z, pool, n_target_seconds, x2, threads=0):
     from oracle import oracle as O
     P = O.Problem(int(z["m2"]), int(z["n1"]), z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"],
                   z["pos_row"], z["pos_col"])
-    nthr = O.max_threads() if threads <= 0 else threads
+    # every host core this process may run on: torchrun exports OMP_NUM_THREADS=1 to its ranks, which
+    # would silently turn the "all host threads" baseline into a single-threaded one
+    nthr = (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else O.max_threads()) \
+        if threads <= 0 else threads
     probe = sample_values(z, 1, 0, 2 * nthr)
     t0 = time.perf_counter()
     O.bench_argmax(P, probe, x2[0], pool, threads=nthr)
