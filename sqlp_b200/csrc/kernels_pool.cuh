@@ -120,7 +120,8 @@ __global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__
 // Per-epigraph vertex tables: rt[k][0] = rho_k = pi_k . rbar (index order),
 // rt[k][1 + c] = tau_kc = sum over column c of Tbar (rows ascending) of T * pi_k[row]
 // -- the per-column gather of `(transfer)' * dual`, epigraph.jl:141.
-__global__ void k_epi_tables(const double *__restrict__ pi, int m2, const double *__restrict__ rbar,
+__global__ void k_epi_tables(const double *__restrict__ pi, int m2, const int *__restrict__ r_idx,
+                             const double *__restrict__ r_val, int r_nnz,
                              const long long *__restrict__ T_colptr, const int *__restrict__ T_rowval,
                              const double *__restrict__ T_nzval, int n1, double *__restrict__ rt,
                              long long k_lo, const long long *__restrict__ d_K)
@@ -131,11 +132,8 @@ __global__ void k_epi_tables(const double *__restrict__ pi, int m2, const double
         const double *row = pi + k * (long long)m2;
         for (int c = threadIdx.x; c < RT; c += blockDim.x) {
             double acc = 0.0;
-            if (c == 0) {
-                for (int j = 0; j < m2; ++j) {
-                    double r = rbar[j];
-                    if (r != 0.0) acc = __dadd_rn(acc, __dmul_rn(row[j], r));
-                }
+            if (c == 0) {   // the non-zeros of rbar in index order: independent loads, one ordered chain
+                for (int q = 0; q < r_nnz; ++q) acc = __dadd_rn(acc, __dmul_rn(row[r_idx[q]], r_val[q]));
             } else {
                 for (long long q = T_colptr[c - 1]; q < T_colptr[c]; ++q)
                     acc = __dadd_rn(acc, __dmul_rn(T_nzval[q], row[T_rowval[q]]));

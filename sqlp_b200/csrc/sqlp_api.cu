@@ -242,6 +242,8 @@ struct sqlp_epi {
     std::vector<int> h_pos_row, h_pos_col, h_elem_j, h_elem_t;
     DevBuf d_rbar, d_colptr, d_rowval, d_nzval;
     DevBuf d_rptr, d_rcol, d_rval;        // CSR copy of Tbar (columns ascending per row) -> k_base
+    DevBuf d_ridx, d_rnz;                 // non-zeros of rbar, index order -> k_epi_tables
+    int r_nnz = 0;
     DevBuf d_slot_elem, d_t_elem, d_elem_base;
     DevBuf d_tj, d_tcol, d_tslot;         // T elements sorted by (row slot, col)  -> k_delta_x
     DevBuf d_cc, d_cj, d_cslot;           // T elements sorted by col              -> reduce
@@ -385,8 +387,8 @@ void epi_tables_sync(sqlp_epi *e)
     int64_t hi = p->upper();
     if (hi > e->rt_synced_lo) {
         int grid = (int)std::min<int64_t>(hi - e->rt_synced_lo, 16 * c->sm_count);
-        LAUNCH(c, k_epi_tables, grid, 128, 0, p->d_pi.as<double>(), (int)p->m2, e->d_rbar.as<double>(),
-               e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
+        LAUNCH(c, k_epi_tables, grid, 128, 0, p->d_pi.as<double>(), (int)p->m2, e->d_ridx.as<int>(),
+               e->d_rnz.as<double>(), e->r_nnz, e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
                (int)e->n1, e->d_rt.as<double>(), (long long)e->rt_synced_lo, p->d_K.as<long long>());
     }
     e->rt_synced_lo = p->K;
@@ -1182,6 +1184,15 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
                 }
             }
             upload(e->d_rbar, e->h_rbar, S(c));
+            {
+                std::vector<int> ri;
+                std::vector<double> rv;
+                for (int64_t j = 0; j < m2; ++j)
+                    if (e->h_rbar[(size_t)j] != 0.0) { ri.push_back((int)j); rv.push_back(e->h_rbar[(size_t)j]); }
+                e->r_nnz = (int)ri.size();
+                upload(e->d_ridx, ri, S(c));
+                upload(e->d_rnz, rv, S(c));
+            }
             upload(e->d_colptr, e->h_colptr, S(c));
             upload(e->d_rowval, e->h_rowval, S(c));
             upload(e->d_nzval, e->h_nzval, S(c));
