@@ -1,0 +1,264 @@
+// host_base.cuh -- errors, NCCL binding, device buffers, the three handles, launch + profiling helpers.
+// Part of the single translation unit sqlp_api.cu (included there, in order).
+#pragma once
+
+namespace {
+
+using namespace sqlp;
+
+thread_local std::string g_err;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            throw Error(SQLP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)            \
+    do {                                    \
+        if (!(cond)) throw Error(code, msg); \
+    } while (0)
+
+template <class F>
+int32_t guard(F &&f)
+{
+    try {
+        f();
+        return SQLP_OK;
+    } catch (const Error &e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        g_err = "host allocation failed";
+        return SQLP_E_NOMEM;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return SQLP_E_INVALID;
+    }
+}
+
+// ---------------------------------------------------------------- NCCL (dlopen) --------
+// Only the scenario-sharded mode needs NCCL, so it is bound lazily; a single-GPU host never
+// loads it.  Types restated from nccl.h (2.x ABI).
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0 };
+enum { ncclFloat64_ = 8 };  // ncclDataType_t: ncclDouble
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+void load_nccl()
+{
+    if (g_nccl.h) return;
+    const char *env = getenv("SQLP_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    REQUIRE(h, SQLP_E_NCCL, "cannot dlopen libnccl.so.2 (set SQLP_NCCL_LIB)");
+    auto sym = [&](const char *s) {
+        void *p = dlsym(h, s);
+        REQUIRE(p, SQLP_E_NCCL, std::string("missing NCCL symbol ") + s);
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))sym("ncclBroadcast");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    g_nccl.h = h;
+}
+#define NK(call)                                                                            \
+    do {                                                                                    \
+        int r_ = (call);                                                                    \
+        if (r_ != ncclSuccess_)                                                             \
+            throw Error(SQLP_E_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------- device buffers -------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    // Grow to at least `need` bytes.  keep = bytes of existing content to preserve;
+    // the remainder is zero-filled.  All work is enqueued on `st`.
+    void ensure(size_t need, size_t keep, cudaStream_t st, bool zero = true)
+    {
+        if (need <= bytes) return;
+        size_t nb = std::max(need, bytes + bytes / 2);
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, nb);
+        if (e != cudaSuccess)
+            throw Error(SQLP_E_NOMEM, std::string("cudaMalloc(") + std::to_string(nb) +
+                                          "): " + cudaGetErrorString(e));
+        if (keep) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
+        if (zero && nb > keep) CK(cudaMemsetAsync((char *)np + keep, 0, nb - keep, st));
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        p = np;
+        bytes = nb;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class T>
+void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
+{
+    b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T), 0, st);
+    if (!v.empty())
+        CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- handles --------------
+struct sqlp_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    int64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profile = false;
+    struct ProfEvent { cudaEvent_t e0, e1; int cls; };
+    std::vector<ProfEvent> prof_events;
+    size_t prof_used = 0;
+    double prof_work[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};   // flops (contraction) or algorithmic bytes
+    bool smem_attr[3] = {false, false, false};
+    // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
+    int contract_mode = 0;        // 0 = automatic, 1 = streaming only, 2 = resident (or streaming), 3 = warp-specialised first
+    int contract_lag_ns = 2000;
+    int ws_smem_set[3] = {0, 0, 0};
+    int contract_grid = 0;        // > 0: force this many CTAs (tests of the span split)
+    int contract_prefetch = 0;    // > 0: items the copies run ahead (tuning knob, environment)
+    int smem_per_sm = 0, smem_optin = 0;
+    bool delta_smem_set = false;
+    int res_smem_set[3] = {0, 0, 0};
+    DevBuf d_piece_val, d_piece_idx;
+    void bind() const { CK(cudaSetDevice(device)); }
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+    do {                                                                 \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        CK(cudaGetLastError());                                          \
+        ++(ctx)->launches;                                               \
+    } while (0)
+
+struct PoolView {   // the pool restricted to one set of stochastic rows, in tile layout
+    std::vector<int> rows;
+    int n_rows = 0, s_pad = 0;
+    DevBuf d_rows, d_piS;
+    int64_t synced_lo = 0;   // vertices < synced_lo are final in d_piS
+};
+
+struct sqlp_pool {
+    sqlp_ctx *ctx = nullptr;
+    int64_t m2 = 0;
+    int64_t cap = 0;        // vertex capacity (multiple of 128)
+    int64_t K = 0;          // confirmed size
+    int64_t pending = 0;    // enqueued pushes whose outcome the host has not read yet
+    DevBuf d_pi, d_hash, d_K, d_scratch, d_vnew, d_vr, d_results;
+    std::vector<PoolView *> views;
+    std::vector<sqlp_epi *> epis;
+    int64_t upper() const { return K + pending; }
+};
+
+struct sqlp_epi {
+    sqlp_ctx *ctx = nullptr;
+    sqlp_pool *pool = nullptr;
+    PoolView *view = nullptr;
+    int64_t m2 = 0, n1 = 0, s = 0;
+    int n_T = 0;
+    // template coefficients
+    std::vector<double> h_rbar;
+    std::vector<int64_t> h_colptr;
+    std::vector<int> h_rowval;
+    std::vector<double> h_nzval;
+    std::vector<int> h_pos_row, h_pos_col, h_elem_j, h_elem_t;
+    DevBuf d_rbar, d_colptr, d_rowval, d_nzval;
+    DevBuf d_rptr, d_rcol, d_rval;        // CSR copy of Tbar (columns ascending per row) -> k_base
+    DevBuf d_ridx, d_rnz;                 // non-zeros of rbar, index order -> k_epi_tables
+    int r_nnz = 0;
+    DevBuf d_slot_elem, d_t_elem, d_elem_base;
+    DevBuf d_tj, d_tcol, d_tslot;         // T elements sorted by (row slot, col)  -> k_delta_x
+    DevBuf d_cc, d_cj, d_cslot;           // T elements sorted by col              -> reduce
+    DevBuf d_mcol, d_mrow, d_mslot;       // T elements sorted by (col, row)       -> eval_dual
+    DevBuf d_ovals, d_ocdf, d_ocnt;       // outcome tables
+    int mo = 0;
+    DevBuf d_kind, d_par_a, d_par_b;      // continuous elements (NORMAL / UNIFORM)
+    bool has_kinds = false, all_continuous = false;
+    // scenario store
+    int64_t n_global = 0, n_local = 0, cap_tiles = 0;
+    double total_weight = 0.0;
+    DevBuf d_D, d_dT, d_w, d_Dx;
+    // per-vertex tables (rho, tau)
+    DevBuf d_rt;
+    int64_t rt_cap = 0, rt_synced_lo = 0;
+    // work buffers
+    DevBuf d_x2, d_base, d_bias, d_best_val, d_best_idx, d_partial, d_partial2, d_out, d_gather,
+        d_flags, d_stage, d_scratch;
+    int64_t bias_stride = 0, out_stride = 0;
+    // the cut list on the device (kernels_cuts.cuh): rows (alpha, beta[n1], weight_mark)
+    double objective_weight = 1.0, lower_bound = 0.0;
+    DevBuf d_cuts, d_cuts_tmp, d_inc, d_prev_inc, d_keep, d_eval, d_rows;
+    int64_t n_cuts = 0, cuts_cap = 0, n_last = 0;
+    bool has_inc = false, has_prev_inc = false;
+    int last_nx = 0;   // points of the last cut formation whose result is still in d_out
+};
+
+namespace {
+
+cudaStream_t S(sqlp_ctx *c) { return c->stream; }
+
+struct ProfScope {   // CUDA events around the launch(es) of one kernel class when profiling is on
+    sqlp_ctx *c;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(sqlp_ctx *c_, int cls, double work) : c(c_)
+    {
+        if (!c->profile) return;
+        if (c->prof_used == c->prof_events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->prof_events.push_back({a, b, cls});
+        }
+        sqlp_ctx::ProfEvent &pe = c->prof_events[c->prof_used++];
+        pe.cls = cls;
+        e1 = pe.e1;
+        c->prof_work[cls] += work;
+        CK(cudaEventRecord(pe.e0, c->stream));
+    }
+    void stop() { if (e1) CK(cudaEventRecord(e1, c->stream)); e1 = nullptr; }
+    ~ProfScope() { if (e1) cudaEventRecord(e1, c->stream); }
+};
+
+
+int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace

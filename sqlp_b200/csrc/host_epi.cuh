@@ -1,0 +1,413 @@
+// host_epi.cuh -- host side of an epigraph: scenario store, contraction plan, cut formation, cut list.
+// Part of the single translation unit sqlp_api.cu (included there, in order).
+#pragma once
+
+namespace {
+
+DeltaTables delta_tables(sqlp_epi *e)
+{
+    DeltaTables tb;
+    tb.s = (int)e->s;
+    tb.n_T = e->n_T;
+    tb.n_rows = e->view->n_rows;
+    tb.slot_elem = e->d_slot_elem.as<int>();
+    tb.t_elem = e->d_t_elem.as<int>();
+    tb.elem_base = e->d_elem_base.as<double>();
+    tb.out_vals = e->d_ovals.as<double>();
+    tb.out_cdf = e->d_ocdf.as<double>();
+    tb.out_cnt = e->d_ocnt.as<int>();
+    tb.mo = e->mo;
+    tb.kind = e->has_kinds ? e->d_kind.as<int>() : nullptr;
+    tb.par_a = e->d_par_a.as<double>();
+    tb.par_b = e->d_par_b.as<double>();
+    return tb;
+}
+
+void epi_reserve_scenarios(sqlp_epi *e, int64_t n_local_new)
+{
+    sqlp_ctx *c = e->ctx;
+    int64_t tiles = (n_local_new + SQLP_TILE - 1) / SQLP_TILE;
+    if (tiles <= e->cap_tiles) return;
+    int64_t ncap = std::max<int64_t>(tiles, std::max<int64_t>(8, e->cap_tiles * 2));
+    int64_t used_tiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
+    size_t per_tile = (size_t)e->view->s_pad * SQLP_TILE * 8;
+    e->d_D.ensure(ncap * per_tile, used_tiles * per_tile, S(c));
+    e->d_w.ensure((size_t)ncap * SQLP_TILE * 8, (size_t)used_tiles * SQLP_TILE * 8, S(c));
+    if (e->n_T)
+        e->d_dT.ensure((size_t)ncap * SQLP_TILE * e->n_T * 8,
+                       (size_t)used_tiles * SQLP_TILE * e->n_T * 8, S(c));
+    e->cap_tiles = ncap;
+}
+
+// add_scenario! for a batch: values on host (v_host), on device (v_dev) or sampled.
+void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_dev,
+             const double *w_host, bool sample, uint64_t seed, uint64_t wseed)
+{
+    if (n_new <= 0) return;
+    sqlp_ctx *c = e->ctx;
+    const int64_t g0 = e->n_global;
+    const int64_t g1 = g0 + n_new;
+    const int64_t nl1 = local_count(g1, c->rank, c->world);
+    epi_reserve_scenarios(e, nl1);
+    // epigraph.jl:89  total_scenario_weight += weight, in scenario order
+    for (int64_t i = 0; i < n_new; ++i) {
+        double w = 1.0;
+        if (sample) { if (wseed) w = 0.5 + u01(wseed, (uint64_t)(g0 + i)); }
+        else if (w_host) w = w_host[i];
+        e->total_weight += w;
+    }
+    DeltaTables tb = delta_tables(e);
+    // algorithmic bytes: 8 s in + 8 s out per scenario (sampled: out only), this rank's share
+    ProfScope prof(c, SQLP_PROF_DELTA, (double)(nl1 - e->n_local) * e->s * (sample ? 8.0 : 16.0));
+    // host values go through a 64 MB staging buffer piece by piece; device-resident or sampled
+    // values need no staging, so the whole batch is one launch
+    const int64_t piece = (sample || v_dev) ? std::max<int64_t>(SQLP_TILE, (n_new / SQLP_TILE + 2) * SQLP_TILE)
+        : std::max<int64_t>(SQLP_TILE, ((int64_t)(64 << 20) / (8 * std::max<int64_t>(e->s, 1))) / SQLP_TILE * SQLP_TILE);
+    for (int64_t off = 0; off < n_new;) {
+        // cut pieces at 128-aligned global ordinals so a tile is never split mid-copy
+        int64_t end = std::min<int64_t>(n_new, ((g0 + off) / SQLP_TILE) * SQLP_TILE + piece - g0);
+        if (end <= off) end = std::min<int64_t>(n_new, off + piece);
+        const int64_t cnt = end - off;
+        const double *vals = nullptr, *wts = nullptr;
+        if (!sample) {
+            if (v_dev) {
+                vals = v_dev + off * e->s;
+            } else {
+                e->d_stage.ensure((size_t)cnt * (e->s + 1) * 8, 0, S(c), false);
+                if (e->s)
+                    CK(cudaMemcpyAsync(e->d_stage.p, v_host + off * e->s, (size_t)cnt * e->s * 8,
+                                       cudaMemcpyHostToDevice, S(c)));
+                vals = e->d_stage.as<double>();
+            }
+            if (w_host) {
+                if (v_dev) e->d_stage.ensure((size_t)cnt * 8, 0, S(c), false);   // weights only
+                double *dw = e->d_stage.as<double>() + (v_dev ? 0 : cnt * e->s);
+                CK(cudaMemcpyAsync(dw, w_host + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, S(c)));
+                wts = dw;
+            }
+        }
+        const int64_t gs = g0 + off;
+        const int blocks = 2 * (int)((gs + cnt - 1) / SQLP_TILE - gs / SQLP_TILE + 1);   // half tiles
+        const int slab = std::min(e->view->s_pad, SQLP_DELTA_SLAB);
+        const size_t dsmem = (size_t)SQLP_DELTA_COLS * delta_stride(slab) * 8;
+        if (!c->delta_smem_set) {
+            const int mx = SQLP_DELTA_COLS * delta_stride(SQLP_DELTA_SLAB) * 8;
+            CK(cudaFuncSetAttribute(k_delta_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            CK(cudaFuncSetAttribute(k_delta_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            c->delta_smem_set = true;
+        }
+        if (sample)
+            LAUNCH(c, k_delta_build<true>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
+                   (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
+                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, (unsigned long long)seed,
+                   (unsigned long long)wseed);
+        else
+            LAUNCH(c, k_delta_build<false>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
+                   (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
+                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, 0ull, 0ull);
+        if (!sample && !v_dev) CK(cudaStreamSynchronize(S(c)));   // staging buffer is reused
+        off = end;
+    }
+    e->n_global = g1;
+    e->n_local = nl1;
+}
+
+// The contraction variant used in production (see DESIGN.md for the measurements behind it).
+template <int NX>
+using ContractVariant = ContractCfg<NX, SQLP_VARIANT_MI, SQLP_VARIANT_STAGES, SQLP_VARIANT_PREFETCH, SQLP_VARIANT_CTAS,
+                                    SQLP_VARIANT_KG>;
+
+template <int NX>
+using ResidentVariant = ResidentCfg<NX, SQLP_RES_WR, SQLP_RES_MI, SQLP_RES_KG, SQLP_RES_CTAS>;
+
+// Resident-scenario kernel: returns false when one unit of scenarios plus a two-stage pool
+// ring does not fit in shared memory (very wide stochastic row sets).
+template <int NX>
+bool launch_contract_resident(sqlp_epi *e, ContractArgs &a)
+{
+    using Cfg = ResidentVariant<NX>;
+    sqlp_ctx *c = e->ctx;
+    const size_t fixed = Cfg::fixed_bytes(a.s_pad), stage = Cfg::stage_bytes();
+    int ctas = Cfg::CTAS;
+    size_t budget = 0;
+    int stages = 0;
+    for (; ctas >= 1; --ctas) {
+        budget = std::min<size_t>((size_t)c->smem_optin, ((size_t)c->smem_per_sm - 1024u * ctas) / ctas);
+        stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
+        if (stages >= 2) break;
+    }
+    if (stages < 2) return false;
+    const size_t smem = fixed + stage * stages;
+    if (c->res_smem_set[NX] < (int)smem) {
+        CK(cudaFuncSetAttribute(k_contract_resident<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->res_smem_set[NX] = (int)smem;
+    }
+    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+    const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;   // host upper bound
+    int grid = ctas * c->sm_count;
+    if (c->contract_grid > 0) grid = c->contract_grid;
+    grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>(nunits * nchunks_ub, nunits)));
+    const size_t pieces = (size_t)grid * 2 * NX * Cfg::ROWS;
+    c->d_piece_val.ensure(pieces * 8, 0, S(c), false);
+    c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
+    a.nstages = stages;
+    a.prefetch = std::max(1, stages - 2);
+    if (c->contract_prefetch > 0) a.prefetch = std::min(c->contract_prefetch, stages - 1);
+    a.piece_val = c->d_piece_val.as<double>();
+    a.piece_idx = c->d_piece_idx.as<int>();
+    LAUNCH(c, k_contract_resident<Cfg>, grid, Cfg::THREADS, smem, a);
+    auto fixup = k_argmax_fixup<Cfg::ROWS, NX>;
+    LAUNCH(c, fixup, grid, 128, 0, a, grid);
+    return true;
+}
+
+// Warp-specialised kernel (one CTA per SM, producer warp + two consumer row groups).
+template <int NX>
+bool launch_contract_ws(sqlp_epi *e, ContractArgs &a)
+{
+    using Cfg = WsCfg<NX, SQLP_WS_KG>;
+    sqlp_ctx *c = e->ctx;
+    const size_t fixed = Cfg::fixed_bytes(a.s_pad), stage = Cfg::stage_bytes();
+    const size_t budget = std::min<size_t>((size_t)c->smem_optin, (size_t)c->smem_per_sm - 1024u);
+    const int stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
+    if (stages < 3) return false;
+    const size_t smem = fixed + stage * stages;
+    if (c->ws_smem_set[NX] < (int)smem) {
+        CK(cudaFuncSetAttribute(k_contract_ws<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->ws_smem_set[NX] = (int)smem;
+    }
+    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+    const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;
+    int grid = c->contract_grid > 0 ? c->contract_grid : c->sm_count;
+    grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>(nunits * nchunks_ub, nunits)));
+    const size_t pieces = (size_t)grid * 2 * NX * Cfg::ROWS;
+    c->d_piece_val.ensure(pieces * 8, 0, S(c), false);
+    c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
+    a.nstages = stages;
+    a.prefetch = 0;
+    a.lag_ns = c->contract_lag_ns;
+    a.piece_val = c->d_piece_val.as<double>();
+    a.piece_idx = c->d_piece_idx.as<int>();
+    LAUNCH(c, k_contract_ws<Cfg>, grid, SQLP_WS_THREADS, smem, a);
+    auto fixup = k_argmax_fixup<Cfg::ROWS, NX>;
+    LAUNCH(c, fixup, grid, 128, 0, a, grid);
+    return true;
+}
+
+template <int NX>
+void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
+{
+    using Cfg = ContractVariant<NX>;
+    sqlp_ctx *c = e->ctx;
+    ContractArgs a;
+    a.D = D;
+    a.PiS = e->view->d_piS.as<double>();
+    a.bias = bias;
+    a.bias_stride = e->bias_stride;
+    a.d_K = e->pool->d_K.as<long long>();
+    a.s_pad = e->view->s_pad;
+    a.ntiles = (int)((e->n_local + SQLP_TILE - 1) / SQLP_TILE);
+    a.n_local = e->n_local;
+    a.best_val = bv;
+    a.best_idx = bi;
+    a.out_stride = e->out_stride;
+    a.nstages = a.prefetch = a.lag_ns = 0;
+    a.piece_val = nullptr;
+    a.piece_idx = nullptr;
+    ProfScope prof(c, SQLP_PROF_CONTRACT, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
+    bool done = false;
+    // automatic: warp-specialised -> resident (fewer ring stages suffice) -> streaming (any s_pad)
+    if (c->contract_mode == 0 || c->contract_mode == 3) done = launch_contract_ws<NX>(e, a);
+    if (!done && c->contract_mode != 1) done = launch_contract_resident<NX>(e, a);
+
+    if (!done) {   // streaming kernel: both operands flow through the ring
+        size_t smem = Cfg::smem_bytes();
+        if (!c->smem_attr[NX]) {   // per device, so per context
+            CK(cudaFuncSetAttribute(k_contract_argmax<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+            c->smem_attr[NX] = true;
+        }
+        const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
+        int grid = (int)std::min<long long>(nunits, (long long)Cfg::CTAS * c->sm_count);
+        LAUNCH(c, k_contract_argmax<Cfg>, grid, SQLP_CT_THREADS, smem, a);
+    }
+    prof.stop();
+}
+
+// Everything of build_sasa_cut for NX points, enqueued on the stream.  x on host or device.
+// Result lands in e->d_out as [NX][n1 + 2] = (alpha, beta[n1], val).
+void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x_dev, bool want_cut)
+{
+    sqlp_ctx *c = e->ctx;
+    sqlp_pool *p = e->pool;
+    const int n1 = (int)e->n1, m2 = (int)e->m2;
+    const int NC = n1 + 2;
+    e->d_x2.ensure((size_t)2 * std::max(n1, 1) * 8, 0, S(c));
+    e->d_out.ensure((size_t)2 * NC * 8, 0, S(c));
+    e->d_flags.ensure(16, 0, S(c));
+    if (x_host)
+        CK(cudaMemcpyAsync(e->d_x2.p, x_host, (size_t)NX * n1 * 8, cudaMemcpyHostToDevice, S(c)));
+    else
+        CK(cudaMemcpyAsync(e->d_x2.p, x_dev, (size_t)NX * n1 * 8, cudaMemcpyDeviceToDevice, S(c)));
+    CK(cudaMemsetAsync(e->d_flags.p, 0, 4, S(c)));
+    CK(cudaMemsetAsync(e->d_out.p, 0, (size_t)2 * NC * 8, S(c)));
+
+    view_sync(p, e->view);
+    if (want_cut) epi_tables_sync(e);
+
+    const int64_t ku = p->upper();
+    const int64_t kpad = round_up(std::max<int64_t>(ku, 1), SQLP_TILE);
+    if (kpad > e->bias_stride) {
+        e->bias_stride = round_up(kpad * 2, SQLP_TILE);
+        e->d_bias.ensure((size_t)2 * e->bias_stride * 8, 0, S(c), false);
+    }
+    const int64_t ntiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
+    if (ntiles * SQLP_TILE > e->out_stride) {
+        e->out_stride = round_up(ntiles * SQLP_TILE * 2, SQLP_TILE);
+        e->d_best_val.ensure((size_t)2 * e->out_stride * 8, 0, S(c), false);
+        e->d_best_idx.ensure((size_t)2 * e->out_stride * 4, 0, S(c), false);
+    }
+    e->d_base.ensure((size_t)2 * m2 * 8, 0, S(c));
+
+    if (ntiles > 0) {
+        ProfScope prof_bias(c, SQLP_PROF_BIAS, 8.0 * (double)ku * m2 + 8.0 * NX * (double)ku);
+        LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
+               e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
+               e->d_x2.as<double>(), e->d_base.as<double>());
+        int bgrid = (int)((kpad + 7) / 8);
+        if (NX == 2)
+            LAUNCH(c, k_bias<2>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
+                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
+                   (long long)e->bias_stride);
+        else
+            LAUNCH(c, k_bias<1>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
+                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
+                   (long long)e->bias_stride);
+
+        prof_bias.stop();
+
+        if (e->n_T == 0) {
+            if (NX == 2)
+                launch_contract<2>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
+                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
+            else
+                launch_contract<1>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
+                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
+        } else {
+            // some element perturbs Tbar: d(x) = delta_rhs - delta_T x is rebuilt per point
+            size_t bytes = (size_t)ntiles * e->view->s_pad * SQLP_TILE * 8;
+            e->d_Dx.ensure(bytes, 0, S(c), false);
+            TransferList tl{e->n_T, e->d_tj.as<int>(), e->d_tcol.as<int>(), e->d_tslot.as<int>()};
+            for (int x = 0; x < NX; ++x) {
+                CK(cudaMemcpyAsync(e->d_Dx.p, e->d_D.p, bytes, cudaMemcpyDeviceToDevice, S(c)));
+                LAUNCH(c, k_delta_x, (int)((e->n_local + 255) / 256), 256, 0, tl,
+                       e->d_x2.as<double>() + (size_t)x * n1, (long long)e->n_local, e->view->s_pad,
+                       e->d_D.as<double>(), e->d_dT.as<double>(), e->d_Dx.as<double>());
+                launch_contract<1>(e, e->d_Dx.as<double>(), e->d_bias.as<double>() + x * e->bias_stride,
+                                   e->d_best_val.as<double>() + x * e->out_stride,
+                                   e->d_best_idx.as<int>() + x * e->out_stride);
+            }
+        }
+    }
+    if (!want_cut) return;
+    e->last_nx = NX;
+
+    const int width = NX * NC;
+    if (ntiles > 0) {
+        e->d_partial.ensure((size_t)ntiles * width * 8, 0, S(c), false);
+        ReduceArgs r;
+        r.D = e->d_D.as<double>();
+        r.dT = e->d_dT.as<double>();
+        r.w = e->d_w.as<double>();
+        r.PiS = e->view->d_piS.as<double>();
+        r.rt = e->d_rt.as<double>();
+        r.best_val = e->d_best_val.as<double>();
+        r.best_idx = e->d_best_idx.as<int>();
+        r.out_stride = e->out_stride;
+        r.n_local = e->n_local;
+        r.s_pad = e->view->s_pad;
+        r.n_rows = e->view->n_rows;
+        r.n1 = n1;
+        r.total_weight = e->total_weight;
+        r.n_T = e->n_T;
+        r.tc_col = e->d_cc.as<int>();
+        r.tc_j = e->d_cj.as<int>();
+        r.tc_slot = e->d_cslot.as<int>();
+        r.partial = e->d_partial.as<double>();
+        r.flags = e->d_flags.as<int>();
+        // algorithmic bytes: per point N (idx + weight + winning dot) + the (rho, tau)
+        // table + the cut; the implementation also re-reads D (8 s_pad N) to recompute the winning dot
+        ProfScope prof_red(c, SQLP_PROF_REDUCE,
+                           NX * (24.0 * (double)e->n_local + 8.0 * (double)ku * (n1 + 1) + 8.0 * (n1 + 1)));
+        if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, 0, r);
+        else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, 0, r);
+        const int group = 64;
+        int64_t ng = (ntiles + group - 1) / group;
+        e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
+        LAUNCH(c, k_sum_groups, (int)ng, 256, 0, e->d_partial.as<double>(), (long long)ntiles, group,
+               width, e->d_partial2.as<double>());
+        LAUNCH(c, k_sum_groups, 1, 256, 0, e->d_partial2.as<double>(), (long long)ng, (int)ng, width,
+               e->d_out.as<double>());
+        prof_red.stop();
+    }
+    if (c->world > 1) {
+        // per-epigraph partials are all-gathered and summed in fixed rank order
+        e->d_gather.ensure((size_t)c->world * width * 8, 0, S(c));
+        NK(g_nccl.AllGather(e->d_out.p, e->d_gather.p, (size_t)width, ncclFloat64_, c->comm, S(c)));
+        LAUNCH(c, k_rank_sum, (width + 127) / 128, 128, 0, e->d_gather.as<double>(), c->world, width,
+               e->d_out.as<double>());
+    }
+}
+
+struct CutHost {
+    std::vector<double> out;
+    int flags = 0;
+};
+
+void epi_cuts_fetch(sqlp_epi *e, int NX, CutHost &h)
+{
+    const int NC = (int)e->n1 + 2;
+    h.out.resize((size_t)NX * NC);
+    CK(cudaMemcpyAsync(h.out.data(), e->d_out.p, (size_t)NX * NC * 8, cudaMemcpyDeviceToHost, S(e->ctx)));
+    CK(cudaMemcpyAsync(&h.flags, e->d_flags.p, 4, cudaMemcpyDeviceToHost, S(e->ctx)));
+}
+
+// ---- device cut list -------------------------------------------------------------------------
+void cuts_reserve(sqlp_epi *e, int64_t need)
+{
+    if (need <= e->cuts_cap) return;
+    const size_t RS = (size_t)e->n1 + 2;
+    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(64, e->cuts_cap * 2));
+    e->d_cuts.ensure((size_t)ncap * RS * 8, (size_t)e->n_cuts * RS * 8, S(e->ctx));
+    e->d_inc.ensure(RS * 8, 0, S(e->ctx));
+    e->d_prev_inc.ensure(RS * 8, 0, S(e->ctx));
+    e->cuts_cap = ncap;
+}
+
+CutList cut_list(sqlp_epi *e, bool last)
+{
+    CutList L;
+    L.cuts = e->d_cuts.as<double>();
+    L.n = (int)(last ? e->n_last : e->n_cuts);
+    L.inc = last ? (e->has_prev_inc ? e->d_prev_inc.as<double>() : nullptr)
+                 : (e->has_inc ? e->d_inc.as<double>() : nullptr);
+    return L;
+}
+
+// est[0 .. nlists * NX): weighted value of the current (and snapshot) approximation at NX device points
+void cuts_evaluate_enqueue(sqlp_epi *e, const double *d_x, int NX, int nlists, double *d_est)
+{
+    sqlp_ctx *c = e->ctx;
+    cuts_reserve(e, 1);
+    LAUNCH(c, k_cuts_evaluate, 1, 256, 0, cut_list(e, false), cut_list(e, true), nlists, d_x, NX, (int)e->n1,
+           e->total_weight, e->lower_bound, e->objective_weight, d_est);
+}
+
+void check_sense(int32_t sense)
+{
+    REQUIRE(sense == SQLP_MIN_SENSE || sense == SQLP_MAX_SENSE, SQLP_E_INVALID, "bad sense");
+    REQUIRE(sense == SQLP_MIN_SENSE, SQLP_E_UNSUPPORTED,
+            "MAX_SENSE is unsupported: the reference's MAX branch never selects a vertex");
+}
+
+}  // namespace

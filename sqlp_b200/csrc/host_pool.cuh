@@ -1,0 +1,101 @@
+// host_pool.cuh -- host side of the dual-vertex pool: capacity, enqueued pushes, view / table sync.
+// Part of the single translation unit sqlp_api.cu (included there, in order).
+#pragma once
+
+namespace {
+
+void pool_reserve(sqlp_pool *p, int64_t need)
+{
+    if (need <= p->cap) return;
+    sqlp_ctx *c = p->ctx;
+    int64_t ncap = std::max<int64_t>(round_up(need, SQLP_TILE), std::max<int64_t>(1024, p->cap * 2));
+    int64_t used = p->upper();
+    p->d_pi.ensure((size_t)ncap * p->m2 * 8, (size_t)used * p->m2 * 8, S(c));
+    p->d_hash.ensure((size_t)ncap * 8, (size_t)used * 8, S(c));
+    for (PoolView *v : p->views) {
+        size_t per_chunk = (size_t)v->s_pad * SQLP_TILE * 8;
+        v->d_piS.ensure((size_t)(ncap / SQLP_TILE) * per_chunk,
+                        (size_t)((used + SQLP_TILE - 1) / SQLP_TILE) * per_chunk, S(c));
+    }
+    for (sqlp_epi *e : p->epis) {
+        e->d_rt.ensure((size_t)ncap * (e->n1 + 1) * 8, (size_t)used * (e->n1 + 1) * 8, S(c));
+        e->rt_cap = ncap;
+    }
+    p->cap = ncap;
+}
+
+// Bring K up to date on the host (one small D2H + sync) if pushes are outstanding.
+void pool_confirm(sqlp_pool *p)
+{
+    if (!p->pending) return;
+    long long K = 0;
+    CK(cudaMemcpyAsync(&K, p->d_K.p, 8, cudaMemcpyDeviceToHost, S(p->ctx)));
+    CK(cudaStreamSynchronize(S(p->ctx)));
+    p->K = K;
+    p->pending = 0;
+}
+
+void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const double *v_dev)
+{
+    sqlp_ctx *c = p->ctx;
+    pool_reserve(p, p->upper() + n);
+    p->d_results.ensure((size_t)n * sizeof(PushResult), 0, S(c));
+    const double *src = v_dev;
+    if (!v_dev || c->world > 1) {
+        p->d_vnew.ensure((size_t)n * p->m2 * 8, 0, S(c));
+        if (v_host && (c->world == 1 || c->rank == 0))
+            CK(cudaMemcpyAsync(p->d_vnew.p, v_host, (size_t)n * p->m2 * 8, cudaMemcpyHostToDevice, S(c)));
+        else if (v_dev && (c->world == 1 || c->rank == 0))
+            CK(cudaMemcpyAsync(p->d_vnew.p, v_dev, (size_t)n * p->m2 * 8, cudaMemcpyDeviceToDevice, S(c)));
+        else
+            REQUIRE(c->world > 1 && c->rank != 0, SQLP_E_INVALID, "push: null vector");
+        if (c->world > 1)   // each new dual vertex is broadcast from rank 0 over NCCL/NVLink
+            NK(g_nccl.Broadcast(p->d_vnew.p, p->d_vnew.p, (size_t)n * p->m2, ncclFloat64_, 0,
+                                c->comm, S(c)));
+        src = p->d_vnew.as<double>();
+    }
+    // algorithmic bytes: the hash scan (8 K per push) + the pushed vector in and, if new, out
+    ProfScope prof(c, SQLP_PROF_POOL, (double)n * (8.0 * (double)p->upper() + 16.0 * (double)p->m2));
+    for (int64_t i = 0; i < n; ++i) {
+        LAUNCH(c, k_pool_prepare, 1, 256, (size_t)p->m2 * 8, src + i * p->m2, (int)p->m2,
+               p->d_vr.as<double>(), p->d_scratch.as<PushScratch>());
+        int64_t ku = p->upper() + i;
+        int grid = (int)std::min<int64_t>(std::max<int64_t>((ku + 7) / 8, 1), 4 * c->sm_count);
+        LAUNCH(c, k_pool_find_commit, grid, 256, 0, p->d_pi.as<double>(),
+               p->d_hash.as<unsigned long long>(), p->d_K.as<long long>(), (int)p->m2,
+               src + i * p->m2, p->d_vr.as<double>(), p->d_scratch.as<PushScratch>(),
+               p->d_results.as<PushResult>() + i);
+    }
+    p->pending += n;
+}
+
+// Bring a view / an epigraph's (rho, tau) tables up to the current pool contents.
+void view_sync(sqlp_pool *p, PoolView *v)
+{
+    sqlp_ctx *c = p->ctx;
+    int64_t hi = p->upper();
+    if (hi > v->synced_lo) {
+        int64_t work = (hi - v->synced_lo) * v->n_rows;
+        int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 8 * c->sm_count);
+        LAUNCH(c, k_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(),
+               v->n_rows, v->s_pad, v->d_piS.as<double>(), (long long)v->synced_lo,
+               p->d_K.as<long long>());
+    }
+    v->synced_lo = p->K;   // only confirmed vertices are final
+}
+
+void epi_tables_sync(sqlp_epi *e)
+{
+    sqlp_pool *p = e->pool;
+    sqlp_ctx *c = e->ctx;
+    int64_t hi = p->upper();
+    if (hi > e->rt_synced_lo) {
+        int grid = (int)std::min<int64_t>(hi - e->rt_synced_lo, 16 * c->sm_count);
+        LAUNCH(c, k_epi_tables, grid, 128, 0, p->d_pi.as<double>(), (int)p->m2, e->d_ridx.as<int>(),
+               e->d_rnz.as<double>(), e->r_nnz, e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
+               (int)e->n1, e->d_rt.as<double>(), (long long)e->rt_synced_lo, p->d_K.as<long long>());
+    }
+    e->rt_synced_lo = p->K;
+}
+
+}  // namespace

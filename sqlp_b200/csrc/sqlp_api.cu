@@ -41,766 +41,9 @@
 #include "kernels_reduce.cuh"
 #include "kernels_cuts.cuh"
 
-namespace {
-
-using namespace sqlp;
-
-thread_local std::string g_err;
-
-struct Error : std::runtime_error {
-    int code;
-    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
-};
-
-#define CK(call)                                                                          \
-    do {                                                                                  \
-        cudaError_t e_ = (call);                                                          \
-        if (e_ != cudaSuccess)                                                            \
-            throw Error(SQLP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
-
-#define REQUIRE(cond, code, msg)            \
-    do {                                    \
-        if (!(cond)) throw Error(code, msg); \
-    } while (0)
-
-template <class F>
-int32_t guard(F &&f)
-{
-    try {
-        f();
-        return SQLP_OK;
-    } catch (const Error &e) {
-        g_err = e.what();
-        return e.code;
-    } catch (const std::bad_alloc &) {
-        g_err = "host allocation failed";
-        return SQLP_E_NOMEM;
-    } catch (const std::exception &e) {
-        g_err = e.what();
-        return SQLP_E_INVALID;
-    }
-}
-
-// ---------------------------------------------------------------- NCCL (dlopen) --------
-// Only the scenario-sharded mode needs NCCL, so it is bound lazily; a single-GPU host never
-// loads it.  Types restated from nccl.h (2.x ABI).
-typedef struct ncclComm *ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclSuccess_ = 0 };
-enum { ncclFloat64_ = 8 };  // ncclDataType_t: ncclDouble
-struct NcclApi {
-    void *h = nullptr;
-    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    int (*CommDestroy)(ncclComm_t) = nullptr;
-    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    const char *(*GetErrorString)(int) = nullptr;
-};
-NcclApi g_nccl;
-
-void load_nccl()
-{
-    if (g_nccl.h) return;
-    const char *env = getenv("SQLP_NCCL_LIB");
-    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
-    void *h = nullptr;
-    for (const char *n : names) {
-        if (!n) continue;
-        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-        if (h) break;
-    }
-    REQUIRE(h, SQLP_E_NCCL, "cannot dlopen libnccl.so.2 (set SQLP_NCCL_LIB)");
-    auto sym = [&](const char *s) {
-        void *p = dlsym(h, s);
-        REQUIRE(p, SQLP_E_NCCL, std::string("missing NCCL symbol ") + s);
-        return p;
-    };
-    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
-    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
-    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
-    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))sym("ncclBroadcast");
-    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
-    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
-    g_nccl.h = h;
-}
-#define NK(call)                                                                            \
-    do {                                                                                    \
-        int r_ = (call);                                                                    \
-        if (r_ != ncclSuccess_)                                                             \
-            throw Error(SQLP_E_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
-    } while (0)
-
-// ---------------------------------------------------------------- device buffers -------
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    // Grow to at least `need` bytes.  keep = bytes of existing content to preserve;
-    // the remainder is zero-filled.  All work is enqueued on `st`.
-    void ensure(size_t need, size_t keep, cudaStream_t st, bool zero = true)
-    {
-        if (need <= bytes) return;
-        size_t nb = std::max(need, bytes + bytes / 2);
-        void *np = nullptr;
-        cudaError_t e = cudaMalloc(&np, nb);
-        if (e != cudaSuccess)
-            throw Error(SQLP_E_NOMEM, std::string("cudaMalloc(") + std::to_string(nb) +
-                                          "): " + cudaGetErrorString(e));
-        if (keep) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
-        if (zero && nb > keep) CK(cudaMemsetAsync((char *)np + keep, 0, nb - keep, st));
-        if (p) {
-            CK(cudaStreamSynchronize(st));
-            cudaFree(p);
-        }
-        p = np;
-        bytes = nb;
-    }
-    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-template <class T>
-void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
-{
-    b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T), 0, st);
-    if (!v.empty())
-        CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-}
-
-}  // namespace
-
-// ---------------------------------------------------------------- handles --------------
-struct sqlp_ctx {
-    int device = 0;
-    int rank = 0, world = 1;
-    int sm_count = 148;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    ncclComm_t comm = nullptr;
-    int64_t launches = 0;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    bool profile = false;
-    struct ProfEvent { cudaEvent_t e0, e1; int cls; };
-    std::vector<ProfEvent> prof_events;
-    size_t prof_used = 0;
-    double prof_work[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};   // flops (contraction) or algorithmic bytes
-    bool smem_attr[3] = {false, false, false};
-    // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
-    int contract_mode = 0;        // 0 = automatic, 1 = streaming only, 2 = resident (or streaming), 3 = warp-specialised first
-    int contract_lag_ns = 2000;
-    int ws_smem_set[3] = {0, 0, 0};
-    int contract_grid = 0;        // > 0: force this many CTAs (tests of the span split)
-    int contract_prefetch = 0;    // > 0: items the copies run ahead (tuning knob, environment)
-    int smem_per_sm = 0, smem_optin = 0;
-    bool delta_smem_set = false;
-    int res_smem_set[3] = {0, 0, 0};
-    DevBuf d_piece_val, d_piece_idx;
-    void bind() const { CK(cudaSetDevice(device)); }
-};
-
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
-    do {                                                                 \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
-        CK(cudaGetLastError());                                          \
-        ++(ctx)->launches;                                               \
-    } while (0)
-
-struct PoolView {   // the pool restricted to one set of stochastic rows, in tile layout
-    std::vector<int> rows;
-    int n_rows = 0, s_pad = 0;
-    DevBuf d_rows, d_piS;
-    int64_t synced_lo = 0;   // vertices < synced_lo are final in d_piS
-};
-
-struct sqlp_pool {
-    sqlp_ctx *ctx = nullptr;
-    int64_t m2 = 0;
-    int64_t cap = 0;        // vertex capacity (multiple of 128)
-    int64_t K = 0;          // confirmed size
-    int64_t pending = 0;    // enqueued pushes whose outcome the host has not read yet
-    DevBuf d_pi, d_hash, d_K, d_scratch, d_vnew, d_vr, d_results;
-    std::vector<PoolView *> views;
-    std::vector<sqlp_epi *> epis;
-    int64_t upper() const { return K + pending; }
-};
-
-struct sqlp_epi {
-    sqlp_ctx *ctx = nullptr;
-    sqlp_pool *pool = nullptr;
-    PoolView *view = nullptr;
-    int64_t m2 = 0, n1 = 0, s = 0;
-    int n_T = 0;
-    // template coefficients
-    std::vector<double> h_rbar;
-    std::vector<int64_t> h_colptr;
-    std::vector<int> h_rowval;
-    std::vector<double> h_nzval;
-    std::vector<int> h_pos_row, h_pos_col, h_elem_j, h_elem_t;
-    DevBuf d_rbar, d_colptr, d_rowval, d_nzval;
-    DevBuf d_rptr, d_rcol, d_rval;        // CSR copy of Tbar (columns ascending per row) -> k_base
-    DevBuf d_ridx, d_rnz;                 // non-zeros of rbar, index order -> k_epi_tables
-    int r_nnz = 0;
-    DevBuf d_slot_elem, d_t_elem, d_elem_base;
-    DevBuf d_tj, d_tcol, d_tslot;         // T elements sorted by (row slot, col)  -> k_delta_x
-    DevBuf d_cc, d_cj, d_cslot;           // T elements sorted by col              -> reduce
-    DevBuf d_mcol, d_mrow, d_mslot;       // T elements sorted by (col, row)       -> eval_dual
-    DevBuf d_ovals, d_ocdf, d_ocnt;       // outcome tables
-    int mo = 0;
-    DevBuf d_kind, d_par_a, d_par_b;      // continuous elements (NORMAL / UNIFORM)
-    bool has_kinds = false, all_continuous = false;
-    // scenario store
-    int64_t n_global = 0, n_local = 0, cap_tiles = 0;
-    double total_weight = 0.0;
-    DevBuf d_D, d_dT, d_w, d_Dx;
-    // per-vertex tables (rho, tau)
-    DevBuf d_rt;
-    int64_t rt_cap = 0, rt_synced_lo = 0;
-    // work buffers
-    DevBuf d_x2, d_base, d_bias, d_best_val, d_best_idx, d_partial, d_partial2, d_out, d_gather,
-        d_flags, d_stage, d_scratch;
-    int64_t bias_stride = 0, out_stride = 0;
-    // the cut list on the device (kernels_cuts.cuh): rows (alpha, beta[n1], weight_mark)
-    double objective_weight = 1.0, lower_bound = 0.0;
-    DevBuf d_cuts, d_cuts_tmp, d_inc, d_prev_inc, d_keep, d_eval, d_rows;
-    int64_t n_cuts = 0, cuts_cap = 0, n_last = 0;
-    bool has_inc = false, has_prev_inc = false;
-    int last_nx = 0;   // points of the last cut formation whose result is still in d_out
-};
-
-namespace {
-
-cudaStream_t S(sqlp_ctx *c) { return c->stream; }
-
-struct ProfScope {   // CUDA events around the launch(es) of one kernel class when profiling is on
-    sqlp_ctx *c;
-    cudaEvent_t e1 = nullptr;
-    ProfScope(sqlp_ctx *c_, int cls, double work) : c(c_)
-    {
-        if (!c->profile) return;
-        if (c->prof_used == c->prof_events.size()) {
-            cudaEvent_t a = nullptr, b = nullptr;
-            CK(cudaEventCreate(&a));
-            CK(cudaEventCreate(&b));
-            c->prof_events.push_back({a, b, cls});
-        }
-        sqlp_ctx::ProfEvent &pe = c->prof_events[c->prof_used++];
-        pe.cls = cls;
-        e1 = pe.e1;
-        c->prof_work[cls] += work;
-        CK(cudaEventRecord(pe.e0, c->stream));
-    }
-    void stop() { if (e1) CK(cudaEventRecord(e1, c->stream)); e1 = nullptr; }
-    ~ProfScope() { if (e1) cudaEventRecord(e1, c->stream); }
-};
-
-
-int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
-
-void pool_reserve(sqlp_pool *p, int64_t need)
-{
-    if (need <= p->cap) return;
-    sqlp_ctx *c = p->ctx;
-    int64_t ncap = std::max<int64_t>(round_up(need, SQLP_TILE), std::max<int64_t>(1024, p->cap * 2));
-    int64_t used = p->upper();
-    p->d_pi.ensure((size_t)ncap * p->m2 * 8, (size_t)used * p->m2 * 8, S(c));
-    p->d_hash.ensure((size_t)ncap * 8, (size_t)used * 8, S(c));
-    for (PoolView *v : p->views) {
-        size_t per_chunk = (size_t)v->s_pad * SQLP_TILE * 8;
-        v->d_piS.ensure((size_t)(ncap / SQLP_TILE) * per_chunk,
-                        (size_t)((used + SQLP_TILE - 1) / SQLP_TILE) * per_chunk, S(c));
-    }
-    for (sqlp_epi *e : p->epis) {
-        e->d_rt.ensure((size_t)ncap * (e->n1 + 1) * 8, (size_t)used * (e->n1 + 1) * 8, S(c));
-        e->rt_cap = ncap;
-    }
-    p->cap = ncap;
-}
-
-// Bring K up to date on the host (one small D2H + sync) if pushes are outstanding.
-void pool_confirm(sqlp_pool *p)
-{
-    if (!p->pending) return;
-    long long K = 0;
-    CK(cudaMemcpyAsync(&K, p->d_K.p, 8, cudaMemcpyDeviceToHost, S(p->ctx)));
-    CK(cudaStreamSynchronize(S(p->ctx)));
-    p->K = K;
-    p->pending = 0;
-}
-
-void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const double *v_dev)
-{
-    sqlp_ctx *c = p->ctx;
-    pool_reserve(p, p->upper() + n);
-    p->d_results.ensure((size_t)n * sizeof(PushResult), 0, S(c));
-    const double *src = v_dev;
-    if (!v_dev || c->world > 1) {
-        p->d_vnew.ensure((size_t)n * p->m2 * 8, 0, S(c));
-        if (v_host && (c->world == 1 || c->rank == 0))
-            CK(cudaMemcpyAsync(p->d_vnew.p, v_host, (size_t)n * p->m2 * 8, cudaMemcpyHostToDevice, S(c)));
-        else if (v_dev && (c->world == 1 || c->rank == 0))
-            CK(cudaMemcpyAsync(p->d_vnew.p, v_dev, (size_t)n * p->m2 * 8, cudaMemcpyDeviceToDevice, S(c)));
-        else
-            REQUIRE(c->world > 1 && c->rank != 0, SQLP_E_INVALID, "push: null vector");
-        if (c->world > 1)   // each new dual vertex is broadcast from rank 0 over NCCL/NVLink
-            NK(g_nccl.Broadcast(p->d_vnew.p, p->d_vnew.p, (size_t)n * p->m2, ncclFloat64_, 0,
-                                c->comm, S(c)));
-        src = p->d_vnew.as<double>();
-    }
-    // algorithmic bytes: the hash scan (8 K per push) + the pushed vector in and, if new, out
-    ProfScope prof(c, SQLP_PROF_POOL, (double)n * (8.0 * (double)p->upper() + 16.0 * (double)p->m2));
-    for (int64_t i = 0; i < n; ++i) {
-        LAUNCH(c, k_pool_prepare, 1, 256, (size_t)p->m2 * 8, src + i * p->m2, (int)p->m2,
-               p->d_vr.as<double>(), p->d_scratch.as<PushScratch>());
-        int64_t ku = p->upper() + i;
-        int grid = (int)std::min<int64_t>(std::max<int64_t>((ku + 7) / 8, 1), 4 * c->sm_count);
-        LAUNCH(c, k_pool_find_commit, grid, 256, 0, p->d_pi.as<double>(),
-               p->d_hash.as<unsigned long long>(), p->d_K.as<long long>(), (int)p->m2,
-               src + i * p->m2, p->d_vr.as<double>(), p->d_scratch.as<PushScratch>(),
-               p->d_results.as<PushResult>() + i);
-    }
-    p->pending += n;
-}
-
-// Bring a view / an epigraph's (rho, tau) tables up to the current pool contents.
-void view_sync(sqlp_pool *p, PoolView *v)
-{
-    sqlp_ctx *c = p->ctx;
-    int64_t hi = p->upper();
-    if (hi > v->synced_lo) {
-        int64_t work = (hi - v->synced_lo) * v->n_rows;
-        int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 8 * c->sm_count);
-        LAUNCH(c, k_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(),
-               v->n_rows, v->s_pad, v->d_piS.as<double>(), (long long)v->synced_lo,
-               p->d_K.as<long long>());
-    }
-    v->synced_lo = p->K;   // only confirmed vertices are final
-}
-
-void epi_tables_sync(sqlp_epi *e)
-{
-    sqlp_pool *p = e->pool;
-    sqlp_ctx *c = e->ctx;
-    int64_t hi = p->upper();
-    if (hi > e->rt_synced_lo) {
-        int grid = (int)std::min<int64_t>(hi - e->rt_synced_lo, 16 * c->sm_count);
-        LAUNCH(c, k_epi_tables, grid, 128, 0, p->d_pi.as<double>(), (int)p->m2, e->d_ridx.as<int>(),
-               e->d_rnz.as<double>(), e->r_nnz, e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
-               (int)e->n1, e->d_rt.as<double>(), (long long)e->rt_synced_lo, p->d_K.as<long long>());
-    }
-    e->rt_synced_lo = p->K;
-}
-
-DeltaTables delta_tables(sqlp_epi *e)
-{
-    DeltaTables tb;
-    tb.s = (int)e->s;
-    tb.n_T = e->n_T;
-    tb.n_rows = e->view->n_rows;
-    tb.slot_elem = e->d_slot_elem.as<int>();
-    tb.t_elem = e->d_t_elem.as<int>();
-    tb.elem_base = e->d_elem_base.as<double>();
-    tb.out_vals = e->d_ovals.as<double>();
-    tb.out_cdf = e->d_ocdf.as<double>();
-    tb.out_cnt = e->d_ocnt.as<int>();
-    tb.mo = e->mo;
-    tb.kind = e->has_kinds ? e->d_kind.as<int>() : nullptr;
-    tb.par_a = e->d_par_a.as<double>();
-    tb.par_b = e->d_par_b.as<double>();
-    return tb;
-}
-
-void epi_reserve_scenarios(sqlp_epi *e, int64_t n_local_new)
-{
-    sqlp_ctx *c = e->ctx;
-    int64_t tiles = (n_local_new + SQLP_TILE - 1) / SQLP_TILE;
-    if (tiles <= e->cap_tiles) return;
-    int64_t ncap = std::max<int64_t>(tiles, std::max<int64_t>(8, e->cap_tiles * 2));
-    int64_t used_tiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
-    size_t per_tile = (size_t)e->view->s_pad * SQLP_TILE * 8;
-    e->d_D.ensure(ncap * per_tile, used_tiles * per_tile, S(c));
-    e->d_w.ensure((size_t)ncap * SQLP_TILE * 8, (size_t)used_tiles * SQLP_TILE * 8, S(c));
-    if (e->n_T)
-        e->d_dT.ensure((size_t)ncap * SQLP_TILE * e->n_T * 8,
-                       (size_t)used_tiles * SQLP_TILE * e->n_T * 8, S(c));
-    e->cap_tiles = ncap;
-}
-
-// add_scenario! for a batch: values on host (v_host), on device (v_dev) or sampled.
-void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_dev,
-             const double *w_host, bool sample, uint64_t seed, uint64_t wseed)
-{
-    if (n_new <= 0) return;
-    sqlp_ctx *c = e->ctx;
-    const int64_t g0 = e->n_global;
-    const int64_t g1 = g0 + n_new;
-    const int64_t nl1 = local_count(g1, c->rank, c->world);
-    epi_reserve_scenarios(e, nl1);
-    // epigraph.jl:89  total_scenario_weight += weight, in scenario order
-    for (int64_t i = 0; i < n_new; ++i) {
-        double w = 1.0;
-        if (sample) { if (wseed) w = 0.5 + u01(wseed, (uint64_t)(g0 + i)); }
-        else if (w_host) w = w_host[i];
-        e->total_weight += w;
-    }
-    DeltaTables tb = delta_tables(e);
-    // algorithmic bytes: 8 s in + 8 s out per scenario (sampled: out only), this rank's share
-    ProfScope prof(c, SQLP_PROF_DELTA, (double)(nl1 - e->n_local) * e->s * (sample ? 8.0 : 16.0));
-    // host values go through a 64 MB staging buffer piece by piece; device-resident or sampled
-    // values need no staging, so the whole batch is one launch
-    const int64_t piece = (sample || v_dev) ? std::max<int64_t>(SQLP_TILE, (n_new / SQLP_TILE + 2) * SQLP_TILE)
-        : std::max<int64_t>(SQLP_TILE, ((int64_t)(64 << 20) / (8 * std::max<int64_t>(e->s, 1))) / SQLP_TILE * SQLP_TILE);
-    for (int64_t off = 0; off < n_new;) {
-        // cut pieces at 128-aligned global ordinals so a tile is never split mid-copy
-        int64_t end = std::min<int64_t>(n_new, ((g0 + off) / SQLP_TILE) * SQLP_TILE + piece - g0);
-        if (end <= off) end = std::min<int64_t>(n_new, off + piece);
-        const int64_t cnt = end - off;
-        const double *vals = nullptr, *wts = nullptr;
-        if (!sample) {
-            if (v_dev) {
-                vals = v_dev + off * e->s;
-            } else {
-                e->d_stage.ensure((size_t)cnt * (e->s + 1) * 8, 0, S(c), false);
-                if (e->s)
-                    CK(cudaMemcpyAsync(e->d_stage.p, v_host + off * e->s, (size_t)cnt * e->s * 8,
-                                       cudaMemcpyHostToDevice, S(c)));
-                vals = e->d_stage.as<double>();
-            }
-            if (w_host) {
-                if (v_dev) e->d_stage.ensure((size_t)cnt * 8, 0, S(c), false);   // weights only
-                double *dw = e->d_stage.as<double>() + (v_dev ? 0 : cnt * e->s);
-                CK(cudaMemcpyAsync(dw, w_host + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, S(c)));
-                wts = dw;
-            }
-        }
-        const int64_t gs = g0 + off;
-        const int blocks = 2 * (int)((gs + cnt - 1) / SQLP_TILE - gs / SQLP_TILE + 1);   // half tiles
-        const int slab = std::min(e->view->s_pad, SQLP_DELTA_SLAB);
-        const size_t dsmem = (size_t)SQLP_DELTA_COLS * delta_stride(slab) * 8;
-        if (!c->delta_smem_set) {
-            const int mx = SQLP_DELTA_COLS * delta_stride(SQLP_DELTA_SLAB) * 8;
-            CK(cudaFuncSetAttribute(k_delta_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-            CK(cudaFuncSetAttribute(k_delta_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-            c->delta_smem_set = true;
-        }
-        if (sample)
-            LAUNCH(c, k_delta_build<true>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
-                   (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
-                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, (unsigned long long)seed,
-                   (unsigned long long)wseed);
-        else
-            LAUNCH(c, k_delta_build<false>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
-                   (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
-                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, 0ull, 0ull);
-        if (!sample && !v_dev) CK(cudaStreamSynchronize(S(c)));   // staging buffer is reused
-        off = end;
-    }
-    e->n_global = g1;
-    e->n_local = nl1;
-}
-
-// The contraction variant used in production (see DESIGN.md for the measurements behind it).
-template <int NX>
-using ContractVariant = ContractCfg<NX, SQLP_VARIANT_MI, SQLP_VARIANT_STAGES, SQLP_VARIANT_PREFETCH, SQLP_VARIANT_CTAS,
-                                    SQLP_VARIANT_KG>;
-
-template <int NX>
-using ResidentVariant = ResidentCfg<NX, SQLP_RES_WR, SQLP_RES_MI, SQLP_RES_KG, SQLP_RES_CTAS>;
-
-// Resident-scenario kernel: returns false when one unit of scenarios plus a two-stage pool
-// ring does not fit in shared memory (very wide stochastic row sets).
-template <int NX>
-bool launch_contract_resident(sqlp_epi *e, ContractArgs &a)
-{
-    using Cfg = ResidentVariant<NX>;
-    sqlp_ctx *c = e->ctx;
-    const size_t fixed = Cfg::fixed_bytes(a.s_pad), stage = Cfg::stage_bytes();
-    int ctas = Cfg::CTAS;
-    size_t budget = 0;
-    int stages = 0;
-    for (; ctas >= 1; --ctas) {
-        budget = std::min<size_t>((size_t)c->smem_optin, ((size_t)c->smem_per_sm - 1024u * ctas) / ctas);
-        stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
-        if (stages >= 2) break;
-    }
-    if (stages < 2) return false;
-    const size_t smem = fixed + stage * stages;
-    if (c->res_smem_set[NX] < (int)smem) {
-        CK(cudaFuncSetAttribute(k_contract_resident<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->res_smem_set[NX] = (int)smem;
-    }
-    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
-    const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;   // host upper bound
-    int grid = ctas * c->sm_count;
-    if (c->contract_grid > 0) grid = c->contract_grid;
-    grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>(nunits * nchunks_ub, nunits)));
-    const size_t pieces = (size_t)grid * 2 * NX * Cfg::ROWS;
-    c->d_piece_val.ensure(pieces * 8, 0, S(c), false);
-    c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
-    a.nstages = stages;
-    a.prefetch = std::max(1, stages - 2);
-    if (c->contract_prefetch > 0) a.prefetch = std::min(c->contract_prefetch, stages - 1);
-    a.piece_val = c->d_piece_val.as<double>();
-    a.piece_idx = c->d_piece_idx.as<int>();
-    LAUNCH(c, k_contract_resident<Cfg>, grid, Cfg::THREADS, smem, a);
-    auto fixup = k_argmax_fixup<Cfg::ROWS, NX>;
-    LAUNCH(c, fixup, grid, 128, 0, a, grid);
-    return true;
-}
-
-// Warp-specialised kernel (one CTA per SM, producer warp + two consumer row groups).
-template <int NX>
-bool launch_contract_ws(sqlp_epi *e, ContractArgs &a)
-{
-    using Cfg = WsCfg<NX, SQLP_WS_KG>;
-    sqlp_ctx *c = e->ctx;
-    const size_t fixed = Cfg::fixed_bytes(a.s_pad), stage = Cfg::stage_bytes();
-    const size_t budget = std::min<size_t>((size_t)c->smem_optin, (size_t)c->smem_per_sm - 1024u);
-    const int stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
-    if (stages < 3) return false;
-    const size_t smem = fixed + stage * stages;
-    if (c->ws_smem_set[NX] < (int)smem) {
-        CK(cudaFuncSetAttribute(k_contract_ws<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->ws_smem_set[NX] = (int)smem;
-    }
-    const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
-    const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;
-    int grid = c->contract_grid > 0 ? c->contract_grid : c->sm_count;
-    grid = (int)std::max<long long>(1, std::min<long long>(grid, std::max<long long>(nunits * nchunks_ub, nunits)));
-    const size_t pieces = (size_t)grid * 2 * NX * Cfg::ROWS;
-    c->d_piece_val.ensure(pieces * 8, 0, S(c), false);
-    c->d_piece_idx.ensure(pieces * 4, 0, S(c), false);
-    a.nstages = stages;
-    a.prefetch = 0;
-    a.lag_ns = c->contract_lag_ns;
-    a.piece_val = c->d_piece_val.as<double>();
-    a.piece_idx = c->d_piece_idx.as<int>();
-    LAUNCH(c, k_contract_ws<Cfg>, grid, SQLP_WS_THREADS, smem, a);
-    auto fixup = k_argmax_fixup<Cfg::ROWS, NX>;
-    LAUNCH(c, fixup, grid, 128, 0, a, grid);
-    return true;
-}
-
-template <int NX>
-void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
-{
-    using Cfg = ContractVariant<NX>;
-    sqlp_ctx *c = e->ctx;
-    ContractArgs a;
-    a.D = D;
-    a.PiS = e->view->d_piS.as<double>();
-    a.bias = bias;
-    a.bias_stride = e->bias_stride;
-    a.d_K = e->pool->d_K.as<long long>();
-    a.s_pad = e->view->s_pad;
-    a.ntiles = (int)((e->n_local + SQLP_TILE - 1) / SQLP_TILE);
-    a.n_local = e->n_local;
-    a.best_val = bv;
-    a.best_idx = bi;
-    a.out_stride = e->out_stride;
-    a.nstages = a.prefetch = a.lag_ns = 0;
-    a.piece_val = nullptr;
-    a.piece_idx = nullptr;
-    ProfScope prof(c, SQLP_PROF_CONTRACT, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
-    bool done = false;
-    // automatic: warp-specialised -> resident (fewer ring stages suffice) -> streaming (any s_pad)
-    if (c->contract_mode == 0 || c->contract_mode == 3) done = launch_contract_ws<NX>(e, a);
-    if (!done && c->contract_mode != 1) done = launch_contract_resident<NX>(e, a);
-
-    if (!done) {   // streaming kernel: both operands flow through the ring
-        size_t smem = Cfg::smem_bytes();
-        if (!c->smem_attr[NX]) {   // per device, so per context
-            CK(cudaFuncSetAttribute(k_contract_argmax<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-            c->smem_attr[NX] = true;
-        }
-        const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
-        int grid = (int)std::min<long long>(nunits, (long long)Cfg::CTAS * c->sm_count);
-        LAUNCH(c, k_contract_argmax<Cfg>, grid, SQLP_CT_THREADS, smem, a);
-    }
-    prof.stop();
-}
-
-// Everything of build_sasa_cut for NX points, enqueued on the stream.  x on host or device.
-// Result lands in e->d_out as [NX][n1 + 2] = (alpha, beta[n1], val).
-void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x_dev, bool want_cut)
-{
-    sqlp_ctx *c = e->ctx;
-    sqlp_pool *p = e->pool;
-    const int n1 = (int)e->n1, m2 = (int)e->m2;
-    const int NC = n1 + 2;
-    e->d_x2.ensure((size_t)2 * std::max(n1, 1) * 8, 0, S(c));
-    e->d_out.ensure((size_t)2 * NC * 8, 0, S(c));
-    e->d_flags.ensure(16, 0, S(c));
-    if (x_host)
-        CK(cudaMemcpyAsync(e->d_x2.p, x_host, (size_t)NX * n1 * 8, cudaMemcpyHostToDevice, S(c)));
-    else
-        CK(cudaMemcpyAsync(e->d_x2.p, x_dev, (size_t)NX * n1 * 8, cudaMemcpyDeviceToDevice, S(c)));
-    CK(cudaMemsetAsync(e->d_flags.p, 0, 4, S(c)));
-    CK(cudaMemsetAsync(e->d_out.p, 0, (size_t)2 * NC * 8, S(c)));
-
-    view_sync(p, e->view);
-    if (want_cut) epi_tables_sync(e);
-
-    const int64_t ku = p->upper();
-    const int64_t kpad = round_up(std::max<int64_t>(ku, 1), SQLP_TILE);
-    if (kpad > e->bias_stride) {
-        e->bias_stride = round_up(kpad * 2, SQLP_TILE);
-        e->d_bias.ensure((size_t)2 * e->bias_stride * 8, 0, S(c), false);
-    }
-    const int64_t ntiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
-    if (ntiles * SQLP_TILE > e->out_stride) {
-        e->out_stride = round_up(ntiles * SQLP_TILE * 2, SQLP_TILE);
-        e->d_best_val.ensure((size_t)2 * e->out_stride * 8, 0, S(c), false);
-        e->d_best_idx.ensure((size_t)2 * e->out_stride * 4, 0, S(c), false);
-    }
-    e->d_base.ensure((size_t)2 * m2 * 8, 0, S(c));
-
-    if (ntiles > 0) {
-        ProfScope prof_bias(c, SQLP_PROF_BIAS, 8.0 * (double)ku * m2 + 8.0 * NX * (double)ku);
-        LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
-               e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
-               e->d_x2.as<double>(), e->d_base.as<double>());
-        int bgrid = (int)((kpad + 7) / 8);
-        if (NX == 2)
-            LAUNCH(c, k_bias<2>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
-                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
-                   (long long)e->bias_stride);
-        else
-            LAUNCH(c, k_bias<1>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
-                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
-                   (long long)e->bias_stride);
-
-        prof_bias.stop();
-
-        if (e->n_T == 0) {
-            if (NX == 2)
-                launch_contract<2>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
-                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
-            else
-                launch_contract<1>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
-                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
-        } else {
-            // some element perturbs Tbar: d(x) = delta_rhs - delta_T x is rebuilt per point
-            size_t bytes = (size_t)ntiles * e->view->s_pad * SQLP_TILE * 8;
-            e->d_Dx.ensure(bytes, 0, S(c), false);
-            TransferList tl{e->n_T, e->d_tj.as<int>(), e->d_tcol.as<int>(), e->d_tslot.as<int>()};
-            for (int x = 0; x < NX; ++x) {
-                CK(cudaMemcpyAsync(e->d_Dx.p, e->d_D.p, bytes, cudaMemcpyDeviceToDevice, S(c)));
-                LAUNCH(c, k_delta_x, (int)((e->n_local + 255) / 256), 256, 0, tl,
-                       e->d_x2.as<double>() + (size_t)x * n1, (long long)e->n_local, e->view->s_pad,
-                       e->d_D.as<double>(), e->d_dT.as<double>(), e->d_Dx.as<double>());
-                launch_contract<1>(e, e->d_Dx.as<double>(), e->d_bias.as<double>() + x * e->bias_stride,
-                                   e->d_best_val.as<double>() + x * e->out_stride,
-                                   e->d_best_idx.as<int>() + x * e->out_stride);
-            }
-        }
-    }
-    if (!want_cut) return;
-    e->last_nx = NX;
-
-    const int width = NX * NC;
-    if (ntiles > 0) {
-        e->d_partial.ensure((size_t)ntiles * width * 8, 0, S(c), false);
-        ReduceArgs r;
-        r.D = e->d_D.as<double>();
-        r.dT = e->d_dT.as<double>();
-        r.w = e->d_w.as<double>();
-        r.PiS = e->view->d_piS.as<double>();
-        r.rt = e->d_rt.as<double>();
-        r.best_val = e->d_best_val.as<double>();
-        r.best_idx = e->d_best_idx.as<int>();
-        r.out_stride = e->out_stride;
-        r.n_local = e->n_local;
-        r.s_pad = e->view->s_pad;
-        r.n_rows = e->view->n_rows;
-        r.n1 = n1;
-        r.total_weight = e->total_weight;
-        r.n_T = e->n_T;
-        r.tc_col = e->d_cc.as<int>();
-        r.tc_j = e->d_cj.as<int>();
-        r.tc_slot = e->d_cslot.as<int>();
-        r.partial = e->d_partial.as<double>();
-        r.flags = e->d_flags.as<int>();
-        // algorithmic bytes: per point N (idx + weight + winning dot) + the (rho, tau)
-        // table + the cut; the implementation also re-reads D (8 s_pad N) to recompute the winning dot
-        ProfScope prof_red(c, SQLP_PROF_REDUCE,
-                           NX * (24.0 * (double)e->n_local + 8.0 * (double)ku * (n1 + 1) + 8.0 * (n1 + 1)));
-        if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, 0, r);
-        else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, 0, r);
-        const int group = 64;
-        int64_t ng = (ntiles + group - 1) / group;
-        e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
-        LAUNCH(c, k_sum_groups, (int)ng, 256, 0, e->d_partial.as<double>(), (long long)ntiles, group,
-               width, e->d_partial2.as<double>());
-        LAUNCH(c, k_sum_groups, 1, 256, 0, e->d_partial2.as<double>(), (long long)ng, (int)ng, width,
-               e->d_out.as<double>());
-        prof_red.stop();
-    }
-    if (c->world > 1) {
-        // per-epigraph partials are all-gathered and summed in fixed rank order
-        e->d_gather.ensure((size_t)c->world * width * 8, 0, S(c));
-        NK(g_nccl.AllGather(e->d_out.p, e->d_gather.p, (size_t)width, ncclFloat64_, c->comm, S(c)));
-        LAUNCH(c, k_rank_sum, (width + 127) / 128, 128, 0, e->d_gather.as<double>(), c->world, width,
-               e->d_out.as<double>());
-    }
-}
-
-struct CutHost {
-    std::vector<double> out;
-    int flags = 0;
-};
-
-void epi_cuts_fetch(sqlp_epi *e, int NX, CutHost &h)
-{
-    const int NC = (int)e->n1 + 2;
-    h.out.resize((size_t)NX * NC);
-    CK(cudaMemcpyAsync(h.out.data(), e->d_out.p, (size_t)NX * NC * 8, cudaMemcpyDeviceToHost, S(e->ctx)));
-    CK(cudaMemcpyAsync(&h.flags, e->d_flags.p, 4, cudaMemcpyDeviceToHost, S(e->ctx)));
-}
-
-// ---- device cut list -------------------------------------------------------------------------
-void cuts_reserve(sqlp_epi *e, int64_t need)
-{
-    if (need <= e->cuts_cap) return;
-    const size_t RS = (size_t)e->n1 + 2;
-    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(64, e->cuts_cap * 2));
-    e->d_cuts.ensure((size_t)ncap * RS * 8, (size_t)e->n_cuts * RS * 8, S(e->ctx));
-    e->d_inc.ensure(RS * 8, 0, S(e->ctx));
-    e->d_prev_inc.ensure(RS * 8, 0, S(e->ctx));
-    e->cuts_cap = ncap;
-}
-
-CutList cut_list(sqlp_epi *e, bool last)
-{
-    CutList L;
-    L.cuts = e->d_cuts.as<double>();
-    L.n = (int)(last ? e->n_last : e->n_cuts);
-    L.inc = last ? (e->has_prev_inc ? e->d_prev_inc.as<double>() : nullptr)
-                 : (e->has_inc ? e->d_inc.as<double>() : nullptr);
-    return L;
-}
-
-// est[0 .. nlists * NX): weighted value of the current (and snapshot) approximation at NX device points
-void cuts_evaluate_enqueue(sqlp_epi *e, const double *d_x, int NX, int nlists, double *d_est)
-{
-    sqlp_ctx *c = e->ctx;
-    cuts_reserve(e, 1);
-    LAUNCH(c, k_cuts_evaluate, 1, 256, 0, cut_list(e, false), cut_list(e, true), nlists, d_x, NX, (int)e->n1,
-           e->total_weight, e->lower_bound, e->objective_weight, d_est);
-}
-
-void check_sense(int32_t sense)
-{
-    REQUIRE(sense == SQLP_MIN_SENSE || sense == SQLP_MAX_SENSE, SQLP_E_INVALID, "bad sense");
-    REQUIRE(sense == SQLP_MIN_SENSE, SQLP_E_UNSUPPORTED,
-            "MAX_SENSE is unsupported: the reference's MAX branch never selects a vertex");
-}
-
-}  // namespace
+#include "host_base.cuh"
+#include "host_pool.cuh"
+#include "host_epi.cuh"
 
 // ================================================================ C ABI =================
 extern "C" {
