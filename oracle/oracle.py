@@ -1,8 +1,12 @@
 """ctypes front-end of ``oracle/sqlp_oracle.c`` (TEST INFRASTRUCTURE ONLY).
 
 The C file restates the reference's Julia hot path line by line (citations in its
-header).  This module only marshals numpy arrays into it.  Parity status: pinned on
-the reference's own lands-sized test vectors, unpinned beyond (no Julia in the image).
+header).  This module marshals numpy arrays into it and adds three plain-Python
+restatements that need no C: the cut bookkeeping next to the path (``cut_evaluate``,
+``cut_master_rows``, ``cut_check_improvement``: epigraph.jl:101-117,177-220, cell.jl:163-202,
+improvement.jl:19-49) and the host twin of the device sampler (``sample_twin``,
+smps_sto.jl:113-149).  Parity status: pinned on the reference's own lands-sized test
+vectors (tests/test_oracle_golden.py), unpinned beyond (no Julia in the image).
 """
 from __future__ import annotations
 

@@ -195,3 +195,23 @@ def test_counter_rng_twin(oracle):
     a = oracle.u01(9, idx)
     b = [oracle.lib().orc_u01(9, int(i)) for i in idx]
     assert list(a) == b and (a >= 0).all() and (a < 1).all()
+
+
+def test_cut_bookkeeping_known_answers(oracle):     # sd_test.jl:166-194
+    """The oracle's restatement of evaluate_epigraph / sync_cuts! rows against the reference's
+    own numbers: two epigraphs of weight 0.5 (lower bounds 0 and 100), total scenario weight 2."""
+    cut1 = (1.0, np.array([2.0, 3, 4, 5]), 1.0)
+    cut2 = (6.0, np.array([7.0, 8, 9, 10]), 2.0)
+    inc = (11.0, np.array([12.0, 13, 14, 15]), 1.0)
+    x10 = np.full(4, 10.0)
+    assert oracle.cut_evaluate([cut1, cut2], inc, x10, 2.0, 0.0, 0.5) == 551.0 * 0.5
+    assert oracle.cut_evaluate([cut1], None, x10, 2.0, 100.0, 0.5) == (141 / 2 + 100 / 2) * 0.5
+    assert oracle.cut_evaluate([cut1], None, -np.ones(4), 2.0, 100.0, 0.5) == 100.0 * 0.5
+    rows = oracle.cut_master_rows([cut1], None, 2.0, 100.0)
+    assert rows[0, 0] == 50.5                                                  # 100 * 0.5 + 1.0 * 0.5
+    rows = oracle.cut_master_rows([cut1, cut2], inc, 2.0, 0.0)
+    assert rows.shape == (3, 5) and (rows[2] == [11, 12, 13, 14, 15]).all() and (rows[1] == [6, 7, 8, 9, 10]).all()
+    last = [([cut1], None, 2.0, 0.0, 1.0)]
+    cur = [([cut1, cut2], inc, 2.0, 0.0, 1.0)]
+    cand, incv, req, improved = oracle.cut_check_improvement(last, cur, x10, np.zeros(4), np.ones(4))
+    assert cand == 551.0 + 40.0 and incv == 11.0 and req == 0.2 * ((0.5 * 141 + 40.0) - 0.5) and improved is False
