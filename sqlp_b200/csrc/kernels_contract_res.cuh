@@ -6,7 +6,7 @@
 // scenarios fits in shared memory next to the pool ring, the streaming kernel of
 // kernels_contract.cuh stays as the fallback for very wide stochastic row sets.
 //
-// What changed against the streaming kernel, and why (profiles/r02_contract_v6_source.txt):
+// What changed against the streaming kernel, and why (profiles/r01d_contract_source_regions.txt):
 //   * the per-item bookkeeping (cursor arithmetic + 5..7 bulk copies per pipeline item) took
 //     14 % of every warp's time.  Here the D sub-tile of a unit (ROWS scenarios x s_pad slots,
 //     61 KB at storm) is loaded ONCE per unit and stays resident while every vertex chunk
