@@ -150,6 +150,68 @@ __global__ void __launch_bounds__(THR) k_dmma_tile_lds(double *out, const double
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// How much DMMA throughput a sub-partition loses while its OTHER warp runs the contraction's
+// epilogue instruction mix (DADD + DSETP + selects on 64 independent values per point):
+// warps 0-3 issue DMMA chains, warps 4-7 (one per sub-partition) run MODE: 0 nothing, 1 DADD only,
+// 2 DADD + DSETP + FSEL/SEL (running max with index).  Both sides loop for a fixed count; the
+// kernel's time is the DMMA warps' time as long as the scalar side is shorter.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dmma_vs_scalar(double *out, const double *in, int scalar_iters)
+{
+    const int warp = threadIdx.x >> 5;
+    if (warp < 4) {
+        double c[32][2], a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = in[threadIdx.x % 32 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b[i] = in[64 + threadIdx.x % 16 + i];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { c[i][0] = i; c[i][1] = threadIdx.x; }
+        for (int it = 0; it < ITERS / 4; ++it) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a[i >> 2]), "d"(b[i & 3]));
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += c[i][0] + c[i][1];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (MODE > 0) {
+        double v[16], best[4];
+        int bidx[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = in[threadIdx.x % 32 + i] + i;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) best[i] = -1e300;
+        for (int it = 0; it < scalar_iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = v[i] + 1.0000001;                       // DADD
+                if (MODE == 2 && v[i] > best[i & 3]) {         // DSETP + FSEL x2 + SEL
+                    best[i & 3] = v[i];
+                    bidx[i & 3] = it * 16 + i;
+                }
+                if (MODE == 3) {   // the same running max on order-preserving integer keys (no DSETP)
+                    long long b = __double_as_longlong(v[i]);
+                    long long key = b ^ ((b >> 63) & 0x7fffffffffffffffll);
+                    long long bk = __double_as_longlong(best[i & 3]);   // best[] holds keys in this mode
+                    if (key > bk) {
+                        best[i & 3] = __longlong_as_double(key);
+                        bidx[i & 3] = it * 16 + i;
+                    }
+                }
+            }
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += v[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s += best[i] + bidx[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    }
+}
+
 // m16n8k16 f64 (sm_90+ shape): A 16x16 (8 regs/thread), B 16x8 (4 regs), C 16x8 (4 regs)
 __global__ void __launch_bounds__(256) k_dmma16(double *out, double a, double b)
 {
@@ -218,6 +280,22 @@ int main()
         measure("dmma_tile32_lds_fed_1warp_per_subpartition", f * 4, [&] { k_dmma_tile_lds<128><<<sms, 128>>>(out, in); });
         measure("dmma_tile32_lds_fed_2warp_per_subpartition", f * 8, [&] { k_dmma_tile_lds<256><<<sms, 256>>>(out, in); });
         measure("dmma_tile32_lds_fed_4warp_per_subpartition", f * 16, [&] { k_dmma_tile_lds<512><<<sms, 512>>>(out, in); });
+    }
+    {
+        double *in; CK(cudaMalloc(&in, 1024)); CK(cudaMemset(in, 0, 1024));
+        const double f = 2.0 * 256 * 32 * (ITERS / 4) * sms * 4;   // four DMMA warps per SM
+        // scalar side: 16 values per iteration; the DMMA side runs 32 * ITERS/4 DMMAs = 16 * 8192 cycles
+        for (int frac = 0; frac < 3; ++frac) {
+            const int iters = frac == 0 ? 0 : (frac == 1 ? 512 : 1024);
+            char name[96];
+            snprintf(name, sizeof name, "dmma_1warp_plus_dadd_x%d_per_lane", iters * 16);
+            if (iters) measure(name, f, [&] { k_dmma_vs_scalar<1><<<sms, 256>>>(out, in, iters); });
+            snprintf(name, sizeof name, "dmma_1warp_plus_argmax_x%d_per_lane", iters * 16);
+            if (iters) measure(name, f, [&] { k_dmma_vs_scalar<2><<<sms, 256>>>(out, in, iters); });
+            snprintf(name, sizeof name, "dmma_1warp_plus_intkey_argmax_x%d_per_lane", iters * 16);
+            if (iters) measure(name, f, [&] { k_dmma_vs_scalar<3><<<sms, 256>>>(out, in, iters); });
+            if (!iters) measure("dmma_1warp_alone", f, [&] { k_dmma_vs_scalar<0><<<sms, 256>>>(out, in, 0); });
+        }
     }
     measure("dmma_m8n8k4", 2.0 * 256 * MMA_CHAINS * ITERS * 8.0 * grid, [&] { k_dmma<<<grid, 256>>>(out, 1.0000001, 1e-9); });
     measure("dmma_m16n8k16", 2.0 * 16 * 8 * 16 * MMA_CHAINS * (ITERS / 4) * 8.0 * grid, [&] { k_dmma16<<<grid, 256>>>(out, 1.0000001, 1e-9); });
