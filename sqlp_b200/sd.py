@@ -280,36 +280,50 @@ def sync_cuts(cell: sdCell):
 
 def solve_master(cell: sdCell, x0, rho: float):
     """``add_regularization!`` + ``optimize!`` (cell.jl:128-132, algorithm.jl:100-112):
-    min cost.x + sum_e w_e eta_e + rho/2 |x - x0|^2 over the first-stage rows and the cut rows."""
+    min cost.x + sum_e w_e eta_e + rho/2 |x - x0|^2 over the first-stage rows and the cut rows.
+
+    Solved in coordinates centred on the proximal point, x = x0 + d and eta_e = eta0_e + zeta_e with
+    eta0_e the value of epigraph e's rows at x0, so that the right-hand sides handed to the QP solver
+    are differences of cut values instead of the cuts' absolute level (1e5..1e6 on baa99-20, where the
+    uncentred model makes HiGHS's active-set QP solver fail).  Multipliers are unchanged by the shift."""
     hc = _highs()
     fs = cell.first_stage
     n1, E = len(fs.cost), len(cell.epi)
     x0 = np.asarray(x0, float)
     ncol = n1 + E
-    rows_A = [np.hstack([fs.A, np.zeros((fs.A.shape[0], E))])] if fs.A.size else []
-    lo, up = list(fs.row_lower), list(fs.row_upper)
-    for i, block in enumerate(cell.cut_rows):              # eta_i - beta.x >= alpha
+    inf = hc.kHighsInf
+    rows_A, lo, up = [], [], []
+    if fs.A.size:
+        Ax0 = fs.A @ x0
+        rows_A.append(np.hstack([fs.A, np.zeros((fs.A.shape[0], E))]))
+        lo += list(fs.row_lower - Ax0)
+        up += list(fs.row_upper - Ax0)
+    eta0 = np.zeros(E)
+    for i, block in enumerate(cell.cut_rows):              # zeta_i - beta.d >= (alpha + beta.x0) - eta0_i
         if len(block) == 0:
             continue
+        at_x0 = block[:, 0] + block[:, 1:] @ x0
+        eta0[i] = at_x0.max()
         R = np.zeros((len(block), ncol))
         R[:, :n1] = -block[:, 1:]
         R[:, n1 + i] = 1.0
         rows_A.append(R)
-        lo += list(block[:, 0])
-        up += [hc.kHighsInf] * len(block)
+        lo += list(at_x0 - eta0[i])
+        up += [np.inf] * len(block)
     A = np.vstack(rows_A) if rows_A else np.zeros((0, ncol))
+    lo, up = np.asarray(lo, float), np.asarray(up, float)
     model = hc.HighsModel()
     lp = model.lp_
     lp.num_col_, lp.num_row_ = ncol, A.shape[0]
-    lp.col_cost_ = np.concatenate([fs.cost - rho * x0, [e.objective_weight for e in cell.epi]])
-    inf = hc.kHighsInf
-    lp.col_lower_ = np.concatenate([np.where(np.isinf(fs.x_lower), -inf, fs.x_lower), np.full(E, -inf)])
-    lp.col_upper_ = np.concatenate([np.where(np.isinf(fs.x_upper), inf, fs.x_upper), np.full(E, inf)])
-    lp.row_lower_ = np.where(np.isinf(lo), -inf, np.asarray(lo, float)) if len(lo) else np.zeros(0)
-    lp.row_upper_ = np.where(np.isinf(up), inf, np.asarray(up, float)) if len(up) else np.zeros(0)
+    lp.col_cost_ = np.concatenate([fs.cost, [e.objective_weight for e in cell.epi]])
+    lp.col_lower_ = np.concatenate([np.where(np.isinf(fs.x_lower), -inf, fs.x_lower - x0), np.full(E, -inf)])
+    lp.col_upper_ = np.concatenate([np.where(np.isinf(fs.x_upper), inf, fs.x_upper - x0), np.full(E, inf)])
+    lp.row_lower_ = np.where(np.isinf(lo), -inf, lo) if len(lo) else np.zeros(0)
+    lp.row_upper_ = np.where(np.isinf(up), inf, up) if len(up) else np.zeros(0)
     M = lp.a_matrix_
     M.format_ = hc.MatrixFormat.kRowwise
     M.num_col_, M.num_row_ = ncol, A.shape[0]
+    A = np.where(np.abs(A) <= 1e-9, 0.0, A)                # what HiGHS would drop with a warning
     nzr, nzc = np.nonzero(A)
     M.start_ = np.concatenate([[0], np.cumsum(np.bincount(nzr, minlength=A.shape[0]))]).astype(np.int32)
     M.index_ = nzc.astype(np.int32)
@@ -322,12 +336,13 @@ def solve_master(cell: sdCell, x0, rho: float):
     H.value_ = np.full(n1, float(rho))
     h = hc._Highs()
     h.setOptionValue("output_flag", False)
-    if h.passModel(model) != hc.HighsStatus.kOk or h.run() != hc.HighsStatus.kOk \
+    ok = (hc.HighsStatus.kOk, hc.HighsStatus.kWarning)
+    if h.passModel(model) not in ok or h.run() not in ok \
             or h.getModelStatus() != hc.HighsModelStatus.kOptimal:
         cell.master_solved = False
         raise RuntimeError(f"master QP not solved: {h.getModelStatus()}")
     sol = h.getSolution()
-    xv = np.asarray(sol.col_value)
+    dv = np.asarray(sol.col_value)
     rd = np.asarray(sol.row_dual)
     at = fs.A.shape[0] if fs.A.size else 0
     for i, epi in enumerate(cell.epi):
@@ -338,8 +353,10 @@ def solve_master(cell: sdCell, x0, rho: float):
         cell.cut_duals[i] = d[:nb - ninc].copy()
         cell.incumbent_cut_dual[i] = float(d[-1]) if ninc else None
     cell.master_solved = True
-    cell.master_objective = float(h.getInfo().objective_function_value) + 0.5 * rho * _dot(x0, x0)
-    return xv[:n1].copy(), xv[n1:].copy()
+    eta = eta0 + dv[n1:]
+    cell.master_objective = float(h.getInfo().objective_function_value) + _dot(fs.cost, x0) + \
+        float(np.dot([e.objective_weight for e in cell.epi], eta0))
+    return x0 + dv[:n1], eta
 
 
 # ---------------------------------------------------------------- one SD iteration ------
