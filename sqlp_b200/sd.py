@@ -158,6 +158,22 @@ def _highs():
     return hc
 
 
+_highs_scheduler_reset = False
+
+
+def _single_thread_highs(h):
+    """These LPs and QPs have tens of variables; on a many-core host HiGHS's task scheduler costs
+    ~50x the solve (80 ms against 1.6 ms per master QP on the 100+-core GPU box).  The scheduler is
+    process-global and refuses a thread count that differs from the one it was started with, so it
+    is reset once and every model of this module then asks for one thread (scipy's linprog, which
+    leaves the option at 0 = "whatever is running", follows)."""
+    global _highs_scheduler_reset
+    if not _highs_scheduler_reset:
+        h.resetGlobalScheduler(True)
+        _highs_scheduler_reset = True
+    h.setOptionValue("threads", 1)
+
+
 @dataclass
 class FirstStage:
     """Root-stage template: min cost.x  s.t.  row_lower <= A x <= row_upper, x_lower <= x <= x_upper."""
@@ -336,6 +352,7 @@ def solve_master(cell: sdCell, x0, rho: float):
     H.value_ = np.full(n1, float(rho))
     h = hc._Highs()
     h.setOptionValue("output_flag", False)
+    _single_thread_highs(h)
     ok = (hc.HighsStatus.kOk, hc.HighsStatus.kWarning)
     if h.passModel(model) not in ok or h.run() not in ok \
             or h.getModelStatus() != hc.HighsModelStatus.kOptimal:

@@ -73,7 +73,16 @@ def main():
         idx = np.minimum((u[:, None] >= cdf).sum(axis=1), cnt - 1)
         return vals[np.arange(s), idx]
 
-    t_lp = t_cut = 0.0
+    t_lp = t_master = 0.0
+    solve_master = sd.solve_master
+
+    def timed_master(*a, **k):
+        nonlocal t_master
+        t = time.perf_counter()
+        out = solve_master(*a, **k)
+        t_master += time.perf_counter() - t
+        return out
+    sd.solve_master = timed_master
     t0 = time.perf_counter()
     for it in range(1, args.iterations + 1):
         def solve(i, x, v):
@@ -89,7 +98,8 @@ def main():
                   f"repl={info.is_improved!s:5s} dual={len(dvs):4d} cuts={len(cell.epi[0].cuts):3d} "
                   f"|x_inc - x_cand|={np.linalg.norm(cell.x_incumbent - cell.x_candidate):.3e}", flush=True)
     wall = time.perf_counter() - t0
-    print(f"done: {args.iterations} iterations in {wall:.2f} s (second-stage LPs {t_lp:.2f} s); "
+    print(f"done: {args.iterations} iterations in {wall:.2f} s (second-stage LPs {t_lp:.2f} s, master QPs "
+          f"{t_master:.2f} s, cut formation + bookkeeping through the library {wall - t_lp - t_master:.2f} s); "
           f"kernels launched: {dvs.ctx.launch_count()}")
     print("x_incumbent =", np.array2string(cell.x_incumbent, precision=4, max_line_width=120))
 
