@@ -54,26 +54,38 @@ def parse():
 # ---------------------------------------------------------------- workload ---------------
 
 def load_instance(name):
-    if name.startswith("synth"):
-        return synthetic_instance(int(name[5:] or 128))
+    if name.startswith("synth"):   # synth<s> or synth<s>T<n_T>
+        body = name[5:] or "128"
+        s_, _, t_ = body.partition("T")
+        return synthetic_instance(int(s_), int(t_ or 0))
     z = dict(np.load(os.path.join(ROOT, "tests", "golden", "instances", f"{name}.npz")))
     return z
 
 
-def synthetic_instance(s):
+def synthetic_instance(s, n_T=0):
     """The storm-shaped synthetic template of SURVEY.md 8(d) C5: m2 = 4 s rows of which the first s
-    are stochastic (RHS only), n1 = s, Tbar = one -1 per first-stage column on rows s..2s-1,
-    rbar_j = 100 + 400 u(6, j) on the stochastic rows, five equiprobable outcomes rbar_j * {0.8..1.2}."""
+    are stochastic (RHS), n1 = s, Tbar = one -1 per first-stage column on rows s..2s-1,
+    rbar_j = 100 + 400 u(6, j) on the stochastic rows, five equiprobable outcomes rbar_j * {0.8..1.2}.
+    With n_T > 0 (the "delta-T variant") n_T stored entries of Tbar are random too, UNIFORM on
+    Tbar * (0.9 .. 1.1): the path no shipped instance exercises (d depends on x, one contraction per point)."""
     m2, n1 = 4 * s, s
     rbar = np.zeros(m2)
     rbar[:s] = 100.0 + 400.0 * u01(6, np.arange(s))
     fac = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
-    return {"m2": np.int64(m2), "n1": np.int64(n1), "rbar": rbar,
-            "T_colptr": np.arange(n1 + 1, dtype=np.int64), "T_rowval": np.arange(s, 2 * s, dtype=np.int64),
-            "T_nzval": -np.ones(n1), "pos_row": np.arange(s, dtype=np.int32),
-            "pos_col": -np.ones(s, dtype=np.int32), "out_vals": rbar[:s, None] * fac[None, :],
-            "out_cdf": np.tile(np.cumsum(np.full(5, 0.2)), (s, 1)), "out_cnt": np.full(s, 5, dtype=np.int32),
-            "pool": np.zeros((0, m2)), "x_ev": 10.0 * u01(3, np.arange(n1)), "x_alt": 10.0 * u01(5, np.arange(n1))}
+    tcols = (np.arange(n_T) * max(1, s // max(n_T, 1))) % n1
+    ne = s + n_T
+    out_vals = np.ones((ne, 5)); out_vals[:s] = rbar[:s, None] * fac[None, :]
+    z = {"m2": np.int64(m2), "n1": np.int64(n1), "rbar": rbar,
+         "T_colptr": np.arange(n1 + 1, dtype=np.int64), "T_rowval": np.arange(s, 2 * s, dtype=np.int64),
+         "T_nzval": -np.ones(n1), "pos_row": np.concatenate([np.arange(s), s + tcols]).astype(np.int32),
+         "pos_col": np.concatenate([-np.ones(s), tcols]).astype(np.int32), "out_vals": out_vals,
+         "out_cdf": np.tile(np.cumsum(np.full(5, 0.2)), (ne, 1)), "out_cnt": np.full(ne, 5, dtype=np.int32),
+         "pool": np.zeros((0, m2)), "x_ev": 10.0 * u01(3, np.arange(n1)), "x_alt": 10.0 * u01(5, np.arange(n1))}
+    if n_T:
+        z["kind"] = np.concatenate([np.zeros(s), np.full(n_T, 2)]).astype(np.int32)
+        z["par_a"] = np.concatenate([np.zeros(s), np.full(n_T, -1.1)])
+        z["par_b"] = np.concatenate([np.zeros(s), np.full(n_T, -0.9)])
+    return z
 
 
 def u01(seed, idx):
@@ -105,8 +117,13 @@ def sample_values(z, seed, g0, n):
     u = u01(seed, (g[:, None] * np.uint64(s) + np.arange(s, dtype=np.uint64)[None, :]))
     idx = (u[:, :, None] >= z["out_cdf"][None, :, :]).sum(axis=2)
     idx = np.minimum(idx, np.maximum(z["out_cnt"][None, :] - 1, 0))
-    return np.take_along_axis(np.broadcast_to(z["out_vals"], (n,) + z["out_vals"].shape),
-                              idx[:, :, None], 2)[:, :, 0].copy()
+    out = np.take_along_axis(np.broadcast_to(z["out_vals"], (n,) + z["out_vals"].shape),
+                             idx[:, :, None], 2)[:, :, 0].copy()
+    if "kind" in z:   # UNIFORM elements: left + (right - left) * ((bits + 1/2) / 2^53), like the device
+        uo = u - (0.0) + 0.5 / 9007199254740992.0
+        cont = z["kind"] == 2
+        out[:, cont] = z["par_a"][cont] + (z["par_b"][cont] - z["par_a"][cont]) * uo[:, cont]
+    return out
 
 
 # ---------------------------------------------------------------- clocks -----------------
@@ -268,6 +285,8 @@ def run_ours(args):
     for e in range(E):
         epi = T.sdEpigraph(coef, 1.0 / E, 0.0, dvs)
         epi.set_outcomes(z["out_vals"], z["out_cdf"], z["out_cnt"])
+        if "kind" in z:
+            epi.set_distributions(z["kind"], z["par_a"], z["par_b"])
         epi.sample_scenarios(n_epi_global, seed=101 + e, weight_seed=201 + e)
         epis.append(epi)
     ctx.synchronize()
