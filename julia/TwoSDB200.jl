@@ -94,6 +94,8 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
             $context(), $pool_of(dvs, length(r)), length(r), size(Tm, 2), length(ridx), ridx, rval,
             colptr, rowval, nzval, length(rows), rows, cols, out))
         $EPIS[epi] = out[]
+        $check(ccall((:sqlp_epi_set_weights, $LIB[]), Int32, (Ptr{Cvoid}, Float64, Float64), out[],
+                     epi.objective_weight, epi.lower_bound))
         $DELTA_OWNER[epi.scenario_delta] = epi
         finalizer(e -> ccall((:sqlp_epi_destroy, $LIB[]), Int32, (Ptr{Cvoid},), $EPIS[e]), epi)
         return epi
@@ -153,6 +155,35 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
                      $EPIS[epi], x_cand, x_inc, alpha, beta, wm, C_NULL))
         return sdCut(alpha[1], beta[:, 1], wm[]), sdCut(alpha[2], beta[:, 2], wm[])
     end
+    # --- optional: the cut list on the device (SURVEY.md 8(f) N1 / N3) ----------------------------
+    # After build_two_cuts: take both cuts into the device list without a host round trip, ask the
+    # device for the incumbent test, and fetch the master rows of sync_cuts! as one dense block.
+    @eval T function commit_cuts!(epi::sdEpigraph; with_incumbent::Bool = true)
+        $check(ccall((:sqlp_epi_cuts_commit, $LIB[]), Int32, (Ptr{Cvoid}, Int32), $EPIS[epi], Int32(with_incumbent)))
+        return
+    end
+    @eval T function delete_cuts!(epi::sdEpigraph, delete_index::Vector{Int})      # deleteat!(epi.cuts, ...)
+        idx = Int64.(delete_index .- 1)
+        $check(ccall((:sqlp_epi_cuts_delete, $LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}), $EPIS[epi], length(idx), idx))
+        return
+    end
+    @eval T function check_improvement_device(cell::sdCell, cost::Vector{Float64})
+        handles = Ptr{Cvoid}[$EPIS[epi] for epi in cell.epi]
+        out = zeros(4)
+        $check(ccall((:sqlp_cell_check_improvement, $LIB[]), Int32,
+                     (Int32, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                     length(handles), handles, cell.x_candidate, cell.x_incumbent, cost, INCUMBENT_SELECTION_Q, out))
+        return sdImprovementInfo(out[1], out[2], out[3], out[4] != 0.0)
+    end
+    @eval T function master_rows(epi::sdEpigraph)      # rows of sync_cuts!: [alpha' beta'] per cut, incumbent last
+        n = Ref{Int64}(0)
+        $check(ccall((:sqlp_epi_master_rows, $LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), $EPIS[epi], C_NULL, n))
+        rows = zeros(length(epi.subproblem_coef.col_lookup) + 1, n[])      # column-major: one column per cut row
+        n[] > 0 && $check(ccall((:sqlp_epi_master_rows, $LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}),
+                                $EPIS[epi], rows, n))
+        return rows
+    end
+
     # --- rand(sto) on the device for a batch (smps_sto.jl:113-149; SURVEY.md 8(f) N2) -------------
     # Outcome tables / distribution parameters are uploaded once, in position-table order; the
     # scenarios never visit the host, so the host-side scenario_list is NOT extended here.
