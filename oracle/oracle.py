@@ -233,9 +233,12 @@ def score_pair(P: Problem, values, x, vertex):
 
 def build_sasa_cut(P: Problem, values, weights, x, pool, total_weight=None, forced_idx=None):
     """Returns dict(alpha, beta, weight_mark, val, max_val, max_idx, status)."""
-    values = _f64(values).reshape(-1, max(P.s, 1))
-    N = len(values)
     weights = _f64(weights)
+    if P.s:
+        values = _f64(values).reshape(-1, P.s)
+        N = len(values)
+    else:                      # no random element: the scenarios differ by their weights only
+        values, N = np.zeros(1), len(weights)
     x, pool = _f64(x), _f64(pool).reshape(-1, P.m2)
     if total_weight is None:
         total_weight = 0.0

@@ -550,3 +550,30 @@ def test_device_profiler_classes(T, oracle):
     assert prof["reduce"][1] == 1 and prof["pool"][1] == 1 and prof["bias"][1] == 1
     assert all(prof[k][0] > 0 for k in prof)
     assert ctx.profile_classes()["contract"][1] == 0         # reset
+
+
+def test_degenerate_shapes(T, oracle):
+    """No scenarios yet (the reference's loops run zero times: alpha = 0, beta = 0, weight_mark = 0),
+    a 1 x 1 x 1 problem, and a template without any random element (s = 0)."""
+    P = synthetic_problem(m2=30, n1=5, s=6)
+    dvs, epi = make_epi(T, P, synthetic_pool(P.m2, 10), [])
+    cut = epi.build_cut(np.ones(5))
+    assert cut.alpha == 0.0 and (cut.beta == 0.0).all() and cut.weight_mark == 0.0
+    mv, mi = epi.argmax(np.ones(5))
+    assert mv.shape == (0,) and mi.shape == (0,)
+
+    P1 = oracle.Problem(3, 1, np.array([1.0, 2.0, 0.0]), np.array([0, 1]), np.array([2]), np.array([-1.0]),
+                        np.array([0], dtype=np.int32), np.array([-1], dtype=np.int32))
+    pool1 = np.array([[2.0, -1.0, 0.5]])
+    _, e1 = make_epi(T, P1, pool1, np.array([[4.0]]))
+    check_cut(oracle, P1, np.array([[4.0]]), np.ones(1), np.array([3.0]), pool1, e1.build_cut(np.array([3.0])))
+
+    P0 = oracle.Problem(4, 2, np.array([1.0, 0, 2, 0]), np.array([0, 1, 2]), np.array([1, 3]), np.array([-1.0, -2.0]),
+                        np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+    pool0 = synthetic_pool(4, 3)
+    _, e0 = make_epi(T, P0, pool0, np.zeros((5, 0)))
+    x = np.array([1.0, 2.0])
+    ref = oracle.build_sasa_cut(P0, np.zeros((5, 0)), np.ones(5), x, pool0)
+    cut = e0.build_cut(x)
+    assert abs(cut.alpha - ref["alpha"]) <= 1e-12 * abs(ref["alpha"]) and np.allclose(cut.beta, ref["beta"], rtol=1e-12)
+    assert cut.weight_mark == 5.0
