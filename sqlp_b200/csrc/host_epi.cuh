@@ -321,6 +321,8 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         r.w = e->d_w.as<double>();
         r.PiS = e->view->d_piS.as<double>();
         r.rt = e->d_rt.as<double>();
+        r.bias = e->n_T == 0 ? e->d_bias.as<double>() : nullptr;
+        r.bias_stride = e->bias_stride;
         r.best_val = e->d_best_val.as<double>();
         r.best_idx = e->d_best_idx.as<int>();
         r.out_stride = e->out_stride;
@@ -336,7 +338,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         r.partial = e->d_partial.as<double>();
         r.flags = e->d_flags.as<int>();
         // algorithmic bytes: per point N (idx + weight + winning dot) + the (rho, tau)
-        // table + the cut; the implementation also re-reads D (8 s_pad N) to recompute the winning dot
+        // table + the cut (with delta_T != 0 the kernel also re-reads D to recompute the winning dot)
         ProfScope prof_red(c, SQLP_PROF_REDUCE,
                            NX * (24.0 * (double)e->n_local + 8.0 * (double)ku * (n1 + 1) + 8.0 * (n1 + 1)));
         if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, 0, r);

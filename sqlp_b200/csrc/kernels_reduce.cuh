@@ -73,6 +73,8 @@ struct ReduceArgs {
     const double *w;          // [n_local]
     const double *PiS;        // [nchunks] fragment-major tiles
     const double *rt;         // [K][n1 + 1]  (rho, tau)
+    const double *bias;       // [NX][bias_stride] of the contraction that produced best_*, or null
+    long long bias_stride;    //   (null: some element perturbs Tbar, the winning dot is recomputed from D)
     const double *best_val;   // [NX][out_stride]
     const int *best_idx;      // [NX][out_stride]
     long long out_stride;
@@ -108,6 +110,11 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             k = a.best_idx[x * a.out_stride + i0 + c];
             if (k < 0) {
                 atomicOr(a.flags, 1);
+            } else if (a.bias) {
+                // delta_T == 0: the contraction's winning score is bias_x[k] + PiS[k] . delta_rhs_i with
+                // exactly this bias, so the dot is the score minus the bias (off by at most half an
+                // ulp of the score) and neither D nor the pool view is read again
+                acc = __dsub_rn(a.best_val[x * a.out_stride + i0 + c], a.bias[x * a.bias_stride + k]);
             } else {
                 // slots in order; a k-group (4 slots) is 512 doubles further in both tiles and its
                 // four slots sit 2 doubles apart, so the walk needs no index arithmetic.  Pad slots
@@ -135,47 +142,47 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
 
     // phase B: thread per (x, output column); scenarios in index order.  The table rows of eight
     // scenarios are fetched before they are used, so the gathers overlap instead of queueing
-    // behind one another; the additions keep the scenario order.
+    // behind one another; the additions keep the scenario order.  The loop body is branch free: a
+    // scenario without argmax contributes fma(0, 0, sum) = sum.
     const int NC = a.n1 + 2;
     const long long RT = a.n1 + 1;
     for (int q = threadIdx.x; q < NX * NC; q += blockDim.x) {
         const int x = q / NC, col = q % NC;
+        const bool is_alpha = (col == 0), is_val = (col == NC - 1);
         double sum = 0.0;
-        int t0 = 0, t1 = 0;
-        if (col >= 1 && col <= a.n1 && a.n_T) {   // delta_T elements landing in this column
+        if (!is_alpha && !is_val && a.n_T) {
+            // beta column with delta_T elements landing in it (no shipped instance has any)
+            int t0 = 0, t1 = 0;
             while (t0 < a.n_T && a.tc_col[t0] < col - 1) ++t0;
             t1 = t0;
             while (t1 < a.n_T && a.tc_col[t1] == col - 1) ++t1;
-        }
-        const bool is_val = (col == NC - 1);
-        const double *src = is_val ? a.best_val + x * a.out_stride + i0 : a.rt + col;
-        for (int cb = 0; cb < cnt; cb += 8) {
-            int kk[8];
-            double tv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = cb + u;
-                kk[u] = (c < cnt) ? k_i[x][c] : -1;
-                tv[u] = (kk[u] >= 0) ? (is_val ? src[c] : src[(long long)kk[u] * RT]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = cb + u, k = kk[u];
+            for (int c = 0; c < cnt; ++c) {
+                const int k = k_i[x][c];
                 if (k < 0) continue;
-                const double p = p_i[c];
-                double term = tv[u];
-                if (col == 0) {
-                    sum = fma(p, term + a_i[x][c], sum);                              // :140
-                } else if (!is_val) {
-                    for (int t = t0; t < t1; ++t) {                                   // :141
-                        const double piv =
-                            a.PiS[(long long)(k >> 7) * a.s_pad * SQLP_TILE + tile_off(k & 127, a.tc_j[t])];
-                        term = fma(a.dT[(i0 + c) * (long long)a.n_T + a.tc_slot[t]], piv, term);
-                    }
-                    sum = fma(-p, term, sum);
-                } else {
-                    sum = fma(p, term, sum);                                          // :142
+                double term = a.rt[(long long)k * RT + col];                           // :141
+                for (int t = t0; t < t1; ++t) {
+                    const double piv =
+                        a.PiS[(long long)(k >> 7) * a.s_pad * SQLP_TILE + tile_off(k & 127, a.tc_j[t])];
+                    term = fma(a.dT[(i0 + c) * (long long)a.n_T + a.tc_slot[t]], piv, term);
                 }
+                sum = fma(-p_i[c], term, sum);
+            }
+        } else {
+            const double *src = is_val ? a.best_val + x * a.out_stride + i0 : a.rt + col;
+            const long long stride = is_val ? 0 : RT;      // table row stride; the value column is per scenario
+            const double sign = (is_alpha || is_val) ? 1.0 : -1.0;                     // :140-142
+            for (int cb = 0; cb < SQLP_TILE; cb += 8) {    // k_i is -1 beyond cnt
+                double tv[8], pw[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = cb + u, k = k_i[x][c];
+                    const bool ok = (k >= 0);
+                    const double v = ok ? (is_val ? src[c] : src[(long long)k * stride]) : 0.0;
+                    tv[u] = is_alpha ? v + (ok ? a_i[x][c] : 0.0) : v;
+                    pw[u] = ok ? sign * p_i[c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum = fma(pw[u], tv[u], sum);
             }
         }
         a.partial[(tile * NX + x) * NC + col] = sum;
