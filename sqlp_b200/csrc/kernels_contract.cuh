@@ -1,4 +1,8 @@
-// kernels_contract.cuh -- the fused fp64 contraction + argmax (the hot kernel).
+// kernels_contract.cuh -- the fused fp64 contraction + argmax, STREAMING variant: both operands
+// flow through the shared-memory ring, so it works for any number of stochastic rows.  It was the
+// hot kernel up to v6 and is now the last fallback behind
+// kernels_contract_ws.cuh and kernels_contract_res.cuh; ContractArgs and the (value, index)
+// order `better` defined here are shared by all three.
 //
 // Reference: the double loop of argmax_procedure, src/sd_algorithm/subprob.jl:148-166:
 //   for each scenario i, for each pool vertex k (insertion order):

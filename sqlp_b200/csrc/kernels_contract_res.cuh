@@ -2,9 +2,10 @@
 // with an even ("stream-K") split of the work over the persistent grid.
 //
 // Same mathematics and same reference lines as kernels_contract.cuh (argmax_procedure,
-// src/sd_algorithm/subprob.jl:148-166); this is the production kernel whenever one unit of
-// scenarios fits in shared memory next to the pool ring, the streaming kernel of
-// kernels_contract.cuh stays as the fallback for very wide stochastic row sets.
+// src/sd_algorithm/subprob.jl:148-166).  Role: the FIRST FALLBACK of the warp-specialised
+// production kernel (kernels_contract_ws.cuh, which includes this file for the work split and
+// the fix-up kernel): it needs only two ring stages next to the resident scenarios; the
+// streaming kernel of kernels_contract.cuh takes over for very wide stochastic row sets.
 //
 // What changed against the streaming kernel, and why (profiles/r01d_contract_source_regions.txt):
 //   * the per-item bookkeeping (cursor arithmetic + 5..7 bulk copies per pipeline item) took
