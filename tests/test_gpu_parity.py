@@ -577,3 +577,29 @@ def test_degenerate_shapes(T, oracle):
     cut = e0.build_cut(x)
     assert abs(cut.alpha - ref["alpha"]) <= 1e-12 * abs(ref["alpha"]) and np.allclose(cut.beta, ref["beta"], rtol=1e-12)
     assert cut.weight_mark == 5.0
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """tests/abi_demo.c, compiled with gcc against include/sqlp_b200.h and linked to the library: the
+    reference's weighted build_sasa_cut case (test/sd_test.jl:207-235) without Python in the loop."""
+    import json
+    import os
+    import subprocess
+    from sqlp_b200 import _lib
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "abi_demo")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.run(["gcc", "-O1", "-o", exe, os.path.join(here, "abi_demo.c"), "-L", libdir, "-lsqlp_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout)
+    assert r["K"] == 2 and r["inserted"] == [1, 1, 0] and r["index"] == [0, 1, 0]
+    # scores 168 vs 169 -> my_dual_2 for RHS = 3; 344 vs 331 -> my_dual for RHS = 7 (sd_test.jl:216-222)
+    assert r["max_idx"] == [1, 0] and r["max_val"] == [169.0, 344.0]
+    d1 = np.array([-4.0, -1.0, -12.0, -0.0, 44.0, 28.0, 5.5]); d2 = np.array([-0.5, 0.0, -8.5, 0.0, 40.5, 24.5, 4.5])
+    r1 = np.array([0, 0, 0, 0, 3.0, 3.0, 2.0]); r2 = np.array([0, 0, 0, 0, 7.0, 3.0, 2.0])
+    Tm = np.zeros((7, 4)); Tm[[0, 1, 2, 3], [0, 1, 2, 3]] = -1.0
+    assert r["alpha"] == 1.5 / 2.0 * (d2 @ r1) + 0.5 / 2.0 * (d1 @ r2)            # sd_test.jl:229,233 (exact ==)
+    assert r["beta"] == list(1.5 / 2.0 * (-Tm.T @ d2) + 0.5 / 2.0 * (-Tm.T @ d1))   # :230,234
+    assert r["weight_mark"] == 2.0 and r["max_sense_status"] == -3
