@@ -33,6 +33,7 @@ extern "C" {
 typedef struct sqlp_ctx sqlp_ctx;   /* one GPU (+ its rank in a scenario-sharded job)   */
 typedef struct sqlp_pool sqlp_pool; /* sdDualVertexSet, dual_set.jl:69-78               */
 typedef struct sqlp_epi sqlp_epi;   /* the device half of sdEpigraph, epigraph.jl:17-45 */
+typedef struct sqlp_smps sqlp_smps; /* spCorType + spTimType + spStoType + the stage-2 tables */
 
 enum {
     SQLP_OK = 0,
@@ -44,7 +45,8 @@ enum {
                                 UndefRefError at epigraph.jl:140                         */
     SQLP_E_NOMEM = -5,
     SQLP_E_NCCL = -6,
-    SQLP_E_RANGE = -7        /* scenario / vertex index out of range                     */
+    SQLP_E_RANGE = -7,       /* scenario / vertex index out of range                     */
+    SQLP_E_IO = -8           /* a file could not be opened                               */
 };
 
 enum { SQLP_MIN_SENSE = 0, SQLP_MAX_SENSE = 1 }; /* MOI.OptimizationSense */
@@ -229,6 +231,71 @@ SQLP_API int32_t sqlp_epi_master_rows(sqlp_epi *epi, double *rows, int64_t *n_ro
 SQLP_API int32_t sqlp_cell_check_improvement(int32_t n_epi, sqlp_epi *const *epi, const double *x_cand,
                                              const double *x_inc, const double *cost, double q_factor,
                                              double *out4);
+
+/* ---------------------------------------------------------------- SMPS reader (next row N4) ------ */
+
+/* read_cor (smps_cor.jl:26-194), read_tim (smps_tim.jl:30-64), read_sto (smps_sto.jl:41-111;
+ * sto_path NULL or "" = no .sto file), the stage-2 split of get_smps_stage_template
+ * (smps_prob.jl:14-102) and extract_coefficients (subprob.jl:15-69) in native host code: the flat
+ * tables the device path consumes, without JuMP.  Host-only, needs no GPU.  Format rules kept from
+ * the reference: '*' comment lines, a line starting in column 1 is a section header, unsupported
+ * sections / bound types / INDEP keywords are errors, the first row must be the 'N' row, later
+ * COLUMNS entries overwrite earlier ones, defaults 0 <= x < +Inf, exact zeros are not stored in
+ * Tbar / W / rbar.  The reference holds the random elements in a Dict (hash order); here element
+ * e is the e-th DISTINCT (column, row) position in order of first appearance in the .sto file. */
+SQLP_API int32_t sqlp_smps_load(const char *cor_path, const char *tim_path, const char *sto_path,
+                                sqlp_smps **out);
+SQLP_API int32_t sqlp_smps_destroy(sqlp_smps *smps);
+
+enum { /* indices into dims[] of sqlp_smps_dims */
+    SQLP_SMPS_ROWS = 0,      /* rows of the cor file, objective row included               */
+    SQLP_SMPS_COLS = 1,
+    SQLP_SMPS_COR_NNZ = 2,   /* stored (row, column) entries as written, zeros included    */
+    SQLP_SMPS_N1 = 3,        /* first-stage columns = columns of Tbar                      */
+    SQLP_SMPS_N2 = 4,
+    SQLP_SMPS_M2 = 5,        /* stage-2 rows = length of a dual vertex                     */
+    SQLP_SMPS_T_NNZ = 6,
+    SQLP_SMPS_W_NNZ = 7,
+    SQLP_SMPS_R_NNZ = 8,
+    SQLP_SMPS_S = 9,         /* random elements                                            */
+    SQLP_SMPS_MAX_OUTCOMES = 10,
+    SQLP_SMPS_PERIODS = 11,
+    SQLP_SMPS_NDIMS = 12
+};
+SQLP_API int32_t sqlp_smps_dims(sqlp_smps *smps, int64_t *dims /*[SQLP_SMPS_NDIMS]*/);
+
+enum { /* `what` of sqlp_smps_name */
+    SQLP_SMPS_COR_NAME = 0, SQLP_SMPS_TIM_NAME = 1, SQLP_SMPS_STO_NAME = 2,
+    SQLP_SMPS_ROW_NAME = 3, SQLP_SMPS_COL_NAME = 4,                /* cor.row_names / col_names */
+    SQLP_SMPS_PERIOD_NAME = 5, SQLP_SMPS_PERIOD_COL = 6, SQLP_SMPS_PERIOD_ROW = 7,
+    SQLP_SMPS_ELEM_COL = 8, SQLP_SMPS_ELEM_ROW = 9                 /* spSmpsPosition of element e */
+};
+/* NUL-terminated copy of a name; SQLP_E_RANGE if index is out of range or buf too small. */
+SQLP_API int32_t sqlp_smps_name(sqlp_smps *smps, int32_t what, int64_t index, char *buf,
+                                int64_t buflen);
+/* spCorType: directions[rows] ('N','G','L','E'), rhs[rows], bounds[cols] and template_matrix as
+ * 0-based CSC with COR_NNZ entries (rows ascending per column).  Any pointer may be NULL. */
+SQLP_API int32_t sqlp_smps_cor(sqlp_smps *smps, char *directions, double *rhs, double *lower,
+                               double *upper, int64_t *colptr /*[cols+1]*/, int64_t *rowval,
+                               double *nzval);
+/* sdSubprobCoefficients (subprob.jl:4-13): rbar dense [m2], Tbar CSC [m2 x n1], W CSC [m2 x n2],
+ * plus the stage-2 cost row [n2] and the first-stage cost row [n1].  Any pointer may be NULL. */
+SQLP_API int32_t sqlp_smps_stage2(sqlp_smps *smps, double *rbar, int64_t *T_colptr,
+                                  int64_t *T_rowval, double *T_nzval, int64_t *W_colptr,
+                                  int64_t *W_rowval, double *W_nzval, double *cost, double *x_cost);
+/* The stochastic-position table and the distributions, arrays of S: pos_row (stage-2 row),
+ * pos_col (Tbar column, -1 = RHS), kind (0 DISCRETE, 1 NORMAL, 2 UNIFORM), par_a / par_b (mean /
+ * variance, left / right), cnt (outcomes of a DISCRETE element) and the rectangular
+ * [S x MAX_OUTCOMES] tables of values and probabilities (zero padded).  Any pointer may be NULL. */
+SQLP_API int32_t sqlp_smps_elements(sqlp_smps *smps, int32_t *pos_row, int32_t *pos_col,
+                                    int32_t *kind, double *par_a, double *par_b, int32_t *cnt,
+                                    double *vals, double *probs);
+/* sdEpigraph(prob, w, lb) straight from the parsed files: sqlp_epi_create with the tables above,
+ * then sqlp_epi_set_outcomes (cdf = left-to-right running sum of the probabilities) and, if any
+ * element is continuous, sqlp_epi_set_distributions -- ready for sqlp_epi_sample_scenarios or
+ * sqlp_epi_add_scenarios (values in element order). */
+SQLP_API int32_t sqlp_epi_create_smps(sqlp_ctx *ctx, sqlp_pool *pool, sqlp_smps *smps,
+                                      sqlp_epi **out);
 
 /* eval_dual(coef, delta, x, dual) -- subprob.jl:128-131 -- for LOCAL scenario `scen` and
  * pool slot `vertex`, in the reference's operation order (debug / parity pin). */

@@ -20,7 +20,7 @@ HEADER = os.path.join(ROOT, "include", "sqlp_b200.h")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
-OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NO_ARGMAX, E_NOMEM, E_NCCL, E_RANGE = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NO_ARGMAX, E_NOMEM, E_NCCL, E_RANGE, E_IO = 0, -1, -2, -3, -4, -5, -6, -7, -8
 MIN_SENSE, MAX_SENSE = 0, 1
 
 
@@ -107,6 +107,14 @@ SIGNATURES = {
     "sqlp_epi_evaluate": [_vp, _vp, _i32, _P(_f64)],
     "sqlp_epi_master_rows": [_vp, _vp, _P(_i64)],
     "sqlp_cell_check_improvement": [_i32, _vp, _vp, _vp, _vp, _f64, _vp],
+    "sqlp_smps_load": [C.c_char_p, C.c_char_p, C.c_char_p, _P(_vp)],
+    "sqlp_smps_destroy": [_vp],
+    "sqlp_smps_dims": [_vp, _vp],
+    "sqlp_smps_name": [_vp, _i32, _i64, C.c_char_p, _i64],
+    "sqlp_smps_cor": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sqlp_smps_stage2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sqlp_smps_elements": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sqlp_epi_create_smps": [_vp, _vp, _vp, _P(_vp)],
 }
 _RESTYPE = {"sqlp_version": C.c_char_p, "sqlp_last_error": C.c_char_p}
 

@@ -4,9 +4,11 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -44,6 +46,7 @@
 #include "host_base.cuh"
 #include "host_pool.cuh"
 #include "host_epi.cuh"
+#include "host_smps.cuh"
 
 // ================================================================ C ABI =================
 extern "C" {
@@ -922,6 +925,165 @@ int32_t sqlp_cell_check_improvement(int32_t n_epi, sqlp_epi *const *epi, const d
         CK(cudaMemcpyAsync(out4, d_out, 32, cudaMemcpyDeviceToHost, S(c)));
         CK(cudaStreamSynchronize(S(c)));
     });
+}
+
+// ---------------------------------------------------------------- SMPS reader (row N4) ---
+int32_t sqlp_smps_load(const char *cor_path, const char *tim_path, const char *sto_path, sqlp_smps **out)
+{
+    return guard([&] {
+        REQUIRE(out, SQLP_E_INVALID, "null argument");
+        *out = nullptr;
+        std::unique_ptr<sqlp_smps> p(new sqlp_smps());
+        smps_read_cor(*p, cor_path);
+        smps_read_tim(*p, tim_path);
+        if (sto_path && *sto_path) smps_read_sto(*p, sto_path);
+        smps_stage2(*p);
+        *out = p.release();
+    });
+}
+
+int32_t sqlp_smps_destroy(sqlp_smps *p)
+{
+    return guard([&] { delete p; });
+}
+
+int32_t sqlp_smps_dims(sqlp_smps *p, int64_t *dims)
+{
+    return guard([&] {
+        REQUIRE(p && dims, SQLP_E_INVALID, "null argument");
+        int64_t cor_nnz = 0;
+        for (auto &c : p->col_entries) cor_nnz += (int64_t)c.size();
+        int64_t d[SQLP_SMPS_NDIMS] = {(int64_t)p->rows.size(), (int64_t)p->cols.size(), cor_nnz, p->n1, p->n2, p->m2,
+                                      (int64_t)p->T_nzval.size(), (int64_t)p->W_nzval.size(), (int64_t)p->r_val.size(),
+                                      (int64_t)p->elems.size(), p->max_outcomes, (int64_t)p->periods.size()};
+        std::copy(d, d + SQLP_SMPS_NDIMS, dims);
+    });
+}
+
+int32_t sqlp_smps_name(sqlp_smps *p, int32_t what, int64_t index, char *buf, int64_t buflen)
+{
+    return guard([&] {
+        REQUIRE(p && buf && buflen > 0, SQLP_E_INVALID, "null argument");
+        const std::string *s = nullptr;
+        auto at = [&](size_t n) { REQUIRE(index >= 0 && (size_t)index < n, SQLP_E_RANGE, "name index out of range"); };
+        switch (what) {
+        case SQLP_SMPS_COR_NAME: s = &p->name; break;
+        case SQLP_SMPS_TIM_NAME: s = &p->tim_name; break;
+        case SQLP_SMPS_STO_NAME: s = &p->sto_name; break;
+        case SQLP_SMPS_ROW_NAME: at(p->rows.size()); s = &p->rows[index]; break;
+        case SQLP_SMPS_COL_NAME: at(p->cols.size()); s = &p->cols[index]; break;
+        case SQLP_SMPS_PERIOD_NAME: at(p->periods.size()); s = &p->periods[index][0]; break;
+        case SQLP_SMPS_PERIOD_COL: at(p->periods.size()); s = &p->periods[index][1]; break;
+        case SQLP_SMPS_PERIOD_ROW: at(p->periods.size()); s = &p->periods[index][2]; break;
+        case SQLP_SMPS_ELEM_COL: at(p->elems.size()); s = &p->elems[index].col; break;
+        case SQLP_SMPS_ELEM_ROW: at(p->elems.size()); s = &p->elems[index].row; break;
+        default: throw Error(SQLP_E_INVALID, "unknown name selector");
+        }
+        REQUIRE((int64_t)s->size() < buflen, SQLP_E_RANGE, "name buffer too small");
+        memcpy(buf, s->c_str(), s->size() + 1);
+    });
+}
+
+int32_t sqlp_smps_cor(sqlp_smps *p, char *directions, double *rhs, double *lower, double *upper,
+                      int64_t *colptr, int64_t *rowval, double *nzval)
+{
+    return guard([&] {
+        REQUIRE(p, SQLP_E_INVALID, "null argument");
+        if (directions) std::copy(p->dir.begin(), p->dir.end(), directions);
+        if (rhs) std::copy(p->rhs.begin(), p->rhs.end(), rhs);
+        if (lower) std::copy(p->lower.begin(), p->lower.end(), lower);
+        if (upper) std::copy(p->upper.begin(), p->upper.end(), upper);
+        int64_t k = 0;
+        if (colptr) colptr[0] = 0;
+        for (size_t j = 0; j < p->col_entries.size(); ++j) {
+            for (auto &kv : p->col_entries[j]) {
+                if (rowval) rowval[k] = kv.first;
+                if (nzval) nzval[k] = kv.second;
+                ++k;
+            }
+            if (colptr) colptr[j + 1] = k;
+        }
+    });
+}
+
+int32_t sqlp_smps_stage2(sqlp_smps *p, double *rbar, int64_t *T_colptr, int64_t *T_rowval, double *T_nzval,
+                         int64_t *W_colptr, int64_t *W_rowval, double *W_nzval, double *cost, double *x_cost)
+{
+    return guard([&] {
+        REQUIRE(p, SQLP_E_INVALID, "null argument");
+        if (rbar) std::copy(p->rhs.begin() + p->r2, p->rhs.end(), rbar);
+        if (T_colptr) std::copy(p->T_colptr.begin(), p->T_colptr.end(), T_colptr);
+        if (T_rowval) std::copy(p->T_rowval.begin(), p->T_rowval.end(), T_rowval);
+        if (T_nzval) std::copy(p->T_nzval.begin(), p->T_nzval.end(), T_nzval);
+        if (W_colptr) std::copy(p->W_colptr.begin(), p->W_colptr.end(), W_colptr);
+        if (W_rowval) std::copy(p->W_rowval.begin(), p->W_rowval.end(), W_rowval);
+        if (W_nzval) std::copy(p->W_nzval.begin(), p->W_nzval.end(), W_nzval);
+        if (cost) std::copy(p->cost.begin(), p->cost.end(), cost);
+        if (x_cost) std::copy(p->x_cost.begin(), p->x_cost.end(), x_cost);
+    });
+}
+
+int32_t sqlp_smps_elements(sqlp_smps *p, int32_t *pos_row, int32_t *pos_col, int32_t *kind, double *par_a,
+                           double *par_b, int32_t *cnt, double *vals, double *probs)
+{
+    return guard([&] {
+        REQUIRE(p, SQLP_E_INVALID, "null argument");
+        const int64_t mo = p->max_outcomes;
+        for (size_t e = 0; e < p->elems.size(); ++e) {
+            const SmpsElement &el = p->elems[e];
+            if (pos_row) pos_row[e] = p->pos_row[e];
+            if (pos_col) pos_col[e] = p->pos_col[e];
+            if (kind) kind[e] = el.kind;
+            if (par_a) par_a[e] = el.a;
+            if (par_b) par_b[e] = el.b;
+            if (cnt) cnt[e] = (int32_t)el.val.size();
+            for (int64_t o = 0; o < mo; ++o) {
+                bool in = o < (int64_t)el.val.size();
+                if (vals) vals[e * mo + o] = in ? el.val[o] : 0.0;
+                if (probs) probs[e * mo + o] = in ? el.prob[o] : 0.0;
+            }
+        }
+    });
+}
+
+int32_t sqlp_epi_create_smps(sqlp_ctx *c, sqlp_pool *pool, sqlp_smps *p, sqlp_epi **out)
+{
+    if (!(c && pool && p && out)) {
+        g_err = "null argument";
+        return SQLP_E_INVALID;
+    }
+    *out = nullptr;
+    sqlp_epi *e = nullptr;
+    int32_t st = sqlp_epi_create(c, pool, p->m2, p->n1, (int64_t)p->r_val.size(), p->r_idx.data(), p->r_val.data(),
+                                 p->T_colptr.data(), p->T_rowval.data(), p->T_nzval.data(), (int64_t)p->elems.size(),
+                                 p->pos_row.data(), p->pos_col.data(), &e);
+    if (st != SQLP_OK) return st;
+    const int64_t s = (int64_t)p->elems.size(), mo = std::max<int64_t>(p->max_outcomes, 1);
+    bool any_cont = false;
+    std::vector<double> vals((size_t)(s * mo), 0.0), cdf((size_t)(s * mo), 0.0), a((size_t)s), b((size_t)s);
+    std::vector<int32_t> cnt((size_t)s, 1), kind((size_t)s);
+    for (int64_t q = 0; q < s; ++q) {
+        const SmpsElement &el = p->elems[(size_t)q];
+        kind[q] = el.kind; a[q] = el.a; b[q] = el.b;
+        if (el.kind != 0) { any_cont = true; continue; }
+        cnt[q] = (int32_t)el.val.size();
+        double run = 0.0;
+        for (size_t o = 0; o < el.val.size(); ++o) {       // cdf = running sum of the probabilities
+            run += el.prob[o];
+            vals[q * mo + o] = el.val[o];
+            cdf[q * mo + o] = run;
+        }
+    }
+    if (s > 0) st = sqlp_epi_set_outcomes(e, mo, vals.data(), cdf.data(), cnt.data());
+    if (st == SQLP_OK && any_cont) st = sqlp_epi_set_distributions(e, kind.data(), a.data(), b.data());
+    if (st != SQLP_OK) {
+        std::string keep = g_err;
+        sqlp_epi_destroy(e);
+        g_err = keep;
+        return st;
+    }
+    *out = e;
+    return SQLP_OK;
 }
 
 int32_t sqlp_eval_dual(sqlp_epi *e, int64_t i, int64_t vertex, const double *x, double *out)

@@ -16,6 +16,11 @@ The reference keeps ``sto.indep`` in a ``Dict`` whose order is hash order
 appearance in the ``.sto`` file.
 
 Everything here is host logic in numpy; nothing in this file computes cuts.
+
+``NativeSmps`` binds the same reader written in C++ inside ``libsqlp_b200.so``
+(``sqlp_smps_*``, ``csrc/host_smps.cuh``): the library builds its device tables straight from the
+three files (``sqlp_epi_create_smps``), so a Julia host needs no JuMP coefficient extraction.  The
+numpy reader above stays as the independent restatement the native one is tested against.
 """
 from __future__ import annotations
 
@@ -150,9 +155,11 @@ def read_sto(path) -> Sto:
             vals, probs = params[index[pos]]
             vals.append(float(tok[2])); probs.append(float(tok[3]))
         elif k in ("NORMAL", "UNIFORM"):
-            index[pos] = len(positions)
-            positions.append(pos); kind.append(k)
-            params.append((float(tok[2]), float(tok[3])))
+            if pos not in index:
+                index[pos] = len(positions)
+                positions.append(pos); kind.append(k); params.append(None)
+            kind[index[pos]] = k                     # a later line replaces the element (indep[pos] = ...)
+            params[index[pos]] = (float(tok[2]), float(tok[3]))
         else:
             raise ValueError(f"unsupported INDEP keyword {k}")
     return Sto(name, positions, kind, params)
@@ -257,3 +264,99 @@ def sample_values(sto: Sto, u: np.ndarray) -> np.ndarray:
             from scipy.special import ndtri
             out[:, e] = p[0] + np.sqrt(p[1]) * ndtri(np.clip(u[:, e], 1e-300, 1 - 1e-16))
     return out
+
+
+class NativeSmps:
+    """``sqlp_smps`` handle: cor + tim + sto parsed and split by the C++ reader of the library."""
+
+    _DIMS = ("rows", "cols", "cor_nnz", "n1", "n2", "m2", "T_nnz", "W_nnz", "r_nnz", "s", "max_outcomes",
+             "periods")
+
+    def __init__(self, cor_path, tim_path, sto_path=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self._h = C.c_void_p()
+        enc = lambda p: None if p is None else str(p).encode()
+        _lib.check(_lib.lib().sqlp_smps_load(enc(cor_path), enc(tim_path), enc(sto_path), C.byref(self._h)))
+        d = np.zeros(len(self._DIMS), dtype=np.int64)
+        _lib.check(_lib.lib().sqlp_smps_dims(self._h, d.ctypes.data))
+        self.dims = dict(zip(self._DIMS, (int(v) for v in d)))
+
+    def close(self):
+        if self._h:
+            self._lib.lib().sqlp_smps_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _name(self, what, index=0):
+        buf = self._C.create_string_buffer(256)
+        self._lib.check(self._lib.lib().sqlp_smps_name(self._h, what, index, buf, 256))
+        return buf.value.decode()
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data
+
+    def cor(self) -> Cor:
+        d = self.dims
+        dirs = np.zeros(d["rows"], dtype="S1")
+        rhs, lo, up = np.zeros(d["rows"]), np.zeros(d["cols"]), np.zeros(d["cols"])
+        colptr = np.zeros(d["cols"] + 1, dtype=np.int64)
+        rowval, nzval = np.zeros(d["cor_nnz"], dtype=np.int64), np.zeros(d["cor_nnz"])
+        self._lib.check(self._lib.lib().sqlp_smps_cor(self._h, self._p(dirs), self._p(rhs), self._p(lo), self._p(up),
+                                                      self._p(colptr), self._p(rowval), self._p(nzval)))
+        rows = [self._name(3, i) for i in range(d["rows"])]
+        cols = [self._name(4, j) for j in range(d["cols"])]
+        entries = {(int(rowval[k]), j): float(nzval[k]) for j in range(d["cols"])
+                   for k in range(colptr[j], colptr[j + 1])}
+        return Cor(self._name(0), [c.decode() for c in dirs], rows, cols, entries, rhs, lo, up,
+                   {r: i for i, r in enumerate(rows)}, {c: j for j, c in enumerate(cols)})
+
+    def tim(self) -> Tim:
+        return Tim(self._name(1), [(self._name(5, i), self._name(6, i), self._name(7, i))
+                                   for i in range(self.dims["periods"])])
+
+    def elements(self):
+        """(pos_row, pos_col, kind, par_a, par_b, cnt, vals[s, mo], probs[s, mo])"""
+        s, mo = self.dims["s"], self.dims["max_outcomes"]
+        pr, pc, kind, cnt = (np.zeros(s, dtype=np.int32) for _ in range(4))
+        a, b = np.zeros(s), np.zeros(s)
+        vals, probs = np.zeros((s, mo)), np.zeros((s, mo))
+        self._lib.check(self._lib.lib().sqlp_smps_elements(self._h, self._p(pr), self._p(pc), self._p(kind), self._p(a),
+                                                           self._p(b), self._p(cnt), self._p(vals), self._p(probs)))
+        return pr, pc, kind, a, b, cnt, vals, probs
+
+    def sto(self) -> Sto:
+        pr, pc, kind, a, b, cnt, vals, probs = self.elements()
+        names = ("DISCRETE", "NORMAL", "UNIFORM")
+        params = [(list(vals[e, :cnt[e]]), list(probs[e, :cnt[e]])) if kind[e] == 0 else (float(a[e]), float(b[e]))
+                  for e in range(len(pr))]
+        return Sto(self._name(2), [(self._name(8, e), self._name(9, e)) for e in range(len(pr))],
+                   [names[k] for k in kind], params)
+
+    def stage2(self) -> Stage2:
+        d = self.dims
+        n1, n2, m2 = d["n1"], d["n2"], d["m2"]
+        rbar, cost, x_cost = np.zeros(m2), np.zeros(n2), np.zeros(n1)
+        Tc, Tr, Tv = np.zeros(n1 + 1, dtype=np.int64), np.zeros(d["T_nnz"], dtype=np.int64), np.zeros(d["T_nnz"])
+        Wc, Wr, Wv = np.zeros(n2 + 1, dtype=np.int64), np.zeros(d["W_nnz"], dtype=np.int64), np.zeros(d["W_nnz"])
+        self._lib.check(self._lib.lib().sqlp_smps_stage2(self._h, self._p(rbar), self._p(Tc), self._p(Tr), self._p(Tv),
+                                                         self._p(Wc), self._p(Wr), self._p(Wv), self._p(cost),
+                                                         self._p(x_cost)))
+        W = np.zeros((m2, n2))
+        for j in range(n2):
+            W[Wr[Wc[j]:Wc[j + 1]], j] = Wv[Wc[j]:Wc[j + 1]]
+        cor = self.cor()
+        r2, c2 = d["rows"] - m2, n1
+        pr, pc = self.elements()[:2]
+        return Stage2(n1=n1, m2=m2, n2=n2, row_names=cor.row_names[r2:], x_names=cor.col_names[:c2],
+                      y_names=cor.col_names[c2:], directions=cor.directions[r2:], rbar=rbar, T_colptr=Tc,
+                      T_rowval=Tr, T_nzval=Tv, W=W, cost=cost, y_lower=cor.lower[c2:].copy(),
+                      y_upper=cor.upper[c2:].copy(), pos_row=pr, pos_col=pc, x_lower=cor.lower[:c2].copy(),
+                      x_upper=cor.upper[:c2].copy(), x_cost=x_cost)

@@ -318,6 +318,29 @@ class sdEpigraph:
         self.scenario_delta = _DeviceDeltaSet(self)
         check(_lib.lib().sqlp_epi_set_weights(self._h, self.objective_weight, self.lower_bound))
 
+    @classmethod
+    def from_smps(cls, native, objective_weight: float, lower_bound: float, dual_vertices: sdDualVertexSet):
+        """``sdEpigraph(prob, w, lb)`` built by the library straight from parsed SMPS files
+        (``smps.NativeSmps``; ``sqlp_epi_create_smps``): coefficient tables, position table, outcome
+        tables and distributions never pass through the host language."""
+        self = cls.__new__(cls)
+        st = native.stage2()
+        sto = native.sto()
+        self.subproblem_coef = sdSubprobCoefficients(
+            st.rbar, st.T_colptr, st.T_rowval, st.T_nzval, st.n1, {r: i for i, r in enumerate(st.row_names)},
+            {c: j for j, c in enumerate(st.x_names)}, list(sto.positions))
+        self.objective_weight, self.lower_bound = float(objective_weight), float(lower_bound)
+        self.dual_vertices, self.ctx = dual_vertices, dual_vertices.ctx
+        self.cuts, self.incumbent_cut = [], None
+        if dual_vertices.m2 is None:
+            dual_vertices._create(st.m2)
+        self.s = len(st.pos_row)
+        self._h = C.c_void_p()
+        check(_lib.lib().sqlp_epi_create_smps(self.ctx._h, dual_vertices._h, native._h, C.byref(self._h)))
+        self.scenario_delta = _DeviceDeltaSet(self)
+        check(_lib.lib().sqlp_epi_set_weights(self._h, self.objective_weight, self.lower_bound))
+        return self
+
     # -- scenario store ---------------------------------------------------------------
     def add_scenarios(self, values, weights=None):
         values = _f64(values).reshape(-1, self.s) if self.s else np.zeros((len(values), 0))

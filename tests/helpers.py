@@ -95,6 +95,26 @@ def synthetic_pool(m2, K, seed=2, scale=1000.0):
     return scale * (2.0 * O.u01(seed, np.arange(K * m2, dtype=np.uint64)).reshape(K, m2) - 1.0)
 
 
+def balanced_pool(P, x, mean_values, K, seed=2, scale=50.0):
+    """A synthetic pool whose vertices all score the same at (x, mean scenario) -- like LP duals of
+    neighbouring bases -- so that the winner changes from scenario to scenario: random entries, then one
+    entry on a deterministic row with a non-zero (rbar - Tbar x) is set to level the scores."""
+    pool = synthetic_pool(P.m2, K, seed=seed, scale=scale)
+    r = P.rbar.copy()
+    T = P.T_dense()
+    for e in range(P.s):
+        if P.pos_col[e] < 0:
+            r[P.pos_row[e]] = mean_values[e]
+        else:
+            T[P.pos_row[e], P.pos_col[e]] = mean_values[e]
+    h = r - T @ x
+    det = [j for j in range(P.m2) if j not in set(P.pos_row.tolist()) and abs(h[j]) > 1e-3]
+    j0 = det[0]
+    sc = pool @ h
+    pool[:, j0] -= (sc - sc.mean()) / h[j0]
+    return pool
+
+
 def check_argmax_parity(P, values, x, pool, got_val, got_idx, rel_gap=1e-12, val_rtol=1e-10):
     """North-star parity rule: indices identical to the oracle except where the oracle's
     score of the device's pick is within rel_gap*max(|best|,1) of the oracle's best."""
@@ -190,3 +210,117 @@ def make_cell(zf, dual_vertices, make_epigraph, x0, n_epi=1, lower_bound=0.0):
     lp = sd.Stage2LP(zf["W"], zf["cost"], zf["y_lower"], zf["y_upper"], zf["directions"], zf["rbar"], T,
                      zf["pos_row"], zf["pos_col"])
     return cell, lp
+
+
+# ---------------------------------------------------------------- SMPS files on the fly --
+
+def write_smps(dirpath, name="synth", n1=5, n2=6, m1=2, m2=7, seed=11, n_rhs_elems=3, n_T_elems=2,
+               continuous=False, quirks=True):
+    """Write a small two-stage problem as .cor/.tim/.sto text (free format, the dialect the reference's
+    readers accept) and return (paths, expected) -- ``expected`` holds the tables a correct reader must
+    produce.  With ``quirks`` the files carry comment lines, an overwritten COLUMNS entry, an explicit zero
+    in the Tbar block, two pairs per line, every bound type and exponent-format numbers."""
+    rng = np.random.default_rng(seed)
+    rows = ["OBJ"] + [f"A{i}" for i in range(m1)] + [f"S2R{i}" for i in range(m2)]
+    dirs = ["N"] + list(rng.choice(list("GLE"), m1)) + list(rng.choice(list("GLE"), m2))
+    cols = [f"X{j}" for j in range(n1)] + [f"Y{j}" for j in range(n2)]
+    nrow, ncol, r2 = len(rows), len(cols), 1 + m1
+    M = np.zeros((nrow, ncol))
+    M[0, :] = np.round(rng.uniform(1, 9, ncol), 3)
+    for j in range(n1):
+        M[1 + rng.integers(m1), j] = np.round(rng.uniform(-3, 3), 2) or 1.0
+        for i in rng.choice(m2, 2, replace=False):
+            M[r2 + i, j] = np.round(rng.uniform(-2, 2), 3) or -1.0
+    for j in range(n2):
+        for i in rng.choice(m2, 3, replace=False):
+            M[r2 + i, n1 + j] = np.round(rng.uniform(-5, 5), 3) or 2.0
+    rhs = np.zeros(nrow)
+    rhs[1:] = np.where(rng.random(nrow - 1) < 0.7, np.round(rng.uniform(-50, 50, nrow - 1), 1), 0.0)
+    lower, upper = np.zeros(ncol), np.full(ncol, np.inf)
+    lines = ["* synthetic core file", f"NAME          {name}", "ROWS"]
+    lines += [f" {d}  {r}" for d, r in zip(dirs, rows)]
+    lines.append("COLUMNS")
+    explicit_zero = None
+    for j, c in enumerate(cols):
+        nz = [(i, M[i, j]) for i in range(nrow) if M[i, j] != 0.0]
+        if quirks and j == 1:                      # first a wrong value, overwritten further down
+            lines.append(f"    {c}    {rows[nz[0][0]]}    123.456")
+        if quirks and j == 2:                      # an explicit zero where Tbar has none
+            zi = next(i for i in range(r2, nrow) if M[i, j] == 0.0)
+            explicit_zero = (zi, j)
+            lines.append(f"    {c}\t{rows[zi]}\t0.0")
+        k = 0
+        while k < len(nz):
+            if quirks and k + 1 < len(nz) and (j + k) % 2 == 0:
+                (i0, v0), (i1, v1) = nz[k], nz[k + 1]
+                lines.append(f"    {c}  {rows[i0]}  {float(v0)!r}   {rows[i1]}  {v1:.6E}")
+                M[i1, j] = float(f"{v1:.6E}")
+                k += 2
+            else:
+                lines.append(f"    {c}  {rows[nz[k][0]]}  {float(nz[k][1])!r}")
+                k += 1
+        if quirks and j == 3:
+            lines.append("* a comment between columns")
+    lines.append("RHS")
+    for i in range(1, nrow):
+        if rhs[i] != 0.0:
+            lines.append(f"    RHS  {rows[i]}  {float(rhs[i])!r}")
+    if quirks:
+        lines.append("BOUNDS")
+        spec = [("UP", 0, 217.0), ("LO", 1, -4.5), ("FX", 2, 3.25), ("FR", 3, None), ("MI", 4, None),
+                ("PL", n1, None), ("UP", n1 + 1, 1e3)]
+        for bt, j, v in spec:
+            lines.append(f" {bt} BND  {cols[j]}" + ("" if v is None else f"  {float(v)!r}"))
+            if bt == "UP": upper[j] = v
+            elif bt == "LO": lower[j] = v
+            elif bt == "FX": lower[j] = upper[j] = v
+            elif bt == "FR": lower[j], upper[j] = -np.inf, np.inf
+            elif bt == "MI": lower[j] = -np.inf
+    lines.append("ENDATA")
+    os.makedirs(dirpath, exist_ok=True)
+    paths = {k: os.path.join(dirpath, f"{name}.{k}") for k in ("cor", "tim", "sto")}
+    with open(paths["cor"], "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    with open(paths["tim"], "w") as fh:
+        fh.write(f"TIME          {name}\nPERIODS       IMPLICIT\n    {cols[0]}  {rows[0]}  TIME1\n"
+                 f"    {cols[n1]}  {rows[r2]}  TIME2\nENDATA\n")
+    # random elements: RHS rows first, then Tbar entries (a stored one and a structural zero)
+    elems = [("RHS", int(i)) for i in rng.choice(m2, n_rhs_elems, replace=False)]
+    taken = set()
+    for e in range(n_T_elems):
+        j = int(rng.integers(n1))
+        stored = [i for i in range(m2) if M[r2 + i, j] != 0.0 and (i, j) not in taken]
+        empty = [i for i in range(m2) if M[r2 + i, j] == 0.0 and (i, j) not in taken]
+        i = (stored if e % 2 == 0 and stored else empty)[0]
+        taken.add((i, j))
+        elems.append((cols[j], i))
+    sto = [f"STOCH         {name}"]
+    kinds, pars, tables = [], [], []
+    for e, (cname, i) in enumerate(elems):
+        base = rhs[r2 + i] if cname == "RHS" else M[r2 + i, cols.index(cname)]
+        base = base if base != 0.0 else 1.5
+        if continuous and e % 2 == 1:
+            kind = "NORMAL" if e % 4 == 1 else "UNIFORM"
+            a, b = (base, 0.25 * abs(base)) if kind == "NORMAL" else (base - 1.0, base + 2.0)
+            sto += [f"INDEP         {kind}", f"    {cname}  S2R{i}  {float(a)!r}  {float(b)!r}"]
+            kinds.append(kind); pars.append((a, b)); tables.append(None)
+        else:
+            n_out = 2 + e % 4
+            vals = [float(np.round(base * (0.7 + 0.15 * o), 4)) for o in range(n_out)]
+            pr = np.full(n_out, 1.0 / n_out)
+            sto.append("INDEP         DISCRETE")
+            if quirks and e == 0:
+                sto.append("* outcomes of the first element")
+            sto += [f"    {cname}  S2R{i}  {float(v)!r}  {float(p)!r}" for v, p in zip(vals, pr)]
+            kinds.append("DISCRETE"); pars.append((0.0, 0.0)); tables.append((vals, list(pr)))
+    sto.append("ENDATA")
+    with open(paths["sto"], "w") as fh:
+        fh.write("\n".join(sto) + "\n")
+    T = M[r2:, :n1]
+    expected = dict(name=name, rows=rows, cols=cols, dirs=dirs, M=M, rhs=rhs, lower=lower, upper=upper, n1=n1, n2=n2,
+                    m2=m2, r2=r2, T=T, W=M[r2:, n1:], rbar=rhs[r2:], cost=M[0, n1:], x_cost=M[0, :n1],
+                    pos_row=np.array([i for _, i in elems], dtype=np.int32),
+                    pos_col=np.array([-1 if c == "RHS" else cols.index(c) for c, _ in elems], dtype=np.int32),
+                    positions=[(c, f"S2R{i}") for c, i in elems], kinds=kinds, pars=pars, tables=tables,
+                    explicit_zero=explicit_zero)
+    return paths, expected
