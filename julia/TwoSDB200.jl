@@ -212,6 +212,35 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
         epi.total_scenario_weight = tw[]
         return
     end
+    # --- SMPS files read by the library (SURVEY.md 8(f) N4; smps_cor.jl / smps_tim.jl / smps_sto.jl,
+    # smps_prob.jl:14-102, subprob.jl:15-69) -- the device epigraph is built straight from the three
+    # files, so the O(m2 (n1 + n2)) normalized_coefficient sweep of extract_coefficients is not needed for
+    # the device side.  The position table is the library's (order of first appearance in the .sto file).
+    @eval T function bind_device_smps!(epi::sdEpigraph, dvs::sdDualVertexSet, cor_path::String, tim_path::String,
+                                       sto_path::String)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        $check(ccall((:sqlp_smps_load, $LIB[]), Int32, (Cstring, Cstring, Cstring, Ref{Ptr{Cvoid}}),
+                     cor_path, tim_path, sto_path, h))
+        dims = zeros(Int64, 12)
+        $check(ccall((:sqlp_smps_dims, $LIB[]), Int32, (Ptr{Cvoid}, Ptr{Int64}), h[], dims))
+        m2 = dims[6]; s = dims[10]
+        name(what, i) = begin
+            buf = zeros(UInt8, 256)
+            $check(ccall((:sqlp_smps_name, $LIB[]), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{UInt8}, Int64),
+                         h[], Int32(what), i, buf, 256))
+            unsafe_string(pointer(buf))
+        end
+        $TABLES[epi.subproblem_coef] = Any[spSmpsPosition(name(8, e), name(9, e)) for e in 0:s-1]
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        $check(ccall((:sqlp_epi_create_smps, $LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                     $context(), $pool_of(dvs, Int(m2)), h[], out))
+        ccall((:sqlp_smps_destroy, $LIB[]), Int32, (Ptr{Cvoid},), h[])
+        $EPIS[epi] = out[]
+        $check(ccall((:sqlp_epi_set_weights, $LIB[]), Int32, (Ptr{Cvoid}, Float64, Float64), out[],
+                     epi.objective_weight, epi.lower_bound))
+        $DELTA_OWNER[epi.scenario_delta] = epi
+        return epi
+    end
     return nothing
 end
 
