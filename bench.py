@@ -477,7 +477,7 @@ def run_ours(args):
         hbm_entry("k_cut_partial + k_sum_groups", prof_steps["reduce"],
                   "timed steps: N (idx + weight + winning dot) + (rho, tau) table + cut per point; the kernel "
                   "also re-reads D (8 s_pad N) and gathers pool rows from L2 to recompute the winning dot exactly"),
-        hbm_entry("k_pool_prepare + k_pool_find_commit", prof_steps["pool"],
+        hbm_entry("k_pool_push", prof_steps["pool"],
                   "timed steps: hash scan 8 K + vector in/out per push (two pushes per scope; latency bound)"),
         hbm_entry("k_base + k_bias", prof_steps["bias"], "timed steps: one pass over the K x m2 pool for both points"),
     ]

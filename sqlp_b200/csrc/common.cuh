@@ -16,6 +16,18 @@
 
 namespace sqlp {
 
+// Programmatic dependent launch (sm_90+): every kernel of the library starts with griddep_sync().
+// `launch_dependents` lets the NEXT kernel of the stream be scheduled while this one still runs (its
+// blocks become resident as resources free up and stop at their own `wait`); `wait` returns once every
+// prerequisite grid has COMPLETED and its writes are visible, so each kernel sees exactly what plain
+// stream order would show it -- only launch latency and block scheduling overlap the predecessor's tail.
+// Both instructions are no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void griddep_sync()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Fragment-major tile layout shared by the scenario store D and the pool view PiS.
 // A tile holds 128 columns (scenarios or vertices) x s_pad row slots.  Slots are grouped by
 // four (one k-step of mma.sync.m8n8k4.f64) and columns by sixteen; inside a (group, column

@@ -145,6 +145,7 @@ struct sqlp_ctx {
     int64_t launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool profile = false;
+    bool pdl = true;              // programmatic dependent launch of every kernel (SQLP_PDL=0: plain stream order)
     struct ProfEvent { cudaEvent_t e0, e1; int cls; };
     std::vector<ProfEvent> prof_events;
     size_t prof_used = 0;
@@ -163,12 +164,27 @@ struct sqlp_ctx {
     void bind() const { CK(cudaSetDevice(device)); }
 };
 
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
-    do {                                                                 \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
-        CK(cudaGetLastError());                                          \
-        ++(ctx)->launches;                                               \
-    } while (0)
+// Every kernel goes through here.  With ctx->pdl (default; SQLP_PDL=0 turns it off) the launch carries
+// the programmatic-stream-serialization attribute: the kernel may be scheduled before its predecessor
+// has drained and synchronises with it by griddep_sync() (common.cuh), its first statement.
+template <class... KArgs, class... Args>
+void launch_kernel(sqlp_ctx *c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    ++c->launches;
+}
+#define LAUNCH(ctx, kernel, grid, block, smem, ...) \
+    launch_kernel((ctx), kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
 
 struct PoolView {   // the pool restricted to one set of stochastic rows, in tile layout
     std::vector<int> rows;

@@ -249,8 +249,12 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         CK(cudaMemcpyAsync(e->d_x2.p, x_host, (size_t)NX * n1 * 8, cudaMemcpyHostToDevice, S(c)));
     else
         CK(cudaMemcpyAsync(e->d_x2.p, x_dev, (size_t)NX * n1 * 8, cudaMemcpyDeviceToDevice, S(c)));
-    CK(cudaMemsetAsync(e->d_flags.p, 0, 4, S(c)));
-    CK(cudaMemsetAsync(e->d_out.p, 0, (size_t)2 * NC * 8, S(c)));
+    // flags are cleared by k_base, the first kernel of the chain, and the reduction writes every entry of
+    // d_out: the two memsets are only needed when there is nothing to launch
+    if (e->n_local == 0) {
+        CK(cudaMemsetAsync(e->d_flags.p, 0, 4, S(c)));
+        CK(cudaMemsetAsync(e->d_out.p, 0, (size_t)2 * NC * 8, S(c)));
+    }
 
     view_sync(p, e->view);
     if (want_cut) epi_tables_sync(e);
@@ -273,7 +277,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         ProfScope prof_bias(c, SQLP_PROF_BIAS, 8.0 * (double)ku * m2 + 8.0 * NX * (double)ku);
         LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
                e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
-               e->d_x2.as<double>(), e->d_base.as<double>());
+               e->d_x2.as<double>(), e->d_base.as<double>(), e->d_flags.as<int>());
         int bgrid = (int)((kpad + 7) / 8);
         if (NX == 2)
             LAUNCH(c, k_bias<2>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
@@ -347,9 +351,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         int64_t ng = (ntiles + group - 1) / group;
         e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
         LAUNCH(c, k_sum_groups, (int)ng, 256, 0, e->d_partial.as<double>(), (long long)ntiles, group,
-               width, e->d_partial2.as<double>());
-        LAUNCH(c, k_sum_groups, 1, 256, 0, e->d_partial2.as<double>(), (long long)ng, (int)ng, width,
-               e->d_out.as<double>());
+               width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), e->d_out.as<double>());
         prof_red.stop();
     }
     if (c->world > 1) {

@@ -99,6 +99,7 @@ __device__ __forceinline__ bool better(double ov, int oi, double v, int i)
 template <class C>
 __global__ void __launch_bounds__(SQLP_CT_THREADS, C::CTAS) k_contract_argmax(ContractArgs a)
 {
+    griddep_sync();
     constexpr int NX = C::NX, MI = C::MI, S = C::STAGES, ROWS = C::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);

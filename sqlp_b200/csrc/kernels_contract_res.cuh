@@ -63,6 +63,7 @@ __host__ __device__ __forceinline__ long long span_at(long long total, int b, in
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(ContractArgs a)
 {
+    griddep_sync();
     constexpr int NX = C::NX, MI = C::MI, ROWS = C::ROWS, WARPS = C::WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ngroups = a.s_pad / 4;
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(Contr
 template <int ROWS, int NX>
 __global__ void k_argmax_fixup(ContractArgs a, int main_grid)
 {
+    griddep_sync();
     const long long K = *a.d_K;
     const int nchunks = (int)((K + SQLP_TILE - 1) / SQLP_TILE);
     if (nchunks == 0) return;

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_cuts_evaluate(CutList cur, CutList last
                                                        double total_weight, double lb, double weight,
                                                        double *__restrict__ out)
 {
+    griddep_sync();
     __shared__ double red[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int RS = n1 + 2;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) k_cuts_evaluate(CutList cur, CutList last
 // The master rows of one epigraph: n discounted cuts, then the undiscounted incumbent cut.
 __global__ void k_cuts_master_rows(CutList L, int n1, double total_weight, double lb, double *__restrict__ rows)
 {
+    griddep_sync();
     const int RS = n1 + 2, RW = n1 + 1;
     const int total = (L.n + (L.inc ? 1 : 0)) * RW;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
@@ -90,6 +92,7 @@ __global__ void k_cuts_master_rows(CutList L, int n1, double total_weight, doubl
 // (alpha, beta, anything) -> (alpha, beta, weight_mark): a reduction result becomes a stored cut.
 __global__ void k_cut_store(const double *__restrict__ src, double weight_mark, int n1, double *__restrict__ dst)
 {
+    griddep_sync();
     for (int q = threadIdx.x; q < n1 + 2; q += blockDim.x) dst[q] = (q == n1 + 1) ? weight_mark : src[q];
 }
 
@@ -97,6 +100,7 @@ __global__ void k_cut_store(const double *__restrict__ src, double weight_mark, 
 __global__ void k_cuts_gather(const double *__restrict__ cuts, const int *__restrict__ keep, int n_keep, int RS,
                               double *__restrict__ tmp)
 {
+    griddep_sync();
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_keep * RS; q += gridDim.x * blockDim.x)
         tmp[q] = cuts[(long long)keep[q / RS] * RS + q % RS];
 }
@@ -107,6 +111,7 @@ __global__ void k_cuts_gather(const double *__restrict__ cuts, const int *__rest
 __global__ void k_improvement(const double *__restrict__ est, int n_epi, const double *__restrict__ cost,
                               const double *__restrict__ x2, int n1, double q_factor, double *__restrict__ out)
 {
+    griddep_sync();
     const int lane = threadIdx.x & 31;
     if (threadIdx.x >= 32) return;
     const double f_cand = warp_dot(cost, x2, n1, lane), f_inc = warp_dot(cost, x2 + n1, n1, lane);

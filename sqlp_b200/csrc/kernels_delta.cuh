@@ -86,6 +86,7 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
               double *__restrict__ w, const double *__restrict__ w_batch, unsigned long long seed,
               unsigned long long wseed)
 {
+    griddep_sync();
     extern __shared__ __align__(16) double sh[];   // [SQLP_DELTA_COLS][stride]
     const long long gblock = g0 / SQLP_TILE + (blockIdx.x >> 1);   // global 128-block
     if ((int)(gblock % world) != rank) return;
@@ -204,6 +205,7 @@ __global__ void k_delta_x(TransferList tl, const double *__restrict__ x, long lo
                           int s_pad, const double *__restrict__ D, const double *__restrict__ dT,
                           double *__restrict__ Dx)
 {
+    griddep_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local) return;
     const long long tbase = (i >> 7) * (long long)s_pad * SQLP_TILE;
@@ -226,6 +228,7 @@ __global__ void k_delta_x(TransferList tl, const double *__restrict__ x, long lo
 __global__ void k_gather_column(const double *__restrict__ Dtile, int c, int n_rows,
                                 double *__restrict__ out)
 {
+    griddep_sync();
     for (int j = threadIdx.x; j < n_rows; j += blockDim.x) out[j] = Dtile[tile_off(c, j)];
 }
 

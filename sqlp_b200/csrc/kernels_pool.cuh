@@ -18,17 +18,18 @@ struct PushResult {
     int32_t pad;
 };
 
-// Scratch shared by the two push kernels (one per pool).
+// Scratch of the push kernel (one per pool).
 struct PushScratch {
     unsigned long long hash;   // hash of the vector being pushed
     int match;                 // lowest stored slot equal to it, INT_MAX if none
     unsigned int done;         // blocks finished (last-block-commits pattern)
 };
 
-// Kernel 1: hash of the new vector (sequential order, one thread) and its rounded copy.
+// hash_dual_vector alone (sqlp_pool_hash, debug / test): hash of the vector and its rounded copy.
 __global__ void k_pool_prepare(const double *__restrict__ v, int m2, double *__restrict__ vr,
                                PushScratch *__restrict__ sc)
 {
+    griddep_sync();
     extern __shared__ double sh[];
     for (int j = threadIdx.x; j < m2; j += blockDim.x) {
         double x = v[j];
@@ -40,19 +41,38 @@ __global__ void k_pool_prepare(const double *__restrict__ v, int m2, double *__r
         double mysum = 0.0;
         for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, sh[j]);
         sc->hash = (unsigned long long)__double_as_longlong(round_sig16(mysum));
-        sc->match = 0x7fffffff;
-        sc->done = 0u;
     }
 }
 
-// Kernel 2: one warp per stored vertex (grid-stride); the last block to finish commits.
-__global__ void k_pool_find_commit(double *__restrict__ pi, unsigned long long *__restrict__ hash,
-                                   long long *__restrict__ d_K, int m2,
-                                   const double *__restrict__ v, const double *__restrict__ vr,
-                                   PushScratch *__restrict__ sc, PushResult *__restrict__ result)
+// One push in one launch: every block computes the hash of the new vector (the sequential 1-norm is one
+// thread's chain of m2 additions -- the same few microseconds whether one block does it or all of them do it
+// side by side, and a launch cheaper than handing it over from a kernel of its own), then the blocks scan
+// the stored hashes, one warp per stored vertex (grid-stride), and the last block to finish commits.
+// `sc` must hold {match = INT_MAX, done = 0} on entry; the committing block restores that for the next push.
+#define SQLP_PUSH_SMEM_DOUBLES 4096
+__global__ void __launch_bounds__(256) k_pool_push(double *__restrict__ pi, unsigned long long *__restrict__ hash,
+                                                   long long *__restrict__ d_K, int m2, const double *__restrict__ v,
+                                                   PushScratch *__restrict__ sc, PushResult *__restrict__ result)
 {
+    griddep_sync();
+    extern __shared__ double sh_abs[];
+    __shared__ unsigned long long h_sh;
+    __shared__ bool is_last;
+    const bool in_smem = m2 <= SQLP_PUSH_SMEM_DOUBLES;
+    if (in_smem)
+        for (int j = threadIdx.x; j < m2; j += blockDim.x) sh_abs[j] = fabs(v[j]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mysum = 0.0;                               // :49-51 sequential, index order
+        if (in_smem)
+            for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, sh_abs[j]);
+        else
+            for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, fabs(v[j]));
+        h_sh = (unsigned long long)__double_as_longlong(round_sig16(mysum));
+    }
+    __syncthreads();
     const long long K = *d_K;
-    const unsigned long long h = sc->hash;
+    const unsigned long long h = h_sh;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -63,7 +83,7 @@ __global__ void k_pool_find_commit(double *__restrict__ pi, unsigned long long *
         const double *row = pi + k * (long long)m2;
         bool same = true;
         for (int j = lane; j < m2; j += 32) {
-            double r1 = vr[j];
+            double r1 = round_sig16(v[j]);
             double r2 = round_sig16(row[j]);
             if (r1 != r2) same = false;                   // :34  NaN != NaN
         }
@@ -71,7 +91,6 @@ __global__ void k_pool_find_commit(double *__restrict__ pi, unsigned long long *
         if (same && lane == 0) atomicMin(&sc->match, (int)k);
     }
 
-    __shared__ bool is_last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -82,6 +101,12 @@ __global__ void k_pool_find_commit(double *__restrict__ pi, unsigned long long *
     if (!is_last) return;
     __threadfence();
     const int match = *((volatile int *)&sc->match);
+    __syncthreads();                                      // everyone has read the match before it is reset
+    if (threadIdx.x == 0) {
+        sc->hash = h;
+        sc->match = 0x7fffffff;
+        sc->done = 0u;
+    }
     if (match != 0x7fffffff) {
         if (threadIdx.x == 0) {
             result->index = match;
@@ -107,6 +132,7 @@ __global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__
                             int n_rows, int s_pad, double *__restrict__ piS, long long k_lo,
                             const long long *__restrict__ d_K)
 {
+    griddep_sync();
     const long long K = *d_K;
     const long long total = (K - k_lo) * n_rows;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -126,6 +152,7 @@ __global__ void k_epi_tables(const double *__restrict__ pi, int m2, const int *_
                              const double *__restrict__ T_nzval, int n1, double *__restrict__ rt,
                              long long k_lo, const long long *__restrict__ d_K)
 {
+    griddep_sync();
     const long long K = *d_K;
     const int RT = n1 + 1;
     for (long long k = k_lo + blockIdx.x; k < K; k += gridDim.x) {

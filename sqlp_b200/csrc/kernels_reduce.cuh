@@ -24,8 +24,10 @@ namespace sqlp {
 __global__ void k_base(const double *__restrict__ rbar, int m2, int n1,
                        const int *__restrict__ R_ptr, const int *__restrict__ R_col,
                        const double *__restrict__ R_val, const double *__restrict__ x2,
-                       double *__restrict__ base)
+                       double *__restrict__ base, int *__restrict__ flags)
 {
+    griddep_sync();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *flags = 0;   // this call's "no argmax" bit
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m2) return;
     const double *x = x2 + (long long)blockIdx.y * n1;
@@ -42,6 +44,7 @@ __global__ void k_bias(const double *__restrict__ pi, int m2, const double *__re
                        const long long *__restrict__ d_K, long long kpad, double *__restrict__ bias,
                        long long bias_stride)
 {
+    griddep_sync();
     const long long K = *d_K;
     const int lane = threadIdx.x & 31;
     const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -93,6 +96,7 @@ struct ReduceArgs {
 template <int NX>
 __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
 {
+    griddep_sync();
     __shared__ double a_i[NX][SQLP_TILE];   // PiS[k*, :] . delta_rhs_i
     __shared__ double p_i[SQLP_TILE];
     __shared__ int k_i[NX][SQLP_TILE];
@@ -189,10 +193,15 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
     }
 }
 
-// out[g][q] = sum over p in [g*group, min(n,(g+1)*group)) of in[p][q], in order.
+// Two ordered levels in one launch.  Level 1: block g writes out[g][q] = sum over p in [g*group,
+// min(n,(g+1)*group)) of in[p][q], in order.  Level 2: the last block to finish adds the group sums in group
+// order into fin[q] and re-arms the counter.  Which block runs level 2 depends on timing, what it computes
+// does not.
 __global__ void k_sum_groups(const double *__restrict__ in, long long n, int group, int width,
-                             double *__restrict__ out)
+                             double *__restrict__ out, unsigned int *__restrict__ counter, double *__restrict__ fin)
 {
+    griddep_sync();
+    __shared__ bool is_last;
     const long long g = blockIdx.x;
     const long long p0 = g * group, p1 = min(n, p0 + group);
     for (int q = threadIdx.x; q < width; q += blockDim.x) {
@@ -200,6 +209,18 @@ __global__ void k_sum_groups(const double *__restrict__ in, long long n, int gro
         for (long long p = p0; p < p1; ++p) s += in[p * width + q];
         out[g * width + q] = s;
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int q = threadIdx.x; q < width; q += blockDim.x) {
+        double s = 0.0;
+        for (long long gg = 0; gg < gridDim.x; ++gg) s += __ldcg(out + gg * width + q);
+        fin[q] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
 }
 
 // eval_dual, subprob.jl:128-131, in the reference's operation order (single thread):
@@ -226,6 +247,7 @@ struct EvalArgs {
 
 __global__ void k_eval_dual(EvalArgs a)
 {
+    griddep_sync();
     if (threadIdx.x || blockIdx.x) return;
     double *y = a.scratch, *r = a.scratch + a.m2;
     for (int j = 0; j < a.m2; ++j) { y[j] = 0.0; r[j] = a.rbar[j]; }
@@ -258,6 +280,7 @@ __global__ void k_eval_dual(EvalArgs a)
 __global__ void k_rank_sum(const double *__restrict__ in, int world, int width,
                            double *__restrict__ out)
 {
+    griddep_sync();
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= width) return;
     double s = 0.0;

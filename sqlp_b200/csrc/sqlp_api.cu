@@ -74,6 +74,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
         else if (!strcmp(m, "resident")) c->contract_mode = 2;
         else if (!strcmp(m, "ws")) c->contract_mode = 3;
     }
+    if (const char *g = getenv("SQLP_PDL")) c->pdl = atoi(g) != 0;
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_LAG_NS")) c->contract_lag_ns = atoi(g);
@@ -244,6 +245,8 @@ int32_t sqlp_pool_create(sqlp_ctx *c, int64_t m2, sqlp_pool **out)
             p->m2 = m2;
             p->d_K.ensure(8, 0, S(c));
             p->d_scratch.ensure(sizeof(PushScratch), 0, S(c));
+            const PushScratch idle = {0ull, 0x7fffffff, 0u};      // what k_pool_push expects and leaves behind
+            CK(cudaMemcpyAsync(p->d_scratch.p, &idle, sizeof idle, cudaMemcpyHostToDevice, S(c)));
             p->d_vr.ensure((size_t)m2 * 8, 0, S(c));
             pool_reserve(p, 1024);
             CK(cudaStreamSynchronize(S(c)));
@@ -332,6 +335,7 @@ int32_t sqlp_pool_hash(sqlp_pool *p, const double *v, uint64_t *hash)
         c->bind();
         p->d_vnew.ensure((size_t)p->m2 * 8, 0, S(c));
         CK(cudaMemcpyAsync(p->d_vnew.p, v, (size_t)p->m2 * 8, cudaMemcpyHostToDevice, S(c)));
+        REQUIRE(p->m2 <= 6000, SQLP_E_UNSUPPORTED, "sqlp_pool_hash (debug) handles m2 <= 6000");
         LAUNCH(c, k_pool_prepare, 1, 256, (size_t)p->m2 * 8, p->d_vnew.as<double>(), (int)p->m2,
                p->d_vr.as<double>(), p->d_scratch.as<PushScratch>());
         PushScratch sc;
