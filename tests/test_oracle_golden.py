@@ -215,3 +215,66 @@ def test_cut_bookkeeping_known_answers(oracle):     # sd_test.jl:166-194
     cur = [([cut1, cut2], inc, 2.0, 0.0, 1.0)]
     cand, incv, req, improved = oracle.cut_check_improvement(last, cur, x10, np.zeros(4), np.ones(4))
     assert cand == 551.0 + 40.0 and incv == 11.0 and req == 0.2 * ((0.5 * 141 + 40.0) - 0.5) and improved is False
+
+
+# ---- the one arithmetic the reference does not pin: LinearAlgebra.dot's summation order ----
+
+def _scores_blocked16(P, vals, x, pool):
+    """score[i, k] with both dots of subprob.jl:155 summed the way OpenBLAS 0.3.21's x86-64 ddot
+    micro-kernels do (restated from their published structure): a prefix of
+    n & -32 elements accumulated in 16 independent lanes (4 vector registers x 4 doubles, fused
+    multiply-add, the registers added pairwise and then across lanes), the tail added one by one."""
+    Tm = P.T_dense()
+    base = P.rbar - Tm @ x
+
+    def ddot(a, b):
+        n = a.shape[-1]
+        n1 = n & -32
+        lanes = np.zeros(a.shape[:-1] + (16,), dtype=np.longdouble)
+        for i in range(0, n1, 16):
+            # fma: product exact in extended precision, one rounding to double per step
+            lanes = (lanes + a[..., i:i + 16].astype(np.longdouble) * b[..., i:i + 16]).astype(np.float64).astype(np.longdouble)
+        lanes = lanes.astype(np.float64)
+        r = (lanes[..., 0:4] + lanes[..., 4:8]) + (lanes[..., 8:12] + lanes[..., 12:16])
+        dot = (r[..., 0] + r[..., 1]) + (r[..., 2] + r[..., 3])
+        for i in range(n1, n):
+            dot = dot + a[..., i] * b[..., i]
+        return dot
+
+    first = ddot(pool, np.broadcast_to(base, pool.shape))                      # [K]
+    dvec = np.zeros((len(vals), P.m2))
+    for e in range(P.s):
+        assert P.pos_col[e] < 0
+        dvec[:, P.pos_row[e]] = vals[:, e] - P.rbar[P.pos_row[e]]
+    second = ddot(pool[None, :, :], dvec[:, None, :])                          # [N, K]
+    return first[None, :] + second
+
+
+@pytest.mark.parametrize("name", ["baa99-20", "ssn", "storm"])
+def test_argmax_does_not_depend_on_the_dot_summation_order(oracle, name):
+    """Julia's ``dot`` is OpenBLAS ``ddot`` whose summation order is architecture dependent, so bitwise
+    parity with the Julia runtime is undefined even CPU to CPU.  On the real instances
+    with their harvested pools the oracle's index-order sums, a 16-lane blocked FMA order and extended
+    precision all select the same vertex for every scenario, except where the gap between best and
+    second best is inside the north-star exemption (1e-12 relative) -- the exemption is what absorbs the
+    unpinned order, and it is rarely needed."""
+    P, z = load_instance(name)
+    N = 300
+    vals = sample_instance_values(z, N, seed=9)
+    pool = z["pool"]
+    x = z["x_alt"]
+    ov, oi = oracle.argmax_procedure(P, vals, x, pool)
+    Tm = P.T_dense()
+    r_i = np.tile(P.rbar, (N, 1))
+    r_i[:, P.pos_row] = vals
+    exact = (r_i.astype(np.longdouble) - (Tm @ x).astype(np.longdouble)[None, :]) @ pool.astype(np.longdouble).T
+    variants = {"blocked16": _scores_blocked16(P, vals, x, pool), "longdouble": exact.astype(np.float64)}
+    for label, sc in variants.items():
+        pick = np.argmax(sc, axis=1)                  # first maximum, like the strict '>' of :156
+        differ = np.nonzero(pick != oi)[0]
+        for i in differ:
+            best = float(exact[i].max())
+            gap = abs(float(exact[i, pick[i]]) - float(exact[i, oi[i]]))
+            assert gap <= 1e-12 * max(abs(best), 1.0), (label, i, gap)
+        rel = np.max(np.abs(sc[np.arange(N), oi] - ov) / np.maximum(np.abs(ov), 1.0))
+        assert rel <= 1e-12, (label, rel)
