@@ -545,6 +545,9 @@ int32_t sqlp_epi_set_outcomes(sqlp_epi *e, int64_t mo, const double *vals, const
             REQUIRE(cnt[q] >= 1 && cnt[q] <= mo, SQLP_E_INVALID, "outcome count out of range");
         std::vector<double> v(vals, vals + e->s * mo), f(cdf, cdf + e->s * mo);
         std::vector<int> n(cnt, cnt + e->s);
+        // only cnt[e] entries of a row are valid: whatever pads the rest must never count as "<= u"
+        for (int64_t q = 0; q < e->s; ++q)
+            for (int64_t o = cnt[q]; o < mo; ++o) f[(size_t)(q * mo + o)] = INFINITY;
         upload(e->d_ovals, v, S(c));
         upload(e->d_ocdf, f, S(c));
         upload(e->d_ocnt, n, S(c));
