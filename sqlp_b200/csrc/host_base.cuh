@@ -168,7 +168,8 @@ struct sqlp_ctx {
 // the programmatic-stream-serialization attribute: the kernel may be scheduled before its predecessor
 // has drained and synchronises with it by griddep_sync() (common.cuh), its first statement.
 template <class... KArgs, class... Args>
-void launch_kernel(sqlp_ctx *c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+void launch_kernel(sqlp_ctx *c, const char *name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                   Args &&...args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -180,11 +181,15 @@ void launch_kernel(sqlp_ctx *c, void (*kernel)(KArgs...), dim3 grid, dim3 block,
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = c->pdl ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (err != cudaSuccess)
+        throw Error(SQLP_E_CUDA, std::string("launch of ") + name + " (grid " + std::to_string(grid.x) + "x" +
+                                     std::to_string(grid.y) + ", block " + std::to_string(block.x) + ", " +
+                                     std::to_string(smem) + " B of dynamic shared memory): " + cudaGetErrorString(err));
     ++c->launches;
 }
 #define LAUNCH(ctx, kernel, grid, block, smem, ...) \
-    launch_kernel((ctx), kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+    launch_kernel((ctx), #kernel, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
 
 struct PoolView {   // the pool restricted to one set of stochastic rows, in tile layout
     std::vector<int> rows;

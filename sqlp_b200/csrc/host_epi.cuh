@@ -138,9 +138,11 @@ bool launch_contract_resident(sqlp_epi *e, ContractArgs &a)
     }
     if (stages < 2) return false;
     const size_t smem = fixed + stage * stages;
-    if (c->res_smem_set[NX] < (int)smem) {
-        CK(cudaFuncSetAttribute(k_contract_resident<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->res_smem_set[NX] = (int)smem;
+    // The attribute belongs to the function on this device, not to the context: every context sets the same
+    // (maximal) value, so a context created later can never lower what an earlier one relies on.
+    if (!c->res_smem_set[NX]) {
+        CK(cudaFuncSetAttribute(k_contract_resident<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        c->res_smem_set[NX] = 1;
     }
     const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
     const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;   // host upper bound
@@ -172,9 +174,9 @@ bool launch_contract_ws(sqlp_epi *e, ContractArgs &a)
     const int stages = budget > fixed ? (int)std::min<size_t>((budget - fixed) / stage, SQLP_RES_MAX_STAGES) : 0;
     if (stages < 3) return false;
     const size_t smem = fixed + stage * stages;
-    if (c->ws_smem_set[NX] < (int)smem) {
-        CK(cudaFuncSetAttribute(k_contract_ws<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->ws_smem_set[NX] = (int)smem;
+    if (!c->ws_smem_set[NX]) {   // the same maximal value from every context (see launch_contract_resident)
+        CK(cudaFuncSetAttribute(k_contract_ws<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        c->ws_smem_set[NX] = 1;
     }
     const long long nunits = (long long)Cfg::UNITS_PER_TILE * a.ntiles;
     const long long nchunks_ub = (e->pool->upper() + SQLP_TILE - 1) / SQLP_TILE;
