@@ -80,6 +80,8 @@ SQLP_API int32_t sqlp_ctx_timer_stop(sqlp_ctx *ctx);
 SQLP_API int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *ctx, double *ms);
 /* Accumulated device time (ms) and launch count of the contraction kernel since the last
  * call with reset != 0; measured with CUDA events around each launch when enabled. */
+/* enable: 0 off, 1 every kernel class, otherwise a mask -- bit (1 + cls) turns on class cls of the list below
+ * (2 = the contraction alone: two event records per launch instead of ten per SD iteration). */
 SQLP_API int32_t sqlp_ctx_profile(sqlp_ctx *ctx, int32_t enable);
 SQLP_API int32_t sqlp_ctx_profile_read(sqlp_ctx *ctx, int32_t reset, double *contract_ms,
                                        int64_t *contract_launches, double *contract_flops);
@@ -187,6 +189,19 @@ SQLP_API int32_t sqlp_epi_build_cuts2(sqlp_epi *epi, const double *x_cand, const
 SQLP_API int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, const double *x_cand,
                                        const double *x_inc, double *alpha, double *beta,
                                        double *weight_mark, double *val /*or NULL*/);
+/* The cut formation of one SD iteration in ONE call and one synchronisation -- sd_iteration!,
+ * algorithm.jl:45-55 and :79-85, minus the LP solves that produce its inputs: for every epigraph
+ * add_scenario!(epi_e, scenario_e, weight_e); then push!(dual_vertices, v) for the n_vertices dual
+ * vertices found at the candidate and the incumbent, in order; then both cuts of every epigraph.
+ * values holds the epigraphs' value vectors back to back ([s_0 | s_1 | ...], table order), weights one
+ * per epigraph (NULL = 1.0); inserted / index [n_vertices] as sqlp_pool_push (may be NULL); cut outputs
+ * as sqlp_cell_build_cuts2.  The epigraphs share one context and one pool.  Same results, bit for bit,
+ * as the separate calls; what it saves is their synchronisations and pageable copies. */
+SQLP_API int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const double *values,
+                                   const double *weights, int64_t n_vertices, const double *vertices,
+                                   int32_t *inserted, int64_t *index, const double *x_cand,
+                                   const double *x_inc, double *alpha, double *beta,
+                                   double *weight_mark, double *val /*or NULL*/);
 /* Enqueue only: d_x2 = [x_cand | x_inc] on the device, d_out = [2][n1 + 2] on the device
  * holding (alpha, beta[n1], val) per x.  Errors such as a missing argmax surface at the
  * next blocking call. */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "sqlp_epi_build_cuts2": [_vp, _vp, _vp, _vp, _vp, _P(_f64), _vp],
     "sqlp_cell_build_cuts2": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "sqlp_epi_build_cuts2_dev": [_vp, _vp, _vp],
+    "sqlp_cell_sd_step": [_i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "sqlp_eval_dual": [_vp, _i64, _i64, _vp, _P(_f64)],
     "sqlp_epi_set_weights": [_vp, _f64, _f64],
     "sqlp_epi_cuts_push": [_vp, _f64, _vp, _f64],

@@ -124,6 +124,27 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct PinnedBuf {   // page-locked host memory: device-to-host copies into it are truly asynchronous
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    void ensure(size_t need)   // contents are not preserved; the caller has drained the stream
+    {
+        if (need <= bytes) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+        if (e != cudaSuccess)
+            throw Error(SQLP_E_NOMEM, std::string("cudaHostAlloc(") + std::to_string(need) + "): " + cudaGetErrorString(e));
+        bytes = need;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 template <class T>
 void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
 {
@@ -144,7 +165,7 @@ struct sqlp_ctx {
     ncclComm_t comm = nullptr;
     int64_t launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    bool profile = false;
+    unsigned profile = 0;         // bit cls: event scopes around the launches of kernel class cls
     bool pdl = true;              // programmatic dependent launch of every kernel (SQLP_PDL=0: plain stream order)
     struct ProfEvent { cudaEvent_t e0, e1; int cls; };
     std::vector<ProfEvent> prof_events;
@@ -161,6 +182,8 @@ struct sqlp_ctx {
     bool delta_smem_set = false;
     int res_smem_set[3] = {0, 0, 0};
     DevBuf d_piece_val, d_piece_idx;
+    DevBuf d_step;                // sqlp_cell_sd_step: the step's scenario values on the device
+    PinnedBuf h_step;             //                    its results on the way back
     void bind() const { CK(cudaSetDevice(device)); }
 };
 
@@ -262,7 +285,7 @@ struct ProfScope {   // CUDA events around the launch(es) of one kernel class wh
     cudaEvent_t e1 = nullptr;
     ProfScope(sqlp_ctx *c_, int cls, double work) : c(c_)
     {
-        if (!c->profile) return;
+        if (!((c->profile >> cls) & 1u)) return;
         if (c->prof_used == c->prof_events.size()) {
             cudaEvent_t a = nullptr, b = nullptr;
             CK(cudaEventCreate(&a));

@@ -347,12 +347,17 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         // table + the cut (with delta_T != 0 the kernel also re-reads D to recompute the winning dot)
         ProfScope prof_red(c, SQLP_PROF_REDUCE,
                            NX * (24.0 * (double)e->n_local + 8.0 * (double)ku * (n1 + 1) + 8.0 * (n1 + 1)));
-        if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, 0, r);
-        else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, 0, r);
+        // tiles and groups are split into 8 sub-ranges summed side by side when the sub-sums fit in the
+        // default 48 KB of dynamic shared memory (n1 <= 382 for two points), else not at all
+        const int nsub = (size_t)8 * width * 8 <= 48 * 1024 ? 8 : 1;
+        const size_t sub_smem = nsub > 1 ? (size_t)nsub * width * 8 : 0;
+        r.nsub = nsub;
+        if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, sub_smem, r);
+        else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, sub_smem, r);
         const int group = 64;
         int64_t ng = (ntiles + group - 1) / group;
         e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
-        LAUNCH(c, k_sum_groups, (int)ng, 256, 0, e->d_partial.as<double>(), (long long)ntiles, group,
+        LAUNCH(c, k_sum_groups, (int)ng, 256, sub_smem, e->d_partial.as<double>(), (long long)ntiles, group, nsub,
                width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), e->d_out.as<double>());
         prof_red.stop();
     }

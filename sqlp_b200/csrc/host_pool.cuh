@@ -89,9 +89,11 @@ void epi_tables_sync(sqlp_epi *e)
     int64_t hi = p->upper();
     if (hi > e->rt_synced_lo) {
         int grid = (int)std::min<int64_t>(hi - e->rt_synced_lo, 16 * c->sm_count);
-        LAUNCH(c, k_epi_tables, grid, 128, 0, p->d_pi.as<double>(), (int)p->m2, e->d_ridx.as<int>(),
-               e->d_rnz.as<double>(), e->r_nnz, e->d_colptr.as<long long>(), e->d_rowval.as<int>(), e->d_nzval.as<double>(),
-               (int)e->n1, e->d_rt.as<double>(), (long long)e->rt_synced_lo, p->d_K.as<long long>());
+        const int stage_rho = e->r_nnz > 0 && e->r_nnz <= 4096;
+        LAUNCH(c, k_epi_tables, grid, 128, stage_rho ? (size_t)e->r_nnz * 8 : 0, p->d_pi.as<double>(), (int)p->m2,
+               e->d_ridx.as<int>(), e->d_rnz.as<double>(), e->r_nnz, e->d_colptr.as<long long>(), e->d_rowval.as<int>(),
+               e->d_nzval.as<double>(), (int)e->n1, e->d_rt.as<double>(), (long long)e->rt_synced_lo,
+               p->d_K.as<long long>(), stage_rho);
     }
     e->rt_synced_lo = p->K;
 }

@@ -351,15 +351,25 @@ __global__ void k_argmax_fixup(ContractArgs a, int main_grid)
         size_t o = (((size_t)b * 2 + 1) * NX + x) * ROWS + row;
         double v = a.piece_val[o];
         int i = a.piece_idx[o];
-        for (int bb = b + 1; bb < main_grid; ++bb) {
-            const long long M0 = span_at(total_cu, bb, main_grid), M1 = span_at(total_cu, bb + 1, main_grid);
-            if (M0 < M1) {
-                o = (((size_t)bb * 2) * NX + x) * ROWS + row;
-                const double ov = a.piece_val[o];
-                const int oi = a.piece_idx[o];
-                if (better(ov, oi, v, i)) { v = ov; i = oi; }
+        // the blocks holding the rest of the unit: b + 1 .. last, found by span arithmetic alone, so their
+        // pieces are fetched four at a time instead of one dependent load after another
+        int last = b + 1;
+        while (last < main_grid - 1 && span_at(total_cu, last + 1, main_grid) < uend) ++last;
+        for (int b0 = b + 1; b0 <= last; b0 += 4) {
+            double ov[4];
+            int oi[4];
+            bool use[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int bb = b0 + u;
+                use[u] = bb <= last && span_at(total_cu, bb, main_grid) < span_at(total_cu, bb + 1, main_grid);
+                o = (((size_t)min(bb, last) * 2) * NX + x) * ROWS + row;
+                ov[u] = a.piece_val[o];
+                oi[u] = a.piece_idx[o];
             }
-            if (M1 >= uend) break;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (use[u] && better(ov[u], oi[u], v, i)) { v = ov[u]; i = oi[u]; }
         }
         const long long sc = unit * ROWS + row;
         if (sc < a.n_local) {

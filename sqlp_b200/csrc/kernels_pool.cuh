@@ -150,23 +150,32 @@ __global__ void k_epi_tables(const double *__restrict__ pi, int m2, const int *_
                              const double *__restrict__ r_val, int r_nnz,
                              const long long *__restrict__ T_colptr, const int *__restrict__ T_rowval,
                              const double *__restrict__ T_nzval, int n1, double *__restrict__ rt,
-                             long long k_lo, const long long *__restrict__ d_K)
+                             long long k_lo, const long long *__restrict__ d_K, int stage_rho)
 {
     griddep_sync();
+    extern __shared__ double prod[];                 // [r_nnz] when stage_rho
     const long long K = *d_K;
     const int RT = n1 + 1;
     for (long long k = k_lo + blockIdx.x; k < K; k += gridDim.x) {
         const double *row = pi + k * (long long)m2;
+        if (stage_rho) {   // the products of rho, fetched by every thread side by side; the ordered chain below
+            for (int q = threadIdx.x; q < r_nnz; q += blockDim.x) prod[q] = __dmul_rn(row[r_idx[q]], r_val[q]);
+            __syncthreads();
+        }
         for (int c = threadIdx.x; c < RT; c += blockDim.x) {
             double acc = 0.0;
-            if (c == 0) {   // the non-zeros of rbar in index order: independent loads, one ordered chain
-                for (int q = 0; q < r_nnz; ++q) acc = __dadd_rn(acc, __dmul_rn(row[r_idx[q]], r_val[q]));
+            if (c == 0) {   // the non-zeros of rbar in index order: one ordered chain
+                if (stage_rho)
+                    for (int q = 0; q < r_nnz; ++q) acc = __dadd_rn(acc, prod[q]);
+                else
+                    for (int q = 0; q < r_nnz; ++q) acc = __dadd_rn(acc, __dmul_rn(row[r_idx[q]], r_val[q]));
             } else {
                 for (long long q = T_colptr[c - 1]; q < T_colptr[c]; ++q)
                     acc = __dadd_rn(acc, __dmul_rn(T_nzval[q], row[T_rowval[q]]));
             }
             rt[k * RT + c] = acc;
         }
+        if (stage_rho) __syncthreads();              // prod is rewritten for the block's next vertex
     }
 }
 

@@ -90,6 +90,7 @@ struct ReduceArgs {
     const int *tc_j;          // [n_T] row slot in S
     const int *tc_slot;       // [n_T] slot in dT
     double *partial;          // [ntiles][NX][n1 + 2]   (alpha, beta[n1], val)
+    int nsub;                 // sub-ranges a tile is split into (1, 2, 4 or 8; > 1 needs nsub * NX * (n1 + 2) doubles of dynamic smem)
     int *flags;               // bit 0: some scenario had no argmax
 };
 
@@ -144,14 +145,21 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
     }
     __syncthreads();
 
-    // phase B: thread per (x, output column); scenarios in index order.  The table rows of eight
-    // scenarios are fetched before they are used, so the gathers overlap instead of queueing
-    // behind one another; the additions keep the scenario order.  The loop body is branch free: a
-    // scenario without argmax contributes fma(0, 0, sum) = sum.
+    // phase B: a work item is (sub-range of the tile's scenarios, point x, output column); a.nsub sub-ranges
+    // of 128 / nsub consecutive scenarios each.  Inside an item the scenarios are added in index order, the
+    // table rows of eight scenarios being fetched before they are used so the gathers overlap; the nsub
+    // sub-sums are then added in sub-range order.  The order is fixed by (N, nsub) alone, so the result is
+    // deterministic; splitting the tile only shortens the chain of dependent gathers a thread walks (16
+    // batches -> 2 at nsub = 8), which is what bounds this kernel at small N.  The loop body is branch
+    // free: a scenario without argmax contributes fma(0, 0, sum) = sum.
+    extern __shared__ double sub_sum[];              // [nsub][NX * NC] when nsub > 1
     const int NC = a.n1 + 2;
     const long long RT = a.n1 + 1;
-    for (int q = threadIdx.x; q < NX * NC; q += blockDim.x) {
+    const int ncols = NX * NC, nsub = a.nsub, per = SQLP_TILE / nsub;
+    for (int item = threadIdx.x; item < nsub * ncols; item += blockDim.x) {
+        const int sub = item / ncols, q = item % ncols;
         const int x = q / NC, col = q % NC;
+        const int c0 = sub * per, c1 = c0 + per;
         const bool is_alpha = (col == 0), is_val = (col == NC - 1);
         double sum = 0.0;
         if (!is_alpha && !is_val && a.n_T) {
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             while (t0 < a.n_T && a.tc_col[t0] < col - 1) ++t0;
             t1 = t0;
             while (t1 < a.n_T && a.tc_col[t1] == col - 1) ++t1;
-            for (int c = 0; c < cnt; ++c) {
+            for (int c = c0; c < min(c1, cnt); ++c) {
                 const int k = k_i[x][c];
                 if (k < 0) continue;
                 double term = a.rt[(long long)k * RT + col];                           // :141
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             const double *src = is_val ? a.best_val + x * a.out_stride + i0 : a.rt + col;
             const long long stride = is_val ? 0 : RT;      // table row stride; the value column is per scenario
             const double sign = (is_alpha || is_val) ? 1.0 : -1.0;                     // :140-142
-            for (int cb = 0; cb < SQLP_TILE; cb += 8) {    // k_i is -1 beyond cnt
+            for (int cb = c0; cb < c1; cb += 8) {          // k_i is -1 beyond cnt
                 double tv[8], pw[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -189,25 +197,53 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
                 for (int u = 0; u < 8; ++u) sum = fma(pw[u], tv[u], sum);
             }
         }
-        a.partial[(tile * NX + x) * NC + col] = sum;
+        if (nsub == 1) a.partial[tile * ncols + q] = sum;
+        else sub_sum[sub * ncols + q] = sum;
+    }
+    if (nsub == 1) return;
+    __syncthreads();
+    for (int q = threadIdx.x; q < ncols; q += blockDim.x) {
+        double sum = sub_sum[q];
+        for (int sub = 1; sub < nsub; ++sub) sum += sub_sum[sub * ncols + q];
+        a.partial[tile * ncols + q] = sum;
     }
 }
 
-// Two ordered levels in one launch.  Level 1: block g writes out[g][q] = sum over p in [g*group,
-// min(n,(g+1)*group)) of in[p][q], in order.  Level 2: the last block to finish adds the group sums in group
-// order into fin[q] and re-arms the counter.  Which block runs level 2 depends on timing, what it computes
-// does not.
-__global__ void k_sum_groups(const double *__restrict__ in, long long n, int group, int width,
-                             double *__restrict__ out, unsigned int *__restrict__ counter, double *__restrict__ fin)
+// Two ordered levels in one launch.  Level 1: block g adds the partial rows [g*group, min(n,(g+1)*group))
+// -- nsub sub-ranges of group / nsub consecutive rows, each added in row order by its own thread (loads
+// batched so they overlap), the sub-sums then added in sub-range order -- into out[g][q].  Level 2: the last
+// block to finish adds the group sums in group order into fin[q] and re-arms the counter.  Which block runs
+// level 2 depends on timing; what it computes does not.
+__global__ void __launch_bounds__(256) k_sum_groups(const double *__restrict__ in, long long n, int group, int nsub,
+                                                    int width, double *__restrict__ out,
+                                                    unsigned int *__restrict__ counter, double *__restrict__ fin)
 {
     griddep_sync();
+    extern __shared__ double sub_sum[];              // [nsub][width] when nsub > 1
     __shared__ bool is_last;
     const long long g = blockIdx.x;
-    const long long p0 = g * group, p1 = min(n, p0 + group);
-    for (int q = threadIdx.x; q < width; q += blockDim.x) {
+    const int per = group / nsub;
+    for (int item = threadIdx.x; item < nsub * width; item += blockDim.x) {
+        const int sub = item / width, q = item % width;
+        const long long p0 = g * group + (long long)sub * per, p1 = min(n, p0 + per);
         double s = 0.0;
-        for (long long p = p0; p < p1; ++p) s += in[p * width + q];
-        out[g * width + q] = s;
+        for (long long p = p0; p < p1; p += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (p + u < p1) ? in[(p + u) * width + q] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];       // + 0.0 leaves a partial sum unchanged (never -0 here: s starts at +0)
+        }
+        if (nsub == 1) out[g * width + q] = s;
+        else sub_sum[item] = s;
+    }
+    if (nsub > 1) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < width; q += blockDim.x) {
+            double s = sub_sum[q];
+            for (int sub = 1; sub < nsub; ++sub) s += sub_sum[sub * width + q];
+            out[g * width + q] = s;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -217,7 +253,13 @@ __global__ void k_sum_groups(const double *__restrict__ in, long long n, int gro
     __threadfence();
     for (int q = threadIdx.x; q < width; q += blockDim.x) {
         double s = 0.0;
-        for (long long gg = 0; gg < gridDim.x; ++gg) s += __ldcg(out + gg * width + q);
+        for (long long gg = 0; gg < gridDim.x; gg += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (gg + u < gridDim.x) ? __ldcg(out + (gg + u) * width + q) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
         fin[q] = s;
     }
     if (threadIdx.x == 0) *counter = 0u;

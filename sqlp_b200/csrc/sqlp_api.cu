@@ -191,7 +191,7 @@ int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *c, double *ms)
 
 int32_t sqlp_ctx_profile(sqlp_ctx *c, int32_t enable)
 {
-    return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->profile = enable != 0; });
+    return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->profile = enable == 1 ? ~0u : (unsigned)enable >> 1; });
 }
 
 int32_t sqlp_ctx_profile_classes(sqlp_ctx *c, int32_t reset, double *ms, int64_t *launches, double *work)
@@ -711,6 +711,83 @@ int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, const double 
             sqlp_epi *e = epi[i];
             finish_cut(e, 2, h[(size_t)i], alpha + 2 * i, beta + boff, weight_mark + i,
                        val ? val + 2 * i : nullptr);
+            boff += 2 * e->n1;
+        }
+    });
+}
+
+int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const double *values, const double *weights,
+                          int64_t n_vertices, const double *vertices, int32_t *inserted, int64_t *index,
+                          const double *x_cand, const double *x_inc, double *alpha, double *beta,
+                          double *weight_mark, double *val)
+{
+    return guard([&] {
+        REQUIRE(n_epi >= 1 && epi && epi[0], SQLP_E_INVALID, "bad epigraph list");
+        REQUIRE(n_vertices >= 0 && (vertices || n_vertices == 0), SQLP_E_INVALID, "bad vertex list");
+        REQUIRE(alpha && weight_mark, SQLP_E_INVALID, "null output");
+        sqlp_ctx *c = epi[0]->ctx;
+        sqlp_pool *p = epi[0]->pool;
+        REQUIRE(c->world == 1 || c->rank != 0 || vertices || n_vertices == 0, SQLP_E_INVALID, "null vertices");
+        c->bind();
+        size_t n_values = 0, n_out = 0;
+        for (int i = 0; i < n_epi; ++i) {
+            sqlp_epi *e = epi[i];
+            REQUIRE(e && e->ctx == c && e->pool == p, SQLP_E_INVALID, "epigraphs must share one context and one pool");
+            REQUIRE((x_cand && x_inc && beta) || e->n1 == 0, SQLP_E_INVALID, "null argument");
+            n_values += (size_t)e->s;
+            n_out += 2 * ((size_t)e->n1 + 2) + 1;                 // two cuts (alpha, beta, val) + the flags word
+        }
+        REQUIRE(values || n_values == 0, SQLP_E_INVALID, "null values");
+        // the drained stream of the previous call makes the two reusable buffers free
+        c->h_step.ensure(((size_t)n_vertices * sizeof(PushResult) / 8 + n_out + 1) * 8);
+        c->d_step.ensure(std::max<size_t>(n_values, 1) * 8, 0, S(c), false);
+        if (n_values)
+            CK(cudaMemcpyAsync(c->d_step.p, values, n_values * 8, cudaMemcpyHostToDevice, S(c)));
+        // algorithm.jl:45-46  add_scenario!(epi, scenario, weight) for every epigraph
+        size_t voff = 0;
+        for (int i = 0; i < n_epi; ++i) {
+            epi_add(epi[i], 1, nullptr, c->d_step.as<double>() + voff, weights ? weights + i : nullptr, false, 0, 0);
+            voff += (size_t)epi[i]->s;
+        }
+        // algorithm.jl:50,54  push!(dual_vertices, dual) for the vertices found at the candidate and the incumbent
+        PushResult *h_res = c->h_step.as<PushResult>();
+        double *h_out = c->h_step.as<double>() + (size_t)n_vertices * sizeof(PushResult) / 8;
+        long long *h_K = reinterpret_cast<long long *>(h_out + n_out);
+        if (n_vertices) {
+            pool_push_enqueue(p, n_vertices, vertices, nullptr);
+            CK(cudaMemcpyAsync(h_res, p->d_results.p, (size_t)n_vertices * sizeof(PushResult), cudaMemcpyDeviceToHost, S(c)));
+        }
+        // algorithm.jl:79-85  the candidate cut and the regenerated incumbent cut of every epigraph
+        std::vector<double> x2;
+        size_t ooff = 0;
+        for (int i = 0; i < n_epi; ++i) {
+            sqlp_epi *e = epi[i];
+            const size_t NC = (size_t)e->n1 + 2;
+            x2.assign((size_t)2 * e->n1, 0.0);
+            for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
+            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true);     // x2 is pageable: staged before the call returns
+            CK(cudaMemcpyAsync(h_out + ooff, e->d_out.p, 2 * NC * 8, cudaMemcpyDeviceToHost, S(c)));
+            CK(cudaMemcpyAsync(h_out + ooff + 2 * NC, e->d_flags.p, 4, cudaMemcpyDeviceToHost, S(c)));
+            ooff += 2 * NC + 1;
+        }
+        CK(cudaMemcpyAsync(h_K, p->d_K.p, 8, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));                          // the step's only synchronisation
+        p->K = *h_K;
+        p->pending = 0;
+        for (int64_t v = 0; v < n_vertices; ++v) {
+            if (inserted) inserted[v] = h_res[v].inserted;
+            if (index) index[v] = h_res[v].index;
+        }
+        ooff = 0;
+        int64_t boff = 0;
+        for (int i = 0; i < n_epi; ++i) {
+            sqlp_epi *e = epi[i];
+            const size_t NC = (size_t)e->n1 + 2;
+            CutHost h;
+            h.out.assign(h_out + ooff, h_out + ooff + 2 * NC);
+            h.flags = *reinterpret_cast<const int *>(h_out + ooff + 2 * NC);
+            finish_cut(e, 2, h, alpha + 2 * i, beta + boff, weight_mark + i, val ? val + 2 * i : nullptr);
+            ooff += 2 * NC + 1;
             boff += 2 * e->n1;
         }
     });

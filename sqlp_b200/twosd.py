@@ -85,7 +85,9 @@ class Context:
         check(_lib.lib().sqlp_ctx_timer_elapsed_ms(self._h, C.byref(ms)))
         return ms.value
 
-    def profile(self, enable: bool):
+    def profile(self, enable):
+        """False / True: every kernel class off / on; an int > 1 is the class mask of ``sqlp_ctx_profile``
+        (2 = the contraction alone)."""
         check(_lib.lib().sqlp_ctx_profile(self._h, int(enable)))
 
     def profile_read(self, reset=True):
@@ -587,6 +589,50 @@ def build_cuts_at_candidate_and_incumbent(epis, x_candidate, x_incumbent):
         e.incumbent_cut = inc
         out.append((cand, inc))
     return out
+
+
+def sd_step(epis, scenarios, weights, vertices, x_candidate, x_incumbent):
+    """The cut formation of one ``sd_iteration!`` (algorithm.jl:45-55, 79-85) in one library call and one
+    synchronisation (``sqlp_cell_sd_step``): ``add_scenario!`` of one scenario per epigraph, ``push!`` of
+    the dual vertices found at the candidate and the incumbent (rows of ``vertices``, in order), then both
+    cuts of every epigraph, which also go to ``epi.cuts`` / ``epi.incumbent_cut``.
+    Returns (inserted [n_vertices] bool, index [n_vertices], [(candidate cut, incumbent cut), ...])."""
+    epis = list(epis)
+    E = len(epis)
+    if E == 0:
+        raise ValueError("a cell has at least one epigraph")
+    if len(scenarios) != E:
+        raise ValueError("one scenario per epigraph")
+    dvs = epis[0].dual_vertices
+    xc, xi = _f64(x_candidate), _f64(x_incumbent)
+    n1 = epis[0].subproblem_coef.n1
+    for e in epis:
+        e._check_x(xc); e._check_x(xi)
+        if e.subproblem_coef.n1 != n1 or e.dual_vertices is not dvs:
+            raise ValueError("epigraphs of one cell share the first stage and the dual-vertex set")
+    vals = [e.subproblem_coef.scenario_values(sc) for e, sc in zip(epis, scenarios)]
+    for e, v in zip(epis, vals):
+        if len(v) != e.s:
+            raise ValueError("scenario does not match the epigraph's position table")
+    flat = _f64(np.concatenate(vals)) if vals and sum(len(v) for v in vals) else np.zeros(1)
+    w = None if weights is None else _f64(weights)
+    if w is not None and len(w) != E:
+        raise ValueError("one weight per epigraph")
+    V = _f64(vertices).reshape(-1, dvs.m2)
+    nv = len(V)
+    ins = np.zeros(max(nv, 1), dtype=np.int32); idx = np.zeros(max(nv, 1), dtype=np.int64)
+    handles = (C.c_void_p * E)(*[e._h for e in epis])
+    alpha = np.zeros((E, 2)); beta = np.zeros((E, 2, n1)); wm = np.zeros(E); val = np.zeros((E, 2))
+    check(_lib.lib().sqlp_cell_sd_step(E, handles, _ptr(flat), _ptr(w), nv, _ptr(V), _ptr(ins), _ptr(idx),
+                                       _ptr(xc), _ptr(xi), _ptr(alpha), _ptr(beta), _ptr(wm), _ptr(val)))
+    out = []
+    for i, e in enumerate(epis):
+        cand = sdCut(alpha[i, 0], beta[i, 0].copy(), wm[i])
+        inc = sdCut(alpha[i, 1], beta[i, 1].copy(), wm[i])
+        e.cuts.append(cand)
+        e.incumbent_cut = inc
+        out.append((cand, inc))
+    return ins[:nv].astype(bool), idx[:nv], out
 
 
 def check_improvement_device(epis, x_candidate, x_incumbent, cost, q_factor=0.2):

@@ -120,3 +120,54 @@ def test_commit_snapshot_and_improvement(T):
         for a, b in zip(got[:3], ref[:3]):
             assert abs(a - b) <= 1e-12 * max(1.0, abs(b))
         assert got[3] == ref[3]
+
+
+def test_sd_step_equals_the_separate_calls_bit_for_bit():
+    """``sqlp_cell_sd_step`` (add_scenario! per epigraph, the iteration's pushes, both cuts of every epigraph;
+    one synchronisation) against the same iteration made of ``add_scenario_``, ``push`` and
+    ``build_cuts_at_candidate_and_incumbent``: identical dedup decisions, slots, cut bits and pool contents
+    over several iterations with two weighted epigraphs, new and duplicate vertices, and dT elements."""
+    from sqlp_b200 import twosd as T
+    from tests.helpers import synthetic_problem, synthetic_values, synthetic_pool
+    P = synthetic_problem(m2=60, n1=14, s=22, n_T=8)
+    coef = lambda: T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
+    pool = synthetic_pool(P.m2, 150)
+    vals = synthetic_values(P, 400)
+    E, iters = 2, 6
+    cells = []
+    for _ in range(2):
+        dvs = T.sdDualVertexSet(m2=P.m2)
+        dvs.push_many(pool[:100])
+        epis = [T.sdEpigraph(coef(), 0.5, 0.0, dvs) for _ in range(E)]
+        for e, epi in enumerate(epis):
+            epi.add_scenarios(vals[e:300:E], 0.5 + O.u01(4, np.arange(len(vals[e:300:E]))))
+        cells.append((dvs, epis))
+    (dvs_a, epis_a), (dvs_b, epis_b) = cells
+    for it in range(iters):
+        xc, xi = 10.0 * O.u01(30 + it, np.arange(P.n1)), 10.0 * O.u01(50 + it, np.arange(P.n1))
+        scen = [vals[300 + it * E + e] for e in range(E)]
+        w = np.array([1.0 + 0.25 * e + 0.5 * it for e in range(E)])
+        verts = np.stack([pool[100 + 2 * it], pool[7 * it], pool[100 + 2 * it + 1], pool[100 + 2 * it]])  # new, dup, new, dup of new
+        ins_a, idx_a, cuts_a = T.sd_step(epis_a, scen, w, verts, xc, xi)
+        for e in range(E):
+            T.add_scenario_(epis_b[e], scen[e], float(w[e]))
+        pushed = [dvs_b.push(v) for v in verts]
+        cuts_b = T.build_cuts_at_candidate_and_incumbent(epis_b, xc, xi)
+        assert list(ins_a) == [p[0] for p in pushed] == [True, False, True, False]
+        assert list(idx_a) == [p[1] for p in pushed]
+        assert len(dvs_a) == len(dvs_b) == 100 + 2 * (it + 1)
+        for (ca, ia), (cb, ib) in zip(cuts_a, cuts_b):
+            for u, v in ((ca, cb), (ia, ib)):
+                assert u.alpha == v.alpha and np.array_equal(u.beta, v.beta) and u.weight_mark == v.weight_mark
+        for e in range(E):
+            assert epis_a[e].counts() == epis_b[e].counts()
+    assert np.array_equal(np.stack(list(dvs_a)), np.stack(list(dvs_b)))
+    # and against the oracle on the final state of one epigraph
+    n0 = len(vals[0:300:E])
+    all_vals = np.vstack([vals[0:300:E]] + [vals[300 + it * E][None, :] for it in range(iters)])
+    all_w = np.concatenate([0.5 + O.u01(4, np.arange(n0)), [1.0 + 0.5 * it for it in range(iters)]])
+    ref = O.build_sasa_cut(P, all_vals, all_w, xc, np.stack(list(dvs_a)), forced_idx=epis_a[0].argmax(xc)[1])
+    cut = cuts_a[0][0]
+    assert abs(cut.alpha - ref["alpha"]) <= 1e-10 * (abs(ref["alpha"]) + 1.0)
+    assert np.max(np.abs(cut.beta - ref["beta"])) <= 1e-10 * (np.abs(ref["beta"]).max() + 1.0)
+    assert cut.weight_mark == ref["weight_mark"]
