@@ -107,17 +107,18 @@ struct DevBuf {
     {
         if (need <= bytes) return;
         size_t nb = std::max(need, bytes + bytes / 2);
+        // stream-ordered allocation from the device's memory pool: growing a buffer in the middle of a run
+        // (N and K grow every SD iteration) neither synchronises the host with the device nor stalls the
+        // device the way cudaMalloc / cudaFree do; the old block goes back to the pool once the work queued
+        // before this point has finished with it
         void *np = nullptr;
-        cudaError_t e = cudaMalloc(&np, nb);
+        cudaError_t e = cudaMallocAsync(&np, nb, st);
         if (e != cudaSuccess)
-            throw Error(SQLP_E_NOMEM, std::string("cudaMalloc(") + std::to_string(nb) +
+            throw Error(SQLP_E_NOMEM, std::string("cudaMallocAsync(") + std::to_string(nb) +
                                           "): " + cudaGetErrorString(e));
         if (keep) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
         if (zero && nb > keep) CK(cudaMemsetAsync((char *)np + keep, 0, nb - keep, st));
-        if (p) {
-            CK(cudaStreamSynchronize(st));
-            cudaFree(p);
-        }
+        if (p) CK(cudaFreeAsync(p, st));
         p = np;
         bytes = nb;
     }

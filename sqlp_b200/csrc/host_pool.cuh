@@ -58,7 +58,7 @@ void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const doub
     ProfScope prof(c, SQLP_PROF_POOL, (double)n * (8.0 * (double)p->upper() + 16.0 * (double)p->m2));
     for (int64_t i = 0; i < n; ++i) {
         int64_t ku = p->upper() + i;
-        int grid = (int)std::min<int64_t>(std::max<int64_t>((ku + 7) / 8, 1), 4 * c->sm_count);
+        int grid = (int)std::min<int64_t>(std::max<int64_t>((ku + 255) / 256, 1), 2 * c->sm_count);
         size_t smem = (size_t)std::min<int64_t>(p->m2, SQLP_PUSH_SMEM_DOUBLES) * 8;
         LAUNCH(c, k_pool_push, grid, 256, smem, p->d_pi.as<double>(), p->d_hash.as<unsigned long long>(),
                p->d_K.as<long long>(), (int)p->m2, src + i * p->m2, p->d_scratch.as<PushScratch>(),

@@ -47,7 +47,7 @@ __global__ void k_pool_prepare(const double *__restrict__ v, int m2, double *__r
 // One push in one launch: every block computes the hash of the new vector (the sequential 1-norm is one
 // thread's chain of m2 additions -- the same few microseconds whether one block does it or all of them do it
 // side by side, and a launch cheaper than handing it over from a kernel of its own), then the blocks scan
-// the stored hashes, one warp per stored vertex (grid-stride), and the last block to finish commits.
+// the stored hashes, one per thread (grid-stride), and the last block to finish commits.
 // `sc` must hold {match = INT_MAX, done = 0} on entry; the committing block restores that for the next push.
 #define SQLP_PUSH_SMEM_DOUBLES 4096
 __global__ void __launch_bounds__(256) k_pool_push(double *__restrict__ pi, unsigned long long *__restrict__ hash,
@@ -74,21 +74,26 @@ __global__ void __launch_bounds__(256) k_pool_push(double *__restrict__ pi, unsi
     const long long K = *d_K;
     const unsigned long long h = h_sh;
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * warps_per_block;
-
-    for (long long k = warp0; k < K; k += nwarps) {
-        if (hash[k] != h) continue;                       // :26 hash gate (warp-uniform)
-        const double *row = pi + k * (long long)m2;
-        bool same = true;
-        for (int j = lane; j < m2; j += 32) {
-            double r1 = round_sig16(v[j]);
-            double r2 = round_sig16(row[j]);
-            if (r1 != r2) same = false;                   // :34  NaN != NaN
+    // the hash gate (:26), one stored hash per thread (coalesced); the rare hit is compared element by
+    // element by the whole warp.  Few blocks: the scan is 8 K bytes, and every block costs one atomic on
+    // the shared counter below.
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long kb = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); kb < K; kb += stride) {
+        const long long mine = kb + lane;
+        unsigned hits = __ballot_sync(0xffffffffu, mine < K && hash[mine] == h);
+        while (hits) {
+            const long long k = kb + (__ffs(hits) - 1);
+            hits &= hits - 1;
+            const double *row = pi + k * (long long)m2;
+            bool same = true;
+            for (int j = lane; j < m2; j += 32) {
+                double r1 = round_sig16(v[j]);
+                double r2 = round_sig16(row[j]);
+                if (r1 != r2) same = false;               // :34  NaN != NaN
+            }
+            same = __all_sync(0xffffffffu, same);
+            if (same && lane == 0) atomicMin(&sc->match, (int)k);
         }
-        same = __all_sync(0xffffffffu, same);
-        if (same && lane == 0) atomicMin(&sc->match, (int)k);
     }
 
     __syncthreads();

@@ -78,6 +78,12 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_LAG_NS")) c->contract_lag_ns = atoi(g);
+    {   // device buffers come from the default memory pool (DevBuf::ensure); keep freed blocks in it
+        cudaMemPool_t mp = nullptr;
+        CK(cudaDeviceGetDefaultMemPool(&mp, device));
+        unsigned long long keep_all = ~0ull;
+        CK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep_all));
+    }
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreate(&c->t0));
