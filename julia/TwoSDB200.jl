@@ -155,6 +155,36 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
                      $EPIS[epi], x_cand, x_inc, alpha, beta, wm, C_NULL))
         return sdCut(alpha[1], beta[:, 1], wm[]), sdCut(alpha[2], beta[:, 2], wm[])
     end
+    # --- optional: the cut formation of one sd_iteration! in one call (algorithm.jl:45-55, 79-85) --
+    # scenarios[i] is epigraph i's new scenario, duals the 2 * n_epi dual vertices found at the candidate
+    # and the incumbent (in the order the reference pushes them).  Keeps the host-side lists in step.
+    @eval T function sd_step!(cell::sdCell, scenarios::Vector{spSmpsScenario}, duals::Vector{Vector{Float64}})
+        E = length(cell.epi)
+        handles = Ptr{Cvoid}[$EPIS[epi] for epi in cell.epi]
+        vals = Float64[]
+        for (epi, sc) in zip(cell.epi, scenarios)
+            push!(epi.scenario_list, sc); push!(epi.scenario_weight, 1.0); epi.total_scenario_weight += 1.0
+            lookup = Dict(p => v for (p, v) in sc)
+            append!(vals, Float64[lookup[p] for p in $TABLES[epi.subproblem_coef]])
+        end
+        m2 = length(duals[1]); n1 = length(cell.x_candidate)
+        V = reduce(vcat, duals)                                   # row-major [n_vertices x m2]
+        ins = zeros(Int32, length(duals)); idx = zeros(Int64, length(duals))
+        alpha = zeros(2, E); beta = zeros(n1, 2, E); wm = zeros(E)
+        $check(ccall((:sqlp_cell_sd_step, $LIB[]), Int32,
+                     (Int32, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int64},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                     E, handles, vals, C_NULL, length(duals), V, ins, idx, cell.x_candidate, cell.x_incumbent,
+                     alpha, beta, wm, C_NULL))
+        for (v, d) in enumerate(duals)
+            ins[v] == 1 && push!(cell.dual_vertices.data, sdDualVertex(d))
+        end
+        for (i, epi) in enumerate(cell.epi)
+            push!(epi.cuts, sdCut(alpha[1, i], beta[:, 1, i], wm[i]))
+            epi.incumbent_cut = sdCut(alpha[2, i], beta[:, 2, i], wm[i])
+        end
+        return
+    end
     # --- optional: the cut list on the device (SURVEY.md 8(f) N1 / N3) ----------------------------
     # After build_two_cuts: take both cuts into the device list without a host round trip, ask the
     # device for the incumbent test, and fetch the master rows of sync_cuts! as one dense block.

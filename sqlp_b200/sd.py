@@ -253,6 +253,7 @@ class sdCell:
     # keep the cut lists on the device as well (sqlp_epi_cuts_*): the incumbent test and the master
     # rows then come from the library (rows N1 / N3); the host lists are still maintained
     device_cuts: bool = False
+    fused_step: bool = False       # one library call per iteration (sqlp_cell_sd_step) instead of add / push / push / cuts
 
     def __post_init__(self):
         n1 = len(self.first_stage.cost)
@@ -391,14 +392,24 @@ def sd_iteration_(cell: sdCell, scenario_list, solve_subproblem, update_incumben
         quad_scalar_schedule = ConstantQuadScalarSchedule(0.1)
     assert len(scenario_list) == len(cell.epi)
     # solve the new scenario's subproblem at candidate and incumbent (algorithm.jl:45-55)
+    # With ``cell.fused_step`` the scenarios and the dual vertices of the iteration are only collected here
+    # and reach the library in ONE call further down (``sqlp_cell_sd_step``): nothing between this loop
+    # and the cut formation reads the scenario store or the pool, so the order of effects is the reference's.
+    fused = bool(getattr(cell, "fused_step", False)) and update_incumbent_cut and not cell.device_cuts
+    step_values, step_duals = [], []
     for i, scen in enumerate(scenario_list):
         epi = cell.epi[i]
         values = epi.subproblem_coef.scenario_values(scen)
-        epi.add_scenarios(values.reshape(1, -1), [1.0])
-        _, _, dual_opt = solve_subproblem(i, cell.x_candidate, values)
-        cell.dual_vertices.push(dual_opt)
-        _, _, dual_opt = solve_subproblem(i, cell.x_incumbent, values)
-        cell.dual_vertices.push(dual_opt)
+        if fused:
+            step_values.append(values)
+        else:
+            epi.add_scenarios(values.reshape(1, -1), [1.0])
+        for x in (cell.x_candidate, cell.x_incumbent):
+            _, _, dual_opt = solve_subproblem(i, x, values)
+            if fused:
+                step_duals.append(np.asarray(dual_opt, dtype=np.float64))
+            else:
+                cell.dual_vertices.push(dual_opt)
     # drop the cuts whose master multiplier is (numerically) zero (algorithm.jl:57-72)
     if cell.master_solved:
         for i, epi in enumerate(cell.epi):
@@ -410,7 +421,13 @@ def sd_iteration_(cell: sdCell, scenario_list, solve_subproblem, update_incumben
             epi.cuts[:] = [epi.cuts[j] for j in keep]
     epi_info_last = [sdEpigraphInfo.of(epi) for epi in cell.epi]
     # the hot path: candidate cut + regenerated incumbent cut (algorithm.jl:79-85)
-    for i, epi in enumerate(cell.epi):
+    if fused:
+        from .twosd import sd_step
+        _, _, pairs = sd_step(cell.epi, step_values, None, np.stack(step_duals), cell.x_candidate, cell.x_incumbent)
+        if on_cuts is not None:
+            for i, (new_cut, inc_cut) in enumerate(pairs):
+                on_cuts(i, new_cut, inc_cut)
+    for i, epi in enumerate(cell.epi if not fused else ()):
         if update_incumbent_cut:
             new_cut, inc_cut = epi.build_cuts2(cell.x_candidate, cell.x_incumbent)
             epi.cuts.append(new_cut)

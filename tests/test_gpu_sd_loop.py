@@ -15,9 +15,9 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("n_epi,schedule,device_cuts", [(1, "constant", False), (2, "adaptive", False),
-                                                        (2, "constant", True)])
-def test_lands_sd_run_matches_oracle_every_iteration(n_epi, schedule, device_cuts):
+@pytest.mark.parametrize("n_epi,schedule,device_cuts,fused", [(1, "constant", False, False), (2, "adaptive", False, False),
+                                                              (2, "constant", True, False), (2, "adaptive", False, True)])
+def test_lands_sd_run_matches_oracle_every_iteration(n_epi, schedule, device_cuts, fused):
     from sqlp_b200 import twosd as T
     zf = load_full_instance("lands")
     P, z = load_instance("lands")
@@ -25,6 +25,7 @@ def test_lands_sd_run_matches_oracle_every_iteration(n_epi, schedule, device_cut
     dvs = T.sdDualVertexSet(m2=P.m2)
     cell, lp = make_cell(zf, dvs, lambda w, lb: T.sdEpigraph(coef, w, lb, dvs), np.full(4, 3.0), n_epi=n_epi)
     cell.device_cuts = device_cuts             # cut lists, incumbent test and master rows on the device
+    cell.fused_step = fused                    # one library call per iteration (sqlp_cell_sd_step)
     shadow = O.DualVertexSet()                 # the oracle's pool, fed the same vertices
     seen = [[] for _ in range(n_epi)]          # scenarios of each epigraph so far
     vals = sample_instance_values(zf, 200 * n_epi, seed=42)
