@@ -271,6 +271,8 @@ class NativeSmps:
 
     _DIMS = ("rows", "cols", "cor_nnz", "n1", "n2", "m2", "T_nnz", "W_nnz", "r_nnz", "s", "max_outcomes",
              "periods")
+    # `what` of sqlp_smps_name (include/sqlp_b200.h)
+    COR_NAME, TIM_NAME, STO_NAME, ROW_NAME, COL_NAME, PERIOD_NAME, PERIOD_COL, PERIOD_ROW, ELEM_COL, ELEM_ROW = range(10)
 
     def __init__(self, cor_path, tim_path, sto_path=None):
         import ctypes as C
@@ -311,15 +313,15 @@ class NativeSmps:
         rowval, nzval = np.zeros(d["cor_nnz"], dtype=np.int64), np.zeros(d["cor_nnz"])
         self._lib.check(self._lib.lib().sqlp_smps_cor(self._h, self._p(dirs), self._p(rhs), self._p(lo), self._p(up),
                                                       self._p(colptr), self._p(rowval), self._p(nzval)))
-        rows = [self._name(3, i) for i in range(d["rows"])]
-        cols = [self._name(4, j) for j in range(d["cols"])]
+        rows = [self._name(self.ROW_NAME, i) for i in range(d["rows"])]
+        cols = [self._name(self.COL_NAME, j) for j in range(d["cols"])]
         entries = {(int(rowval[k]), j): float(nzval[k]) for j in range(d["cols"])
                    for k in range(colptr[j], colptr[j + 1])}
-        return Cor(self._name(0), [c.decode() for c in dirs], rows, cols, entries, rhs, lo, up,
+        return Cor(self._name(self.COR_NAME), [c.decode() for c in dirs], rows, cols, entries, rhs, lo, up,
                    {r: i for i, r in enumerate(rows)}, {c: j for j, c in enumerate(cols)})
 
     def tim(self) -> Tim:
-        return Tim(self._name(1), [(self._name(5, i), self._name(6, i), self._name(7, i))
+        return Tim(self._name(self.TIM_NAME), [(self._name(self.PERIOD_NAME, i), self._name(self.PERIOD_COL, i), self._name(self.PERIOD_ROW, i))
                                    for i in range(self.dims["periods"])])
 
     def elements(self):
@@ -337,7 +339,7 @@ class NativeSmps:
         names = ("DISCRETE", "NORMAL", "UNIFORM")
         params = [(list(vals[e, :cnt[e]]), list(probs[e, :cnt[e]])) if kind[e] == 0 else (float(a[e]), float(b[e]))
                   for e in range(len(pr))]
-        return Sto(self._name(2), [(self._name(8, e), self._name(9, e)) for e in range(len(pr))],
+        return Sto(self._name(self.STO_NAME), [(self._name(self.ELEM_COL, e), self._name(self.ELEM_ROW, e)) for e in range(len(pr))],
                    [names[k] for k in kind], params)
 
     def stage2(self) -> Stage2:

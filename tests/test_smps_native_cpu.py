@@ -172,3 +172,32 @@ def test_name_accessor_bounds(tmp_path):
     assert L.sqlp_smps_name(n._h, 3, 0, buf, 2) == _lib.E_RANGE       # "OBJ" does not fit in 2 bytes
     assert L.sqlp_smps_name(n._h, 99, 0, buf, 64) == _lib.E_INVALID
     assert L.sqlp_smps_name(n._h, 3, 0, buf, 64) == 0 and buf.value == b"OBJ"
+
+
+def test_smps_reader_from_plain_c(tmp_path):
+    """tests/abi_smps_demo.c: gcc against include/sqlp_b200.h, linked to the library, no Python and no GPU in
+    the loop -- the tables it prints are the ones the files were generated from."""
+    import json
+    import subprocess
+    paths, ex = write_smps(str(tmp_path), seed=17, continuous=True, n1=5, n2=7, m1=2, m2=8, n_rhs_elems=3, n_T_elems=2)
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "abi_smps_demo")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.run(["gcc", "-O1", "-o", exe, os.path.join(here, "abi_smps_demo.c"), "-L", libdir, "-lsqlp_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe, paths["cor"], paths["tim"], paths["sto"]], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout)
+    assert (r["name"], r["n1"], r["n2"], r["m2"], r["s"]) == (ex["name"], ex["n1"], ex["n2"], ex["m2"], len(ex["positions"]))
+    assert r["rbar"] == list(ex["rbar"])
+    T = np.zeros_like(ex["T"])
+    for i, j, v in r["T"]:
+        T[i, j] = v
+    assert np.array_equal(T, ex["T"]) and r["T_nnz"] == np.count_nonzero(ex["T"])
+    for e, el in enumerate(r["elements"]):
+        assert (el["col"], el["row"]) == ex["positions"][e]
+        assert el["pos"] == [int(ex["pos_row"][e]), int(ex["pos_col"][e])]
+        assert el["kind"] == {"DISCRETE": 0, "NORMAL": 1, "UNIFORM": 2}[ex["kinds"][e]]
+        if ex["kinds"][e] == "DISCRETE":
+            assert [o[0] for o in el["outcomes"]] == ex["tables"][e][0]
+            assert [o[1] for o in el["outcomes"]] == ex["tables"][e][1]
