@@ -170,6 +170,27 @@ class ClockSampler(threading.Thread):
 
 # ---------------------------------------------------------------- CPU reference arm -----
 
+def cpu_reference_single_thread(z, pool, n_target_seconds, x2):
+    """The same loop the way the reference itself runs it: ONE thread (the reference has no threading,
+    so its "Julia thread count" is 1) and the oracle's index-order dots, on a short prefix."""
+    from oracle import oracle as O
+    P = O.Problem(int(z["m2"]), int(z["n1"]), z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"],
+                  z["pos_row"], z["pos_col"])
+    probe = sample_values(z, 1, 0, 2)
+    t0 = time.perf_counter()
+    O.bench_argmax(P, probe, x2[0], pool, threads=1, dot_kind=0)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(max(2, min(2000, rate * n_target_seconds / 2)))
+    vals = sample_values(z, 1, 0, n)
+    t0 = time.perf_counter()
+    for x in x2:
+        O.bench_argmax(P, vals, x, pool, threads=1, dot_kind=0)
+    dt = time.perf_counter() - t0
+    return {"value": 2.0 * n * len(pool) / dt, "unit": UNIT, "cores": 1,
+            "sample": f"first {n} scenarios x all {len(pool)} vertices x 2 points in {dt:.2f} s; one thread, "
+                      f"index-order dots (the reference's own structure: single-threaded Julia)"}
+
+
 def cpu_reference(z, pool, n_target_seconds, x2, threads=0):
     """The reference's argmax loop (oracle restatement, reference loop structure, all host
     cores, 8-accumulator dots) on a bounded prefix of the workload's scenarios."""
@@ -507,6 +528,7 @@ def run_ours(args):
             "gpu_launches": launches, "setup_s": t_setup}
     if not args.no_cpu_baseline and world == 1:
         base, _, _ = cpu_reference(z, pool_all[:K0], args.cpu_seconds, [x_c, x_i])
+        base["single_thread"] = cpu_reference_single_thread(z, pool_all[:K0], min(4.0, args.cpu_seconds), [x_c, x_i])
         line["cpu_baseline"] = base
     print(json.dumps(line))
     if world > 1:
