@@ -56,12 +56,16 @@ void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const doub
     }
     // algorithmic bytes: the hash scan (8 K per push) + the pushed vector in and, if new, out
     ProfScope prof(c, SQLP_PROF_POOL, (double)n * (8.0 * (double)p->upper() + 16.0 * (double)p->m2));
-    for (int64_t i = 0; i < n; ++i) {
+    // SQLP_PUSH_BATCH vectors per launch (fewer when their 1-norm terms would not fit in shared memory)
+    const int64_t per = p->m2 > SQLP_PUSH_SMEM_DOUBLES
+        ? 1 : std::max<int64_t>(1, std::min<int64_t>(SQLP_PUSH_BATCH, SQLP_PUSH_SMEM_DOUBLES / p->m2));
+    for (int64_t i = 0; i < n; i += per) {
+        const int nb = (int)std::min<int64_t>(per, n - i);
         int64_t ku = p->upper() + i;
         int grid = (int)std::min<int64_t>(std::max<int64_t>((ku + 255) / 256, 1), 2 * c->sm_count);
-        size_t smem = (size_t)std::min<int64_t>(p->m2, SQLP_PUSH_SMEM_DOUBLES) * 8;
+        size_t smem = (size_t)nb * p->m2 <= SQLP_PUSH_SMEM_DOUBLES ? (size_t)nb * p->m2 * 8 : 0;
         LAUNCH(c, k_pool_push, grid, 256, smem, p->d_pi.as<double>(), p->d_hash.as<unsigned long long>(),
-               p->d_K.as<long long>(), (int)p->m2, src + i * p->m2, p->d_scratch.as<PushScratch>(),
+               p->d_K.as<long long>(), (int)p->m2, src + i * p->m2, nb, p->d_scratch.as<PushScratch>(),
                p->d_results.as<PushResult>() + i);
     }
     p->pending += n;

@@ -19,10 +19,11 @@ struct PushResult {
 };
 
 // Scratch of the push kernel (one per pool).
+#define SQLP_PUSH_BATCH 8              // vectors per launch
 struct PushScratch {
-    unsigned long long hash;   // hash of the vector being pushed
-    int match;                 // lowest stored slot equal to it, INT_MAX if none
-    unsigned int done;         // blocks finished (last-block-commits pattern)
+    unsigned long long hash;           // hash of the (last) vector pushed, for sqlp_pool_hash
+    int match[SQLP_PUSH_BATCH];        // lowest stored slot equal to vector i, INT_MAX if none
+    unsigned int done;                 // blocks finished (last-block-commits pattern)
 };
 
 // hash_dual_vector alone (sqlp_pool_hash, debug / test): hash of the vector and its rounded copy.
@@ -44,55 +45,69 @@ __global__ void k_pool_prepare(const double *__restrict__ v, int m2, double *__r
     }
 }
 
-// One push in one launch: every block computes the hash of the new vector (the sequential 1-norm is one
-// thread's chain of m2 additions -- the same few microseconds whether one block does it or all of them do it
-// side by side, and a launch cheaper than handing it over from a kernel of its own), then the blocks scan
-// the stored hashes, one per thread (grid-stride), and the last block to finish commits.
-// `sc` must hold {match = INT_MAX, done = 0} on entry; the committing block restores that for the next push.
-#define SQLP_PUSH_SMEM_DOUBLES 4096
+// Up to SQLP_PUSH_BATCH pushes in one launch, with the result of pushing them one after the other.
+//   1. every block computes the hashes of all n vectors: the reference's hash is a SEQUENTIAL 1-norm, one
+//      chain of m2 dependent additions per vector, so lane i of warp 0 walks the chain of vector i and the n
+//      chains cost the time of one;
+//   2. the blocks scan the stored hashes, one per thread (grid-stride), against all n hashes; the rare hit is
+//      compared element by element by the whole warp (dual_set.jl:26-39) and the lowest equal slot kept;
+//   3. the last block to finish resolves the pushes IN ORDER: vector i is a duplicate of the lowest equal
+//      stored slot if there is one (stored slots are lower than any slot this batch appends, so first-match
+//      order is kept), else of the first EARLIER vector of this batch that was appended and equals it, else it
+//      is appended (dual_set.jl:84-93).
+// `sc` must hold {match[] = INT_MAX, done = 0} on entry; the committing block restores that.
+// Dynamic shared memory: n * m2 doubles when n * m2 <= SQLP_PUSH_SMEM_DOUBLES (the host batches accordingly),
+// none for a single very long vector.
+#define SQLP_PUSH_SMEM_DOUBLES 5632   // 44 KB: with the static arrays below 48 KB, no opt-in needed
+__device__ __forceinline__ bool rounded_equal_block(const double *__restrict__ a, const double *__restrict__ b, int m2)
+{
+    bool same = true;
+    for (int j = threadIdx.x; j < m2; j += blockDim.x)
+        if (round_sig16(a[j]) != round_sig16(b[j])) same = false;   // :34  NaN != NaN
+    return __syncthreads_and(same);
+}
+
 __global__ void __launch_bounds__(256) k_pool_push(double *__restrict__ pi, unsigned long long *__restrict__ hash,
                                                    long long *__restrict__ d_K, int m2, const double *__restrict__ v,
-                                                   PushScratch *__restrict__ sc, PushResult *__restrict__ result)
+                                                   int n, PushScratch *__restrict__ sc, PushResult *__restrict__ result)
 {
     griddep_sync();
     extern __shared__ double sh_abs[];
-    __shared__ unsigned long long h_sh;
+    __shared__ unsigned long long h_sh[SQLP_PUSH_BATCH];
+    __shared__ long long slot_sh[SQLP_PUSH_BATCH];        // last block: slot a vector of this batch was appended to, or -1
     __shared__ bool is_last;
-    const bool in_smem = m2 <= SQLP_PUSH_SMEM_DOUBLES;
+    const bool in_smem = (long long)n * m2 <= SQLP_PUSH_SMEM_DOUBLES;
     if (in_smem)
-        for (int j = threadIdx.x; j < m2; j += blockDim.x) sh_abs[j] = fabs(v[j]);
+        for (int j = threadIdx.x; j < n * m2; j += blockDim.x) sh_abs[j] = fabs(v[j]);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < n) {
+        const int i = threadIdx.x;
         double mysum = 0.0;                               // :49-51 sequential, index order
         if (in_smem)
-            for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, sh_abs[j]);
+            for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, sh_abs[i * m2 + j]);
         else
-            for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, fabs(v[j]));
-        h_sh = (unsigned long long)__double_as_longlong(round_sig16(mysum));
+            for (int j = 0; j < m2; ++j) mysum = __dadd_rn(mysum, fabs(v[(long long)i * m2 + j]));
+        h_sh[i] = (unsigned long long)__double_as_longlong(round_sig16(mysum));
     }
     __syncthreads();
     const long long K = *d_K;
-    const unsigned long long h = h_sh;
     const int lane = threadIdx.x & 31;
-    // the hash gate (:26), one stored hash per thread (coalesced); the rare hit is compared element by
-    // element by the whole warp.  Few blocks: the scan is 8 K bytes, and every block costs one atomic on
-    // the shared counter below.
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long kb = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); kb < K; kb += stride) {
         const long long mine = kb + lane;
-        unsigned hits = __ballot_sync(0xffffffffu, mine < K && hash[mine] == h);
-        while (hits) {
-            const long long k = kb + (__ffs(hits) - 1);
-            hits &= hits - 1;
-            const double *row = pi + k * (long long)m2;
-            bool same = true;
-            for (int j = lane; j < m2; j += 32) {
-                double r1 = round_sig16(v[j]);
-                double r2 = round_sig16(row[j]);
-                if (r1 != r2) same = false;               // :34  NaN != NaN
+        const unsigned long long hk = mine < K ? hash[mine] : 0ull;
+        for (int i = 0; i < n; ++i) {
+            unsigned hits = __ballot_sync(0xffffffffu, mine < K && hk == h_sh[i]);   // :26 hash gate
+            while (hits) {
+                const long long k = kb + (__ffs(hits) - 1);
+                hits &= hits - 1;
+                const double *row = pi + k * (long long)m2, *vi = v + (long long)i * m2;
+                bool same = true;
+                for (int j = lane; j < m2; j += 32)
+                    if (round_sig16(vi[j]) != round_sig16(row[j])) same = false;      // :34  NaN != NaN
+                same = __all_sync(0xffffffffu, same);
+                if (same && lane == 0) atomicMin(&sc->match[i], (int)k);
             }
-            same = __all_sync(0xffffffffu, same);
-            if (same && lane == 0) atomicMin(&sc->match, (int)k);
         }
     }
 
@@ -105,28 +120,42 @@ __global__ void __launch_bounds__(256) k_pool_push(double *__restrict__ pi, unsi
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const int match = *((volatile int *)&sc->match);
-    __syncthreads();                                      // everyone has read the match before it is reset
-    if (threadIdx.x == 0) {
-        sc->hash = h;
-        sc->match = 0x7fffffff;
-        sc->done = 0u;
-    }
-    if (match != 0x7fffffff) {
-        if (threadIdx.x == 0) {
-            result->index = match;
-            result->inserted = 0;
+    long long Kcur = K;
+    for (int i = 0; i < n; ++i) {                         // the pushes, in order
+        long long m = *((volatile int *)&sc->match[i]);
+        if (m == 0x7fffffff) {
+            m = -1;
+            for (int e = 0; e < i && m < 0; ++e)          // earlier vectors of this batch that were appended
+                if (slot_sh[e] >= 0 && h_sh[e] == h_sh[i] &&
+                    rounded_equal_block(v + (long long)i * m2, v + (long long)e * m2, m2))
+                    m = slot_sh[e];
         }
-        return;
+        __syncthreads();
+        if (m >= 0) {
+            if (threadIdx.x == 0) {
+                slot_sh[i] = -1;
+                result[i].index = m;
+                result[i].inserted = 0;
+            }
+        } else {
+            double *dst = pi + Kcur * (long long)m2;      // :91 append
+            for (int j = threadIdx.x; j < m2; j += blockDim.x) dst[j] = v[(long long)i * m2 + j];
+            if (threadIdx.x == 0) {
+                hash[Kcur] = h_sh[i];
+                slot_sh[i] = Kcur;
+                result[i].index = Kcur;
+                result[i].inserted = 1;
+            }
+            ++Kcur;
+        }
+        __syncthreads();
     }
-    double *dst = pi + K * (long long)m2;                 // :91 append
-    for (int j = threadIdx.x; j < m2; j += blockDim.x) dst[j] = v[j];
     if (threadIdx.x == 0) {
-        hash[K] = h;
-        result->index = K;
-        result->inserted = 1;
+        sc->hash = h_sh[n - 1];
+        for (int i = 0; i < SQLP_PUSH_BATCH; ++i) sc->match[i] = 0x7fffffff;
+        sc->done = 0u;
         __threadfence();
-        *d_K = K + 1;
+        *d_K = Kcur;
     }
 }
 

@@ -251,7 +251,10 @@ int32_t sqlp_pool_create(sqlp_ctx *c, int64_t m2, sqlp_pool **out)
             p->m2 = m2;
             p->d_K.ensure(8, 0, S(c));
             p->d_scratch.ensure(sizeof(PushScratch), 0, S(c));
-            const PushScratch idle = {0ull, 0x7fffffff, 0u};      // what k_pool_push expects and leaves behind
+            PushScratch idle;                                     // what k_pool_push expects and leaves behind
+            idle.hash = 0ull;
+            idle.done = 0u;
+            for (int i = 0; i < SQLP_PUSH_BATCH; ++i) idle.match[i] = 0x7fffffff;
             CK(cudaMemcpyAsync(p->d_scratch.p, &idle, sizeof idle, cudaMemcpyHostToDevice, S(c)));
             p->d_vr.ensure((size_t)m2 * 8, 0, S(c));
             pool_reserve(p, 1024);
