@@ -246,6 +246,43 @@ def stage2_tables(cor: Cor, tim: Tim, sto: Sto | None = None) -> Stage2:
         x_lower=cor.lower[:c2].copy(), x_upper=cor.upper[:c2].copy(), x_cost=x_cost)
 
 
+def discrete_tables(sto: Sto):
+    """Rectangular outcome tables of the DISCRETE elements: (vals [s, mo], cdf [s, mo], cnt [s]); the cdf of a
+    row is the running sum of its probabilities, padded with 1.0 (continuous elements: one dummy outcome)."""
+    s = len(sto.positions)
+    mo = max([len(p[0]) for k, p in zip(sto.kind, sto.params) if k == "DISCRETE"] + [1])
+    vals, cdf, cnt = np.zeros((s, mo)), np.ones((s, mo)), np.ones(s, dtype=np.int32)
+    for e, (k, p) in enumerate(zip(sto.kind, sto.params)):
+        if k == "DISCRETE":
+            n = len(p[0])
+            cnt[e] = n
+            vals[e, :n] = p[0]
+            cdf[e, :n] = np.cumsum(p[1])
+    return vals, cdf, cnt
+
+
+def full_tables(cor: Cor, st: Stage2, sto: Sto) -> dict:
+    """Everything a host SD loop needs besides the cut formation: the first-stage rows
+    ``row_lower <= A1 x <= row_upper`` (rows 1 .. r2-1 of the cor file restricted to the first-stage columns),
+    bounds and costs of both stages, W, and the outcome tables -- the layout of
+    ``tests/golden/instances/<name>_full.npz`` and of ``tools/run_sd.py``."""
+    r2 = len(cor.row_names) - st.m2
+    A1 = np.zeros((r2 - 1, st.n1))
+    for (i, j), v in cor.entries.items():
+        if 1 <= i < r2:
+            if j >= st.n1:
+                raise ValueError("a first-stage row touches a second-stage column")
+            A1[i - 1, j] = v
+    dirs1, b1 = cor.directions[1:r2], cor.rhs[1:r2]
+    lo = np.array([b if d in "GE" else -np.inf for d, b in zip(dirs1, b1)])
+    up = np.array([b if d in "LE" else np.inf for d, b in zip(dirs1, b1)])
+    vals, cdf, cnt = discrete_tables(sto)
+    return dict(n1=st.n1, m2=st.m2, n2=st.n2, rbar=st.rbar, T_colptr=st.T_colptr, T_rowval=st.T_rowval,
+                T_nzval=st.T_nzval, pos_row=st.pos_row, pos_col=st.pos_col, x_lower=st.x_lower, x_upper=st.x_upper,
+                x_cost=st.x_cost, A1=A1, row_lower=lo, row_upper=up, W=st.W, cost=st.cost, y_lower=st.y_lower,
+                y_upper=st.y_upper, directions=np.array(st.directions), out_vals=vals, out_cdf=cdf, out_cnt=cnt)
+
+
 def sample_values(sto: Sto, u: np.ndarray) -> np.ndarray:
     """Realised values [N, s] from uniforms ``u`` [N, s] (inverse CDF for DISCRETE and
     UNIFORM; NORMAL by the inverse normal CDF).  Mirrors ``rand(sto)``

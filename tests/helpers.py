@@ -324,3 +324,65 @@ def write_smps(dirpath, name="synth", n1=5, n2=6, m1=2, m2=7, seed=11, n_rhs_ele
                     positions=[(c, f"S2R{i}") for c, i in elems], kinds=kinds, pars=pars, tables=tables,
                     explicit_zero=explicit_zero)
     return paths, expected
+
+
+def write_smps_from_full(zf, dirpath, name):
+    """Write a ``<name>_full.npz`` fixture back as .cor/.tim/.sto text, so that file-based paths (the native
+    SMPS reader, ``tools/run_sd.py --smps``) can run on real instances where the reference checkout is absent."""
+    n1, n2, m2 = int(zf["n1"]), int(zf["n2"]), int(zf["m2"])
+    A1, W = zf["A1"], zf["W"]
+    m1 = len(A1)
+    T = np.zeros((m2, n1))
+    for j in range(n1):
+        for q in range(zf["T_colptr"][j], zf["T_colptr"][j + 1]):
+            T[zf["T_rowval"][q], j] = zf["T_nzval"][q]
+    rows = ["OBJ"] + [f"R1_{i}" for i in range(m1)] + [f"R2_{i}" for i in range(m2)]
+    dirs1, rhs1 = [], []
+    for lo, up in zip(zf["row_lower"], zf["row_upper"]):
+        d = "E" if lo == up else ("G" if np.isfinite(lo) else "L")
+        dirs1.append(d)
+        rhs1.append(lo if d in "GE" else up)
+    dirs = ["N"] + dirs1 + [str(d) for d in zf["directions"]]
+    rhs = np.concatenate([[0.0], rhs1, zf["rbar"]])
+    cols = [f"X{j}" for j in range(n1)] + [f"Y{j}" for j in range(n2)]
+    M = np.zeros((len(rows), n1 + n2))
+    M[0, :n1], M[0, n1:] = zf["x_cost"], zf["cost"]
+    M[1:1 + m1, :n1] = A1
+    M[1 + m1:, :n1], M[1 + m1:, n1:] = T, W
+    lines = [f"NAME          {name}", "ROWS"] + [f" {d}  {r}" for d, r in zip(dirs, rows)] + ["COLUMNS"]
+    for j, c in enumerate(cols):
+        lines += [f"    {c}  {rows[i]}  {float(M[i, j])!r}" for i in range(len(rows)) if M[i, j] != 0.0]
+    lines.append("RHS")
+    lines += [f"    RHS  {rows[i]}  {float(rhs[i])!r}" for i in range(1, len(rows)) if rhs[i] != 0.0]
+    lower = np.concatenate([zf["x_lower"], zf["y_lower"]])
+    upper = np.concatenate([zf["x_upper"], zf["y_upper"]])
+    bnd = []
+    for c, lo, up in zip(cols, lower, upper):
+        if np.isneginf(lo) and np.isposinf(up):
+            bnd.append(f" FR BND  {c}")
+            continue
+        if lo != 0.0:
+            bnd.append(f" MI BND  {c}" if np.isneginf(lo) else f" LO BND  {c}  {float(lo)!r}")
+        if np.isfinite(up):
+            bnd.append(f" UP BND  {c}  {float(up)!r}")
+    if bnd:
+        lines += ["BOUNDS"] + bnd
+    lines.append("ENDATA")
+    os.makedirs(dirpath, exist_ok=True)
+    prefix = os.path.join(dirpath, name)
+    with open(prefix + ".cor", "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    with open(prefix + ".tim", "w") as fh:
+        fh.write(f"TIME          {name}\nPERIODS       IMPLICIT\n    {cols[0]}  {rows[0]}  TIME1\n"
+                 f"    {cols[n1]}  {rows[1 + m1]}  TIME2\nENDATA\n")
+    sto = [f"STOCH         {name}", "INDEP         DISCRETE"]
+    for e in range(len(zf["pos_row"])):
+        cname = "RHS" if zf["pos_col"][e] < 0 else cols[int(zf["pos_col"][e])]
+        cdf = zf["out_cdf"][e]
+        for o in range(int(zf["out_cnt"][e])):
+            prob = zf["probs"][e][o] if "probs" in zf else cdf[o] - (cdf[o - 1] if o else 0.0)
+            sto.append(f"    {cname}  R2_{int(zf['pos_row'][e])}  {float(zf['out_vals'][e, o])!r}  {float(prob)!r}")
+    sto.append("ENDATA")
+    with open(prefix + ".sto", "w") as fh:
+        fh.write("\n".join(sto) + "\n")
+    return prefix

@@ -70,3 +70,39 @@ def test_epigraph_from_smps_files(tmp_path, continuous, n_T):
     assert epi_a.counts()[0] == N + 1
     drhs, _ = O.delta_coefficients(P, twin[0])
     assert np.array_equal(epi_a.delta(N).delta_rhs, drhs)
+
+
+def test_sd_run_from_smps_text_equals_the_run_from_tables(tmp_path):
+    """lands written as .cor/.tim/.sto text, read by the native reader, the epigraph built by
+    ``sqlp_epi_create_smps`` and the whole SD loop run in fused mode (one ``sqlp_cell_sd_step`` per
+    iteration): every cut equals, bit for bit, the cut of the same loop over an epigraph built from the
+    fixture's tables with separate calls."""
+    from sqlp_b200 import sd, twosd as T
+    from tests.helpers import load_full_instance, make_cell, sample_instance_values, write_smps_from_full
+    zf = load_full_instance("lands")
+    prefix = write_smps_from_full(zf, str(tmp_path), "lands")
+    native = smps.NativeSmps(prefix + ".cor", prefix + ".tim", prefix + ".sto")
+    ft = smps.full_tables(native.cor(), native.stage2(), native.sto())
+    cells, logs = [], ([], [])
+    for from_files in (True, False):
+        dvs = T.sdDualVertexSet(m2=int(zf["m2"]))
+        if from_files:
+            mk = lambda w, lb: T.sdEpigraph.from_smps(native, w, lb, dvs)
+        else:
+            coef = T.sdSubprobCoefficients.from_tables(zf["rbar"], zf["T_colptr"], zf["T_rowval"], zf["T_nzval"],
+                                                       zf["pos_row"], zf["pos_col"])
+            mk = lambda w, lb: T.sdEpigraph(coef, w, lb, dvs)
+        cell, lp = make_cell(ft if from_files else zf, dvs, mk, np.full(4, 3.0), n_epi=2)
+        cell.fused_step = from_files
+        cells.append((cell, lp))
+    vals = sample_instance_values(zf, 2 * 60, seed=5)
+    for it in range(60):
+        scen = [vals[2 * it], vals[2 * it + 1]]
+        for (cell, lp), log in zip(cells, logs):
+            sd.sd_iteration_(cell, scen, lambda i, x, v: lp.solve(x, v),
+                             on_cuts=lambda i, cand, inc: log.append((cand.alpha, cand.beta.copy(), inc.alpha, inc.beta.copy())))
+    assert len(logs[0]) == len(logs[1]) == 120
+    for a, b in zip(*logs):
+        assert a[0] == b[0] and a[2] == b[2] and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    assert np.array_equal(cells[0][0].x_incumbent, cells[1][0].x_incumbent)
+    assert len(cells[0][0].dual_vertices) == len(cells[1][0].dual_vertices) > 3

@@ -201,3 +201,32 @@ def test_smps_reader_from_plain_c(tmp_path):
         if ex["kinds"][e] == "DISCRETE":
             assert [o[0] for o in el["outcomes"]] == ex["tables"][e][0]
             assert [o[1] for o in el["outcomes"]] == ex["tables"][e][1]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["lands", "baa99-20"])
+def test_full_tables_from_the_native_reader_equal_the_committed_fixtures(name):
+    """``smps.full_tables`` over the native reader (what ``tools/run_sd.py --smps`` runs on) reproduces the
+    ``<name>_full.npz`` fixtures the SD-loop tests use."""
+    from tests.helpers import load_full_instance
+    n = smps.NativeSmps(*_paths(name))
+    got = smps.full_tables(n.cor(), n.stage2(), n.sto())
+    ref = load_full_instance(name)
+    for key, val in got.items():
+        assert np.array_equal(np.asarray(val), ref[key]), key
+
+
+@pytest.mark.parametrize("name", ["lands", "baa99-20"])
+def test_real_instances_round_trip_through_smps_text(tmp_path, name):
+    """A committed full fixture written back as SMPS text and read by the native reader gives the fixture's
+    tables again -- real instance data for the file-based paths where the reference checkout is absent."""
+    from tests.helpers import load_full_instance, write_smps_from_full
+    zf = load_full_instance(name)
+    prefix = write_smps_from_full(zf, str(tmp_path), name)
+    n = smps.NativeSmps(prefix + ".cor", prefix + ".tim", prefix + ".sto")
+    got = smps.full_tables(n.cor(), n.stage2(), n.sto())
+    for key, val in got.items():
+        if key == "out_cdf":          # probabilities went through text as differences of the cdf
+            assert np.allclose(np.asarray(val), zf[key], rtol=0, atol=1e-15), key
+        else:
+            assert np.array_equal(np.asarray(val), zf[key]), key

@@ -26,6 +26,10 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--instance", default="lands", help="a tests/golden/instances/<name>_full.npz fixture")
+    ap.add_argument("--smps", default=None, metavar="PREFIX",
+                    help="read PREFIX.cor / .tim / .sto with the library's native SMPS reader instead of a fixture "
+                         "(e.g. spInput/lands/lands); the device epigraph is built straight from the files")
+    ap.add_argument("--fused", action="store_true", help="one library call per iteration (sqlp_cell_sd_step)")
     ap.add_argument("--iterations", type=int, default=200)
     ap.add_argument("--lower-bound", type=float, default=0.0)
     ap.add_argument("--rho", type=float, default=0.1)
@@ -34,15 +38,25 @@ def main():
     ap.add_argument("--x0", type=float, nargs="*", default=None)
     args = ap.parse_args()
 
-    from sqlp_b200 import sd, twosd as T
-    zf = dict(np.load(os.path.join(ROOT, "tests", "golden", "instances", f"{args.instance}_full.npz")))
+    from sqlp_b200 import sd, smps, twosd as T
+    native = sto = None
+    if args.smps:
+        native = smps.NativeSmps(args.smps + ".cor", args.smps + ".tim", args.smps + ".sto")
+        sto = native.sto()
+        zf = smps.full_tables(native.cor(), native.stage2(), sto)
+    else:
+        zf = dict(np.load(os.path.join(ROOT, "tests", "golden", "instances", f"{args.instance}_full.npz")))
     n1, m2, s = int(zf["n1"]), int(zf["m2"]), len(zf["pos_row"])
-    coef = T.sdSubprobCoefficients.from_tables(zf["rbar"], zf["T_colptr"], zf["T_rowval"], zf["T_nzval"],
-                                               zf["pos_row"], zf["pos_col"])
     dvs = T.sdDualVertexSet(m2=m2)
     fs = sd.FirstStage(zf["x_cost"], zf["A1"], zf["row_lower"], zf["row_upper"], zf["x_lower"], zf["x_upper"])
-    cell = sd.sdCell(fs, dvs, device_cuts=True)
-    sd.bind_epigraph_(cell, T.sdEpigraph(coef, 1.0, args.lower_bound, dvs))
+    cell = sd.sdCell(fs, dvs, device_cuts=not args.fused, fused_step=args.fused)
+    if native is not None:
+        epi = T.sdEpigraph.from_smps(native, 1.0, args.lower_bound, dvs)
+    else:
+        coef = T.sdSubprobCoefficients.from_tables(zf["rbar"], zf["T_colptr"], zf["T_rowval"], zf["T_nzval"],
+                                                   zf["pos_row"], zf["pos_col"])
+        epi = T.sdEpigraph(coef, 1.0, args.lower_bound, dvs)
+    sd.bind_epigraph_(cell, epi)
     Tm = np.zeros((m2, n1))
     for j in range(n1):
         for q in range(zf["T_colptr"][j], zf["T_colptr"][j + 1]):
@@ -68,8 +82,10 @@ def main():
     rng = np.random.default_rng(args.seed)
     cdf, vals, cnt = zf["out_cdf"], zf["out_vals"], zf["out_cnt"]
 
-    def draw():                         # rand(sto) for INDEP DISCRETE elements
+    def draw():                         # rand(sto): INDEP DISCRETE from the tables, NORMAL / UNIFORM when read from files
         u = rng.random(s)
+        if sto is not None:
+            return smps.sample_values(sto, u[None, :])[0]
         idx = np.minimum((u[:, None] >= cdf).sum(axis=1), cnt - 1)
         return vals[np.arange(s), idx]
 
