@@ -1,0 +1,61 @@
+"""The screening pass of DESIGN.md section 10, restated on the CPU (``oracle/screen.py``): bf16 x 2 operands,
+three products, fp32 accumulation, a Cauchy-Schwarz error bound -- and the exact arithmetic deciding among the
+survivors.  The claim under test: the survivors always contain the vertex the full FP64 sweep selects, so the
+screened argmax IS the oracle's argmax (same index, same value), while only a handful of vertices per scenario
+need the exact score.  CPU only; no kernel exists for this yet."""
+import numpy as np
+import pytest
+
+from oracle import screen as S
+from tests.helpers import load_instance, sample_instance_values, synthetic_pool, synthetic_problem, synthetic_values
+
+
+def test_bf16_split_error_budget():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(20000) * 10.0 ** rng.integers(-6, 7, 20000)
+    hi, lo = S.split2(x)
+    assert np.all(np.abs(x - hi) <= S.U_B * np.abs(x) * (1 + 2.0 ** -14))
+    assert np.all(np.abs(x - hi - lo) <= 1.001 * S.U_B ** 2 * np.abs(x))
+    for part in (hi, lo):                                  # both parts are bf16 numbers: 8 significant bits
+        m, _ = np.frexp(part)
+        assert np.all(m * 256 == np.round(m * 256))
+    a, b = rng.standard_normal((50, 117)), rng.standard_normal((40, 117))
+    err = np.abs(S.approx_dots(a, b) - b @ a.T)
+    bound = S.eps(117) * np.outer(np.linalg.norm(b, axis=1), np.linalg.norm(a, axis=1))
+    assert np.all(err <= bound) and err.max() > 1e-4 * bound.max()      # holds, and is not vacuous by 4 orders
+
+
+@pytest.mark.parametrize("name,max_mean", [("baa99-20", 1.2), ("ssn", 1.2), ("storm", 2.0)])
+def test_screened_argmax_is_the_oracle_argmax_on_real_instances(oracle, name, max_mean):
+    P, z = load_instance(name)
+    N = 400
+    vals = sample_instance_values(z, N, seed=12)
+    pool = z["pool"]
+    for x in (z["x_ev"], z["x_alt"]):
+        ov, oi = oracle.argmax_procedure(P, vals, x, pool)
+        mv, mi, ncand = S.argmax_screened(P, vals, x, pool)
+        assert np.array_equal(mi, oi) and np.array_equal(mv, ov)
+        assert ncand.min() >= 1
+        if x is z["x_alt"]:     # away from the harvest point (where real pools hold exact ties)
+            assert ncand.mean() <= max_mean, ncand.mean()
+
+
+def test_screened_argmax_with_ties_near_ties_and_dominant_bias(oracle):
+    """Adversarial pool: exact duplicates of the winner's stochastic part (first index must win), vertices one
+    ulp-scale step away, a bias six orders above the dots, a NaN vertex, an all-zero scenario."""
+    P = synthetic_problem(m2=90, n1=10, s=40)
+    N, K = 300, 400
+    vals = synthetic_values(P, N)
+    vals[7] = P.rbar[P.pos_row]                              # delta == 0
+    pool = synthetic_pool(P.m2, K, scale=30.0)
+    pool[50] = pool[10]                                      # exact duplicate scores: index 10 must win over 50
+    pool[51] = pool[10] * (1.0 + 2.0 ** -40)                 # a near tie
+    det = [j for j in range(P.m2) if j not in set(P.pos_row.tolist())]
+    pool[:, det[0]] *= 1.0e6                                 # bias >> dot
+    pool[200, 3] = np.nan                                    # never wins (subprob.jl:156)
+    x = 10.0 * oracle.u01(3, np.arange(P.n1))
+    ov, oi = oracle.argmax_procedure(P, vals, x, pool)
+    mv, mi, ncand = S.argmax_screened(P, vals, x, pool)
+    assert np.array_equal(mi, oi) and np.array_equal(mv, ov)
+    assert not (mi == 200).any() and not (mi == 50).any()
+    assert ncand.max() < K
