@@ -1,0 +1,670 @@
+// kernels_screen.cuh -- the SCREENING pass of the argmax on the 5th-generation tensor cores, and the
+// exact FP64 decision among the vertices it leaves.
+//
+// Reference: argmax_procedure, src/sd_algorithm/subprob.jl:148-166 -- for every scenario the FIRST pool
+// vertex maximising  score[k, i] = bias_x[k] + PiS[k, :] . d_i.  The FP64 sweep of kernels_contract_ws.cuh
+// evaluates all K x N scores exactly.  Only the vertices that can still win need that: this file computes
+// every score APPROXIMATELY with tcgen05.mma (bf16 operands, fp32 accumulators in tensor memory), bounds
+// the error rigorously, keeps per scenario the vertices whose upper bound reaches the best lower bound, and
+// evaluates those exactly -- with the same mma.sync.m8n8k4.f64 chain, in the same order, as the FP64 sweep,
+// so best_idx AND best_val are bit-identical to it (the true argmax is provably among the candidates, and
+// so is every vertex tying with it, hence "first index among the maxima" is preserved).
+//
+// Approximate score.  Every fp64 operand is split into two bf16 parts, p = ph + pl + rp with
+// |rp| <= 2^-16 |p| (two successive round-to-nearest conversions, the second of the exact remainder),
+// likewise d = dh + dl + rd.  Three products are kept, dh ph + dl ph + dh pl, each exact in fp32; they are
+// accumulated by the tensor core in fp32 as ONE accumulation of 3 * sp terms (sp = row slots padded to 16):
+//     per K-step of 16 slots:  D += [dh | dl](A, 128 scenarios) x [ph | ph]    (two instructions)
+//                              D += [dh](A)                     x [pl]         (one instruction)
+// Error budget per (k, i), Q = ||PiS[k]||_2 ||d_i||_2 >= sum_j |p_j d_j| (Cauchy-Schwarz):
+//     dropped products            <= 3 * 2^-16 * (1 + 2^-8)       Q
+//     fp32 accumulation, any order, truncating adders allowed      <= (3 sp + 8) * 2^-22 * 1.02  Q
+//     bias rounded to fp32 after a common shift, final fp32 add    <= 2^-23 (|b32[k]| + 1.02 Q)
+//     the FP64 sweep's own rounding                                <= 2^-40 (|b32[k]| + Q)
+// E(tile) = coef_q * max_k ||PiS[k]|| (256 vertices) * max_i ||d_i|| (128 scenarios) + coef_b * max |b32|,
+// all norms rounded up, thresholds rounded towards "more candidates".
+//
+// Data layouts (tc05.cuh): scenario store DB[unit][part hi,lo][slab][128 scenarios][8] bf16, one contiguous
+// block of 512 sp bytes per unit; pool view PiB[chunk of 256 vertices][K-step][hi,lo][slab 2][256][8] bf16,
+// one contiguous 16 KB block per (chunk, K-step) = one pipeline stage; shifted fp32 biases
+// b32c[chunk][NX * 256 + 4] with the chunk's largest vertex norm in the last slot group.
+//
+// Kernel k_screen: one persistent CTA per SM, 320 threads:
+//   warps 0-7  epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (one scenario per thread), columns
+//              128 (w / 4) .. +127 of the 128 x 256 accumulator; per score one FADD per point and one FMNMX
+//              per point; every 8 columns one compare against the running threshold; the rare hit appends
+//              (vertex, upper bound) to the thread's own candidate list -- no atomics, no cross-lane traffic.
+//   warp 8     producer: bulk async copies (TMA 1-D) of the unit's scenarios (resident for the whole sweep),
+//              of the biases of a chunk and of the ring stages.
+//   warp 9     one thread issues tcgen05.mma; tcgen05.commit releases ring stages and publishes accumulators.
+// Two accumulators of 256 columns (all 512 TMEM columns) alternate, so the epilogue of chunk c runs under
+// the MMAs of chunk c + 1.
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+#include "kernels_contract.cuh"
+
+namespace sqlp {
+
+#define SCR_THREADS 320
+#define SCR_NB 256                 // vertices per screening chunk (N of the MMA)
+#define SCR_UNIT 128               // scenarios per unit (M of the MMA)
+#define SCR_STAGE_BYTES 16384      // one K-step of a chunk: [hi, lo][2 slabs][256][8] bf16
+#define SCR_MAX_STAGES 8
+#define SCR_BIAS_BUFS 4
+#define SCR_CAP 32                 // candidate list entries per (scenario, point, K-range, column half)
+#define SCR_DEAD (-3.0e38f)        // shifted bias of a vertex that can never win (or does not exist)
+
+struct ScreenCtl {                 // written by k_screen_prep, read by every kernel of the chain
+    double shift[2];               // c_x: b32 = fp32(bias_x - c_x)
+    float bmax[2];                 // largest |b32| over the live vertices of point x
+    float coef_q;                  // E = coef_q * pnmax * dnmax + coef_b * bmax + tiny
+    float coef_b;
+    int bad;                       // 1: non-finite or out-of-range operands -- screening is skipped
+    unsigned int overflow;         // candidate lists that overflowed (k_screen), reset by k_screen_prep
+    unsigned int ovf_limit;        // more overflowed lists than this: the FP64 sweep runs instead
+    unsigned long long n_emit;     // statistics: candidates emitted / evaluated exactly
+    unsigned long long n_eval;
+    int live[2];                   // vertices that may win at point x
+};
+
+__device__ __forceinline__ bool screen_falls_back(const ScreenCtl *ctl)
+{
+    return ctl->bad != 0 || ctl->overflow > ctl->ovf_limit;
+}
+
+template <int NX>
+__host__ __device__ constexpr int scr_bias_floats() { return NX * SCR_NB + 4; }
+
+struct ScreenArgs {
+    const __nv_bfloat16 *DB;       // [nunits][2][sp / 8][128][8]
+    const __nv_bfloat16 *PiB;      // [nchunks][sp / 16][2][2][256][8]
+    const float *b32c;             // [nchunks][NX * 256 + 4]
+    const float *dnmax_unit;       // [nunits] largest ||d_i|| of the unit, rounded up
+    ScreenCtl *ctl;
+    const long long *d_K;
+    int sp;                        // row slots padded to a multiple of 16
+    int nunits;
+    int R;                         // K-ranges a unit's sweep is split into (work items = nunits * R)
+    int nstages;
+    long long n_local;
+    long long npad;                // nunits * 128
+    int2 *cand;                    // [((x * R + r) * 2 + h) * npad + i][SCR_CAP]  (vertex, upper bound bits)
+    int *cnt;                      // [((x * R + r) * 2 + h) * npad + i]
+    float *lfin;                   // same shape: the thread's final lower bound of the best score
+    float *dbg;                    // optional [128][256] raw accumulators of the first tile of block 0
+    int desc_mode;                 // 0: LBO = K-direction, SBO = row-group direction (tc05.cuh); 1: swapped (probe only)
+};
+
+// dynamic shared memory of k_screen
+__host__ __device__ inline size_t scr_smem_bytes(int sp, int nstages, int nx)
+{
+    return 2048 + (size_t)512 * sp + (size_t)nstages * SCR_STAGE_BYTES +
+           (size_t)SCR_BIAS_BUFS * (nx * SCR_NB + 4) * 4;   // alignment slack + barrier block + A + ring + biases
+}
+
+template <int NX>
+__global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
+{
+    griddep_sync();
+    if (screen_falls_back(a.ctl)) return;
+    extern __shared__ __align__(16) unsigned char scr_raw[];
+    // carve: [barriers + tmem pointer | A | B ring | bias buffers], 1 KB aligned
+    const uint32_t raw0 = smem_u32(scr_raw);
+    const uint32_t base = (raw0 + 1023u) & ~1023u;
+    unsigned char *basep = scr_raw + (base - raw0);
+    const int S = a.nstages;
+    const int J = a.sp / 16;
+    constexpr int BF = scr_bias_floats<NX>();
+    const uint32_t bars = base;                                  // 8-byte mbarriers
+    const uint32_t bfull0 = bars, bempty0 = bars + 8 * SCR_MAX_STAGES;
+    const uint32_t tfull0 = bars + 16 * SCR_MAX_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t afull = tempty0 + 16, aempty = afull + 8;
+    const uint32_t biasfull0 = aempty + 8, biasempty0 = biasfull0 + 8 * SCR_BIAS_BUFS;
+    const uint32_t tmem_slot = biasempty0 + 8 * SCR_BIAS_BUFS;   // < base + 1024
+    const uint32_t A_s = base + 1024;
+    const uint32_t B_s = A_s + 512u * a.sp;
+    const uint32_t bias_s = B_s + (uint32_t)S * SCR_STAGE_BYTES;
+    const float *biasp = reinterpret_cast<const float *>(basep + 1024 + (size_t)512 * a.sp + (size_t)S * SCR_STAGE_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long K = *a.d_K;
+    const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
+    const int cpr = (nch + a.R - 1) / max(a.R, 1);               // chunks per K-range
+    const int items = a.nunits * a.R;
+
+    if (tid == 0) {
+        for (int q = 0; q < S; ++q) { mbar_init(bfull0 + 8 * q, 1); mbar_init(bempty0 + 8 * q, 1); }
+        for (int q = 0; q < 2; ++q) { mbar_init(tfull0 + 8 * q, 1); mbar_init(tempty0 + 8 * q, 8); }
+        mbar_init(afull, 1);
+        mbar_init(aempty, 1);
+        for (int q = 0; q < SCR_BIAS_BUFS; ++q) { mbar_init(biasfull0 + 8 * q, 1); mbar_init(biasempty0 + 8 * q, 8); }
+        mbar_fence_init();
+    }
+    if (warp == 9) tc05::tmem_alloc(tmem_slot, 512);
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(basep + (tmem_slot - base));
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ producer ------------
+        if (lane == 0) {
+            int stage = 0;
+            unsigned sph = 0, bb = 0, bph = 0, it = 0;
+            for (int w = blockIdx.x; w < items; w += gridDim.x) {
+                const int r = w / a.nunits, u = w - r * a.nunits;
+                const int c0 = r * cpr, c1 = min(nch, c0 + cpr);
+                if (c0 >= c1) continue;
+                mbar_wait(aempty, (it & 1u) ^ 1u);               // every MMA of the previous item has read A
+                mbar_arrive_expect_tx(afull, 512u * a.sp);
+                bulk_g2s(A_s, a.DB + (size_t)u * 256 * a.sp, 512u * a.sp, afull);
+                ++it;
+                for (int c = c0; c < c1; ++c) {
+                    mbar_wait(biasempty0 + 8 * bb, bph ^ 1u);
+                    mbar_arrive_expect_tx(biasfull0 + 8 * bb, BF * 4);
+                    bulk_g2s(bias_s + bb * BF * 4, a.b32c + (size_t)c * BF, BF * 4, biasfull0 + 8 * bb);
+                    if (++bb == SCR_BIAS_BUFS) { bb = 0; bph ^= 1u; }
+                    const unsigned char *src = reinterpret_cast<const unsigned char *>(a.PiB) + (size_t)c * J * SCR_STAGE_BYTES;
+                    for (int j = 0; j < J; ++j) {
+                        mbar_wait(bempty0 + 8 * stage, sph ^ 1u);
+                        mbar_arrive_expect_tx(bfull0 + 8 * stage, SCR_STAGE_BYTES);
+                        bulk_g2s(B_s + stage * SCR_STAGE_BYTES, src + (size_t)j * SCR_STAGE_BYTES, SCR_STAGE_BYTES,
+                                 bfull0 + 8 * stage);
+                        if (++stage == S) { stage = 0; sph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------------------------ MMA issuer ----------
+        if (lane == 0) {
+            const uint32_t idesc = tc05::idesc_bf16_f32(SCR_UNIT, SCR_NB);
+            const uint32_t part = (uint32_t)(a.sp / 8) * 2048u;   // bytes of A's hi part (sp / 8 slabs of 128 rows)
+            int stage = 0;
+            unsigned sph = 0, t = 0, it = 0;
+            for (int w = blockIdx.x; w < items; w += gridDim.x) {
+                const int r = w / a.nunits;
+                const int c0 = r * cpr, c1 = min(nch, c0 + cpr);
+                if (c0 >= c1) continue;
+                mbar_wait(afull, it & 1u);
+                ++it;
+                for (int c = c0; c < c1; ++c, ++t) {
+                    const unsigned b = t & 1u;
+                    mbar_wait(tempty0 + 8 * b, ((t >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+                    tc05::fence_after_sync();
+                    const uint32_t d_tmem = tmem + b * SCR_NB;
+                    for (int j = 0; j < J; ++j) {
+                        mbar_wait(bfull0 + 8 * stage, sph);
+                        tc05::fence_after_sync();
+                        const uint32_t Ah = A_s + (uint32_t)j * 4096u, Al = Ah + part;
+                        const uint32_t Bh = B_s + stage * SCR_STAGE_BYTES, Bl = Bh + 8192u;
+                        const uint32_t la = a.desc_mode ? 128u : 2048u, sa = a.desc_mode ? 2048u : 128u;
+                        const uint32_t lb = a.desc_mode ? 128u : 4096u, sb = a.desc_mode ? 4096u : 128u;
+                        const uint64_t dAh = tc05::smem_desc(Ah, la, sa), dAl = tc05::smem_desc(Al, la, sa);
+                        const uint64_t dBh = tc05::smem_desc(Bh, lb, sb), dBl = tc05::smem_desc(Bl, lb, sb);
+                        tc05::mma_bf16_ss(d_tmem, dAh, dBh, idesc, j > 0 ? 1u : 0u);   // dh . ph
+                        tc05::mma_bf16_ss(d_tmem, dAl, dBh, idesc, 1u);                // dl . ph
+                        tc05::mma_bf16_ss(d_tmem, dAh, dBl, idesc, 1u);                // dh . pl
+                        tc05::commit(bempty0 + 8 * stage);                             // stage free once these complete
+                        if (++stage == S) { stage = 0; sph ^= 1u; }
+                    }
+                    tc05::commit(tfull0 + 8 * b);
+                }
+                tc05::commit(aempty);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps 0-7 --
+        const int q = warp & 3, h = warp >> 2;
+        const int row = 32 * q + lane;
+        const float coef_q = a.ctl->coef_q;
+        float cb[NX];
+#pragma unroll
+        for (int x = 0; x < NX; ++x) cb[x] = __fmaf_ru(a.ctl->coef_b, a.ctl->bmax[x], 1e-30f);
+        unsigned t = 0, bb = 0, bph = 0;
+        unsigned long long emitted = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x) {
+            const int r = w / a.nunits, u = w - r * a.nunits;
+            const int c0 = r * cpr, c1 = min(nch, c0 + cpr);
+            if (c0 >= c1) continue;
+            const long long i = (long long)u * SCR_UNIT + row;
+            const bool valid = i < a.n_local;
+            const float dnu = a.dnmax_unit[u];
+            const float eq = __fmul_ru(coef_q, dnu);
+            float L[NX];
+            int n[NX];
+            long long slot[NX];
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                L[x] = -INFINITY;
+                n[x] = 0;
+                slot[x] = ((long long)(x * a.R + r) * 2 + h) * a.npad + i;
+            }
+            for (int c = c0; c < c1; ++c, ++t) {
+                const unsigned b = t & 1u;
+                mbar_wait(biasfull0 + 8 * bb, bph);
+                const float *bs = biasp + bb * BF;
+                const float pnmax = bs[NX * SCR_NB];
+                float E[NX], E2[NX], thr[NX];
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    E[x] = __fmaf_ru(eq, pnmax, cb[x]);
+                    E2[x] = __fadd_ru(E[x], E[x]);
+                    thr[x] = __fadd_rd(L[x], -E[x]);              // candidate iff t >= L - E
+                }
+                mbar_wait(tfull0 + 8 * b, (t >> 1) & 1u);
+                tc05::fence_after_sync();
+                const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + b * SCR_NB + h * 128;
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t v[32];
+                    tc05::ld_32x32b_x32(taddr + g * 32, v);
+                    tc05::wait_ld();
+                    if (a.dbg && blockIdx.x == 0 && t == 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) a.dbg[row * SCR_NB + h * 128 + g * 32 + e] = __uint_as_float(v[e]);
+                    }
+#pragma unroll
+                    for (int s8 = 0; s8 < 4; ++s8) {
+#pragma unroll
+                        for (int x = 0; x < NX; ++x) {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8 + 4);
+                            float tt[8];
+                            tt[0] = __uint_as_float(v[s8 * 8 + 0]) + b0.x;
+                            tt[1] = __uint_as_float(v[s8 * 8 + 1]) + b0.y;
+                            tt[2] = __uint_as_float(v[s8 * 8 + 2]) + b0.z;
+                            tt[3] = __uint_as_float(v[s8 * 8 + 3]) + b0.w;
+                            tt[4] = __uint_as_float(v[s8 * 8 + 4]) + b1.x;
+                            tt[5] = __uint_as_float(v[s8 * 8 + 5]) + b1.y;
+                            tt[6] = __uint_as_float(v[s8 * 8 + 6]) + b1.z;
+                            tt[7] = __uint_as_float(v[s8 * 8 + 7]) + b1.w;
+                            const float gm = fmaxf(fmaxf(fmaxf(tt[0], tt[1]), fmaxf(tt[2], tt[3])),
+                                                   fmaxf(fmaxf(tt[4], tt[5]), fmaxf(tt[6], tt[7])));
+                            if (gm >= thr[x]) {
+                                // rare: some of the eight may still win.  Dead / padded vertices (SCR_DEAD) and
+                                // rows beyond the epigraph's scenarios never enter a list.
+                                const int kb = c * SCR_NB + h * 128 + g * 32 + s8 * 8;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    if (tt[e] >= thr[x] && tt[e] > -1.0e38f && valid) {
+                                        if (n[x] < SCR_CAP)
+                                            a.cand[slot[x] * SCR_CAP + n[x]] =
+                                                make_int2(kb + e, __float_as_int(__fadd_ru(tt[e], E[x])));
+                                        ++n[x];
+                                        ++emitted;
+                                    }
+                                }
+                                thr[x] = fmaxf(thr[x], __fadd_rd(gm, -E2[x]));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < NX; ++x) L[x] = __fadd_rd(thr[x], E[x]);   // = max(L, best t of the tile - E)
+                tc05::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(tempty0 + 8 * b);
+                    mbar_arrive(biasempty0 + 8 * bb);
+                }
+                if (++bb == SCR_BIAS_BUFS) { bb = 0; bph ^= 1u; }
+            }
+            if (valid) {
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    a.cnt[slot[x]] = n[x];
+                    a.lfin[slot[x]] = L[x];
+                    if (n[x] > SCR_CAP) atomicAdd(&a.ctl->overflow, 1u);
+                }
+            }
+        }
+        // statistics, one atomic per warp
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, off);
+        if (lane == 0 && emitted) atomicAdd(&a.ctl->n_emit, emitted);
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 9) {
+        tc05::fence_after_sync();
+        tc05::tmem_dealloc(tmem, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operand builders.  Both are idempotent over [lo, n) and run lazily before a screening pass.
+
+__device__ __forceinline__ void split_bf16(double p, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
+{
+    hi = __double2bfloat16(p);
+    lo = __double2bfloat16(p - (double)__bfloat162float(hi));     // the remainder is exact in fp64
+}
+__device__ __forceinline__ float norm_up(double sumsq)
+{
+    return __double2float_ru(sqrt(sumsq) * (1.0 + 0x1p-40));
+}
+__device__ __forceinline__ void atomic_max_pos(float *addr, float v)   // v >= 0: integer order = float order
+{
+    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+}
+
+// Pool view for screening: vertices [k_lo, K) restricted to the stochastic rows, split in bf16 hi / lo,
+// plus ||PiS[k]||_2 (rounded up) and its maximum per chunk of 256.  One warp per vertex.
+__global__ void k_screen_view_sync(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows, int n_rows,
+                                   int sp, __nv_bfloat16 *__restrict__ PiB, float *__restrict__ pn,
+                                   float *__restrict__ pnmax, int *__restrict__ bad, long long k_lo,
+                                   const long long *__restrict__ d_K)
+{
+    griddep_sync();
+    const long long K = *d_K;
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const int J = sp / 16;
+    for (long long k = k_lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nw) {
+        const long long c = k / SCR_NB;
+        const int v = (int)(k % SCR_NB);
+        double ss = 0.0;
+        for (int j = lane; j < sp; j += 32) {
+            const double p = j < n_rows ? pi[k * m2 + s_rows[j]] : 0.0;
+            __nv_bfloat16 hi, lo;
+            split_bf16(p, hi, lo);
+            const size_t off = ((size_t)(c * J + j / 16) * 2) * (2 * SCR_NB * 8) + (size_t)((j % 16) / 8) * (SCR_NB * 8) +
+                               (size_t)v * 8 + (j % 8);
+            PiB[off] = hi;
+            PiB[off + 2 * SCR_NB * 8] = lo;
+            ss = fma(p, p, ss);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        if (lane == 0) {
+            const float nrm = norm_up(ss);
+            pn[k] = nrm;
+            if (nrm < 1.0e18f) atomic_max_pos(pnmax + c, nrm);
+            else *bad = 1;                                        // Inf / NaN / out of bf16-safe range
+        }
+    }
+}
+
+// Scenario store for screening: local scenarios [lo, n_local) from the FP64 tiles, split in bf16 hi / lo,
+// plus the largest ||d_i||_2 per unit of 128 and overall.  One warp per scenario.
+__global__ void k_screen_scen_sync(const double *__restrict__ D, int s_pad, int sp, __nv_bfloat16 *__restrict__ DB,
+                                   float *__restrict__ dnmax_unit, float *__restrict__ dnmax_all,
+                                   int *__restrict__ bad, long long lo, long long n_local)
+{
+    griddep_sync();
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_local; i += nw) {
+        const long long u = i / SCR_UNIT;
+        const int row = (int)(i % SCR_UNIT);
+        const double *Dt = D + (i >> 7) * (long long)s_pad * SQLP_TILE;
+        double ss = 0.0;
+        for (int j = lane; j < sp; j += 32) {
+            const double d = j < s_pad ? Dt[tile_off((int)(i & 127), j)] : 0.0;
+            __nv_bfloat16 hi, lw;
+            split_bf16(d, hi, lw);
+            const size_t off = (size_t)u * (2 * sp * SCR_UNIT) + (size_t)(j / 8) * (SCR_UNIT * 8) + (size_t)row * 8 + (j % 8);
+            DB[off] = hi;
+            DB[off + (size_t)sp * SCR_UNIT] = lw;
+            ss = fma(d, d, ss);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        if (lane == 0) {
+            const float nrm = norm_up(ss);
+            if (nrm < 1.0e18f) {
+                atomic_max_pos(dnmax_unit + u, nrm);
+                atomic_max_pos(dnmax_all, nrm);
+            } else {
+                *bad = 1;
+            }
+        }
+    }
+}
+
+// Per call: shifted fp32 biases in the chunk-packed layout, the vertices that cannot win anywhere
+// (Cauchy-Schwarz in exact arithmetic: bias_k + ||PiS_k|| max||d|| < max_k' (bias_k' - ||PiS_k'|| max||d||)),
+// the error-bound coefficients and the fall-back decision.  One block.
+template <int NX>
+__global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__ bias, long long bias_stride,
+                                                      const float *__restrict__ pn, const float *__restrict__ pnmax,
+                                                      const float *__restrict__ dnmax_all, const int *__restrict__ view_bad,
+                                                      const int *__restrict__ epi_bad, const long long *__restrict__ d_K,
+                                                      int sp, unsigned int ovf_limit, float *__restrict__ b32c,
+                                                      ScreenCtl *__restrict__ ctl)
+{
+    griddep_sync();
+    __shared__ double red[32];
+    __shared__ double lbg[NX];
+    __shared__ float fmx[NX];
+    __shared__ int nlive[NX];
+    __shared__ int sbad;
+    const long long K = *d_K;
+    const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
+    constexpr int BF = scr_bias_floats<NX>();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double dn = (double)*dnmax_all * (1.0 + 0x1p-20);
+    if (tid == 0) sbad = (*view_bad | *epi_bad) ? 1 : 0;
+    if (tid < NX) { fmx[tid] = 0.f; nlive[tid] = 0; }
+    __syncthreads();
+    for (int x = 0; x < NX; ++x) {
+        double m = -INFINITY;
+        bool pinf = false;
+        for (long long k = tid; k < K; k += blockDim.x) {
+            const double b = bias[x * bias_stride + k];
+            if (b == INFINITY) pinf = true;
+            if (isfinite(b)) m = fmax(m, b - (double)pn[k] * dn);
+        }
+        if (pinf) sbad = 1;                                        // a +Inf score wins everywhere: leave it to the FP64 sweep
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        if (tid == 0) {
+            double mm = -INFINITY;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
+            lbg[x] = mm;
+        }
+        __syncthreads();
+    }
+    for (int x = 0; x < NX; ++x) {
+        const double lb = lbg[x];
+        float mx = 0.f;
+        int live = 0;
+        for (long long k = tid; k < (long long)nch * SCR_NB; k += blockDim.x) {
+            float out = SCR_DEAD;
+            if (k < K) {
+                const double b = bias[x * bias_stride + k];
+                const double q = (double)pn[k] * dn;
+                if (isfinite(b) && isfinite(lb) && b + q + 1e-9 * (fabs(lb) + q) >= lb) {
+                    out = __double2float_rn(b - lb);
+                    if (!(fabsf(out) < 1.0e30f)) sbad = 1;
+                    mx = fmaxf(mx, fabsf(out));
+                    ++live;
+                }
+            }
+            b32c[(k / SCR_NB) * BF + x * SCR_NB + (k % SCR_NB)] = out;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            live += __shfl_xor_sync(0xffffffffu, live, off);
+        }
+        if (lane == 0) {
+            atomic_max_pos(&fmx[x], mx);
+            atomicAdd(&nlive[x], live);
+        }
+    }
+    float pmx = 0.f;
+    for (int c = tid; c < nch; c += blockDim.x) {
+        const float p = pnmax[c];
+        b32c[(long long)c * BF + NX * SCR_NB] = p;
+        b32c[(long long)c * BF + NX * SCR_NB + 1] = 0.f;
+        b32c[(long long)c * BF + NX * SCR_NB + 2] = 0.f;
+        b32c[(long long)c * BF + NX * SCR_NB + 3] = 0.f;
+        pmx = fmaxf(pmx, p);
+    }
+    if ((double)pmx * dn > 1.0e30) sbad = 1;
+    __syncthreads();
+    if (tid == 0) {
+        const double cq = (3.0 * 0x1p-16 * (1.0 + 0x1p-7) + (3.0 * sp + 8.0) * 0x1p-22 * 1.02 + 1.02 * 0x1p-23 + 0x1p-40) *
+                          (1.0 + 0x1p-10);
+        ctl->coef_q = __double2float_ru(cq);
+        ctl->coef_b = __double2float_ru((0x1p-23 + 0x1p-40) * (1.0 + 0x1p-10));
+        for (int x = 0; x < NX; ++x) {
+            ctl->shift[x] = lbg[x];
+            ctl->bmax[x] = fmx[x];
+            ctl->live[x] = nlive[x];
+        }
+        ctl->bad = sbad;
+        ctl->overflow = 0u;
+        ctl->ovf_limit = ovf_limit;
+        ctl->n_emit = 0ull;
+        ctl->n_eval = 0ull;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The exact decision.  One warp per scenario: the candidates that survive the final lower bound are scored
+// with the FP64 sweep's own arithmetic -- mma.sync.m8n8k4.f64 over the k-groups in ascending order from a
+// zero accumulator, then + bias -- eight vertices per chain (the eight rows of A all hold the scenario), and
+// compared on (value desc, index asc).  A scenario whose list overflowed is swept over all K vertices.
+struct ResolveArgs {
+    const double *D;            // FP64 scenario tiles (fragment-major)
+    const double *PiS;          // FP64 pool view (fragment-major)
+    const double *bias;         // [NX][bias_stride]
+    long long bias_stride;
+    int s_pad;
+    const long long *d_K;
+    long long n_local, npad;
+    int R;
+    const int2 *cand;
+    const int *cnt;
+    const float *lfin;
+    double *best_val;           // [NX][out_stride]
+    int *best_idx;
+    long long out_stride;
+    ScreenCtl *ctl;
+    int force_full;             // tests: sweep every vertex for every scenario with this kernel's arithmetic
+};
+
+template <int NX>
+__global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
+{
+    griddep_sync();
+    if (!a.force_full && screen_falls_back(a.ctl)) return;
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long K = *a.d_K;
+    const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
+    const int cpr = (nch + a.R - 1) / max(a.R, 1);
+    const int ng = a.s_pad / 4;
+    const size_t tile_doubles = (size_t)a.s_pad * SQLP_TILE;
+    unsigned long long evald = 0;
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.n_local; i += nw) {
+        double best[NX];
+        int bidx[NX];
+#pragma unroll
+        for (int x = 0; x < NX; ++x) { best[x] = -INFINITY; bidx[x] = -1; }
+        const int ci = (int)(i & 127);
+        const double *Drow = a.D + (size_t)(i >> 7) * tile_doubles +
+                             ((((size_t)(ci >> 4)) * 32 + (ci & 7) * 4 + (lane & 3)) << 1) + ((ci >> 3) & 1);
+        int qk = 0, qx = 0, qn = 0;
+        auto flush = [&]() {
+            if (qn == 0) return;
+            const int kfirst = __shfl_sync(0xffffffffu, qk, 0);
+            int kk = __shfl_sync(0xffffffffu, qk, lane >> 2);
+            if ((lane >> 2) >= qn) kk = kfirst;                      // unused columns repeat a valid vertex
+            const int cv = kk & 127;
+            const double *Prow = a.PiS + (size_t)(kk >> 7) * tile_doubles +
+                                 ((((size_t)(cv >> 4)) * 32 + (cv & 7) * 4 + (lane & 3)) << 1) + ((cv >> 3) & 1);
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int g = 0; g < ng; ++g) {
+                const double av = Drow[(size_t)g * 512], bv = Prow[(size_t)g * 512];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc0), "+d"(acc1)
+                             : "d"(av), "d"(bv));
+            }
+            for (int j = 0; j < qn; ++j) {
+                const double dot = __shfl_sync(0xffffffffu, (j & 1) ? acc1 : acc0, j >> 1);
+                const int kj = __shfl_sync(0xffffffffu, qk, j);
+                const int xj = __shfl_sync(0xffffffffu, qx, j);
+                if (kj < K) {
+#pragma unroll
+                    for (int x = 0; x < NX; ++x) {
+                        const double v = dot + a.bias[x * a.bias_stride + kj];   // the sweep's epilogue: acc + bias
+                        if ((xj < 0 || x == xj) && (v > best[x] || (v == best[x] && bidx[x] >= 0 && kj < bidx[x]))) {
+                            best[x] = v;
+                            bidx[x] = kj;
+                        }
+                    }
+                }
+            }
+            evald += qn;
+            qn = 0;
+        };
+        auto push = [&](int k, int x) {
+            if (lane == qn) { qk = k; qx = x; }
+            if (++qn == 8) flush();
+        };
+        // final lower bounds and overflow over the thread lists of this scenario
+        float LB[NX];
+        bool full = a.force_full != 0;
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            float lb = -INFINITY;
+            int ovf = 0;
+            for (int s = lane; s < 2 * a.R; s += 32) {
+                const int r = s >> 1;
+                if (r * cpr >= nch) continue;                         // empty K-range: nothing was written
+                const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
+                lb = fmaxf(lb, a.lfin[slot]);
+                ovf |= a.cnt[slot] > SCR_CAP;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, off));
+                ovf |= __shfl_xor_sync(0xffffffffu, ovf, off);
+            }
+            LB[x] = lb;
+            full = full || ovf;
+        }
+        if (full) {
+            for (long long k0 = 0; k0 < K; k0 += 8) {              // qx = -1: the dot serves every point
+                if (lane < 8) { qk = (int)min(k0 + lane, K - 1); qx = -1; }
+                qn = (int)min((long long)8, K - k0);
+                flush();
+            }
+        } else {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                for (int s = 0; s < 2 * a.R; ++s) {
+                    if ((s >> 1) * cpr >= nch) continue;
+                    const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
+                    const int n = a.cnt[slot];
+                    int2 e = make_int2(0, 0);
+                    if (lane < n) e = a.cand[slot * SCR_CAP + lane];
+                    unsigned pass = __ballot_sync(0xffffffffu, lane < n && __int_as_float(e.y) >= LB[x]);
+                    while (pass) {
+                        const int src = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        push(__shfl_sync(0xffffffffu, e.x, src), x);
+                    }
+                }
+            }
+            flush();
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                a.best_val[x * a.out_stride + i] = best[x];
+                a.best_idx[x * a.out_stride + i] = bidx[x];
+            }
+        }
+    }
+    if (lane == 0 && evald) atomicAdd(&a.ctl->n_eval, evald);
+}
+
+}  // namespace sqlp
