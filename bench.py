@@ -44,6 +44,12 @@ def parse():
     ap.add_argument("--vertices", type=int, default=16384)
     ap.add_argument("--epigraphs", type=int, default=4)
     ap.add_argument("--instance", default="storm")
+    ap.add_argument("--pool", default="real", choices=["real", "synthetic"],
+                    help="dual-vertex pool of the headline leg: harvested LP duals (tests/golden/pools, SURVEY C4) or the "
+                         "round-1 pool (94 harvested + uniform synthetic vertices)")
+    ap.add_argument("--screen", type=int, default=-1, help="override the library's screening mode (0 off, 1 auto, 2 always)")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the other-pool leg and the strong-scaled leg")
+    ap.add_argument("--parity-n", type=int, default=512, help="scenarios of the bench's own state checked against the oracle")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dev-only", action="store_true",
@@ -99,10 +105,30 @@ def u01(seed, idx):
     return (zz >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
-def make_pool(z, K, extra):
-    """K + extra vertices: the harvested real storm vertices first, then synthetic ones
-    pi_kj = scale * (2u - 1), distinct under the dedup rule."""
+def real_pool(name, n):
+    """The first n vertices of the largest committed harvest of this instance (tools/harvest_pool.py: stage-2 LP
+    duals through the reference's dedup rule, in LP order -- a prefix of a harvest IS the smaller harvest)."""
+    d = os.path.join(ROOT, "tests", "golden", "pools")
+    best = None
+    for f in os.listdir(d) if os.path.isdir(d) else []:
+        if f.startswith(name + "_K") and f.endswith(".npz"):
+            k = int(f[len(name) + 2:-4])
+            if k >= n and (best is None or k < best[0]):
+                best = (k, f)
+    if best is None:
+        return None
+    return np.ascontiguousarray(np.load(os.path.join(d, best[1]))["pool"][:n])
+
+
+def make_pool(z, K, extra, kind="synthetic", name=None):
+    """K + extra distinct vertices.  kind "real": harvested LP duals only.  kind "synthetic": the
+    round-1 pool -- the 94 harvested vertices of the instance fixture, then pi_kj = scale * (2u - 1)."""
     m2 = int(z["m2"])
+    if kind == "real" and name and not name.startswith("synth"):
+        P = real_pool(name, K + extra)
+        if P is not None:
+            return P
+        raise SystemExit(f"no harvested pool with {K + extra} vertices for {name}: run tools/harvest_pool.py")
     real = z["pool"]
     n_syn = K + extra - len(real)
     scale = float(np.abs(real).max()) if len(real) else 1000.0
@@ -224,7 +250,7 @@ def run_reference(args):
     if rank != 0:
         return
     z = load_instance(args.instance)
-    pool = make_pool(z, args.vertices, 0)
+    pool = make_pool(z, args.vertices, 0, pool_kind(args), args.instance)
     n1 = int(z["n1"])
     x2 = [z["x_ev"], z["x_alt"]] if "x_ev" in z else [10 * u01(3, np.arange(n1)), 10 * u01(5, np.arange(n1))]
     per_step = max(1.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
@@ -248,9 +274,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def pool_kind(args):
+    return "synthetic" if args.instance.startswith("synth") else args.pool
+
+
 def workload_config(args, z, world):
     return {"workload": f"{args.instance} shape: cut formation of one SD iteration "
                         f"(append 1 scenario + 2 pool pushes per epigraph, candidate + incumbent cut)",
+            "pool": ("harvested stage-2 LP duals (HiGHS) through the reference's dedup rule" if pool_kind(args) == "real"
+                     else "94 harvested + uniform synthetic vertices"),
             "instance": args.instance, "s": int(len(z["pos_row"])), "m2": int(z["m2"]), "n1": int(z["n1"]),
             "K_vertices": args.vertices, "N_scenarios_per_gpu": args.scen_per_gpu,
             "N_scenarios_total": args.scen_per_gpu * world, "epigraphs": args.epigraphs,
@@ -259,6 +291,48 @@ def workload_config(args, z, world):
 
 
 # ---------------------------------------------------------------- our arm ----------------
+
+class Cell:
+    """A pool + E weighted epigraphs with their scenarios sampled on the device."""
+
+    def __init__(self, T, ctx, z, coef, pool_all, K0, E, n_epi_global):
+        self.T, self.ctx, self.z, self.E, self.K0, self.n_epi_global = T, ctx, z, E, K0, n_epi_global
+        self.pool_all = pool_all
+        m2 = int(z["m2"])
+        self.dvs = T.sdDualVertexSet(ctx=ctx, m2=m2)
+        ins, _ = self.dvs.push_many(pool_all[:K0])
+        assert ins.all() and len(self.dvs) == K0, "workload vertices are not distinct under the dedup rule"
+        self.epis = []
+        for e in range(E):
+            epi = T.sdEpigraph(coef, 1.0 / E, 0.0, self.dvs)
+            epi.set_outcomes(z["out_vals"], z["out_cdf"], z["out_cnt"])
+            if "kind" in z:
+                epi.set_distributions(z["kind"], z["par_a"], z["par_b"])
+            epi.sample_scenarios(n_epi_global, seed=101 + e, weight_seed=201 + e)
+            self.epis.append(epi)
+        self.t_next = 0          # SD iterations performed so far on this cell
+
+    def step_inputs(self, t):
+        """Iteration t: E new scenarios, E new vertices + E duplicates (pushed new, dup, new, dup ...)."""
+        z, E, K0, m2 = self.z, self.E, self.K0, int(self.z["m2"])
+        g = self.n_epi_global + t
+        scen = np.stack([sample_values(z, 101 + e, g, 1)[0] for e in range(E)])      # [E, s]
+        newv = self.pool_all[K0 + t * E: K0 + (t + 1) * E]                            # [E, m2]
+        dupv = self.pool_all[(7 * t + 3 * np.arange(E)) % K0]
+        verts = np.empty((2 * E, m2))
+        verts[0::2] = newv
+        verts[1::2] = dupv
+        return scen, verts
+
+    def evals_of(self, t):
+        """Evaluations of iteration t: 2 points x K x N with K, N after this iteration's pushes / scenarios."""
+        return 2.0 * (self.K0 + self.E * (t + 1)) * ((self.n_epi_global + t + 1) * self.E)
+
+    def close(self):
+        for e in self.epis:
+            e.close()
+        self.dvs.close()
+
 
 def run_ours(args):
     import torch
@@ -282,6 +356,8 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)     # a real (non-NULL) stream shared with the library
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    if args.screen >= 0:
+        ctx.set_screen(args.screen)
     L = _lib.lib()
 
     z = load_instance(args.instance)
@@ -289,53 +365,12 @@ def run_ours(args):
     E, K0 = args.epigraphs, args.vertices
     n_steps = args.steps + args.warmup
     total_steps = 2 * n_steps + 2            # device-resident leg + e2e leg (+ slack)
-    pool_all = make_pool(z, K0, E * total_steps)
+    kind = pool_kind(args)
+    pool_all = make_pool(z, K0, E * total_steps, kind, args.instance)
     x_c = np.ascontiguousarray(z["x_ev"])
     x_i = np.ascontiguousarray(z["x_alt"])
-
     coef = T.sdSubprobCoefficients.from_tables(z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"],
                                                z["pos_row"], z["pos_col"])
-    dvs = T.sdDualVertexSet(ctx=ctx, m2=m2)
-    t_setup = time.perf_counter()
-    ctx.profile(True)
-    ctx.profile_classes(reset=True)
-    ins, _ = dvs.push_many(pool_all[:K0])
-    assert ins.all() and len(dvs) == K0, "workload vertices are not distinct under the dedup rule"
-    epis = []
-    n_epi_global = (args.scen_per_gpu * world) // E
-    for e in range(E):
-        epi = T.sdEpigraph(coef, 1.0 / E, 0.0, dvs)
-        epi.set_outcomes(z["out_vals"], z["out_cdf"], z["out_cnt"])
-        if "kind" in z:
-            epi.set_distributions(z["kind"], z["par_a"], z["par_b"])
-        epi.sample_scenarios(n_epi_global, seed=101 + e, weight_seed=201 + e)
-        epis.append(epi)
-    ctx.synchronize()
-    t_setup = time.perf_counter() - t_setup
-    prof_setup = ctx.profile_classes(reset=True)
-
-    # bulk add_scenario! from realised values (the 16 s bytes-per-scenario form of the delta build):
-    # a scratch epigraph, values already on the device, timed by the library's event scopes
-    n_bulk = min(262144, max(128, n_epi_global))
-    vals_bulk = torch.from_numpy(sample_values(z, 7, 0, 4096)).to(dev).repeat((n_bulk + 4095) // 4096, 1)[:n_bulk].contiguous()
-    scratch = T.sdEpigraph(coef, 1.0, 0.0, dvs)
-    for _ in range(4):
-        _lib.check(L.sqlp_epi_add_scenarios_dev(scratch._h, n_bulk, C.c_void_p(vals_bulk.data_ptr()), None))
-        ctx.synchronize()
-        prof_bulk = ctx.profile_classes(reset=True)      # keeps the last (warm) one
-    del scratch, vals_bulk
-    ctx.profile(False)
-
-    # per-step inputs: E new scenarios, E new vertices + E duplicates, 2 points
-    def step_inputs(t):
-        g = n_epi_global + t
-        scen = np.stack([sample_values(z, 101 + e, g, 1)[0] for e in range(E)])      # [E, s]
-        newv = pool_all[K0 + t * E: K0 + (t + 1) * E]                                  # [E, m2]
-        dupv = pool_all[(7 * t + 3 * np.arange(E)) % K0]
-        verts = np.empty((2 * E, m2))
-        verts[0::2] = newv
-        verts[1::2] = dupv
-        return scen, verts
 
     def barrier():
         if world > 1:
@@ -350,77 +385,108 @@ def run_ours(args):
         return float(tns.item())
 
     x2_dev = torch.from_numpy(np.concatenate([x_c, x_i])).to(dev)
-    out_dev = torch.zeros(E, 2, n1 + 2, dtype=torch.float64, device=dev)
 
-    # ---- leg 1: device-resident inputs, no host sync inside the timed region ----------------
-    staged = []
-    for t in range(n_steps):
-        scen, verts = step_inputs(t)
-        staged.append((torch.from_numpy(scen).to(dev), torch.from_numpy(verts).to(dev)))
-    torch.cuda.synchronize()
+    def device_leg(cell, warmup, steps, want_profiles):
+        """`warmup` untimed + `steps` timed SD iterations with every input already resident in HBM and no host
+        synchronisation inside the timed region.  One library call per class of work: E x add_scenario!, ONE push
+        of the iteration's 2E vertices, E x (candidate + incumbent cut)."""
+        Ecell = cell.E
+        out_dev = torch.zeros(Ecell, 2, n1 + 2, dtype=torch.float64, device=dev)
+        t0 = cell.t_next
+        staged = []
+        for t in range(warmup + steps):
+            scen, verts = cell.step_inputs(t0 + t)
+            staged.append((torch.from_numpy(scen).to(dev), torch.from_numpy(verts).to(dev)))
+        torch.cuda.synchronize()
 
-    def dev_step(t):
-        scen_d, verts_d = staged[t]
-        for e, epi in enumerate(epis):
-            _lib.check(L.sqlp_epi_add_scenarios_dev(epi._h, 1, C.c_void_p(scen_d[e].data_ptr()), None))
-            _lib.check(L.sqlp_pool_push_dev(dvs._h, 2, C.c_void_p(verts_d[2 * e].data_ptr())))
-        for e, epi in enumerate(epis):
-            _lib.check(L.sqlp_epi_build_cuts2_dev(epi._h, C.c_void_p(x2_dev.data_ptr()),
-                                                  C.c_void_p(out_dev[e].data_ptr())))
+        def dev_step(t):
+            scen_d, verts_d = staged[t]
+            for e, epi in enumerate(cell.epis):
+                _lib.check(L.sqlp_epi_add_scenarios_dev(epi._h, 1, C.c_void_p(scen_d[e].data_ptr()), None))
+            _lib.check(L.sqlp_pool_push_dev(cell.dvs._h, 2 * Ecell, C.c_void_p(verts_d.data_ptr())))
+            for e, epi in enumerate(cell.epis):
+                _lib.check(L.sqlp_epi_build_cuts2_dev(epi._h, C.c_void_p(x2_dev.data_ptr()),
+                                                      C.c_void_p(out_dev[e].data_ptr())))
 
-    # warm-up steps: after the first one every kernel class is bracketed by events (roofline_other); the
-    # timed steps bracket the contraction alone, so the instrumentation costs two event records per launch
-    for t in range(args.warmup):
-        dev_step(t)
-        if t == 0:
-            ctx.synchronize()
-            ctx.profile(True)
-            ctx.profile_classes(reset=True)
-    prof_warm = ctx.profile_classes(reset=True)
-    barrier()
-    ctx.profile(2)
-    ctx.profile_read(reset=True)
-    launches0 = ctx.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for t in range(args.warmup, n_steps):
-        dev_step(t)
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.finish()
-    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = ctx.launch_count() - launches0
-    prof_steps = ctx.profile_classes(reset=True)
-    c_ms, c_launches, c_flops = prof_steps["contract"]
+        # warm-up steps: after the first one every kernel class is bracketed by events (roofline_other); the timed
+        # steps bracket only the argmax kernels, so the instrumentation costs two event records per launch
+        prof_warm = None
+        for t in range(warmup):
+            dev_step(t)
+            if t == 0 and want_profiles:
+                ctx.synchronize()
+                ctx.profile(True)
+                ctx.profile_classes(reset=True)
+        if want_profiles:
+            prof_warm = ctx.profile_classes(reset=True)
+        barrier()
+        ctx.profile(2)
+        ctx.profile_classes(reset=True)
+        launches0 = ctx.launch_count()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for t in range(warmup, warmup + steps):
+            dev_step(t)
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.finish()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = ctx.launch_count() - launches0
+        prof = ctx.profile_classes(reset=True)
+        ctx.profile(False)
+        evals = sum(cell.evals_of(t0 + t) for t in range(warmup, warmup + steps))
+        cell.t_next = t0 + warmup + steps
+        K_after = len(cell.dvs)
+        assert K_after == cell.K0 + Ecell * cell.t_next, (K_after, cell.K0, Ecell, cell.t_next)
+        return {"ms": ms, "ms_per_step": ms / max(1, steps), "value": evals / (ms * 1e-3), "launches": launches,
+                "prof": prof, "prof_warm": prof_warm, "clocks": clocks, "out": out_dev.cpu().numpy(),
+                "screen": cell.epis[0].screen_stats()}
+
+    # ---------------------------------------------------------------- headline cell ----------
+    t_setup = time.perf_counter()
+    ctx.profile(True)
+    ctx.profile_classes(reset=True)
+    n_epi_global = (args.scen_per_gpu * world) // E
+    cell = Cell(T, ctx, z, coef, pool_all, K0, E, n_epi_global)
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    prof_setup = ctx.profile_classes(reset=True)
+
+    # bulk add_scenario! from realised values (the 16 s bytes-per-scenario form of the delta build):
+    # a scratch epigraph, values already on the device, timed by the library's event scopes
+    n_bulk = min(262144, max(128, n_epi_global))
+    vals_bulk = torch.from_numpy(sample_values(z, 7, 0, 4096)).to(dev).repeat((n_bulk + 4095) // 4096, 1)[:n_bulk].contiguous()
+    scratch = T.sdEpigraph(coef, 1.0, 0.0, cell.dvs)
+    for _ in range(4):
+        _lib.check(L.sqlp_epi_add_scenarios_dev(scratch._h, n_bulk, C.c_void_p(vals_bulk.data_ptr()), None))
+        ctx.synchronize()
+        prof_bulk = ctx.profile_classes(reset=True)      # keeps the last (warm) one
+    scratch.close()
+    del scratch, vals_bulk
     ctx.profile(False)
-    K_after = len(dvs)
-    assert K_after == K0 + E * n_steps, (K_after, K0, E, n_steps)
-    cut_check = out_dev.cpu().numpy()
 
-    # evaluations performed by global step t (K grows by E new vertices per step, N by E)
-    def evals_of(t):
-        return 2.0 * (K0 + E * (t + 1)) * ((n_epi_global + t + 1) * E)
-
-    evals_dev = sum(evals_of(t) for t in range(args.warmup, n_steps))
-    value = evals_dev / (ms_dev * 1e-3)
+    # ---- leg 1: device-resident inputs ---------------------------------------------------------
+    leg = device_leg(cell, args.warmup, args.steps, True)
+    ms_dev, value, launches, clocks = leg["ms"], leg["value"], leg["launches"], leg["clocks"]
+    prof_steps, prof_warm, cut_check = leg["prof"], leg["prof_warm"], leg["out"]
 
     if args.dev_only:
-        c_tf = c_flops / (c_ms * 1e-3) * 1e-12
-        print(json.dumps({"dev_only": True, "value": value, "ms_per_step": ms_dev / max(1, args.steps),
-                          "roofline": {"achieved": c_tf, "frac": c_tf / 36.69, "avg_launch_ms": c_ms / max(1, c_launches)}}))
+        if rank == 0:
+            print(json.dumps({"dev_only": True, "value": value, "ms_per_step": leg["ms_per_step"], "pool": kind,
+                              "prof": prof_steps, "screen": leg["screen"]}))
         return
+
     # ---- leg 2: end to end through the blocking host API (host buffers in, cuts out) -------
-    base_t = n_steps
+    base_t = cell.t_next
     host_in = []
     for t in range(n_steps):
-        scen, verts = step_inputs(base_t + t)
+        scen, verts = cell.step_inputs(base_t + t)
         host_in.append((torch.from_numpy(scen).pin_memory(), torch.from_numpy(verts).pin_memory()))
     xc_p, xi_p = torch.from_numpy(x_c).pin_memory(), torch.from_numpy(x_i).pin_memory()
     alpha = np.zeros((E, 2)); beta = np.zeros((E, 2, n1)); wm = np.zeros(E); val = np.zeros((E, 2))
-    handles = (C.c_void_p * E)(*[e._h for e in epis])
-
+    handles = (C.c_void_p * E)(*[e._h for e in cell.epis])
     ins = np.zeros(2 * E, dtype=np.int32); idx = np.zeros(2 * E, dtype=np.int64)
 
     def e2e_step(t):
@@ -442,48 +508,56 @@ def run_ours(args):
         e2e_step(t)
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    evals_e2e = sum(evals_of(base_t + t) for t in range(args.warmup, n_steps))
+    evals_e2e = sum(cell.evals_of(base_t + t) for t in range(args.warmup, n_steps))
+    cell.t_next = base_t + n_steps
     e2e_value = evals_e2e / (ms_e2e * 1e-3)
     h2d = (E * s + 2 * E * m2 + 2 * n1) * 8
     d2h = E * (2 * (n1 + 2) + 1) * 8 + 2 * E * 16
+    assert list(ins) == [1, 0] * E, f"dedup decisions of the last step: {ins}"      # new, duplicate, new, ...
 
-    # sanity: G5 invariant alpha + beta.x == val on the last step's cuts
-    for e in range(0 if not os.environ.get('SQLP_BENCH_NOCHECK') else E, E):
+    # G5 on the last step's cuts: alpha + beta.x == sum_i p_i max_val_i
+    for e in range(E):
         for xi_, x in enumerate((x_c, x_i)):
             lhs = alpha[e, xi_] + beta[e, xi_] @ x
             assert abs(lhs - val[e, xi_]) <= 1e-9 * (abs(alpha[e, xi_]) + np.abs(beta[e, xi_] * x).sum()), \
                 "cut invariant violated"
-    assert os.environ.get('SQLP_BENCH_NOCHECK') or np.isfinite(cut_check).all()
+    assert np.isfinite(cut_check).all()
+
+    # ---- parity of the bench's OWN state against the oracle -----------------------------------
+    parity = parity_sample(args, T, dist if world > 1 else None, cell, world, rank, alpha, beta, x_c, x_i, pool_all)
+
+    # ---- the other pool, and the strong-scaled form of the job, in the same run -----------------
+    other = strong = None
+    if not args.no_extra_legs and not args.instance.startswith("synth"):
+        cell.close()
+        del cell
+        torch.cuda.empty_cache()
+        okind = "synthetic" if kind == "real" else "real"
+        opool = make_pool(z, K0, E * (n_steps + 1), okind, args.instance)
+        ocell = Cell(T, ctx, z, coef, opool, K0, E, n_epi_global)
+        oleg = device_leg(ocell, args.warmup, args.steps, False)
+        other = leg_summary(oleg, okind, ocell)
+        ocell.close()
+        del ocell
+        if world > 1:
+            # C4 as BASELINE.json names it: N = scen_per_gpu scenarios IN TOTAL, sharded over the GPUs
+            scell = Cell(T, ctx, z, coef, pool_all, K0, E, args.scen_per_gpu // E)
+            sleg = device_leg(scell, args.warmup, args.steps, False)
+            strong = leg_summary(sleg, kind, scell)
+            strong["N_total"] = args.scen_per_gpu
+            # the weak-scaled step of this run does, per GPU, exactly the work of the 1-GPU form of this job
+            strong["efficiency_vs_n1"] = (leg["ms_per_step"] / world) / sleg["ms_per_step"]
+            strong["efficiency_note"] = ("1-GPU time taken from this run's weak-scaled step (the same per-GPU work: "
+                                         f"{args.scen_per_gpu} scenarios x all vertices)")
+            scell.close()
+            del scell
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak = None
-    peak_src = "unmeasured"
-    if os.path.exists(FP64_PEAK_FILE):
-        with open(FP64_PEAK_FILE) as fh:
-            pk = json.load(fh)
-        peak = pk["dfma"]["sustained_tflops"]
-        peak_src = "measured DFMA-chain microkernel, sustained (profiles/fp64_peak.json; MEASURED_PEAKS.json has no FP64 figure)"
-    achieved = c_flops / (c_ms * 1e-3) * 1e-12 if c_ms > 0 else None
-    traffic, traffic_src = None, None
-    tfile = os.path.join(ROOT, "profiles", "contract_traffic.json")
-    if os.path.exists(tfile):   # dram bytes of one launch at this shape, from the committed ncu capture
-        with open(tfile) as fh:
-            tj = json.load(fh)
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        traffic_src = tj["source"]
-    roofline = {"bound": "tensor", "pipe": "fp64 tensor (DMMA, mma.sync.m8n8k4.f64; tcgen05 has no fp64)",
-                "kernel": "k_contract_ws<NX=2> + k_argmax_fixup", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": (achieved / peak) if (achieved and peak) else None,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "launches": c_launches, "avg_launch_ms": c_ms / max(1, c_launches),
-                "share_of_step": c_ms / ms_dev if ms_dev else None,
-                "note": "executed flops = 2*s*K*N per launch, counted once although the launch serves both "
-                        "points (candidate and incumbent share the contraction); s = 117 algorithmic rows "
-                        "(120 executed after padding to whole k-groups)"}
+    rl = rooflines(leg, args)
     # the HBM-bound kernels: algorithmic bytes over event-timed device time
     hbm_peak, hbm_src = 6552.3, "fallback (MEASURED_PEAKS.json absent)"
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -508,24 +582,30 @@ def run_ours(args):
         hbm_entry("k_cut_partial + k_sum_groups", prof_warm["reduce"],
                   "warm-up steps after the first: N (idx + weight + winning dot) + (rho, tau) table + cut per point"),
         hbm_entry("k_pool_push", prof_warm["pool"],
-                  "warm-up steps after the first: hash scan 8 K + vector in/out per push (two pushes per scope; "
+                  "warm-up steps after the first: hash scan 8 K + vector in/out per push (2E pushes per scope; "
                   "latency bound)"),
         hbm_entry("k_base + k_bias", prof_warm["bias"],
-                  "warm-up steps after the first: one pass over the K x m2 pool for both points"),
+                  "warm-up steps after the first: one pass over the K x m2 pool for both points, once per cell "
+                  "(epigraphs with the same template share it)"),
     ]
     others = [o for o in others if o]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / max(1, args.steps),
+            "warmup": args.warmup, "ms_per_step": leg["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (real storm template + outcome tables, counter-RNG scenarios, "
-                    "94 harvested + synthetic vertices)",
+            "data": "synthetic scenarios (counter RNG over the real storm outcome tables) on the real storm template; "
+                    + ("REAL dual-vertex pool: harvested stage-2 LP duals" if kind == "real"
+                       else "94 harvested + synthetic dual vertices"),
             "config": workload_config(args, z, world),
-            "cut_formation_ms_per_sd_iter": ms_dev / max(1, args.steps),
-            "executed_tflops": c_flops / (ms_dev * 1e-3) * 1e-12,
-            "roofline": roofline, "roofline_other": others, "peak_hbm_source": hbm_src, "clocks": clocks,
+            "cut_formation_ms_per_sd_iter": leg["ms_per_step"],
+            "roofline": rl["dominant"], "roofline_kernels": rl["all"], "roofline_other": others,
+            "peak_hbm_source": hbm_src, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / max(1, args.steps)},
-            "gpu_launches": launches, "setup_s": t_setup}
+            "gpu_launches": launches, "setup_s": t_setup, "screening": leg["screen"], "parity_sample": parity}
+    if other:
+        line["other_pool"] = other
+    if strong:
+        line["strong"] = strong
     if not args.no_cpu_baseline and world == 1:
         base, _, _ = cpu_reference(z, pool_all[:K0], args.cpu_seconds, [x_c, x_i])
         base["single_thread"] = cpu_reference_single_thread(z, pool_all[:K0], min(4.0, args.cpu_seconds), [x_c, x_i])
@@ -533,6 +613,152 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def leg_summary(leg, kind, cell):
+    r = rooflines(leg, None)
+    return {"pool": kind, "ms_per_step": leg["ms_per_step"], "value": leg["value"], "unit": UNIT,
+            "gpu_launches": leg["launches"], "screening": leg["screen"], "roofline": r["dominant"],
+            "share_of_step": r["dominant"]["share_of_step"] if r["dominant"] else None, "clocks": leg["clocks"]}
+
+
+def rooflines(leg, args):
+    """One entry per argmax kernel class that ran in the timed steps; `dominant` = the one with the most device time.
+    achieved = work of the launches (flops counted with the pool size each launch saw) / their CUDA-event time."""
+    prof, ms_dev = leg["prof"], leg["ms"]
+    fp64_peak, fp64_src = None, "unmeasured"
+    if os.path.exists(FP64_PEAK_FILE):
+        with open(FP64_PEAK_FILE) as fh:
+            fp64_peak = json.load(fh)["dfma"]["sustained_tflops"]
+        fp64_src = "measured DFMA-chain microkernel, sustained (profiles/fp64_peak.json; MEASURED_PEAKS.json has no FP64 figure)"
+    bf16_peak, bf16_src = 1392.7, "fallback"
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        with open(mp) as fh:
+            bf16_peak, bf16_src = float(json.load(fh)["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS, inside a long run)"
+    traffic = {}
+    tfile = os.path.join(ROOT, "profiles", "contract_traffic.json")
+    if os.path.exists(tfile):   # dram bytes of one launch at the bench shape, from the committed ncu captures
+        with open(tfile) as fh:
+            traffic = json.load(fh)
+    out = []
+
+    def entry(cls, kernel, pipe, peak, peak_src, note, tkey):
+        ms, n, work = prof[cls]
+        if n == 0 or ms <= 0 or work <= 0:
+            return
+        tf = work / (ms * 1e-3) * 1e-12
+        tj = traffic.get(tkey) if isinstance(traffic.get(tkey), dict) else (traffic if tkey == "fp64" and "dram_bytes_read" in traffic else None)
+        out.append({"bound": "tensor", "pipe": pipe, "kernel": kernel, "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                    "frac": tf / peak if peak else None,
+                    "traffic": (tj["dram_bytes_read"] + tj["dram_bytes_write"]) if tj else None,
+                    "traffic_source": tj["source"] if tj else None, "peak_source": peak_src, "launches": n,
+                    "avg_launch_ms": ms / n, "share_of_step": ms / ms_dev if ms_dev else None, "note": note})
+
+    entry("contract", "k_contract_ws<NX=2> + k_argmax_fixup", "fp64 tensor (DMMA, mma.sync.m8n8k4.f64; tcgen05 has no fp64)",
+          fp64_peak, fp64_src,
+          "flops = 2*s*K*N per launch with the K the launch saw, counted once although the launch serves both points "
+          "(candidate and incumbent share the contraction); s = algorithmic rows (117 at storm, 120 executed)", "fp64")
+    entry("screen", "k_screen<NX=2> (tcgen05.mma kind::f16, bf16 x 2 operands, fp32 accumulators in TMEM)",
+          "5th-generation tensor cores, bf16", bf16_peak, bf16_src,
+          "EXECUTED flops = 2 * 3 products * sp * K_pad * N_pad per launch (sp = rows padded to 16, K to 256, N to 128); "
+          "algorithmically the launch stands for 2*s*K*N fp64 flops of the sweep it replaces", "screen")
+    entry("fallback", "k_contract_ws behind a screening pass (ran because the pass fell back)", "fp64 tensor (DMMA)",
+          fp64_peak, fp64_src, "time only: launches that found the pass successful exit at once", "fp64")
+    res = prof["resolve"]
+    extra = None
+    if res[1] > 0:
+        extra = {"kernel": "k_screen_resolve", "launches": res[1], "avg_launch_ms": res[0] / res[1],
+                 "share_of_step": res[0] / ms_dev if ms_dev else None,
+                 "what": "exact FP64 (DMMA chain) scores of the candidates, first-index maximum"}
+    dom = max(out, key=lambda r: r["share_of_step"] or 0.0) if out else None
+    return {"dominant": dom, "all": out + ([extra] if extra else [])}
+
+
+def parity_sample(args, T, dist, cell, world, rank, alpha, beta, x_c, x_i, pool_all):
+    """A sample of the bench's own final state against the oracle (reference subprob.jl:148-166,
+    epigraph.jl:134-143): argmax of `parity-n` local scenarios at full K under the north-star rule, and the cuts of
+    epigraph 0 against the oracle's accumulation over ALL its scenarios on the device's selection."""
+    from oracle import oracle as O
+    z, E = cell.z, cell.E
+    K = len(cell.dvs)
+    pool = pool_all[:K]                      # every push of a new vertex was inserted (asserted), in this order
+    P = O.Problem(int(z["m2"]), int(z["n1"]), z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"], z["pos_row"], z["pos_col"])
+    rng = np.random.default_rng(12345 + rank)
+    res = {"n": 0, "mismatch": 0, "exempt": 0, "max_rel_val_err": 0.0, "max_rel_cut_err": None, "K": K}
+    per = max(1, args.parity_n // (2 * E))
+    mi_epi0 = {}
+    for e, epi in enumerate(cell.epis):
+        n_glob, n_loc, _ = epi.counts()
+        for xi_, x in enumerate((x_c, x_i)):
+            mv, mi = epi.argmax(x)
+            if e == 0:
+                mi_epi0[xi_] = (mv, mi)
+            loc = np.sort(rng.choice(n_loc, size=min(per, n_loc), replace=False))
+            glob = (loc // 128 * world + rank) * 128 + loc % 128           # rank r holds blocks r, r + world, ...
+            vals = np.concatenate([sample_values(z, 101 + e, int(g), 1) for g in glob]) if len(glob) else np.zeros((0, P.s))
+            ov, oi, _ = O.bench_argmax(P, vals, x, pool, threads=0, dot_kind=0)
+            for j in np.nonzero(oi != mi[loc])[0]:
+                sc, _ = O.score_pair(P, vals[j], x, pool[mi[loc][j]])
+                if ov[j] - sc <= 1e-12 * max(abs(ov[j]), 1.0):
+                    res["exempt"] += 1
+                else:
+                    res["mismatch"] += 1
+            res["n"] += len(loc)
+            if len(loc):
+                res["max_rel_val_err"] = max(res["max_rel_val_err"],
+                                             float(np.max(np.abs(mv[loc] - ov) / np.maximum(np.abs(ov), 1.0))))
+    # cuts of epigraph 0 on the device's selection, all scenarios (every rank contributes its indices)
+    epi = cell.epis[0]
+    n_glob, n_loc, W = epi.counts()
+    idx_glob = {}
+    for xi_ in (0, 1):
+        mi = mi_epi0[xi_][1]
+        if world > 1:
+            import torch
+            cap = (n_glob // 128 // world + 2) * 128
+            mine = torch.full((cap,), -1, dtype=torch.int64, device="cuda")
+            mine[:n_loc] = torch.from_numpy(mi).cuda()
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            full = np.full(n_glob, -1, dtype=np.int64)
+            for r in range(world):
+                loc = np.arange(cap)
+                g = (loc // 128 * world + r) * 128 + loc % 128
+                ok = g < n_glob
+                a = allr[r].cpu().numpy()
+                full[g[ok]] = a[ok]
+            idx_glob[xi_] = full
+        else:
+            idx_glob[xi_] = mi
+    if rank == 0:
+        g = np.arange(n_glob, dtype=np.uint64)
+        vals = np.empty((n_glob, P.s))
+        for a in range(0, n_glob, 32768):
+            vals[a:a + 32768] = sample_values(z, 101, a, min(32768, n_glob - a))
+        w = 0.5 + u01(201, g)
+        worst = 0.0
+        for xi_, x in enumerate((x_c, x_i)):
+            ref = O.build_sasa_cut(P, vals, w, x, pool, forced_idx=idx_glob[xi_])
+            p = w / ref["weight_mark"]
+            sel = pool[idx_glob[xi_]]
+            r_i = np.tile(P.rbar, (n_glob, 1))
+            r_i[:, P.pos_row] = vals
+            sa = np.sum(p * np.abs(np.einsum("ij,ij->i", sel, r_i))) + 1e-300
+            sb = (p[:, None] * np.abs(sel @ P.T_dense())).sum(axis=0) + 1e-300
+            worst = max(worst, abs(alpha[0, xi_] - ref["alpha"]) / max(sa, abs(ref["alpha"])),
+                        float(np.max(np.abs(beta[0, xi_] - ref["beta"]) / np.maximum(sb, np.abs(ref["beta"])))))
+        res["max_rel_cut_err"] = worst
+        res["cut_check"] = f"epigraph 0, both points, all {n_glob} scenarios, oracle accumulation on the device's selection"
+    res["rule"] = "index identical, or oracle score of the device's pick within 1e-12 relative of the oracle's best (exempt)"
+    if world > 1:
+        import torch
+        t = torch.tensor([res["n"], res["mismatch"], res["exempt"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        res["n"], res["mismatch"], res["exempt"] = (int(v) for v in t.tolist())
+    assert res["mismatch"] == 0, res
+    assert res["max_rel_cut_err"] is None or res["max_rel_cut_err"] <= 1e-10, res
+    return res
 
 
 if __name__ == "__main__":

@@ -85,10 +85,19 @@ SQLP_API int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *ctx, double *ms);
 SQLP_API int32_t sqlp_ctx_profile(sqlp_ctx *ctx, int32_t enable);
 SQLP_API int32_t sqlp_ctx_profile_read(sqlp_ctx *ctx, int32_t reset, double *contract_ms,
                                        int64_t *contract_launches, double *contract_flops);
-/* The same for every kernel class, arrays of 5: 0 contraction (work = flops), 1 delta build,
- * 2 cut reduction, 3 pool push, 4 bias vectors (work = algorithmic bytes). */
-SQLP_API int32_t sqlp_ctx_profile_classes(sqlp_ctx *ctx, int32_t reset, double *ms /*[5]*/,
-                                          int64_t *launches /*[5]*/, double *work /*[5]*/);
+/* The same for every kernel class, arrays of SQLP_PROF_NCLASS = 8: 0 FP64 contraction (work = flops, counted with
+ * the pool size each launch saw), 1 delta build, 2 cut reduction, 3 pool push, 4 bias vectors (work = algorithmic
+ * bytes), 5 screening pass on tcgen05 (work = executed bf16 flops), 6 exact decision among its
+ * candidates (work = scenario-points), 7 the FP64 sweep launched behind a screening pass (runs only on fall-back). */
+#define SQLP_PROF_NCLASS 8
+SQLP_API int32_t sqlp_ctx_profile_classes(sqlp_ctx *ctx, int32_t reset, double *ms /*[8]*/,
+                                          int64_t *launches /*[8]*/, double *work /*[8]*/);
+/* The argmax of subprob.jl:148-166 through a SCREENING pass: every score approximately on the 5th-generation
+ * tensor cores (bf16 x 2 operands, fp32 accumulation, rigorous error bound), then the FP64 arithmetic of the
+ * full sweep on the vertices that can still win -- same indices, same values, bit for bit.  mode 0: never
+ * (every score in FP64), 1: automatic (default; large shapes, and not for a while after a pass fell back),
+ * 2: whenever the shape allows it.  The environment variable SQLP_SCREEN sets the initial mode. */
+SQLP_API int32_t sqlp_ctx_set_screen(sqlp_ctx *ctx, int32_t mode);
 
 /* ---------------------------------------------------------------- dual-vertex pool -- */
 
@@ -202,6 +211,10 @@ SQLP_API int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const do
                                    int32_t *inserted, int64_t *index, const double *x_cand,
                                    const double *x_inc, double *alpha, double *beta,
                                    double *weight_mark, double *val /*or NULL*/);
+/* Screening statistics of an epigraph (synchronises): out[0] passes seen by the host, [1] of which fell back to
+ * the FP64 sweep, and for the last pass seen: [2] candidates emitted, [3] exact evaluations, [4] overflowed
+ * candidate lists, [5] non-finite / out-of-range operands, [6..7] vertices that could win at each point. */
+SQLP_API int32_t sqlp_epi_screen_stats(sqlp_epi *epi, int64_t *out /*[8]*/);
 /* Enqueue only: d_x2 = [x_cand | x_inc] on the device, d_out = [2][n1 + 2] on the device
  * holding (alpha, beta[n1], val) per x.  Errors such as a missing argmax surface at the
  * next blocking call. */

@@ -11,7 +11,10 @@
 #define SQLP_PROF_REDUCE 2
 #define SQLP_PROF_POOL 3
 #define SQLP_PROF_BIAS 4
-#define SQLP_PROF_CLASSES 5
+#define SQLP_PROF_SCREEN 5     // tcgen05 screening kernel (work = executed bf16 flops)
+#define SQLP_PROF_RESOLVE 6    // exact decision among the candidates (work = exact evaluations)
+#define SQLP_PROF_FALLBACK 7   // the FP64 sweep launched behind a screening pass (runs only if that fell back)
+#define SQLP_PROF_CLASSES 8
 #define SQLP_BK 8      // stochastic rows per pipeline slab (s is padded to a multiple)
 
 namespace sqlp {
@@ -101,6 +104,25 @@ __host__ __device__ __forceinline__ int64_t local_count(int64_t n_global, int ra
     int64_t n = mine * SQLP_TILE;
     if (rem && (int)(full % world) == rank) n += rem;
     return n;
+}
+
+// ---- control block of a screening pass (kernels_screen.cuh); the FP64 sweep reads it as its gate ----
+struct ScreenCtl {                 // written by k_screen_prep, read by every kernel of the chain
+    double shift[2];               // c_x: b32 = fp32(bias_x - c_x)
+    float bmax[2];                 // largest |b32| over the live vertices of point x
+    float coef_q;                  // E = coef_q * pnmax * dnmax + coef_b * bmax + tiny
+    float coef_b;
+    int bad;                       // 1: non-finite or out-of-range operands -- screening is skipped
+    unsigned int overflow;         // candidate lists that overflowed (k_screen), reset by k_screen_prep
+    unsigned int ovf_limit;        // more overflowed lists than this: the FP64 sweep runs instead
+    unsigned long long n_emit;     // statistics: candidates emitted / evaluated exactly
+    unsigned long long n_eval;
+    int live[2];                   // vertices that may win at point x
+};
+
+__device__ __forceinline__ bool screen_falls_back(const ScreenCtl *ctl)
+{
+    return ctl->bad != 0 || ctl->overflow > ctl->ovf_limit;
 }
 
 // ---- mbarrier + bulk async copy (TMA 1-D, SASS UBLKCP) -------------------------------------

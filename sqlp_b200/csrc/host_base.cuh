@@ -168,10 +168,11 @@ struct sqlp_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     unsigned profile = 0;         // bit cls: event scopes around the launches of kernel class cls
     bool pdl = true;              // programmatic dependent launch of every kernel (SQLP_PDL=0: plain stream order)
-    struct ProfEvent { cudaEvent_t e0, e1; int cls; };
+    struct ProfEvent { cudaEvent_t e0, e1; int cls; double per_k; int k_quantum; long long *k_seen; };
+    std::vector<long long *> prof_kslots;   // pinned blocks of 1024 pool sizes, one slot per event scope
     std::vector<ProfEvent> prof_events;
     size_t prof_used = 0;
-    double prof_work[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};   // flops (contraction) or algorithmic bytes
+    double prof_work[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0, 0, 0, 0};   // flops (contraction, screening) or algorithmic bytes
     bool smem_attr[3] = {false, false, false};
     // contraction plan: which kernel, forced grid (tests), piece buffers of the even split
     int contract_mode = 0;        // 0 = automatic, 1 = streaming only, 2 = resident (or streaming), 3 = warp-specialised first
@@ -183,6 +184,11 @@ struct sqlp_ctx {
     bool delta_smem_set = false;
     int res_smem_set[3] = {0, 0, 0};
     DevBuf d_piece_val, d_piece_idx;
+    // screening pass (kernels_screen.cuh): 0 = off, 1 = automatic (default), 2 = whenever the shape allows it
+    int screen_mode = 1;
+    bool screen_smem_set[3] = {false, false, false};
+    DevBuf d_cand, d_cnt, d_lfin; // candidate lists of the running pass (shared by the context's epigraphs: stream order)
+    DevBuf d_cell, d_cellg;       // sharded job: the rows of a call's epigraphs back to back, and their all-gather
     DevBuf d_step;                // sqlp_cell_sd_step: the step's scenario values on the device
     PinnedBuf h_step;             //                    its results on the way back
     void bind() const { CK(cudaSetDevice(device)); }
@@ -220,6 +226,10 @@ struct PoolView {   // the pool restricted to one set of stochastic rows, in til
     int n_rows = 0, s_pad = 0;
     DevBuf d_rows, d_piS;
     int64_t synced_lo = 0;   // vertices < synced_lo are final in d_piS
+    // the same rows as bf16 hi / lo operands of the screening pass, built on first use
+    int sp = 0;              // row slots padded to a multiple of 16
+    DevBuf d_piB, d_pn, d_pnmax, d_vbad;
+    int64_t scr_synced_lo = 0, scr_cap = 0;   // vertices final in d_piB / capacity (multiple of 256)
 };
 
 struct sqlp_pool {
@@ -269,12 +279,24 @@ struct sqlp_epi {
     DevBuf d_x2, d_base, d_bias, d_best_val, d_best_idx, d_partial, d_partial2, d_out, d_gather,
         d_flags, d_stage, d_scratch;
     int64_t bias_stride = 0, out_stride = 0;
+    double *cur_bias = nullptr;    // bias vectors of the running call: this epigraph's, or those of a twin (same
+    int64_t cur_bias_stride = 0;   //   template, pool and points) earlier in the same call
+    int tmpl_id = 0;               // epigraphs of a pool with equal (rbar, Tbar) share an id
     // the cut list on the device (kernels_cuts.cuh): rows (alpha, beta[n1], weight_mark)
     double objective_weight = 1.0, lower_bound = 0.0;
     DevBuf d_cuts, d_cuts_tmp, d_inc, d_prev_inc, d_keep, d_eval, d_rows;
     int64_t n_cuts = 0, cuts_cap = 0, n_last = 0;
     bool has_inc = false, has_prev_inc = false;
     int last_nx = 0;   // points of the last cut formation whose result is still in d_out
+    // screening pass: bf16 scenario operands, per-call control block, what the host has learnt
+    DevBuf d_DB, d_dnu, d_dnall, d_ebad, d_b32c, d_ctl;
+    int64_t scr_synced = 0, scr_units_cap = 0;
+    PinnedBuf h_ctl;               // the control block of the last pass, copied back without a synchronisation
+    cudaEvent_t ctl_event = nullptr;
+    bool ctl_pending = false;
+    int scr_skip = 0, scr_backoff = 0;   // calls to leave the pass out after it fell back (doubles up to 1024)
+    int64_t scr_runs = 0, scr_fallbacks = 0;
+    ScreenCtl scr_last = {};       // statistics of the last pass the host has seen
 };
 
 namespace {
@@ -284,25 +306,56 @@ cudaStream_t S(sqlp_ctx *c) { return c->stream; }
 struct ProfScope {   // CUDA events around the launch(es) of one kernel class when profiling is on
     sqlp_ctx *c;
     cudaEvent_t e1 = nullptr;
-    ProfScope(sqlp_ctx *c_, int cls, double work) : c(c_)
+    // work: flops or algorithmic bytes of the scope.  With `pool` the work is PER VERTEX and is multiplied, when the
+    // profile is read, by the pool size the launch actually saw (rounded up to `quantum`): the size lives on the
+    // device (pushes are enqueued, not awaited), so it is copied into a pinned slot right behind the launch.
+    ProfScope(sqlp_ctx *c_, int cls, double work, sqlp_pool *pool = nullptr, int quantum = 1)
+        : c(c_)
     {
         if (!((c->profile >> cls) & 1u)) return;
         if (c->prof_used == c->prof_events.size()) {
             cudaEvent_t a = nullptr, b = nullptr;
             CK(cudaEventCreate(&a));
             CK(cudaEventCreate(&b));
-            c->prof_events.push_back({a, b, cls});
+            const size_t idx = c->prof_events.size();
+            if (idx / 1024 == c->prof_kslots.size()) {
+                long long *blk = nullptr;
+                CK(cudaHostAlloc((void **)&blk, 1024 * sizeof(long long), cudaHostAllocDefault));
+                c->prof_kslots.push_back(blk);
+            }
+            c->prof_events.push_back({a, b, cls, 0.0, 1, c->prof_kslots[idx / 1024] + idx % 1024});
         }
         sqlp_ctx::ProfEvent &pe = c->prof_events[c->prof_used++];
         pe.cls = cls;
+        pe.per_k = pool ? work : 0.0;
+        pe.k_quantum = quantum;
+        pool_ = pool;
+        idx_ = c->prof_used - 1;
         e1 = pe.e1;
-        c->prof_work[cls] += work;
+        if (!pool) c->prof_work[cls] += work;
         CK(cudaEventRecord(pe.e0, c->stream));
     }
-    void stop() { if (e1) CK(cudaEventRecord(e1, c->stream)); e1 = nullptr; }
-    ~ProfScope() { if (e1) cudaEventRecord(e1, c->stream); }
+    sqlp_pool *pool_ = nullptr;
+    size_t idx_ = 0;
+    void stop();
+    ~ProfScope();
 };
 
+
+
+inline void ProfScope::stop()
+{
+    if (!e1) return;
+    CK(cudaEventRecord(e1, c->stream));
+    if (pool_) CK(cudaMemcpyAsync(c->prof_events[idx_].k_seen, pool_->d_K.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    e1 = nullptr;
+}
+inline ProfScope::~ProfScope()
+{
+    if (!e1) return;
+    cudaEventRecord(e1, c->stream);
+    if (pool_) cudaMemcpyAsync(c->prof_events[idx_].k_seen, pool_->d_K.p, 8, cudaMemcpyDeviceToHost, c->stream);
+}
 
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 

@@ -197,7 +197,8 @@ bool launch_contract_ws(sqlp_epi *e, ContractArgs &a)
 }
 
 template <int NX>
-void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi)
+void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *bv, int *bi,
+                     const ScreenCtl *gate = nullptr)
 {
     using Cfg = ContractVariant<NX>;
     sqlp_ctx *c = e->ctx;
@@ -205,7 +206,7 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.D = D;
     a.PiS = e->view->d_piS.as<double>();
     a.bias = bias;
-    a.bias_stride = e->bias_stride;
+    a.bias_stride = e->cur_bias_stride;
     a.d_K = e->pool->d_K.as<long long>();
     a.s_pad = e->view->s_pad;
     a.ntiles = (int)((e->n_local + SQLP_TILE - 1) / SQLP_TILE);
@@ -216,7 +217,10 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.nstages = a.prefetch = a.lag_ns = 0;
     a.piece_val = nullptr;
     a.piece_idx = nullptr;
-    ProfScope prof(c, SQLP_PROF_CONTRACT, 2.0 * (double)e->view->n_rows * (double)e->pool->upper() * (double)e->n_local);
+    a.gate = gate;
+    // behind a screening pass the sweep only runs if that pass fell back: its time goes to its own class
+    ProfScope prof(c, gate ? SQLP_PROF_FALLBACK : SQLP_PROF_CONTRACT,
+                   gate ? 0.0 : 2.0 * (double)e->view->n_rows * (double)e->n_local, gate ? nullptr : e->pool);
     bool done = false;
     // automatic: warp-specialised -> resident (fewer ring stages suffice) -> streaming (any s_pad)
     if (c->contract_mode == 0 || c->contract_mode == 3) done = launch_contract_ws<NX>(e, a);
@@ -236,9 +240,185 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     prof.stop();
 }
 
+// ---- screening pass (kernels_screen.cuh) --------------------------------------------------------
+// What the host has learnt from the control block of an earlier pass (copied back without a synchronisation).
+void screen_learn(sqlp_epi *e)
+{
+    if (!e->ctl_pending || cudaEventQuery(e->ctl_event) != cudaSuccess) return;
+    e->ctl_pending = false;
+    const ScreenCtl &h = *e->h_ctl.as<ScreenCtl>();
+    e->scr_last = h;
+    ++e->scr_runs;
+    if (h.bad != 0 || h.overflow > h.ovf_limit) {
+        // it fell back to the FP64 sweep (non-finite operands, or candidate lists overflowing: a pool of
+        // near-ties such as storm's real duals): leave the pass out for a while, longer every time
+        ++e->scr_fallbacks;
+        e->scr_backoff = std::min(1024, std::max(16, e->scr_backoff * 2));
+        e->scr_skip = e->scr_backoff;
+    } else {
+        e->scr_backoff = 0;
+    }
+}
+
+// Is the pass worth trying for this call?  Needs: no random element in Tbar (d does not depend on x), operands
+// that fit the kernel's shared memory, and enough work to amortise its fixed cost.
+bool screen_wanted(sqlp_epi *e, int NX)
+{
+    sqlp_ctx *c = e->ctx;
+    if (c->screen_mode == 0 || e->n_T != 0 || e->n_local == 0 || e->view->n_rows == 0) return false;
+    const int sp = (int)round_up(e->view->n_rows, 16);
+    if (scr_smem_bytes(sp, 3, NX) > (size_t)c->smem_optin) return false;
+    screen_learn(e);
+    if (c->screen_mode == 2) return true;
+    if (e->scr_skip > 0) { --e->scr_skip; return false; }
+    const int64_t K = e->pool->upper();
+    return K >= 1024 && e->n_local >= 1024 && (double)K * (double)e->n_local >= (double)(1 << 24);
+}
+
+void screen_sync_operands(sqlp_epi *e)
+{
+    sqlp_ctx *c = e->ctx;
+    sqlp_pool *p = e->pool;
+    PoolView *v = e->view;
+    if (!v->sp) {
+        v->sp = (int)round_up(v->n_rows, 16);
+        v->d_vbad.ensure(16, 0, S(c));
+    }
+    const int J = v->sp / 16;
+    const int64_t hi = p->upper();
+    if (hi > v->scr_cap) {
+        const int64_t ncap = round_up(std::max<int64_t>(hi, std::max<int64_t>(1024, v->scr_cap * 2)), SCR_NB);
+        const size_t per_chunk = (size_t)J * SCR_STAGE_BYTES;
+        v->d_piB.ensure((size_t)(ncap / SCR_NB) * per_chunk, (size_t)(v->scr_cap / SCR_NB) * per_chunk, S(c));
+        v->d_pn.ensure((size_t)ncap * 4, (size_t)v->scr_cap * 4, S(c));
+        v->d_pnmax.ensure((size_t)(ncap / SCR_NB) * 4, (size_t)(v->scr_cap / SCR_NB) * 4, S(c));
+        v->scr_cap = ncap;
+    }
+    if (hi > v->scr_synced_lo) {
+        const int64_t work = hi - v->scr_synced_lo;
+        const int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 8 * c->sm_count);
+        LAUNCH(c, k_screen_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(), v->n_rows, v->sp,
+               v->d_piB.as<__nv_bfloat16>(), v->d_pn.as<float>(), v->d_pnmax.as<float>(), v->d_vbad.as<int>(),
+               (long long)v->scr_synced_lo, p->d_K.as<long long>());
+    }
+    v->scr_synced_lo = p->K;   // only confirmed vertices are final
+    const int64_t units = (e->n_local + SCR_UNIT - 1) / SCR_UNIT;
+    if (units > e->scr_units_cap) {
+        const int64_t ncap = std::max<int64_t>(units, std::max<int64_t>(8, e->scr_units_cap * 2));
+        e->d_DB.ensure((size_t)ncap * 512 * v->sp, (size_t)e->scr_units_cap * 512 * v->sp, S(c));
+        e->d_dnu.ensure((size_t)ncap * 4, (size_t)e->scr_units_cap * 4, S(c));
+        e->d_dnall.ensure(16, 0, S(c));
+        e->d_ebad.ensure(16, 0, S(c));
+        e->scr_units_cap = ncap;
+    }
+    if (e->n_local > e->scr_synced) {
+        const int64_t work = e->n_local - e->scr_synced;
+        const int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 16 * c->sm_count);
+        LAUNCH(c, k_screen_scen_sync, grid, 256, 0, e->d_D.as<double>(), v->s_pad, v->sp, e->d_DB.as<__nv_bfloat16>(),
+               e->d_dnu.as<float>(), e->d_dnall.as<float>(), e->d_ebad.as<int>(), (long long)e->scr_synced,
+               (long long)e->n_local);
+        e->scr_synced = e->n_local;
+    }
+}
+
+// Screening + exact decision for NX points, enqueued behind k_bias.  Returns the control block the FP64
+// sweep is gated on (it still has to be launched: it runs if, and only if, this pass fell back).
+template <int NX>
+const ScreenCtl *screen_enqueue(sqlp_epi *e)
+{
+    sqlp_ctx *c = e->ctx;
+    sqlp_pool *p = e->pool;
+    PoolView *v = e->view;
+    screen_sync_operands(e);
+    const int64_t ku = p->upper();
+    const int64_t nch = (ku + SCR_NB - 1) / SCR_NB;
+    const int64_t nunits = (e->n_local + SCR_UNIT - 1) / SCR_UNIT, npad = nunits * SCR_UNIT;
+    constexpr int BF = scr_bias_floats<NX>();
+    e->d_b32c.ensure((size_t)std::max<int64_t>(nch, 1) * BF * 4, 0, S(c), false);
+    e->d_ctl.ensure(sizeof(ScreenCtl), 0, S(c));
+    // split a unit's sweep into K-ranges when there are too few units to fill the GPU
+    int R = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * c->sm_count + nunits - 1) / nunits), std::max<int64_t>(nch, 1));
+    const size_t nslots = (size_t)NX * R * 2 * npad;
+    c->d_cand.ensure(nslots * SCR_CAP * sizeof(int2), 0, S(c), false);
+    c->d_cnt.ensure(nslots * 4, 0, S(c), false);
+    c->d_lfin.ensure(nslots * 4, 0, S(c), false);
+    // more overflowing lists than this and the pass gives up: each one costs a full sweep of its scenario
+    const unsigned ovf_limit = (unsigned)std::min<int64_t>(e->n_local / 64 + 16, 1 << 20);
+    LAUNCH(c, k_screen_prep<NX>, 1, 1024, 0, e->cur_bias, (long long)e->cur_bias_stride, v->d_pn.as<float>(),
+           v->d_pnmax.as<float>(), e->d_dnall.as<float>(), v->d_vbad.as<int>(), e->d_ebad.as<int>(),
+           p->d_K.as<long long>(), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>());
+    int nstages = SCR_MAX_STAGES;
+    while (nstages > 3 && scr_smem_bytes(v->sp, nstages, NX) > (size_t)c->smem_optin) --nstages;
+    const size_t smem = scr_smem_bytes(v->sp, nstages, NX);
+    if (!c->screen_smem_set[NX]) {
+        CK(cudaFuncSetAttribute(k_screen<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        c->screen_smem_set[NX] = true;
+    }
+    ScreenArgs sa;
+    sa.DB = e->d_DB.as<__nv_bfloat16>();
+    sa.PiB = v->d_piB.as<__nv_bfloat16>();
+    sa.b32c = e->d_b32c.as<float>();
+    sa.dnmax_unit = e->d_dnu.as<float>();
+    sa.ctl = e->d_ctl.as<ScreenCtl>();
+    sa.d_K = p->d_K.as<long long>();
+    sa.sp = v->sp;
+    sa.nunits = (int)nunits;
+    sa.R = R;
+    sa.nstages = nstages;
+    sa.n_local = e->n_local;
+    sa.npad = npad;
+    sa.cand = c->d_cand.as<int2>();
+    sa.cnt = c->d_cnt.as<int>();
+    sa.lfin = c->d_lfin.as<float>();
+    sa.dbg = nullptr;
+    sa.desc_mode = 0;
+    const int grid = (int)std::min<int64_t>(c->sm_count, nunits * R);
+    {
+        // executed bf16 flops: three products over sp slots for every (vertex of a whole chunk, scenario of a whole unit)
+        ProfScope prof(c, SQLP_PROF_SCREEN, 6.0 * v->sp * (double)npad, p, SCR_NB);
+        LAUNCH(c, k_screen<NX>, grid, SCR_THREADS, smem, sa);
+    }
+    ResolveArgs ra;
+    ra.D = e->d_D.as<double>();
+    ra.PiS = v->d_piS.as<double>();
+    ra.bias = e->cur_bias;
+    ra.bias_stride = e->cur_bias_stride;
+    ra.s_pad = v->s_pad;
+    ra.d_K = p->d_K.as<long long>();
+    ra.n_local = e->n_local;
+    ra.npad = npad;
+    ra.R = R;
+    ra.cand = c->d_cand.as<int2>();
+    ra.cnt = c->d_cnt.as<int>();
+    ra.lfin = c->d_lfin.as<float>();
+    ra.best_val = e->d_best_val.as<double>();
+    ra.best_idx = e->d_best_idx.as<int>();
+    ra.out_stride = e->out_stride;
+    ra.ctl = e->d_ctl.as<ScreenCtl>();
+    ra.force_full = 0;
+    {
+        ProfScope prof(c, SQLP_PROF_RESOLVE, (double)NX * (double)e->n_local);
+        const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + 7) / 8, 1), 8 * c->sm_count);
+        LAUNCH(c, k_screen_resolve<NX>, rgrid, 256, 0, ra);
+    }
+    // the control block goes back to the host asynchronously; screen_learn() reads it at a later call
+    if (!e->ctl_event) CK(cudaEventCreateWithFlags(&e->ctl_event, cudaEventDisableTiming));
+    if (!e->ctl_pending) {
+        e->h_ctl.ensure(sizeof(ScreenCtl));
+        CK(cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(ScreenCtl), cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaEventRecord(e->ctl_event, S(c)));
+        e->ctl_pending = true;
+    }
+    return e->d_ctl.as<ScreenCtl>();
+}
+
 // Everything of build_sasa_cut for NX points, enqueued on the stream.  x on host or device.
 // Result lands in e->d_out as [NX][n1 + 2] = (alpha, beta[n1], val).
-void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x_dev, bool want_cut)
+// bias_from: an epigraph of the same call with the same template, pool and points whose bias vectors are
+// reused instead of recomputed.  cell_slot (sharded jobs): where this epigraph's row (NX * (n1 + 2) doubles + the
+// flag word) goes in the cell's gather buffer; the caller then runs cell_gather() once for the whole cell.
+void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x_dev, bool want_cut,
+                      sqlp_epi *bias_from = nullptr, double *cell_slot = nullptr)
 {
     sqlp_ctx *c = e->ctx;
     sqlp_pool *p = e->pool;
@@ -275,7 +455,15 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
     }
     e->d_base.ensure((size_t)2 * m2 * 8, 0, S(c));
 
-    if (ntiles > 0) {
+    if (ntiles > 0 && bias_from && bias_from->bias_stride >= kpad) {
+        // the same template, pool and points as an earlier epigraph of this call: its bias vectors are ours.
+        // k_base, the kernel that clears the flag word, is skipped with them.
+        CK(cudaMemsetAsync(e->d_flags.p, 0, 4, S(c)));
+        e->cur_bias = bias_from->cur_bias;
+        e->cur_bias_stride = bias_from->cur_bias_stride;
+    } else if (ntiles > 0) {
+        e->cur_bias = e->d_bias.as<double>();
+        e->cur_bias_stride = e->bias_stride;
         ProfScope prof_bias(c, SQLP_PROF_BIAS, 8.0 * (double)ku * m2 + 8.0 * NX * (double)ku);
         LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
                e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
@@ -291,14 +479,20 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
                    (long long)e->bias_stride);
 
         prof_bias.stop();
+    }
+    if (ntiles > 0) {
 
         if (e->n_T == 0) {
+            // screening on the 5th-generation tensor cores + exact decision among the candidates; the FP64 sweep
+            // is launched behind it and runs only if the pass fell back (a device-side decision, no host round trip)
+            const ScreenCtl *gate = nullptr;
+            if (screen_wanted(e, NX)) gate = NX == 2 ? screen_enqueue<2>(e) : screen_enqueue<1>(e);
             if (NX == 2)
-                launch_contract<2>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
-                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
+                launch_contract<2>(e, e->d_D.as<double>(), e->cur_bias,
+                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>(), gate);
             else
-                launch_contract<1>(e, e->d_D.as<double>(), e->d_bias.as<double>(),
-                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>());
+                launch_contract<1>(e, e->d_D.as<double>(), e->cur_bias,
+                                   e->d_best_val.as<double>(), e->d_best_idx.as<int>(), gate);
         } else {
             // some element perturbs Tbar: d(x) = delta_rhs - delta_T x is rebuilt per point
             size_t bytes = (size_t)ntiles * e->view->s_pad * SQLP_TILE * 8;
@@ -309,7 +503,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
                 LAUNCH(c, k_delta_x, (int)((e->n_local + 255) / 256), 256, 0, tl,
                        e->d_x2.as<double>() + (size_t)x * n1, (long long)e->n_local, e->view->s_pad,
                        e->d_D.as<double>(), e->d_dT.as<double>(), e->d_Dx.as<double>());
-                launch_contract<1>(e, e->d_Dx.as<double>(), e->d_bias.as<double>() + x * e->bias_stride,
+                launch_contract<1>(e, e->d_Dx.as<double>(), e->cur_bias + x * e->cur_bias_stride,
                                    e->d_best_val.as<double>() + x * e->out_stride,
                                    e->d_best_idx.as<int>() + x * e->out_stride);
             }
@@ -327,8 +521,8 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         r.w = e->d_w.as<double>();
         r.PiS = e->view->d_piS.as<double>();
         r.rt = e->d_rt.as<double>();
-        r.bias = e->n_T == 0 ? e->d_bias.as<double>() : nullptr;
-        r.bias_stride = e->bias_stride;
+        r.bias = e->n_T == 0 ? e->cur_bias : nullptr;
+        r.bias_stride = e->cur_bias_stride;
         r.best_val = e->d_best_val.as<double>();
         r.best_idx = e->d_best_idx.as<int>();
         r.out_stride = e->out_stride;
@@ -357,17 +551,59 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         const int group = 64;
         int64_t ng = (ntiles + group - 1) / group;
         e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
+        // sharded job: the row and its flag word go straight into the cell's gather buffer
+        double *fin = cell_slot ? cell_slot : e->d_out.as<double>();
         LAUNCH(c, k_sum_groups, (int)ng, 256, sub_smem, e->d_partial.as<double>(), (long long)ntiles, group, nsub,
-               width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), e->d_out.as<double>());
+               width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), fin,
+               (const int *)e->d_flags.as<int>(), cell_slot != nullptr);
         prof_red.stop();
+    } else if (cell_slot) {
+        CK(cudaMemsetAsync(cell_slot, 0, (size_t)(width + 1) * 8, S(c)));   // this rank holds no scenario
     }
-    if (c->world > 1) {
-        // per-epigraph partials are all-gathered and summed in fixed rank order
-        e->d_gather.ensure((size_t)c->world * width * 8, 0, S(c));
-        NK(g_nccl.AllGather(e->d_out.p, e->d_gather.p, (size_t)width, ncclFloat64_, c->comm, S(c)));
-        LAUNCH(c, k_rank_sum, (width + 127) / 128, 128, 0, e->d_gather.as<double>(), c->world, width,
-               e->d_out.as<double>());
+}
+
+// Sharded job: ONE all-gather for all the epigraphs of a call (their rows sit back to back in the context's
+// cell buffer, each followed by its "no argmax" word), then the rank-ordered sum of every row into the
+// epigraph's d_out and the OR of the flag words into its d_flags -- the same bits on every rank.
+struct CellGather {
+    sqlp_ctx *c;
+    int NX;
+    std::vector<sqlp_epi *> epis;
+    std::vector<size_t> off;
+    size_t total = 0;
+    CellGather(sqlp_ctx *c_, int NX_, int n_epi, sqlp_epi *const *epi) : c(c_), NX(NX_)
+    {
+        if (c->world <= 1) return;
+        for (int i = 0; i < n_epi; ++i) {
+            epis.push_back(epi[i]);
+            off.push_back(total);
+            total += (size_t)NX * ((size_t)epi[i]->n1 + 2) + 1;
+        }
+        c->d_cell.ensure(total * 8, 0, S(c), false);
+        c->d_cellg.ensure((size_t)c->world * total * 8, 0, S(c), false);
     }
+    double *slot(int i) const { return c->world > 1 ? c->d_cell.as<double>() + off[(size_t)i] : nullptr; }
+    void run()
+    {
+        if (c->world <= 1 || epis.empty()) return;
+        NK(g_nccl.AllGather(c->d_cell.p, c->d_cellg.p, total, ncclFloat64_, c->comm, S(c)));
+        for (size_t i = 0; i < epis.size(); ++i) {
+            sqlp_epi *e = epis[i];
+            const int width = NX * ((int)e->n1 + 2);
+            LAUNCH(c, k_rank_sum, (width + 1 + 127) / 128, 128, 0, c->d_cellg.as<double>() + off[i], c->world,
+                   (long long)total, width, e->d_out.as<double>(), e->d_flags.as<int>());
+        }
+    }
+};
+
+// Among the epigraphs of one call: the first earlier one whose bias vectors this one can reuse.
+sqlp_epi *bias_twin(int i, sqlp_epi *const *epi)
+{
+    for (int j = 0; j < i; ++j)
+        if (epi[j]->pool == epi[i]->pool && epi[j]->tmpl_id == epi[i]->tmpl_id && epi[j]->n_local > 0 &&
+            epi[j]->cur_bias != nullptr)
+            return epi[j];
+    return nullptr;
 }
 
 struct CutHost {

@@ -38,6 +38,10 @@ void pool_confirm(sqlp_pool *p)
 void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const double *v_dev)
 {
     sqlp_ctx *c = p->ctx;
+    // enqueue-only hosts (sqlp_pool_push_dev + sqlp_epi_build_cuts2_dev) never read the outcome of a push, and
+    // duplicates do not grow the pool: without this the host's upper bound K + pending -- and every buffer
+    // and grid sized from it -- would grow without limit.  One small read-back every 64 pushes.
+    if (p->pending >= 64) pool_confirm(p);
     pool_reserve(p, p->upper() + n);
     p->d_results.ensure((size_t)n * sizeof(PushResult), 0, S(c));
     const double *src = v_dev;

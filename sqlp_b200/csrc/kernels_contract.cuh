@@ -89,7 +89,13 @@ struct ContractArgs {
     int lag_ns;             // warp-specialised variant: start-up delay of the second row group
     double *piece_val;      // [grid][2][NX][ROWS] partial results of units cut by a span boundary
     int *piece_idx;
+    const ScreenCtl *gate;  // non-null: a screening pass ran first; the sweep runs only if that fell back
 };
+
+__device__ __forceinline__ bool sweep_gated_off(const ContractArgs &a)
+{
+    return a.gate != nullptr && !screen_falls_back(a.gate);
+}
 
 __device__ __forceinline__ bool better(double ov, int oi, double v, int i)
 {
@@ -100,6 +106,7 @@ template <class C>
 __global__ void __launch_bounds__(SQLP_CT_THREADS, C::CTAS) k_contract_argmax(ContractArgs a)
 {
     griddep_sync();
+    if (sweep_gated_off(a)) return;
     constexpr int NX = C::NX, MI = C::MI, S = C::STAGES, ROWS = C::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);

@@ -64,6 +64,7 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_contract_resident(ContractArgs a)
 {
     griddep_sync();
+    if (sweep_gated_off(a)) return;
     constexpr int NX = C::NX, MI = C::MI, ROWS = C::ROWS, WARPS = C::WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ngroups = a.s_pad / 4;
@@ -335,6 +336,7 @@ template <int ROWS, int NX>
 __global__ void k_argmax_fixup(ContractArgs a, int main_grid)
 {
     griddep_sync();
+    if (sweep_gated_off(a)) return;
     const long long K = *a.d_K;
     const int nchunks = (int)((K + SQLP_TILE - 1) / SQLP_TILE);
     if (nchunks == 0) return;

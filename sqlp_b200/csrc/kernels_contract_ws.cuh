@@ -53,6 +53,7 @@ template <class C>
 __global__ void __launch_bounds__(SQLP_WS_THREADS, 1) k_contract_ws(ContractArgs a)
 {
     griddep_sync();
+    if (sweep_gated_off(a)) return;
     constexpr int NX = C::NX, MI = C::MI, ROWS = C::ROWS, GR = C::GROUP_ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ngroups = a.s_pad / 4;

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
         const int x = q / SQLP_TILE, c = q % SQLP_TILE;
         int k = -1;
         double acc = 0.0;
+        bool need_dot = false;
         if (c < cnt) {
             k = a.best_idx[x * a.out_stride + i0 + c];
             if (k < 0) {
@@ -119,14 +120,21 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
                 // delta_T == 0: the contraction's winning score is bias_x[k] + PiS[k] . delta_rhs_i with
                 // exactly this bias, so the dot is the score minus the bias (off by at most half an
                 // ulp of the score) and neither D nor the pool view is read again
-                acc = __dsub_rn(a.best_val[x * a.out_stride + i0 + c], a.bias[x * a.bias_stride + k]);
-            } else {
+                const double sc = a.best_val[x * a.out_stride + i0 + c];
+                acc = __dsub_rn(sc, a.bias[x * a.bias_stride + k]);
+                // ... unless the score is so much larger than what alpha is made of (rho_k + dot) that half an
+                // ulp of it shows at the 1e-10 level: |tau_k . x| >> |rho_k|, |dot| (x far from the data's
+                // scale).  Then the dot is recomputed from D like in the delta_T != 0 case below.
+                need_dot = fabs(sc) > 8192.0 * fmax(fabs(a.rt[(long long)k * (a.n1 + 1)]), fabs(acc));
+            }
+            if (k >= 0 && (!a.bias || need_dot)) {
                 // slots in order; a k-group (4 slots) is 512 doubles further in both tiles and its
                 // four slots sit 2 doubles apart, so the walk needs no index arithmetic.  Pad slots
                 // are zero in both operands and add nothing.
                 const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE + tile_off(k & 127, 0);
                 const double *Dc = Dt + tile_off(c, 0);
                 const int ng = a.s_pad / 4;   // even: s_pad is a multiple of 8
+                acc = 0.0;
                 for (int g = 0; g < ng; g += 2, P += 1024, Dc += 1024) {
                     double pv[8], dv[8];   // sixteen loads in flight, then the ordered chain
 #pragma unroll
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
 // level 2 depends on timing; what it computes does not.
 __global__ void __launch_bounds__(256) k_sum_groups(const double *__restrict__ in, long long n, int group, int nsub,
                                                     int width, double *__restrict__ out,
-                                                    unsigned int *__restrict__ counter, double *__restrict__ fin)
+                                                    unsigned int *__restrict__ counter, double *__restrict__ fin,
+                                                    const int *__restrict__ flags_in, bool flag_behind_row)
 {
     griddep_sync();
     extern __shared__ double sub_sum[];              // [nsub][width] when nsub > 1
@@ -262,6 +271,9 @@ __global__ void __launch_bounds__(256) k_sum_groups(const double *__restrict__ i
         }
         fin[q] = s;
     }
+    // sharded job: the "no argmax" bit travels with the row (one more double), so that after the all-gather every
+    // rank reaches the same verdict (k_cut_partial, the previous kernel of the stream, has set it)
+    if (threadIdx.x == 0 && flag_behind_row) fin[width] = (double)(*flags_in & 1);
     if (threadIdx.x == 0) *counter = 0u;
 }
 
@@ -318,16 +330,19 @@ __global__ void k_eval_dual(EvalArgs a)
     *a.out = s;
 }
 
-// Rank-ordered sum of all-gathered partials: out[q] = sum_r in[r][q], r = 0..world-1.
-__global__ void k_rank_sum(const double *__restrict__ in, int world, int width,
-                           double *__restrict__ out)
+// Rank-ordered sum of all-gathered partials: out[q] = sum_r in[r * stride + q], r = 0..world-1, q < width; the
+// double behind each rank's row is its "no argmax" bit, OR-ed into flags_out so that every rank raises (or not)
+// together.
+__global__ void k_rank_sum(const double *__restrict__ in, int world, long long stride, int width,
+                           double *__restrict__ out, int *__restrict__ flags_out)
 {
     griddep_sync();
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= width) return;
+    if (q > width) return;
     double s = 0.0;
-    for (int r = 0; r < world; ++r) s += in[(long long)r * width + q];
-    out[q] = s;
+    for (int r = 0; r < world; ++r) s += in[(long long)r * stride + q];
+    if (q < width) out[q] = s;
+    else *flags_out = s > 0.0 ? 1 : 0;
 }
 
 }  // namespace sqlp

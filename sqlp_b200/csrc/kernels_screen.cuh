@@ -55,24 +55,6 @@ namespace sqlp {
 #define SCR_CAP 32                 // candidate list entries per (scenario, point, K-range, column half)
 #define SCR_DEAD (-3.0e38f)        // shifted bias of a vertex that can never win (or does not exist)
 
-struct ScreenCtl {                 // written by k_screen_prep, read by every kernel of the chain
-    double shift[2];               // c_x: b32 = fp32(bias_x - c_x)
-    float bmax[2];                 // largest |b32| over the live vertices of point x
-    float coef_q;                  // E = coef_q * pnmax * dnmax + coef_b * bmax + tiny
-    float coef_b;
-    int bad;                       // 1: non-finite or out-of-range operands -- screening is skipped
-    unsigned int overflow;         // candidate lists that overflowed (k_screen), reset by k_screen_prep
-    unsigned int ovf_limit;        // more overflowed lists than this: the FP64 sweep runs instead
-    unsigned long long n_emit;     // statistics: candidates emitted / evaluated exactly
-    unsigned long long n_eval;
-    int live[2];                   // vertices that may win at point x
-};
-
-__device__ __forceinline__ bool screen_falls_back(const ScreenCtl *ctl)
-{
-    return ctl->bad != 0 || ctl->overflow > ctl->ovf_limit;
-}
-
 template <int NX>
 __host__ __device__ constexpr int scr_bias_floats() { return NX * SCR_NB + 4; }
 

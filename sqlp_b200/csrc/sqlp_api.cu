@@ -42,6 +42,7 @@
 #include "kernels_pool.cuh"
 #include "kernels_reduce.cuh"
 #include "kernels_cuts.cuh"
+#include "kernels_screen.cuh"
 
 #include "host_base.cuh"
 #include "host_pool.cuh"
@@ -75,6 +76,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
         else if (!strcmp(m, "ws")) c->contract_mode = 3;
     }
     if (const char *g = getenv("SQLP_PDL")) c->pdl = atoi(g) != 0;
+    if (const char *g = getenv("SQLP_SCREEN")) c->screen_mode = std::max(0, std::min(2, atoi(g)));
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_LAG_NS")) c->contract_lag_ns = atoi(g);
@@ -141,6 +143,7 @@ int32_t sqlp_ctx_destroy(sqlp_ctx *c)
         cudaStreamSynchronize(c->stream);
         if (c->comm) g_nccl.CommDestroy(c->comm);
         for (auto &pr : c->prof_events) { cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1); }
+        for (long long *blk : c->prof_kslots) cudaFreeHost(blk);
         if (c->t0) cudaEventDestroy(c->t0);
         if (c->t1) cudaEventDestroy(c->t1);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -197,7 +200,41 @@ int32_t sqlp_ctx_timer_elapsed_ms(sqlp_ctx *c, double *ms)
 
 int32_t sqlp_ctx_profile(sqlp_ctx *c, int32_t enable)
 {
-    return guard([&] { REQUIRE(c, SQLP_E_INVALID, "null ctx"); c->profile = enable == 1 ? ~0u : (unsigned)enable >> 1; });
+    return guard([&] {
+        REQUIRE(c, SQLP_E_INVALID, "null ctx");
+        c->profile = enable == 1 ? ~0u : (unsigned)enable >> 1;
+        // the contraction's mask bit also covers what can stand in for it: screening, exact decision, gated sweep
+        if ((c->profile >> SQLP_PROF_CONTRACT) & 1u)
+            c->profile |= (1u << SQLP_PROF_SCREEN) | (1u << SQLP_PROF_RESOLVE) | (1u << SQLP_PROF_FALLBACK);
+    });
+}
+
+int32_t sqlp_ctx_set_screen(sqlp_ctx *c, int32_t mode)
+{
+    return guard([&] {
+        REQUIRE(c, SQLP_E_INVALID, "null ctx");
+        REQUIRE(mode >= 0 && mode <= 2, SQLP_E_INVALID, "screen mode must be 0 (off), 1 (automatic) or 2 (always)");
+        c->screen_mode = mode;
+    });
+}
+
+int32_t sqlp_epi_screen_stats(sqlp_epi *e, int64_t *out /*[8]*/)
+{
+    return guard([&] {
+        REQUIRE(e && out, SQLP_E_INVALID, "null argument");
+        e->ctx->bind();
+        CK(cudaStreamSynchronize(S(e->ctx)));
+        screen_learn(e);
+        const ScreenCtl &h = e->scr_last;
+        out[0] = e->scr_runs;
+        out[1] = e->scr_fallbacks;
+        out[2] = (int64_t)h.n_emit;
+        out[3] = (int64_t)h.n_eval;
+        out[4] = (int64_t)h.overflow;
+        out[5] = h.bad;
+        out[6] = h.live[0];
+        out[7] = h.live[1];
+    });
 }
 
 int32_t sqlp_ctx_profile_classes(sqlp_ctx *c, int32_t reset, double *ms, int64_t *launches, double *work)
@@ -206,18 +243,21 @@ int32_t sqlp_ctx_profile_classes(sqlp_ctx *c, int32_t reset, double *ms, int64_t
         REQUIRE(c, SQLP_E_INVALID, "null ctx");
         c->bind();
         CK(cudaStreamSynchronize(c->stream));
-        double t[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};
-        int64_t n[SQLP_PROF_CLASSES] = {0, 0, 0, 0, 0};
+        double t[SQLP_PROF_CLASSES] = {}, w[SQLP_PROF_CLASSES] = {};
+        int64_t n[SQLP_PROF_CLASSES] = {};
         for (size_t i = 0; i < c->prof_used; ++i) {
+            const sqlp_ctx::ProfEvent &pe = c->prof_events[i];
             float f = 0;
-            CK(cudaEventElapsedTime(&f, c->prof_events[i].e0, c->prof_events[i].e1));
-            t[c->prof_events[i].cls] += f;
-            ++n[c->prof_events[i].cls];
+            CK(cudaEventElapsedTime(&f, pe.e0, pe.e1));
+            t[pe.cls] += f;
+            ++n[pe.cls];
+            // work per vertex x the pool size THIS launch saw (copied back right behind it)
+            if (pe.per_k > 0.0) w[pe.cls] += pe.per_k * (double)round_up(*pe.k_seen, pe.k_quantum);
         }
         for (int k = 0; k < SQLP_PROF_CLASSES; ++k) {
             if (ms) ms[k] = t[k];
             if (launches) launches[k] = n[k];
-            if (work) work[k] = c->prof_work[k];
+            if (work) work[k] = c->prof_work[k] + w[k];
         }
         if (reset) {
             c->prof_used = 0;
@@ -268,6 +308,8 @@ int32_t sqlp_pool_destroy(sqlp_pool *p)
 {
     return guard([&] {
         if (!p) return;
+        // an epigraph keeps pointers into its pool (vertex rows, views): it has to go first
+        REQUIRE(p->epis.empty(), SQLP_E_INVALID, "destroy the epigraphs bound to this pool before the pool");
         cudaSetDevice(p->ctx->device);
         cudaStreamSynchronize(p->ctx->stream);
         for (PoolView *v : p->views) delete v;
@@ -500,6 +542,10 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
             e->rt_cap = p->cap;
             e->d_scratch.ensure((size_t)(2 * m2 + 2 + rows.size() + 1) * 8, 0, S(c));
             CK(cudaStreamSynchronize(S(c)));
+            e->tmpl_id = (int)p->epis.size() + 1;
+            for (sqlp_epi *o : p->epis)
+                if (o->n1 == e->n1 && o->h_rbar == e->h_rbar && o->h_colptr == e->h_colptr && o->h_rowval == e->h_rowval &&
+                    o->h_nzval == e->h_nzval) { e->tmpl_id = o->tmpl_id; break; }
             p->epis.push_back(e);
         } catch (...) { delete e; throw; }
         *out = e;
@@ -514,6 +560,7 @@ int32_t sqlp_epi_destroy(sqlp_epi *e)
         cudaStreamSynchronize(e->ctx->stream);
         auto &v = e->pool->epis;
         v.erase(std::remove(v.begin(), v.end(), e), v.end());
+        if (e->ctl_event) cudaEventDestroy(e->ctl_event);
         delete e;
     });
 }
@@ -652,6 +699,7 @@ int32_t sqlp_epi_argmax(sqlp_epi *e, const double *x, int32_t sense, double *max
         c->bind();
         if (e->n_local == 0) return;
         REQUIRE(max_val && max_idx, SQLP_E_INVALID, "null output");
+        e->cur_bias = nullptr;
         epi_cuts_enqueue(e, 1, x, nullptr, false);
         std::vector<int> idx((size_t)e->n_local);
         CK(cudaMemcpyAsync(max_val, e->d_best_val.p, (size_t)e->n_local * 8, cudaMemcpyDeviceToHost, S(c)));
@@ -683,7 +731,10 @@ int32_t sqlp_epi_build_cut(sqlp_epi *e, const double *x, double *alpha, double *
         REQUIRE(e && alpha && (beta || e->n1 == 0) && (x || e->n1 == 0), SQLP_E_INVALID, "null argument");
         sqlp_ctx *c = e->ctx;
         c->bind();
-        epi_cuts_enqueue(e, 1, x, nullptr, true);
+        e->cur_bias = nullptr;
+        CellGather cg(c, 1, 1, &e);
+        epi_cuts_enqueue(e, 1, x, nullptr, true, nullptr, cg.slot(0));
+        cg.run();
         CutHost h;
         epi_cuts_fetch(e, 1, h);
         pool_confirm(e->pool);
@@ -705,14 +756,19 @@ int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, const double 
         std::vector<CutHost> h((size_t)n_epi);
         std::vector<double> x2;
         for (int i = 0; i < n_epi; ++i) {
+            REQUIRE(epi[i] && epi[i]->ctx == c, SQLP_E_INVALID, "epigraphs must share one context");
+            epi[i]->cur_bias = nullptr;
+        }
+        CellGather cg(c, 2, n_epi, epi);
+        for (int i = 0; i < n_epi; ++i) {
             sqlp_epi *e = epi[i];
-            REQUIRE(e && e->ctx == c, SQLP_E_INVALID, "epigraphs must share one context");
             REQUIRE((x_cand && x_inc && beta) || e->n1 == 0, SQLP_E_INVALID, "null argument");
             x2.assign((size_t)2 * e->n1, 0.0);
             for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
-            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true);
-            epi_cuts_fetch(e, 2, h[(size_t)i]);   // x2 is pageable: staged before the call returns
+            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true, bias_twin(i, epi), cg.slot(i));   // x2 is pageable: staged now
         }
+        cg.run();
+        for (int i = 0; i < n_epi; ++i) epi_cuts_fetch(epi[i], 2, h[(size_t)i]);
         for (int i = 0; i < n_epi; ++i) pool_confirm(epi[i]->pool);
         CK(cudaStreamSynchronize(S(c)));
         int64_t boff = 0;
@@ -769,12 +825,18 @@ int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const double *val
         // algorithm.jl:79-85  the candidate cut and the regenerated incumbent cut of every epigraph
         std::vector<double> x2;
         size_t ooff = 0;
+        for (int i = 0; i < n_epi; ++i) epi[i]->cur_bias = nullptr;
+        CellGather cg(c, 2, n_epi, epi);
+        for (int i = 0; i < n_epi; ++i) {
+            sqlp_epi *e = epi[i];
+            x2.assign((size_t)2 * e->n1, 0.0);
+            for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
+            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true, bias_twin(i, epi), cg.slot(i));   // x2 is pageable: staged now
+        }
+        cg.run();                                                 // sharded job: one all-gather for the whole cell
         for (int i = 0; i < n_epi; ++i) {
             sqlp_epi *e = epi[i];
             const size_t NC = (size_t)e->n1 + 2;
-            x2.assign((size_t)2 * e->n1, 0.0);
-            for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
-            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true);     // x2 is pageable: staged before the call returns
             CK(cudaMemcpyAsync(h_out + ooff, e->d_out.p, 2 * NC * 8, cudaMemcpyDeviceToHost, S(c)));
             CK(cudaMemcpyAsync(h_out + ooff + 2 * NC, e->d_flags.p, 4, cudaMemcpyDeviceToHost, S(c)));
             ooff += 2 * NC + 1;
@@ -817,7 +879,10 @@ int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *e, const double *d_x2, double *d_out)
         REQUIRE(e && d_out && (d_x2 || e->n1 == 0), SQLP_E_INVALID, "null argument");
         sqlp_ctx *c = e->ctx;
         c->bind();
-        epi_cuts_enqueue(e, 2, nullptr, d_x2, true);
+        e->cur_bias = nullptr;
+        CellGather cg(c, 2, 1, &e);
+        epi_cuts_enqueue(e, 2, nullptr, d_x2, true, nullptr, cg.slot(0));
+        cg.run();
         CK(cudaMemcpyAsync(d_out, e->d_out.p, (size_t)2 * (e->n1 + 2) * 8, cudaMemcpyDeviceToDevice, S(c)));
     });
 }

@@ -95,15 +95,19 @@ class Context:
         check(_lib.lib().sqlp_ctx_profile_read(self._h, int(reset), C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
 
-    PROFILE_CLASSES = ("contract", "delta", "reduce", "pool", "bias")
+    PROFILE_CLASSES = ("contract", "delta", "reduce", "pool", "bias", "screen", "resolve", "fallback")
 
     def profile_classes(self, reset=True):
         """{class: (device ms, event scopes, work)}; work = flops for the contraction, algorithmic bytes else."""
         import numpy as np
-        ms, n, wk = np.zeros(5), np.zeros(5, dtype=np.int64), np.zeros(5)
+        ms, n, wk = np.zeros(8), np.zeros(8, dtype=np.int64), np.zeros(8)
         check(_lib.lib().sqlp_ctx_profile_classes(self._h, int(reset), ms.ctypes.data_as(C.c_void_p),
                                                   n.ctypes.data_as(C.c_void_p), wk.ctypes.data_as(C.c_void_p)))
         return {k: (float(ms[i]), int(n[i]), float(wk[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
+
+    def set_screen(self, mode: int):
+        """0: every score in FP64; 1: screening pass on the tensor cores when it pays (default); 2: always."""
+        check(_lib.lib().sqlp_ctx_set_screen(self._h, int(mode)))
 
     def close(self):
         if self._h:
@@ -125,15 +129,21 @@ def default_context(device: int = 0) -> Context:
 class sdDualVertexSet:
     """Device-resident dual-vertex pool with the reference's dedup rule.
 
-    The reference allows vectors of different lengths in one set (they simply never
-    compare equal, dual_set.jl:26); on the device every vertex has the stage-2 row count
-    ``m2``, fixed by the first push, and a vector of another length raises ``ValueError``.
+    The reference allows vectors of different lengths in one set: they never compare equal
+    (dual_set.jl:26), so they only count and iterate (test/dual_set_test.jl:23-26).  The device pool
+    holds vertices of ONE length ``m2`` -- the stage-2 row count, fixed by the first push or by the
+    epigraph the set is bound to; a vector of another length goes to a side pool of its own length
+    (same device dedup rule among its peers) and keeps its place in the insertion order.  Only
+    vertices of length ``m2`` are ever scored: a vector of another length cannot be a dual of the
+    epigraph's subproblem (``dot`` would throw in the reference, subprob.jl:155).
     """
 
     def __init__(self, data=(), ctx: Context | None = None, m2: int | None = None):
         self.ctx = ctx or default_context()
         self._h = C.c_void_p()
         self.m2 = None
+        self._side: dict[int, "sdDualVertexSet"] = {}      # other lengths -> their own pool
+        self._side_at: list[tuple[int, int, int]] = []     # (main-pool size when inserted, length, side slot)
         if m2 is not None:
             self._create(int(m2))
         for d in data:                       # dual_set.jl:98-104
@@ -151,10 +161,41 @@ class sdDualVertexSet:
         if self.m2 is None:
             self._create(len(v))
         if len(v) != self.m2:
-            raise ValueError(f"vertex length {len(v)} != pool vertex length {self.m2}")
+            # dual_set.jl:26: never equal to a vertex of another length -- dedup among its own kind only
+            side = self._side.get(len(v))
+            if side is None:
+                side = self._side[len(v)] = sdDualVertexSet(ctx=self.ctx, m2=len(v))
+            ins, slot = side.push(v)
+            if ins:
+                self._side_at.append((self._main_len(), len(v), slot))
+            pos = [q for q, (_, ln, sl) in enumerate(self._side_at) if ln == len(v) and sl == slot][0]
+            return ins, self._global_index_of_side(pos)
         ins, idx = C.c_int32(), C.c_int64()
         check(_lib.lib().sqlp_pool_push(self._h, _ptr(v), C.byref(ins), C.byref(idx)))
-        return bool(ins.value), idx.value
+        return bool(ins.value), self._global_index_of_main(idx.value)
+
+    # -- insertion order over the main pool and the side pools ------------------------------
+    def _main_len(self):
+        K = C.c_int64()
+        check(_lib.lib().sqlp_pool_size(self._h, C.byref(K)))
+        return K.value
+
+    def _global_index_of_main(self, k):
+        return k + sum(1 for at, _, _ in self._side_at if at <= k)
+
+    def _global_index_of_side(self, pos):
+        return self._side_at[pos][0] + pos
+
+    def _order(self):
+        """[(length, slot)] in insertion order: side entry q sits after `at` main vertices."""
+        out, q = [], 0
+        for k in range(self._main_len()):
+            while q < len(self._side_at) and self._side_at[q][0] <= k:
+                out.append(self._side_at[q][1:])
+                q += 1
+            out.append((self.m2, k))
+        out.extend(t[1:] for t in self._side_at[q:])
+        return out
 
     def push_many(self, V):
         V = _f64(V)
@@ -171,21 +212,33 @@ class sdDualVertexSet:
     def __len__(self):                       # dual_set.jl:109-111
         if self.m2 is None:
             return 0
-        K = C.c_int64()
-        check(_lib.lib().sqlp_pool_size(self._h, C.byref(K)))
-        return K.value
+        return self._main_len() + len(self._side_at)
 
-    def __getitem__(self, k):
-        n = len(self)
-        if not 0 <= k < n:
-            raise IndexError(k)
+    def _main_get(self, k):
         out = np.zeros(self.m2)
         check(_lib.lib().sqlp_pool_get(self._h, int(k), _ptr(out)))
         return out
 
+    def __getitem__(self, k):
+        """Vertex ``k`` in insertion order.  Without vectors of another length (every SD run) this is
+        the device slot the argmax returns."""
+        if not self._side_at:
+            if not 0 <= k < self._main_len():
+                raise IndexError(k)
+            return self._main_get(k)
+        order = self._order()
+        if not 0 <= k < len(order):
+            raise IndexError(k)
+        ln, slot = order[k]
+        return self._main_get(slot) if ln == self.m2 else self._side[ln]._main_get(slot)
+
     def __iter__(self):                      # dual_set.jl:116-122, insertion order
-        for k in range(len(self)):
-            yield self[k]
+        if not self._side_at:
+            for k in range(self._main_len()):
+                yield self._main_get(k)
+            return
+        for ln, slot in self._order():
+            yield self._main_get(slot) if ln == self.m2 else self._side[ln]._main_get(slot)
 
     def hash(self, v) -> int:
         v = _f64(v)
@@ -194,8 +247,11 @@ class sdDualVertexSet:
         return h.value
 
     def close(self):
+        for side in self._side.values():
+            side.close()
+        self._side = {}
         if self._h:
-            _lib.lib().sqlp_pool_destroy(self._h)
+            check(_lib.lib().sqlp_pool_destroy(self._h))
             self._h = C.c_void_p()
 
 
@@ -464,6 +520,12 @@ class sdEpigraph:
         if n.value:
             check(_lib.lib().sqlp_epi_master_rows(self._h, _ptr(rows), C.byref(n)))
         return rows
+
+    def screen_stats(self) -> dict:
+        out = np.zeros(8, dtype=np.int64)
+        check(_lib.lib().sqlp_epi_screen_stats(self._h, _ptr(out)))
+        keys = ("passes", "fallbacks", "emitted", "evaluated", "overflowed_lists", "bad_operands", "live_0", "live_1")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def eval_dual(self, local_scen, vertex, x):
         x = _f64(x)

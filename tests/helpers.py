@@ -37,6 +37,35 @@ def sample_instance_values(z, N, seed=1):
                               idx[:, :, None], 2)[:, :, 0].copy()
 
 
+def load_pool(name, K):
+    """A REAL dual-vertex pool of K vertices (tools/harvest_pool.py; committed under tests/golden/pools).  If the
+    cache is missing it is rebuilt from the committed LP fixture -- the same recipe, the same image, so the
+    same vertices."""
+    d = os.path.join(GOLDEN, "pools")
+    have = sorted(int(f[len(name) + 2:-4]) for f in os.listdir(d) if f.startswith(name + "_K") and f.endswith(".npz"))
+    have = [k for k in have if k >= K]
+    if have:          # vertices are kept in LP order: the first K of a larger harvest ARE the harvest of K
+        return np.ascontiguousarray(np.load(os.path.join(d, f"{name}_K{have[0]}.npz"))["pool"][:K])
+    from tools.harvest_pool import harvest
+    return np.ascontiguousarray(harvest(name, K, verbose=False))
+
+
+def sampled_values_at(z, seed, g):
+    """Host twin of the device sampler (sqlp_epi_sample_scenarios) for the scenario ordinals ``g``:
+    u = u01(seed, g * s + e), value = vals[e][min(#{c : cdf[e][c] <= u}, cnt[e] - 1)]."""
+    s = len(z["pos_row"])
+    g = np.asarray(g, dtype=np.uint64)
+    out = np.empty((len(g), s))
+    for a in range(0, len(g), 65536):                      # bounded temporaries
+        gg = g[a:a + 65536]
+        u = O.u01(seed, gg[:, None] * np.uint64(s) + np.arange(s, dtype=np.uint64)[None, :])
+        idx = (u[:, :, None] >= z["out_cdf"][None, :, :]).sum(axis=2)
+        idx = np.minimum(idx, np.maximum(z["out_cnt"][None, :] - 1, 0))
+        out[a:a + 65536] = np.take_along_axis(np.broadcast_to(z["out_vals"], (len(gg),) + z["out_vals"].shape),
+                                              idx[:, :, None], 2)[:, :, 0]
+    return out
+
+
 def synthetic_problem(m2=64, n1=16, s=24, n_T=0, seed=6, first_stoch_row=0):
     """Storm/lands-like synthetic template: Tbar = one -1 per first-stage
     column, rbar in [100, 500) on the stochastic rows.  ``n_T`` of the ``s`` random

@@ -73,19 +73,23 @@ def check_cut(oracle, P, values, weights, x, pool, cut, val=None, epi=None):
 V1, V2, V3, V4, V5 = [1., 2, 3], [1.0000000001, 2, 3], [4., 5, 6], [4., 5, 6, 7], [3., 2, 1]
 
 
-def test_dual_set_reference_cases(T):         # test/dual_set_test.jl:16-33
+def test_dual_set_reference_cases(T):         # test/dual_set_test.jl:16-33, line for line
     dvs = T.sdDualVertexSet()
     sizes = []
-    for v in (V1, V2, V3):
+    for v in (V1, V2, V3, V4, V5):             # V4 has another length: never equal, counted (dual_set.jl:26)
         assert T.push_(dvs, v) is dvs          # push! returns the set
         sizes.append(len(dvs))
-    with pytest.raises(ValueError):            # a 4-vector can never equal a 3-vector
-        T.push_(dvs, V4)
-    T.push_(dvs, V5)
-    sizes.append(len(dvs))
-    assert sizes == [1, 1, 2, 3]
-    assert len(T.sdDualVertexSet([V1, V2, V3, V5])) == 3
-    assert [list(v) for v in dvs] == [V1, V3, V5]      # insertion order, first copy kept
+    assert sizes == [1, 1, 2, 3, 4]
+    dvs2 = T.sdDualVertexSet([V1, V2, V3, V4, V5])         # "Initialize with De-duplication"
+    assert len(dvs2) == 4
+    assert len(list(dvs2)) == 4                # "Iterate"
+    assert [list(v) for v in dvs] == [V1, V3, V4, V5]      # insertion order, first copy kept
+    assert [list(dvs[k]) for k in range(4)] == [V1, V3, V4, V5]
+    # a second vector of the odd length is deduplicated among its own kind, and keeps the order
+    assert dvs.push([4.0000000001, 5, 6, 7]) == (False, 2)
+    assert dvs.push([9., 9, 9, 9]) == (True, 4) and len(dvs) == 5
+    assert dvs.push(V5) == (False, 3)
+    dvs.close(); dvs2.close()
 
 
 def test_dedup_bit_exact_vs_oracle(T, oracle):

@@ -1,0 +1,160 @@
+"""The screening pass (tcgen05, csrc/kernels_screen.cuh) against the FP64 sweep it stands in for.
+
+Exactness is the bar, not a tolerance: with the pass forced on (``ctx.set_screen(2)``) ``argmax_procedure`` must
+return the SAME indices and the SAME values, bit for bit, as with the pass off (``set_screen(0)``: every score in
+FP64, reference ``subprob.jl:148-166``), and so must the cuts built from them -- on real pools, synthetic pools,
+exact duplicates and near-ties, NaN / Inf vertices, empty pools, ragged sizes, few scenarios (the sweep split in
+K-ranges) and many.  Parity of the FP64 sweep itself with the oracle is the business of the other test files.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import (load_instance, load_pool, sample_instance_values, sampled_values_at, synthetic_pool,
+                           synthetic_problem, synthetic_values)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    from sqlp_b200 import twosd
+    return twosd
+
+
+@pytest.fixture()
+def ctx(T):
+    c = T.default_context()
+    yield c
+    c.set_screen(1)
+
+
+def coef_of(T, P):
+    return T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
+
+
+def both_ways(T, ctx, P, pool, vals, w, xs, expect_fallback=None):
+    dvs = T.sdDualVertexSet(m2=P.m2)
+    if len(pool):
+        dvs.push_many(pool)
+    epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+    epi.add_scenarios(vals, w)
+    res = {}
+    for mode in (0, 2):
+        ctx.set_screen(mode)
+        got = []
+        for x in xs:
+            got.append(epi.argmax(x))
+        try:
+            cuts, val = epi.build_cuts2(xs[0], xs[-1], with_val=True)
+            got.append((np.array([cuts[0].alpha, cuts[1].alpha]), np.stack([cuts[0].beta, cuts[1].beta]), val))
+        except T.NoArgmaxError:
+            got.append("no argmax")
+        res[mode] = got
+    st = epi.screen_stats()
+    assert st["passes"] >= 1, "the screening pass never ran"
+    for a, b in zip(res[0], res[2]):
+        if isinstance(a, str):
+            assert a == b
+            continue
+        for u, v in zip(a, b):
+            u, v = np.asarray(u), np.asarray(v)
+            assert u.dtype == v.dtype and u.shape == v.shape
+            assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), (u, v)
+    if expect_fallback is not None:
+        assert (st["fallbacks"] > 0) == expect_fallback, st
+    epi.close()
+    dvs.close()
+    return st
+
+
+@pytest.mark.parametrize("name,K,N", [("baa99-20", 1024, 3000), ("ssn", 5000, 20000), ("storm", 2048, 5000)])
+def test_real_pools_bit_identical(T, ctx, name, K, N):
+    P, z = load_instance(name)
+    pool = load_pool(name, {"baa99-20": 1024, "ssn": 5000, "storm": 16384}[name])[:K]
+    vals = sampled_values_at(z, 1, np.arange(N))
+    w = 0.5 + np.arange(N) % 7 / 7.0
+    st = both_ways(T, ctx, P, pool, vals, w, (z["x_ev"], z["x_alt"]))
+    print(name, st)
+
+
+def test_storm_real_pool_falls_back(T, ctx):
+    """Storm's real duals tie by the dozen: the candidate lists overflow and the pass hands over to the FP64 sweep
+    on the device (no host round trip) -- same answers."""
+    P, z = load_instance("storm")
+    pool = load_pool("storm", 16384)
+    N = 4000
+    vals = sampled_values_at(z, 7, np.arange(N))
+    st = both_ways(T, ctx, P, pool, vals, np.ones(N), (z["x_ev"], z["x_alt"]))
+    print("storm K=16384 real:", st)
+
+
+@pytest.mark.parametrize("N,K,s", [(1000, 300, 13), (700, 1500, 117), (129, 127, 20), (3000, 129, 86), (5, 2000, 40),
+                                   (40000, 4096, 117)])
+def test_synthetic_shapes_bit_identical(T, ctx, N, K, s):
+    P = synthetic_problem(m2=max(64, s + 11), n1=16, s=s, first_stoch_row=3)
+    vals = synthetic_values(P, N, seed=3)
+    pool = synthetic_pool(P.m2, K, seed=5, scale=700.0)
+    x = 5.0 * np.cos(np.arange(P.n1))
+    both_ways(T, ctx, P, pool, vals, None, (x, 2.0 * x + 1.0), expect_fallback=False)
+
+
+def test_adversarial_pool(T, ctx):
+    """Exact duplicates (on the stochastic rows), 2^-40 near-ties, a bias 1e6 above the dots, zero scenarios."""
+    P = synthetic_problem(m2=80, n1=12, s=30, first_stoch_row=5)
+    N, K = 2500, 1200
+    vals = synthetic_values(P, N, seed=9)
+    vals[7] = P.rbar[P.pos_row]                                    # a scenario with d = 0
+    pool = synthetic_pool(P.m2, K, seed=6, scale=300.0)
+    S = P.pos_row
+    for k in range(100, 400, 3):                                   # same stochastic rows, same bias: exact ties
+        pool[k] = pool[k - 100]
+        pool[k, 0] += 1.0                                          # distinct for the dedup rule ...
+    other = [j for j in range(P.m2) if j not in set(S.tolist())]
+    base = P.rbar - P.T_dense() @ np.ones(P.n1)
+    for k in range(100, 400, 3):
+        j = next(j for j in other if j != 0 and abs(base[j]) > 1e-3)
+        pool[k, j] -= base[0] / base[j]                            # ... with (almost) the same bias
+    for k in range(500, 700):
+        pool[k] = pool[k - 500] * (1.0 + 2.0 ** -40)               # near-ties (kept apart by column 1 below)
+        pool[k, 1] += 1e-3 * k
+    pool[800:900, other[1]] += 1e6 / max(abs(base[other[1]]), 1e-3)    # biases far above the dots
+    x = np.ones(P.n1)
+    both_ways(T, ctx, P, pool, vals, None, (x, 0.5 * x))
+
+
+def test_nonfinite_vertices_and_empty_pool(T, ctx):
+    P = synthetic_problem(m2=64, n1=10, s=24)
+    N = 900
+    vals = synthetic_values(P, N, seed=2)
+    pool = synthetic_pool(P.m2, 600, seed=8)
+    x = np.linspace(0.0, 3.0, P.n1)
+    p1 = pool.copy(); p1[17, P.pos_row[3]] = np.nan               # NaN on a stochastic row: the pass steps aside
+    both_ways(T, ctx, P, p1, vals, None, (x, x + 1.0), expect_fallback=True)
+    p2 = pool.copy(); p2[5, 60] = np.inf                           # Inf off the stochastic rows: a +-Inf / NaN bias
+    both_ways(T, ctx, P, p2, vals, None, (x, x + 1.0))
+    p3 = pool.copy(); p3[9, 61] = np.nan
+    both_ways(T, ctx, P, p3, vals, None, (x, x + 1.0))
+    both_ways(T, ctx, P, pool[:0], vals, None, (x, x + 1.0))       # empty pool: nothing beats -Inf
+    both_ways(T, ctx, P, np.full((3, P.m2), np.nan), vals, None, (x, x + 1.0))
+
+
+def test_growing_pool_and_scenarios(T, ctx):
+    """The bf16 operands follow pushes and add_scenario! like the FP64 view does (an SD run: one scenario and two
+    vertices per iteration)."""
+    P, z = load_instance("ssn")
+    pool = load_pool("ssn", 5000)
+    dvs = T.sdDualVertexSet(m2=P.m2)
+    dvs.push_many(pool[:1500])
+    epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+    vals = sampled_values_at(z, 2, np.arange(4000))
+    epi.add_scenarios(vals[:3000], None)
+    x = z["x_ev"]
+    for it in range(6):
+        dvs.push_many(pool[1500 + 40 * it: 1500 + 40 * (it + 1)])
+        epi.add_scenarios(vals[3000 + 100 * it: 3000 + 100 * (it + 1)], None)
+        ctx.set_screen(0)
+        a = epi.argmax(x)
+        ctx.set_screen(2)
+        b = epi.argmax(x)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
+    assert epi.screen_stats()["passes"] >= 6
