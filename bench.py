@@ -440,9 +440,15 @@ def run_ours(args):
         cell.t_next = t0 + warmup + steps
         K_after = len(cell.dvs)
         assert K_after == cell.K0 + Ecell * cell.t_next, (K_after, cell.K0, Ecell, cell.t_next)
+        cols, nrel = cell.epis[0].view_columns()
         return {"ms": ms, "ms_per_step": ms / max(1, steps), "value": evals / (ms * 1e-3), "launches": launches,
                 "prof": prof, "prof_warm": prof_warm, "clocks": clocks, "out": out_dev.cpu().numpy(),
-                "screen": cell.epis[0].screen_stats()}
+                "screen": cell.epis[0].screen_stats(),
+                "sweep": {"pool_vertices": K_after, "columns_swept": cols, "relevant_rows": nrel, "rows": m2,
+                          "note": "evaluations are counted as the reference performs them (2 points x K x N per "
+                                  "iteration); vertices equal on every relevant row have bit-identical scores and "
+                                  "only the first of a class can be the first maximum (subprob.jl:156), so the "
+                                  "sweep visits one column per class -- same indices, values and cuts"}}
 
     # ---------------------------------------------------------------- headline cell ----------
     t_setup = time.perf_counter()
@@ -601,7 +607,8 @@ def run_ours(args):
             "peak_hbm_source": hbm_src, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / max(1, args.steps)},
-            "gpu_launches": launches, "setup_s": t_setup, "screening": leg["screen"], "parity_sample": parity}
+            "gpu_launches": launches, "setup_s": t_setup, "screening": leg["screen"], "sweep": leg["sweep"],
+            "parity_sample": parity}
     if other:
         line["other_pool"] = other
     if strong:
@@ -618,7 +625,8 @@ def run_ours(args):
 def leg_summary(leg, kind, cell):
     r = rooflines(leg, None)
     return {"pool": kind, "ms_per_step": leg["ms_per_step"], "value": leg["value"], "unit": UNIT,
-            "gpu_launches": leg["launches"], "screening": leg["screen"], "roofline": r["dominant"],
+            "gpu_launches": leg["launches"], "screening": leg["screen"], "sweep": leg["sweep"], "roofline": r["dominant"],
+            "roofline_kernels": r["all"],
             "share_of_step": r["dominant"]["share_of_step"] if r["dominant"] else None, "clocks": leg["clocks"]}
 
 

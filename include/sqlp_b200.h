@@ -172,6 +172,15 @@ SQLP_API int32_t sqlp_epi_sample_scenarios(sqlp_epi *epi, int64_t n_new, uint64_
 SQLP_API int32_t sqlp_epi_counts(sqlp_epi *epi, int64_t *n_global, int64_t *n_local,
                                  double *total_weight);
 
+/* Score-equivalent vertices.  A vertex enters scores and cut coefficients only through the RELEVANT rows (a
+ * random element lives there, or rbar != 0, or Tbar has an entry); elsewhere rbar - Tbar x is exactly zero for
+ * every x.  Vertices equal on the relevant rows (a degenerate stage-2 LP returns many: storm's 16 384 harvested
+ * duals are 3 599 classes) have bit-identical scores, and argmax_procedure keeps the FIRST maximum
+ * (subprob.jl:156), so only the first vertex of a class can ever be selected: the sweep visits one column per
+ * class and returns the same indices, values and cuts.  columns = classes of the current pool (= its size when
+ * every row is relevant); SQLP_TWINS=0 in the environment turns the classification off. */
+SQLP_API int32_t sqlp_epi_view_columns(sqlp_epi *epi, int64_t *columns, int64_t *relevant_rows);
+
 /* delta_coefficients readback for LOCAL scenario i -- subprob.jl:104-121:
  * delta_rhs dense [m2], delta_T one value per table element (0 for RHS elements). */
 SQLP_API int32_t sqlp_epi_delta(sqlp_epi *epi, int64_t local_scen, double *delta_rhs,

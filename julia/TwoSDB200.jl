@@ -7,15 +7,19 @@
 #     include("julia/TwoSDB200.jl"); using .TwoSDB200
 #     TwoSDB200.enable!(TwoSD; lib = "/path/to/libsqlp_b200.so", device = 0)
 #
-# `enable!` overrides five methods of TwoSD, keeping their signatures and return types
-# (SURVEY.md 8(b)):
-#     sdEpigraph(prob, w, lb)                  src/sd_algorithm/epigraph.jl:52-61
+# `enable!` overrides four methods of TwoSD, keeping their signatures and return types
+# (SURVEY.md 8(b)); the fifth, the constructor, is left exactly as it is:
+#     sdEpigraph(prob, w, lb)                  src/sd_algorithm/epigraph.jl:52-61   (unchanged: the device
+#                                              epigraph is created LAZILY, at the first call below that
+#                                              names the dual-vertex set -- the constructor does not)
 #     add_scenario!(epi, scenario, weight)     src/sd_algorithm/epigraph.jl:81-96
 #     Base.push!(dvs::sdDualVertexSet, v)      src/sd_algorithm/dual_set.jl:84-93
 #     argmax_procedure(coef, deltas, x, dvs)   src/sd_algorithm/subprob.jl:141-169
 #     build_sasa_cut(epi, x, dvs)::sdCut       src/sd_algorithm/epigraph.jl:125-146
 # Host-side lists (scenario_list, scenario_weight, dvs.data) are still maintained so the rest of
-# TwoSD (sd_iteration!, check_improvement, sync_cuts!) runs unchanged.
+# TwoSD (sd_iteration!, check_improvement, sync_cuts!) runs unchanged -- and so that a device
+# epigraph bound late can replay the scenarios added before it existed.  No host code has to call
+# anything new: `test/sd_test.jl` and `test/dual_set_test.jl` run as they are.
 module TwoSDB200
 
 using SparseArrays
@@ -26,7 +30,11 @@ const CTX = Ref{Ptr{Cvoid}}(C_NULL)
 struct DeviceState
     pool::Ptr{Cvoid}
 end
-const POOLS = IdDict{Any,Ptr{Cvoid}}()        # sdDualVertexSet => sqlp_pool*
+const POOLS = IdDict{Any,Ptr{Cvoid}}()        # sdDualVertexSet => sqlp_pool* (vertices of the set's main length)
+const POOL_LEN = IdDict{Any,Int}()            # sdDualVertexSet => that length (fixed by the first vertex)
+const SIDE = IdDict{Any,Dict{Int,Ptr{Cvoid}}}()   # sdDualVertexSet => pools of vectors of OTHER lengths
+                                              # (dual_set.jl:26: never equal to the others, only counted)
+const REPLAYED = IdDict{Any,Int}()            # sdEpigraph => scenarios of epi.scenario_list already on the device
 const EPIS = IdDict{Any,Ptr{Cvoid}}()         # sdEpigraph      => sqlp_epi*
 const DELTA_OWNER = IdDict{Any,Any}()         # epi.scenario_delta => epi
 const TABLES = IdDict{Any,Vector{Any}}()      # sdSubprobCoefficients => position table
@@ -48,19 +56,27 @@ function context()
 end
 const DEVICE = Ref{Int}(0)
 
+function new_pool(m2::Int)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sqlp_pool_create, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), context(), m2, out))
+    return out[]
+end
+
+"The device pool holding the vertices of length `m2` of this set: the main pool (created on first use, with the
+vertices pushed before it existed replayed in order) or, for any other length, a side pool of its own."
 function pool_of(dvs, m2::Int)
-    get!(POOLS, dvs) do
-        out = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:sqlp_pool_create, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
-                    context(), m2, out))
-        # replay vertices that were pushed before the pool existed
+    if !haskey(POOLS, dvs)
+        POOL_LEN[dvs] = m2
+        POOLS[dvs] = new_pool(m2)
         for dv in dvs.data
+            length(dv.data) == m2 || continue
             ins = Ref{Int32}(0); idx = Ref{Int64}(0)
             check(ccall((:sqlp_pool_push, LIB[]), Int32,
-                        (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}, Ref{Int64}), out[], dv.data, ins, idx))
+                        (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}, Ref{Int64}), POOLS[dvs], dv.data, ins, idx))
         end
-        out[]
     end
+    POOL_LEN[dvs] == m2 && return POOLS[dvs]
+    return get!(() -> new_pool(m2), get!(() -> Dict{Int,Ptr{Cvoid}}(), SIDE, dvs), m2)
 end
 
 "Position table (row, col | -1) of the instance's random elements, fixed once from `sto`."
@@ -79,37 +95,61 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
     LIB[] = lib; DEVICE[] = device
     sto === nothing && error("pass the spStoType so the position table can be resolved once")
 
-    # --- sdEpigraph(prob, w, lb): also create the device epigraph --------------------------------
-    @eval T function bind_device!(epi::sdEpigraph, dvs::sdDualVertexSet)
-        coef = epi.subproblem_coef
-        order, rows, cols = $position_table($T, coef, $sto)
-        $TABLES[coef] = order
-        r = coef.rhs; Tm = coef.transfer
-        ridx = Int64.(r.nzind .- 1); rval = Float64.(r.nzval)
-        colptr = Int64.(Tm.colptr .- 1); rowval = Int64.(Tm.rowval .- 1); nzval = Float64.(Tm.nzval)
-        out = Ref{Ptr{Cvoid}}(C_NULL)
-        $check(ccall((:sqlp_epi_create, $LIB[]), Int32,
-            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64},
-             Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
-            $context(), $pool_of(dvs, length(r)), length(r), size(Tm, 2), length(ridx), ridx, rval,
-            colptr, rowval, nzval, length(rows), rows, cols, out))
-        $EPIS[epi] = out[]
-        $check(ccall((:sqlp_epi_set_weights, $LIB[]), Int32, (Ptr{Cvoid}, Float64, Float64), out[],
-                     epi.objective_weight, epi.lower_bound))
-        $DELTA_OWNER[epi.scenario_delta] = epi
-        finalizer(e -> ccall((:sqlp_epi_destroy, $LIB[]), Int32, (Ptr{Cvoid},), $EPIS[e]), epi)
-        return epi
+    # --- the device half of an sdEpigraph, created at the first call that names the dual-vertex set ----
+    # (sdEpigraph(prob, w, lb) itself -- epigraph.jl:52-61 -- is untouched: it does not know the set.)
+    @eval T function device_epi(epi::sdEpigraph, dvs::sdDualVertexSet)
+        if !haskey($EPIS, epi)
+            coef = epi.subproblem_coef
+            order, rows, cols = $position_table($T, coef, $sto)
+            $TABLES[coef] = order
+            r = coef.rhs; Tm = coef.transfer
+            ridx = Int64.(r.nzind .- 1); rval = Float64.(r.nzval)
+            colptr = Int64.(Tm.colptr .- 1); rowval = Int64.(Tm.rowval .- 1); nzval = Float64.(Tm.nzval)
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            $check(ccall((:sqlp_epi_create, $LIB[]), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64},
+                 Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+                $context(), $pool_of(dvs, length(r)), length(r), size(Tm, 2), length(ridx), ridx, rval,
+                colptr, rowval, nzval, length(rows), rows, cols, out))
+            $EPIS[epi] = out[]
+            $REPLAYED[epi] = 0
+            $check(ccall((:sqlp_epi_set_weights, $LIB[]), Int32, (Ptr{Cvoid}, Float64, Float64), out[],
+                         epi.objective_weight, epi.lower_bound))
+            $DELTA_OWNER[epi.scenario_delta] = epi
+            finalizer(e -> ccall((:sqlp_epi_destroy, $LIB[]), Int32, (Ptr{Cvoid},), $EPIS[e]), epi)
+        end
+        # scenarios added while no device epigraph existed (or through the host list alone): one batched call
+        n0 = $REPLAYED[epi]; n1 = length(epi.scenario_list)
+        if n1 > n0
+            order = $TABLES[epi.subproblem_coef]
+            vals = Matrix{Float64}(undef, length(order), n1 - n0)        # column-major = [n_new x s] row-major
+            for (c, sc) in enumerate(epi.scenario_list[n0+1:n1])
+                lookup = Dict(p => v for (p, v) in sc)
+                vals[:, c] = Float64[lookup[p] for p in order]
+            end
+            $check(ccall((:sqlp_epi_add_scenarios, $LIB[]), Int32,
+                         (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), $EPIS[epi], n1 - n0, vals,
+                         Float64.(epi.scenario_weight[n0+1:n1])))
+            $REPLAYED[epi] = n1
+        end
+        return $EPIS[epi]
     end
+    @eval T bind_device!(epi::sdEpigraph, dvs::sdDualVertexSet) = (device_epi(epi, dvs); epi)   # optional: bind early
 
     # --- add_scenario!(epi, scenario, weight) -- epigraph.jl:81-96 --------------------------------
     @eval T function add_scenario!(epi::sdEpigraph, scenario::spSmpsScenario, weight::Float64 = 1.0)
         push!(epi.scenario_list, scenario)
         push!(epi.scenario_weight, weight)
         epi.total_scenario_weight += weight
-        lookup = Dict(p => v for (p, v) in scenario)
-        vals = Float64[lookup[p] for p in $TABLES[epi.subproblem_coef]]
-        $check(ccall((:sqlp_epi_add_scenarios, $LIB[]), Int32,
-                     (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), $EPIS[epi], 1, vals, [weight]))
+        # the deltas live on the device: epi.scenario_delta stays empty and only identifies the epigraph
+        $DELTA_OWNER[epi.scenario_delta] = epi
+        if haskey($EPIS, epi) && $REPLAYED[epi] == length(epi.scenario_list) - 1
+            lookup = Dict(p => v for (p, v) in scenario)
+            vals = Float64[lookup[p] for p in $TABLES[epi.subproblem_coef]]
+            $check(ccall((:sqlp_epi_add_scenarios, $LIB[]), Int32,
+                         (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), $EPIS[epi], 1, vals, [weight]))
+            $REPLAYED[epi] += 1
+        end                                   # else: replayed when the device epigraph is bound (device_epi)
         return
     end
 
@@ -119,7 +159,9 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
         $check(ccall((:sqlp_pool_push, $LIB[]), Int32,
                      (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}, Ref{Int64}),
                      $pool_of(dvs, length(new_vec)), new_vec, ins, idx))
-        ins[] == 1 && push!(dvs.data, sdDualVertex(new_vec))   # keeps dvs.data in device order
+        # dvs.data keeps the reference's insertion order over ALL lengths (length, iterate: dual_set.jl:109-122);
+        # the main pool's slots are the positions of the main-length vertices in it (what argmax_procedure maps back)
+        ins[] == 1 && push!(dvs.data, sdDualVertex(new_vec))
         return dvs
     end
 
@@ -128,13 +170,16 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
             x::Vector{Float64}, dual_vertices::sdDualVertexSet;
             sense::MOI.OptimizationSense = MIN_SENSE)
         epi = $DELTA_OWNER[delta_set]
+        device_epi(epi, dual_vertices)
         n = length(epi.scenario_list)
         max_val = Vector{Float64}(undef, n); max_idx = Vector{Int64}(undef, n)
         $check(ccall((:sqlp_epi_argmax, $LIB[]), Int32,
                      (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Int64}),
                      $EPIS[epi], x, sense == MIN_SENSE ? Int32(0) : Int32(1), max_val, max_idx))
         any(<(0), max_idx) && throw(UndefRefError())
-        max_arg = Ref{Vector{Float64}}[Ref(dual_vertices.data[k + 1].data) for k in max_idx]
+        m2 = $POOL_LEN[dual_vertices]
+        main = [dv for dv in dual_vertices.data if length(dv.data) == m2]      # device slot k <-> k-th vertex of length m2
+        max_arg = Ref{Vector{Float64}}[Ref(main[k + 1].data) for k in max_idx]
         return max_val, max_arg
     end
 
@@ -143,16 +188,17 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
         alpha = Ref{Float64}(0); wm = Ref{Float64}(0); beta = zeros(length(x))
         $check(ccall((:sqlp_epi_build_cut, $LIB[]), Int32,
                      (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
-                     $EPIS[epi], x, alpha, beta, wm, C_NULL))
+                     device_epi(epi, dual_vertices), x, alpha, beta, wm, C_NULL))
         return sdCut(alpha[], beta, wm[])
     end
 
     # --- both cuts of one iteration (algorithm.jl:80,83) in one pass ------------------------------
-    @eval T function build_two_cuts(epi::sdEpigraph, x_cand::Vector{Float64}, x_inc::Vector{Float64})
+    @eval T function build_two_cuts(epi::sdEpigraph, x_cand::Vector{Float64}, x_inc::Vector{Float64},
+                                    dual_vertices::sdDualVertexSet)
         alpha = zeros(2); beta = zeros(length(x_cand), 2); wm = Ref{Float64}(0)
         $check(ccall((:sqlp_epi_build_cuts2, $LIB[]), Int32,
                      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
-                     $EPIS[epi], x_cand, x_inc, alpha, beta, wm, C_NULL))
+                     device_epi(epi, dual_vertices), x_cand, x_inc, alpha, beta, wm, C_NULL))
         return sdCut(alpha[1], beta[:, 1], wm[]), sdCut(alpha[2], beta[:, 2], wm[])
     end
     # --- optional: the cut formation of one sd_iteration! in one call (algorithm.jl:45-55, 79-85) --
@@ -160,10 +206,11 @@ function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, st
     # and the incumbent (in the order the reference pushes them).  Keeps the host-side lists in step.
     @eval T function sd_step!(cell::sdCell, scenarios::Vector{spSmpsScenario}, duals::Vector{Vector{Float64}})
         E = length(cell.epi)
-        handles = Ptr{Cvoid}[$EPIS[epi] for epi in cell.epi]
+        handles = Ptr{Cvoid}[device_epi(epi, cell.dual_vertices) for epi in cell.epi]
         vals = Float64[]
         for (epi, sc) in zip(cell.epi, scenarios)
             push!(epi.scenario_list, sc); push!(epi.scenario_weight, 1.0); epi.total_scenario_weight += 1.0
+            $REPLAYED[epi] += 1
             lookup = Dict(p => v for (p, v) in sc)
             append!(vals, Float64[lookup[p] for p in $TABLES[epi.subproblem_coef]])
         end

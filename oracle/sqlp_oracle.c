@@ -283,10 +283,25 @@ ORC_API double orc_eval_dual(const orc_problem *P, const double *values,
  * reference's undefined Ref), and optionally second[N] = best score among the
  * vertices that were NOT selected (for the parity rule's gap exemption).
  * dot_kind: 0 = index-order dot (oracle of record), 1 = 8-accumulator dot (timing). */
+/* forced (may be NULL): scenario i is scored against vertex forced[i] alone -- what a checker needs when
+ * the selection is given (the cut on a validated selection), O(N m2) instead of O(N K m2). */
+static void orc_argmax_range_f(const orc_problem *P, int64_t i0, int64_t i1,
+                               const double *values, const double *x, const double *pool,
+                               int64_t K, double *max_val, int64_t *max_idx,
+                               double *second, int dot_kind, const int64_t *forced);
+
 static void orc_argmax_range(const orc_problem *P, int64_t i0, int64_t i1,
                              const double *values, const double *x, const double *pool,
                              int64_t K, double *max_val, int64_t *max_idx,
                              double *second, int dot_kind)
+{
+    orc_argmax_range_f(P, i0, i1, values, x, pool, K, max_val, max_idx, second, dot_kind, NULL);
+}
+
+static void orc_argmax_range_f(const orc_problem *P, int64_t i0, int64_t i1,
+                               const double *values, const double *x, const double *pool,
+                               int64_t K, double *max_val, int64_t *max_idx,
+                               double *second, int dot_kind, const int64_t *forced)
 {
     int64_t m2 = P->m2;
     double *base = malloc((size_t)m2 * sizeof(double));
@@ -306,7 +321,8 @@ static void orc_argmax_range(const orc_problem *P, int64_t i0, int64_t i1,
         orc_delta_vector(P, ord, nt, drhs, dT, x, scratch, dvec); /* :149 */
         double cur = -INFINITY, sec = -INFINITY;                /* :151 */
         int64_t arg = -1;
-        for (int64_t k = 0; k < K; ++k) {                       /* :154 */
+        const int64_t kb = forced ? forced[i] : 0, ke = forced ? forced[i] + 1 : K;
+        for (int64_t k = (kb < 0 ? 0 : kb); k < (kb < 0 ? 0 : ke); ++k) {   /* :154 */
             const double *p = pool + k * m2;
             double v = dot_kind ? orc_dot_simd8(p, base, m2) + orc_dot_simd8(p, dvec, m2)
                                 : orc_dot_seq(p, base, m2) + orc_dot_seq(p, dvec, m2); /* :155 */
@@ -382,7 +398,8 @@ ORC_API int32_t orc_build_sasa_cut(const orc_problem *P, int64_t N, const double
     int64_t m2 = P->m2, n1 = P->n1;
     double *max_val = max_val_out ? max_val_out : malloc((size_t)(N ? N : 1) * sizeof(double));
     int64_t *max_idx = max_idx_out ? max_idx_out : malloc((size_t)(N ? N : 1) * sizeof(int64_t));
-    orc_argmax_range(P, 0, N, values, x, pool, K, max_val, max_idx, NULL, 0); /* :127 */
+    /* :127 -- with a forced selection only the selected vertices are scored (max_val = their scores) */
+    orc_argmax_range_f(P, 0, N, values, x, pool, K, max_val, max_idx, NULL, 0, forced_idx);
 
     double alpha = 0.0, val = 0.0;                               /* :130-132 */
     for (int64_t j = 0; j < n1; ++j) beta_out[j] = 0.0;

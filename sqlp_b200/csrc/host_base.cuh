@@ -168,6 +168,7 @@ struct sqlp_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     unsigned profile = 0;         // bit cls: event scopes around the launches of kernel class cls
     bool pdl = true;              // programmatic dependent launch of every kernel (SQLP_PDL=0: plain stream order)
+    bool twins = true;            // leave score-equivalent vertices out of the sweep (SQLP_TWINS=0: every vertex)
     struct ProfEvent { cudaEvent_t e0, e1; int cls; double per_k; int k_quantum; long long *k_seen; };
     std::vector<long long *> prof_kslots;   // pinned blocks of 1024 pool sizes, one slot per event scope
     std::vector<ProfEvent> prof_events;
@@ -226,9 +227,19 @@ struct PoolView {   // the pool restricted to one set of stochastic rows, in til
     int n_rows = 0, s_pad = 0;
     DevBuf d_rows, d_piS;
     int64_t synced_lo = 0;   // vertices < synced_lo are final in d_piS
+    // score-equivalent vertices (kernels_pool.cuh, "twins"): with rows that can never enter a score the view holds
+    // one column per CLASS of vertices equal on the relevant rows; d_act[v] = pool slot of the first vertex of class v
+    std::vector<int> rel;    // relevant rows: stochastic rows + rows of rbar != 0 + rows of Tbar entries
+    bool twins = false;      // rel is a proper subset of the rows: classification is on
+    DevBuf d_rel, d_twin, d_act, d_hk, d_tkey, d_trep, d_tflag;
+    int64_t twin_cap = 0;    // pool capacity the tables are sized for
+    int64_t twin_epoch = -1, scr_epoch = -1;   // pool push epochs the classification / the bf16 operands are up to
+    unsigned int tmask = 0;
+    const long long *d_Kv(const sqlp_pool *p) const;   // columns of the view (device resident)
+    const int *act() const { return twins ? d_act.as<int>() : nullptr; }
     // the same rows as bf16 hi / lo operands of the screening pass, built on first use
     int sp = 0;              // row slots padded to a multiple of 16
-    DevBuf d_piB, d_pn, d_pnmax, d_vbad;
+    DevBuf d_piB, d_pn, d_pnmax, d_vbad, d_scr_lo;
     int64_t scr_synced_lo = 0, scr_cap = 0;   // vertices final in d_piB / capacity (multiple of 256)
 };
 
@@ -238,11 +249,17 @@ struct sqlp_pool {
     int64_t cap = 0;        // vertex capacity (multiple of 128)
     int64_t K = 0;          // confirmed size
     int64_t pending = 0;    // enqueued pushes whose outcome the host has not read yet
+    int64_t push_epoch = 0; // bumped by every enqueued push: views compare it with the epoch they last synced at
     DevBuf d_pi, d_hash, d_K, d_scratch, d_vnew, d_vr, d_results;
     std::vector<PoolView *> views;
     std::vector<sqlp_epi *> epis;
     int64_t upper() const { return K + pending; }
 };
+
+inline const long long *PoolView::d_Kv(const sqlp_pool *p) const
+{
+    return twins ? &d_twin.as<TwinState>()->Kv : p->d_K.as<long long>();
+}
 
 struct sqlp_epi {
     sqlp_ctx *ctx = nullptr;
@@ -309,9 +326,10 @@ struct ProfScope {   // CUDA events around the launch(es) of one kernel class wh
     // work: flops or algorithmic bytes of the scope.  With `pool` the work is PER VERTEX and is multiplied, when the
     // profile is read, by the pool size the launch actually saw (rounded up to `quantum`): the size lives on the
     // device (pushes are enqueued, not awaited), so it is copied into a pinned slot right behind the launch.
-    ProfScope(sqlp_ctx *c_, int cls, double work, sqlp_pool *pool = nullptr, int quantum = 1)
+    ProfScope(sqlp_ctx *c_, int cls, double work, sqlp_pool *pool = nullptr, int quantum = 1, PoolView *view = nullptr)
         : c(c_)
     {
+        kptr_ = pool ? (view ? view->d_Kv(pool) : pool->d_K.as<long long>()) : nullptr;
         if (!((c->profile >> cls) & 1u)) return;
         if (c->prof_used == c->prof_events.size()) {
             cudaEvent_t a = nullptr, b = nullptr;
@@ -336,6 +354,7 @@ struct ProfScope {   // CUDA events around the launch(es) of one kernel class wh
         CK(cudaEventRecord(pe.e0, c->stream));
     }
     sqlp_pool *pool_ = nullptr;
+    const long long *kptr_ = nullptr;     // the size the launch sees: view columns (twins) or pool vertices
     size_t idx_ = 0;
     void stop();
     ~ProfScope();
@@ -347,14 +366,14 @@ inline void ProfScope::stop()
 {
     if (!e1) return;
     CK(cudaEventRecord(e1, c->stream));
-    if (pool_) CK(cudaMemcpyAsync(c->prof_events[idx_].k_seen, pool_->d_K.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pool_) CK(cudaMemcpyAsync(c->prof_events[idx_].k_seen, kptr_, 8, cudaMemcpyDeviceToHost, c->stream));
     e1 = nullptr;
 }
 inline ProfScope::~ProfScope()
 {
     if (!e1) return;
     cudaEventRecord(e1, c->stream);
-    if (pool_) cudaMemcpyAsync(c->prof_events[idx_].k_seen, pool_->d_K.p, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (pool_) cudaMemcpyAsync(c->prof_events[idx_].k_seen, kptr_, 8, cudaMemcpyDeviceToHost, c->stream);
 }
 
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }

@@ -207,7 +207,7 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.PiS = e->view->d_piS.as<double>();
     a.bias = bias;
     a.bias_stride = e->cur_bias_stride;
-    a.d_K = e->pool->d_K.as<long long>();
+    a.d_K = e->view->d_Kv(e->pool);             // columns of the view (= pool size without twins)
     a.s_pad = e->view->s_pad;
     a.ntiles = (int)((e->n_local + SQLP_TILE - 1) / SQLP_TILE);
     a.n_local = e->n_local;
@@ -220,7 +220,7 @@ void launch_contract(sqlp_epi *e, const double *D, const double *bias, double *b
     a.gate = gate;
     // behind a screening pass the sweep only runs if that pass fell back: its time goes to its own class
     ProfScope prof(c, gate ? SQLP_PROF_FALLBACK : SQLP_PROF_CONTRACT,
-                   gate ? 0.0 : 2.0 * (double)e->view->n_rows * (double)e->n_local, gate ? nullptr : e->pool);
+                   gate ? 0.0 : 2.0 * (double)e->view->n_rows * (double)e->n_local, gate ? nullptr : e->pool, 1, e->view);
     bool done = false;
     // automatic: warp-specialised -> resident (fewer ring stages suffice) -> streaming (any s_pad)
     if (c->contract_mode == 0 || c->contract_mode == 3) done = launch_contract_ws<NX>(e, a);
@@ -294,14 +294,17 @@ void screen_sync_operands(sqlp_epi *e)
         v->d_pnmax.ensure((size_t)(ncap / SCR_NB) * 4, (size_t)(v->scr_cap / SCR_NB) * 4, S(c));
         v->scr_cap = ncap;
     }
-    if (hi > v->scr_synced_lo) {
-        const int64_t work = hi - v->scr_synced_lo;
+    if (v->scr_epoch != p->push_epoch && hi > 0) {
+        const int64_t work = std::max<int64_t>(1, hi - std::min(v->scr_synced_lo, hi));
         const int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 8 * c->sm_count);
+        v->d_scr_lo.ensure(16, 0, S(c));     // device-side mark: view columns below it are final in d_piB
         LAUNCH(c, k_screen_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(), v->n_rows, v->sp,
                v->d_piB.as<__nv_bfloat16>(), v->d_pn.as<float>(), v->d_pnmax.as<float>(), v->d_vbad.as<int>(),
-               (long long)v->scr_synced_lo, p->d_K.as<long long>());
+               v->d_scr_lo.as<long long>(), v->d_Kv(p), v->act());
+        LAUNCH(c, k_screen_mark, 1, 32, 0, v->d_scr_lo.as<long long>(), v->d_Kv(p));
     }
-    v->scr_synced_lo = p->K;   // only confirmed vertices are final
+    v->scr_synced_lo = p->K;                // confirmed vertices: a lower bound of the device's mark (in pool slots)
+    v->scr_epoch = p->push_epoch;
     const int64_t units = (e->n_local + SCR_UNIT - 1) / SCR_UNIT;
     if (units > e->scr_units_cap) {
         const int64_t ncap = std::max<int64_t>(units, std::max<int64_t>(8, e->scr_units_cap * 2));
@@ -346,7 +349,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     const unsigned ovf_limit = (unsigned)std::min<int64_t>(e->n_local / 64 + 16, 1 << 20);
     LAUNCH(c, k_screen_prep<NX>, 1, 1024, 0, e->cur_bias, (long long)e->cur_bias_stride, v->d_pn.as<float>(),
            v->d_pnmax.as<float>(), e->d_dnall.as<float>(), v->d_vbad.as<int>(), e->d_ebad.as<int>(),
-           p->d_K.as<long long>(), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>());
+           v->d_Kv(p), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>());
     int nstages = SCR_MAX_STAGES;
     while (nstages > 3 && scr_smem_bytes(v->sp, nstages, NX) > (size_t)c->smem_optin) --nstages;
     const size_t smem = scr_smem_bytes(v->sp, nstages, NX);
@@ -360,7 +363,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     sa.b32c = e->d_b32c.as<float>();
     sa.dnmax_unit = e->d_dnu.as<float>();
     sa.ctl = e->d_ctl.as<ScreenCtl>();
-    sa.d_K = p->d_K.as<long long>();
+    sa.d_K = v->d_Kv(p);
     sa.sp = v->sp;
     sa.nunits = (int)nunits;
     sa.R = R;
@@ -375,7 +378,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     const int grid = (int)std::min<int64_t>(c->sm_count, nunits * R);
     {
         // executed bf16 flops: three products over sp slots for every (vertex of a whole chunk, scenario of a whole unit)
-        ProfScope prof(c, SQLP_PROF_SCREEN, 6.0 * v->sp * (double)npad, p, SCR_NB);
+        ProfScope prof(c, SQLP_PROF_SCREEN, 6.0 * v->sp * (double)npad, p, SCR_NB, v);
         LAUNCH(c, k_screen<NX>, grid, SCR_THREADS, smem, sa);
     }
     ResolveArgs ra;
@@ -384,7 +387,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     ra.bias = e->cur_bias;
     ra.bias_stride = e->cur_bias_stride;
     ra.s_pad = v->s_pad;
-    ra.d_K = p->d_K.as<long long>();
+    ra.d_K = v->d_Kv(p);
     ra.n_local = e->n_local;
     ra.npad = npad;
     ra.R = R;
@@ -471,12 +474,12 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         int bgrid = (int)((kpad + 7) / 8);
         if (NX == 2)
             LAUNCH(c, k_bias<2>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
-                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
-                   (long long)e->bias_stride);
+                   e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(),
+                   (long long)e->bias_stride, e->view->act());
         else
             LAUNCH(c, k_bias<1>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
-                   p->d_K.as<long long>(), (long long)kpad, e->d_bias.as<double>(),
-                   (long long)e->bias_stride);
+                   e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(),
+                   (long long)e->bias_stride, e->view->act());
 
         prof_bias.stop();
     }
@@ -521,6 +524,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         r.w = e->d_w.as<double>();
         r.PiS = e->view->d_piS.as<double>();
         r.rt = e->d_rt.as<double>();
+        r.act = e->view->act();
         r.bias = e->n_T == 0 ? e->cur_bias : nullptr;
         r.bias_stride = e->cur_bias_stride;
         r.best_val = e->d_best_val.as<double>();

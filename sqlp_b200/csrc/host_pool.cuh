@@ -73,6 +73,7 @@ void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const doub
                p->d_results.as<PushResult>() + i);
     }
     p->pending += n;
+    ++p->push_epoch;
 }
 
 // Bring a view / an epigraph's (rho, tau) tables up to the current pool contents.
@@ -80,6 +81,50 @@ void view_sync(sqlp_pool *p, PoolView *v)
 {
     sqlp_ctx *c = p->ctx;
     int64_t hi = p->upper();
+    if (v->twins) {
+        // classify the new vertices on the device (the device keeps its own "synced" mark, so nothing here
+        // depends on which pushes the host has confirmed) and fill the columns of the new classes
+        if (v->twin_cap != p->cap) {
+            // first use, or the pool's capacity grew: size the tables for it and start over
+            size_t tsize = 1;
+            while (tsize < (size_t)4 * (size_t)p->cap) tsize <<= 1;
+            v->tmask = (unsigned int)(tsize - 1);
+            v->d_twin.ensure(sizeof(TwinState), 0, S(c));
+            CK(cudaMemsetAsync(v->d_twin.p, 0, sizeof(TwinState), S(c)));
+            v->d_act.ensure((size_t)p->cap * 4, 0, S(c), false);
+            v->d_hk.ensure((size_t)p->cap * 8, 0, S(c), false);
+            v->d_tflag.ensure((size_t)p->cap, 0, S(c), false);
+            v->d_tkey.ensure(tsize * 8, 0, S(c), false);
+            v->d_trep.ensure(tsize * 4, 0, S(c), false);
+            CK(cudaMemsetAsync(v->d_tkey.p, 0xFF, tsize * 8, S(c)));
+            CK(cudaMemsetAsync(v->d_trep.p, 0x7F, tsize * 4, S(c)));      // 0x7F7F7F7F: above every pool index
+            v->twin_cap = p->cap;
+            v->synced_lo = 0;
+            v->twin_epoch = -1;
+        }
+        if (v->twin_epoch != p->push_epoch && hi > 0) {
+            // the kernels take their range [synced, K) from the device; the host only needs an upper bound of its length
+            const int64_t work = std::max<int64_t>(1, hi - std::min(v->synced_lo, hi));
+            const int wgrid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 8 * c->sm_count);
+            TwinState *st = v->d_twin.as<TwinState>();
+            LAUNCH(c, k_twin_hash, wgrid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rel.as<int>(), (int)v->rel.size(),
+                   p->d_K.as<long long>(), (const TwinState *)st, v->d_hk.as<unsigned long long>(),
+                   v->d_tkey.as<unsigned long long>(), v->d_trep.as<int>(), v->tmask);
+            LAUNCH(c, k_twin_mark, wgrid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rel.as<int>(), (int)v->rel.size(),
+                   p->d_K.as<long long>(), (const TwinState *)st, (const unsigned long long *)v->d_hk.as<unsigned long long>(),
+                   (const unsigned long long *)v->d_tkey.as<unsigned long long>(), (const int *)v->d_trep.as<int>(), v->tmask,
+                   v->d_tflag.as<unsigned char>());
+            LAUNCH(c, k_twin_compact, 1, 1024, 0, p->d_K.as<long long>(), st, (const unsigned char *)v->d_tflag.as<unsigned char>(),
+                   v->d_act.as<int>());
+            const int64_t fwork = work * v->n_rows;
+            const int fgrid = (int)std::min<int64_t>(std::max<int64_t>((fwork + 255) / 256, 1), 8 * c->sm_count);
+            LAUNCH(c, k_view_fill, fgrid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(), v->n_rows, v->s_pad,
+                   v->d_piS.as<double>(), (const TwinState *)st, (const int *)v->d_act.as<int>());
+        }
+        v->synced_lo = p->K;                // confirmed vertices: a lower bound of the device's mark
+        v->twin_epoch = p->push_epoch;
+        return;
+    }
     if (hi > v->synced_lo) {
         int64_t work = (hi - v->synced_lo) * v->n_rows;
         int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 8 * c->sm_count);

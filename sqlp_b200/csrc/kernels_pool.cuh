@@ -213,4 +213,173 @@ __global__ void k_epi_tables(const double *__restrict__ pi, int m2, const int *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Score-equivalent vertices ("twins").  A vertex enters a score only through the rows where
+//   rbar != 0, or Tbar has an entry, or a random element lives            (the RELEVANT rows):
+//   score_x[k, i] = pi_k . (rbar - Tbar x) + pi_k|_S . d_i,   rho_k = pi_k . rbar,   tau_k = Tbar' pi_k.
+// On every other row (rbar - Tbar x) is exactly +0.0 for every x.  Degenerate stage-2 LPs return many optimal
+// duals that differ ONLY there (storm: 16 384 harvested vertices are 3 599 classes): distinct for the
+// reference's dedup rule (dual_set.jl:24-40 compares all rows), identical -- bit for bit -- in every score
+// and every cut coefficient.  argmax_procedure keeps the FIRST maximum (subprob.jl:156), so a later twin can
+// never be selected: leaving it out of the sweep changes no index, no value and no cut.
+// The pool view therefore holds one column per CLASS: act[v] = pool index of the first vertex of class v,
+// ascending, so "first view slot" = "first pool index".  A vertex with a non-finite entry anywhere is kept
+// apart (never a representative, never shadowed): 0 * Inf is NaN, not zero.
+// Everything is decided on the device (pushes are enqueued, not awaited) and deterministically: the
+// representative of a class is its LOWEST pool index (atomicMin), whatever the thread order.
+struct TwinState {
+    long long synced;      // pool vertices [0, synced) have been classified
+    long long Kv;          // classes = columns of the view
+    long long Kv_prev;     // Kv before the last classification (the fill kernels work on [Kv_prev, Kv))
+};
+#define SQLP_TWIN_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ unsigned long long twin_mix(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// One warp per new vertex: hash of its relevant rows (order-independent sum of position-keyed element hashes),
+// finiteness of ALL its rows, and its entry in the table (lowest pool index per hash value).
+__global__ void k_twin_hash(const double *__restrict__ pi, int m2, const int *__restrict__ rel, int n_rel,
+                            const long long *__restrict__ d_K, const TwinState *__restrict__ st,
+                            unsigned long long *__restrict__ hk, unsigned long long *__restrict__ tkey,
+                            int *__restrict__ trep, unsigned int tmask)
+{
+    griddep_sync();
+    const long long K = *d_K, lo = st->synced;
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long k = lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nw) {
+        const double *row = pi + k * (long long)m2;
+        bool fin = true;
+        for (int j = lane; j < m2; j += 32) fin = fin && isfinite(row[j]);
+        unsigned long long h = 0;
+        for (int q = lane; q < n_rel; q += 32)
+            h += twin_mix((unsigned long long)__double_as_longlong(row[rel[q]]) ^ ((unsigned long long)(q + 1) * 0xD6E8FEB86659FD93ULL));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
+        fin = __all_sync(0xffffffffu, fin);
+        h &= ~1ull;                                     // bit 0 of the stored word says "finite"
+        if (h == (SQLP_TWIN_EMPTY & ~1ull)) h = 2;
+        if (lane == 0) {
+            hk[k] = h | (fin ? 1ull : 0ull);
+            if (fin) {
+                unsigned int p = (unsigned int)(h >> 17) & tmask;
+                for (;;) {
+                    const unsigned long long old = atomicCAS(tkey + p, SQLP_TWIN_EMPTY, h);
+                    if (old == SQLP_TWIN_EMPTY || old == h) { atomicMin(trep + p, (int)k); break; }
+                    p = (p + 1) & tmask;
+                }
+            }
+        }
+    }
+}
+
+// One warp per new vertex: is it the first of its class?  flag[k - synced] = 1 keeps it.
+__global__ void k_twin_mark(const double *__restrict__ pi, int m2, const int *__restrict__ rel, int n_rel,
+                            const long long *__restrict__ d_K, const TwinState *__restrict__ st,
+                            const unsigned long long *__restrict__ hk, const unsigned long long *__restrict__ tkey,
+                            const int *__restrict__ trep, unsigned int tmask, unsigned char *__restrict__ flag)
+{
+    griddep_sync();
+    const long long K = *d_K, lo = st->synced;
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long k = lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nw) {
+        const unsigned long long w = hk[k];
+        bool keep = true;
+        if (w & 1ull) {
+            const unsigned long long h = w & ~1ull;
+            unsigned int p = (unsigned int)(h >> 17) & tmask;
+            while (tkey[p] != h) p = (p + 1) & tmask;    // inserted by k_twin_hash: always found
+            const int r = trep[p];
+            if (r != (int)k) {
+                // same hash, lower index: a twin iff the relevant rows agree bit for bit (else a hash collision)
+                const double *a = pi + k * (long long)m2, *b = pi + (long long)r * m2;
+                bool same = true;
+                for (int q = lane; q < n_rel; q += 32)
+                    same = same && (__double_as_longlong(a[rel[q]]) == __double_as_longlong(b[rel[q]]));
+                keep = !__all_sync(0xffffffffu, same);
+            }
+        }
+        if (lane == 0) flag[k - lo] = keep ? 1 : 0;
+    }
+}
+
+// One block: the kept vertices, in pool order, get the next view slots.
+__global__ void __launch_bounds__(1024) k_twin_compact(const long long *__restrict__ d_K, TwinState *__restrict__ st,
+                                                       const unsigned char *__restrict__ flag, int *__restrict__ act)
+{
+    griddep_sync();
+    __shared__ int wsum[32], wexcl[32];
+    __shared__ int total_sh;
+    __shared__ long long base_sh;
+    const long long K = *d_K, lo = st->synced;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_sh = st->Kv;
+    __syncthreads();
+    for (long long k0 = lo; k0 < K; k0 += blockDim.x) {
+        const long long k = k0 + threadIdx.x;
+        const int f = (k < K) ? (int)flag[k - lo] : 0;
+        int incl = f;                                    // inclusive scan inside the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {                                 // scan of the 32 warp totals
+            const int v = wsum[lane];
+            int ws = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, ws, off);
+                if (lane >= off) ws += t;
+            }
+            wexcl[lane] = ws - v;
+            if (lane == 31) total_sh = ws;
+        }
+        __syncthreads();
+        const long long base = base_sh;
+        if (f) act[base + wexcl[warp] + incl - 1] = (int)k;
+        __syncthreads();
+        if (threadIdx.x == 0) base_sh = base + total_sh;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        st->Kv_prev = st->Kv;
+        st->Kv = base_sh;
+        st->synced = K;
+    }
+}
+
+// View columns [Kv_prev, Kv) from the pool rows of their representatives (same tile layout as k_view_sync).
+__global__ void k_view_fill(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows, int n_rows, int s_pad,
+                            double *__restrict__ piS, const TwinState *__restrict__ st, const int *__restrict__ act)
+{
+    griddep_sync();
+    const long long v0 = st->Kv_prev, v1 = st->Kv;
+    const long long total = (v1 - v0) * n_rows;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long v = v0 + t / n_rows;
+        const int j = (int)(t % n_rows);
+        piS[(v >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(v & 127), j)] = pi[(long long)act[v] * m2 + s_rows[j]];
+    }
+}
+
+// argmax_procedure's indices back from view slots to pool slots.
+__global__ void k_unmap_idx(int *__restrict__ idx, long long n, const int *__restrict__ act)
+{
+    griddep_sync();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = idx[i];
+        if (v >= 0) idx[i] = act[v];
+    }
+}
+
 }  // namespace sqlp

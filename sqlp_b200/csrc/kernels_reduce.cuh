@@ -39,10 +39,11 @@ __global__ void k_base(const double *__restrict__ rbar, int m2, int n1,
 // bias_x[k] = dot(pi_k, base_x)  (the first dot of subprob.jl:155), one warp per vertex,
 // lanes stride the row, fixed shuffle tree.  Slots K..kpad-1 get -inf so padded vertices
 // of the last chunk can never win.
+// With twins (kernels_pool.cuh) k runs over the view's columns and act[k] is the pool slot of the class's first vertex.
 template <int NX>
 __global__ void k_bias(const double *__restrict__ pi, int m2, const double *__restrict__ base,
                        const long long *__restrict__ d_K, long long kpad, double *__restrict__ bias,
-                       long long bias_stride)
+                       long long bias_stride, const int *__restrict__ act)
 {
     griddep_sync();
     const long long K = *d_K;
@@ -53,7 +54,7 @@ __global__ void k_bias(const double *__restrict__ pi, int m2, const double *__re
         if (lane < NX) bias[lane * bias_stride + k] = -INFINITY;
         return;
     }
-    const double *row = pi + k * (long long)m2;
+    const double *row = pi + (act ? (long long)act[k] : k) * (long long)m2;
     double s[NX];
 #pragma unroll
     for (int x = 0; x < NX; ++x) s[x] = 0.0;
@@ -75,7 +76,8 @@ struct ReduceArgs {
     const double *dT;         // [n_local][n_T] or null
     const double *w;          // [n_local]
     const double *PiS;        // [nchunks] fragment-major tiles
-    const double *rt;         // [K][n1 + 1]  (rho, tau)
+    const double *rt;         // [K][n1 + 1]  (rho, tau), by POOL slot
+    const int *act;           // view column -> pool slot (twins), or null: the identity
     const double *bias;       // [NX][bias_stride] of the contraction that produced best_*, or null
     long long bias_stride;    //   (null: some element perturbs Tbar, the winning dot is recomputed from D)
     const double *best_val;   // [NX][out_stride]
@@ -100,7 +102,8 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
     griddep_sync();
     __shared__ double a_i[NX][SQLP_TILE];   // PiS[k*, :] . delta_rhs_i
     __shared__ double p_i[SQLP_TILE];
-    __shared__ int k_i[NX][SQLP_TILE];
+    __shared__ int k_i[NX][SQLP_TILE];        // winning view column (bias, pool view)
+    __shared__ int kp_i[NX][SQLP_TILE];       // its pool slot (rho, tau table)
     const long long tile = blockIdx.x;
     const long long i0 = tile * SQLP_TILE;
     const int cnt = (int)min((long long)SQLP_TILE, a.n_local - i0);
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
                 // ... unless the score is so much larger than what alpha is made of (rho_k + dot) that half an
                 // ulp of it shows at the 1e-10 level: |tau_k . x| >> |rho_k|, |dot| (x far from the data's
                 // scale).  Then the dot is recomputed from D like in the delta_T != 0 case below.
-                need_dot = fabs(sc) > 8192.0 * fmax(fabs(a.rt[(long long)k * (a.n1 + 1)]), fabs(acc));
+                need_dot = fabs(sc) > 8192.0 * fmax(fabs(a.rt[(long long)(a.act ? a.act[k] : k) * (a.n1 + 1)]), fabs(acc));
             }
             if (k >= 0 && (!a.bias || need_dot)) {
                 // slots in order; a k-group (4 slots) is 512 doubles further in both tiles and its
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
         }
         a_i[x][c] = acc;
         k_i[x][c] = k;
+        kp_i[x][c] = (k >= 0 && a.act) ? a.act[k] : k;
     }
     __syncthreads();
 
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
             for (int c = c0; c < min(c1, cnt); ++c) {
                 const int k = k_i[x][c];
                 if (k < 0) continue;
-                double term = a.rt[(long long)k * RT + col];                           // :141
+                double term = a.rt[(long long)kp_i[x][c] * RT + col];                  // :141
                 for (int t = t0; t < t1; ++t) {
                     const double piv =
                         a.PiS[(long long)(k >> 7) * a.s_pad * SQLP_TILE + tile_off(k & 127, a.tc_j[t])];
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(256) k_cut_partial(ReduceArgs a)
                 double tv[8], pw[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int c = cb + u, k = k_i[x][c];
+                    const int c = cb + u, k = kp_i[x][c];
                     const bool ok = (k >= 0);
                     const double v = ok ? (is_val ? src[c] : src[(long long)k * stride]) : 0.0;
                     tv[u] = is_alpha ? v + (ok ? a_i[x][c] : 0.0) : v;

@@ -334,22 +334,25 @@ __device__ __forceinline__ void atomic_max_pos(float *addr, float v)   // v >= 0
 
 // Pool view for screening: vertices [k_lo, K) restricted to the stochastic rows, split in bf16 hi / lo,
 // plus ||PiS[k]||_2 (rounded up) and its maximum per chunk of 256.  One warp per vertex.
+// k runs over the view's columns [*mark, K); act (twins, kernels_pool.cuh) maps a column to its pool slot.  The
+// mark is advanced by k_screen_mark, the next kernel of the stream.
 __global__ void k_screen_view_sync(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows, int n_rows,
                                    int sp, __nv_bfloat16 *__restrict__ PiB, float *__restrict__ pn,
-                                   float *__restrict__ pnmax, int *__restrict__ bad, long long k_lo,
-                                   const long long *__restrict__ d_K)
+                                   float *__restrict__ pnmax, int *__restrict__ bad, long long *__restrict__ mark,
+                                   const long long *__restrict__ d_K, const int *__restrict__ act)
 {
     griddep_sync();
-    const long long K = *d_K;
+    const long long K = *d_K, k_lo = *mark;
     const int lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     const int J = sp / 16;
     for (long long k = k_lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nw) {
         const long long c = k / SCR_NB;
         const int v = (int)(k % SCR_NB);
+        const long long kp = act ? (long long)act[k] : k;
         double ss = 0.0;
         for (int j = lane; j < sp; j += 32) {
-            const double p = j < n_rows ? pi[k * m2 + s_rows[j]] : 0.0;
+            const double p = j < n_rows ? pi[kp * m2 + s_rows[j]] : 0.0;
             __nv_bfloat16 hi, lo;
             split_bf16(p, hi, lo);
             const size_t off = ((size_t)(c * J + j / 16) * 2) * (2 * SCR_NB * 8) + (size_t)((j % 16) / 8) * (SCR_NB * 8) +
@@ -367,6 +370,12 @@ __global__ void k_screen_view_sync(const double *__restrict__ pi, int m2, const 
             else *bad = 1;                                        // Inf / NaN / out of bf16-safe range
         }
     }
+}
+
+__global__ void k_screen_mark(long long *__restrict__ mark, const long long *__restrict__ d_K)
+{
+    griddep_sync();
+    if (threadIdx.x == 0 && blockIdx.x == 0) *mark = *d_K;
 }
 
 // Scenario store for screening: local scenarios [lo, n_local) from the FP64 tiles, split in bf16 hi / lo,

@@ -77,6 +77,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     }
     if (const char *g = getenv("SQLP_PDL")) c->pdl = atoi(g) != 0;
     if (const char *g = getenv("SQLP_SCREEN")) c->screen_mode = std::max(0, std::min(2, atoi(g)));
+    if (const char *g = getenv("SQLP_TWINS")) c->twins = atoi(g) != 0;
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_LAG_NS")) c->contract_lag_ns = atoi(g);
@@ -450,12 +451,22 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
             }
             std::sort(rows.begin(), rows.end());
             rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
-            // share the pool view with any epigraph that has the same row set
+            // relevant rows: the only rows through which a vertex enters a score or a cut coefficient
+            std::vector<int> rel(rows);
+            for (int64_t j = 0; j < m2; ++j)
+                if (e->h_rbar[(size_t)j] != 0.0) rel.push_back((int)j);
+            for (int64_t q = 0; q < nnz; ++q) rel.push_back(e->h_rowval[(size_t)q]);
+            std::sort(rel.begin(), rel.end());
+            rel.erase(std::unique(rel.begin(), rel.end()), rel.end());
+            // share the pool view with any epigraph that has the same row sets
             for (PoolView *v : p->views)
-                if (v->rows == rows) e->view = v;
+                if (v->rows == rows && v->rel == rel) e->view = v;
             if (!e->view) {
                 PoolView *v = new PoolView();
                 v->rows = rows;
+                v->rel = rel;
+                v->twins = c->twins && (int64_t)rel.size() < m2;   // some row can never matter: classes may exist
+                if (v->twins) upload(v->d_rel, rel, S(c));
                 v->n_rows = (int)rows.size();
                 v->s_pad = (int)std::max<int64_t>(SQLP_BK, round_up(v->n_rows, SQLP_BK));
                 upload(v->d_rows, rows, S(c));
@@ -658,6 +669,21 @@ int32_t sqlp_epi_counts(sqlp_epi *e, int64_t *n_global, int64_t *n_local, double
     });
 }
 
+int32_t sqlp_epi_view_columns(sqlp_epi *e, int64_t *columns, int64_t *relevant_rows)
+{
+    return guard([&] {
+        REQUIRE(e, SQLP_E_INVALID, "null epigraph");
+        sqlp_ctx *c = e->ctx;
+        c->bind();
+        view_sync(e->pool, e->view);
+        long long kv = 0;
+        CK(cudaMemcpyAsync(&kv, e->view->d_Kv(e->pool), 8, cudaMemcpyDeviceToHost, S(c)));
+        CK(cudaStreamSynchronize(S(c)));
+        if (columns) *columns = kv;
+        if (relevant_rows) *relevant_rows = (int64_t)e->view->rel.size();
+    });
+}
+
 int32_t sqlp_epi_delta(sqlp_epi *e, int64_t i, double *delta_rhs, double *delta_T)
 {
     return guard([&] {
@@ -702,6 +728,9 @@ int32_t sqlp_epi_argmax(sqlp_epi *e, const double *x, int32_t sense, double *max
         e->cur_bias = nullptr;
         epi_cuts_enqueue(e, 1, x, nullptr, false);
         std::vector<int> idx((size_t)e->n_local);
+        if (e->view->twins)   // the sweep works on view columns: back to pool slots (the Refs the reference returns)
+            LAUNCH(c, k_unmap_idx, (int)std::min<int64_t>((e->n_local + 255) / 256, 4 * c->sm_count), 256, 0,
+                   e->d_best_idx.as<int>(), (long long)e->n_local, e->view->act());
         CK(cudaMemcpyAsync(max_val, e->d_best_val.p, (size_t)e->n_local * 8, cudaMemcpyDeviceToHost, S(c)));
         CK(cudaMemcpyAsync(idx.data(), e->d_best_idx.p, (size_t)e->n_local * 4, cudaMemcpyDeviceToHost, S(c)));
         pool_confirm(e->pool);

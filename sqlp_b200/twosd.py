@@ -521,6 +521,12 @@ class sdEpigraph:
             check(_lib.lib().sqlp_epi_master_rows(self._h, _ptr(rows), C.byref(n)))
         return rows
 
+    def view_columns(self):
+        """(classes of score-equivalent vertices the sweep visits, relevant rows) -- ``sqlp_epi_view_columns``."""
+        kv, nr = C.c_int64(), C.c_int64()
+        check(_lib.lib().sqlp_epi_view_columns(self._h, C.byref(kv), C.byref(nr)))
+        return kv.value, nr.value
+
     def screen_stats(self) -> dict:
         out = np.zeros(8, dtype=np.int64)
         check(_lib.lib().sqlp_epi_screen_stats(self._h, _ptr(out)))

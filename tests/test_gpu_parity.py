@@ -552,7 +552,8 @@ def test_device_profiler_classes(T, oracle):
     assert prof["contract"][1] == 1 and prof["contract"][2] == 2.0 * s * K * N
     assert prof["delta"][1] == 1 and prof["delta"][2] == 16.0 * s * N
     assert prof["reduce"][1] == 1 and prof["pool"][1] == 1 and prof["bias"][1] == 1
-    assert all(prof[k][0] > 0 for k in prof)
+    assert all(prof[k][0] > 0 for k in ("contract", "delta", "reduce", "pool", "bias"))
+    assert prof["screen"][1] == 0 and prof["fallback"][1] == 0      # a shape this small is swept in FP64
     assert ctx.profile_classes()["contract"][1] == 0         # reset
 
 

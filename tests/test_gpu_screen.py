@@ -158,3 +158,85 @@ def test_growing_pool_and_scenarios(T, ctx):
         b = epi.argmax(x)
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
     assert epi.screen_stats()["passes"] >= 6
+
+
+# ---- score-equivalent vertices ("twins", csrc/kernels_pool.cuh) ---------------------------------------------
+
+def test_twins_leave_results_bit_identical(T, monkeypatch):
+    """storm's real duals: 16 384 vertices, far fewer classes on the relevant rows.  The sweep over one column per
+    class must give the argmax (pool slots!), the values and the cuts of the sweep over every vertex, bit for bit --
+    with the pool pushed at once or a few vertices per iteration, FP64 sweep or screening pass."""
+    P, z = load_instance("storm")
+    pool = load_pool("storm", 16384)[:6000]
+    N = 3000
+    vals = sampled_values_at(z, 3, np.arange(N))
+    w = 0.5 + (np.arange(N) % 5) / 5.0
+    xs = (z["x_ev"], z["x_alt"])
+
+    def run(twins, incremental, screen):
+        monkeypatch.setenv("SQLP_TWINS", "1" if twins else "0")
+        ctx = T.Context(0)
+        ctx.set_screen(screen)
+        dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+        epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+        epi.add_scenarios(vals, w)
+        if incremental:
+            dvs.push_many(pool[:900])
+            for a in range(900, len(pool), 700):               # crosses capacity doublings of the pool
+                dvs.push_many(pool[a:a + 700])
+                epi.argmax(xs[0])
+        else:
+            dvs.push_many(pool)
+        out = [epi.argmax(x) for x in xs]
+        (c0, c1), val = epi.build_cuts2(*xs, with_val=True)
+        cols = epi.view_columns()
+        res = (out, np.array([c0.alpha, c1.alpha]), np.stack([c0.beta, c1.beta]), val, cols)
+        epi.close(); dvs.close(); ctx.close()
+        return res
+
+    ref = run(False, False, 0)
+    assert ref[4] == (len(pool), P.m2) or ref[4][0] == len(pool)
+    for twins, inc, screen in ((True, False, 0), (True, True, 0), (True, False, 2), (True, True, 2)):
+        got = run(twins, inc, screen)
+        assert got[4][0] < len(pool) // 2 and got[4][1] < P.m2, got[4]       # classes, relevant rows
+        for (rv, ri), (gv, gi) in zip(ref[0], got[0]):
+            assert np.array_equal(ri, gi) and np.array_equal(rv.view(np.uint64), gv.view(np.uint64))
+        for a, b in zip(ref[1:4], got[1:4]):
+            assert np.array_equal(np.asarray(a).view(np.uint64), np.asarray(b).view(np.uint64))
+    print("storm K=6000 real:", got[4][0], "classes on", got[4][1], "relevant rows of", P.m2)
+
+
+def test_twins_keep_nonfinite_vertices_apart(T, monkeypatch):
+    """0 * Inf is NaN: a vertex with a non-finite entry on an irrelevant row is neither a representative nor
+    shadowed."""
+    P = synthetic_problem(m2=64, n1=10, s=24)
+    N, K = 700, 300
+    vals = synthetic_values(P, N, seed=2)
+    pool = synthetic_pool(P.m2, K, seed=8)
+    rel = np.zeros(P.m2, bool)
+    rel[P.pos_row] = True; rel[P.rbar != 0] = True; rel[P.T_rowval] = True
+    free = np.nonzero(~rel)[0]
+    assert len(free) >= 2
+    for k in range(50, 150):                     # twins of vertices 0..99: differ on an irrelevant row only
+        pool[k] = pool[k - 50]
+        pool[k, free[0]] += 1.0 + k
+    pool[10, free[1]] = np.inf                   # the representative of 60 is not finite: 60 must stay in the sweep
+    pool[70, free[1]] = np.nan                   # a shadowed vertex that is not finite: kept apart, never wins
+    x = np.linspace(0.5, 2.0, P.n1)
+
+    def run(twins):
+        monkeypatch.setenv("SQLP_TWINS", "1" if twins else "0")
+        ctx = T.Context(0)
+        dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+        dvs.push_many(pool)
+        epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+        epi.add_scenarios(vals, None)
+        mv, mi = epi.argmax(x)
+        cut = epi.build_cut(x)
+        cols = epi.view_columns()[0]
+        epi.close(); dvs.close(); ctx.close()
+        return mv, mi, cut, cols
+    a, b = run(False), run(True)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
+    assert a[2].alpha == b[2].alpha and np.array_equal(a[2].beta, b[2].beta)
+    assert a[3] == K and b[3] == K - 100 + 2, (a[3], b[3])      # 100 twins, 2 of them kept apart
