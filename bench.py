@@ -745,6 +745,7 @@ def parity_sample(args, T, dist, cell, world, rank, alpha, beta, x_c, x_i, pool_
         for a in range(0, n_glob, 32768):
             vals[a:a + 32768] = sample_values(z, 101, a, min(32768, n_glob - a))
         w = 0.5 + u01(201, g)
+        w[cell.n_epi_global:] = 1.0          # the scenarios the SD iterations appended carry weight 1 (algorithm.jl:46)
         worst = 0.0
         for xi_, x in enumerate((x_c, x_i)):
             ref = O.build_sasa_cut(P, vals, w, x, pool, forced_idx=idx_glob[xi_])

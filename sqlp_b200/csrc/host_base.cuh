@@ -57,6 +57,9 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -83,6 +86,9 @@ void load_nccl()
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
     g_nccl.Broadcast = (decltype(g_nccl.Broadcast))sym("ncclBroadcast");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
     g_nccl.h = h;
 }
@@ -160,6 +166,10 @@ void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
 struct sqlp_ctx {
     int device = 0;
     int rank = 0, world = 1;
+    // one host thread driving several GPUs (sqlp_ctx_create_multi): the leader (rank 0) lists the contexts of
+    // ranks 1 .. world-1; every handle created on the leader carries its shards on them the same way
+    std::vector<sqlp_ctx *> peers;
+    bool one_process = false;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -253,6 +263,7 @@ struct sqlp_pool {
     DevBuf d_pi, d_hash, d_K, d_scratch, d_vnew, d_vr, d_results;
     std::vector<PoolView *> views;
     std::vector<sqlp_epi *> epis;
+    std::vector<sqlp_pool *> peers;   // multi-GPU context: the replicas on ranks 1 .. world-1
     int64_t upper() const { return K + pending; }
 };
 
@@ -265,6 +276,7 @@ struct sqlp_epi {
     sqlp_ctx *ctx = nullptr;
     sqlp_pool *pool = nullptr;
     PoolView *view = nullptr;
+    std::vector<sqlp_epi *> peers;    // multi-GPU context: the shards on ranks 1 .. world-1
     int64_t m2 = 0, n1 = 0, s = 0;
     int n_T = 0;
     // template coefficients

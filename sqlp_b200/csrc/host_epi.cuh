@@ -587,10 +587,15 @@ struct CellGather {
         c->d_cellg.ensure((size_t)c->world * total * 8, 0, S(c), false);
     }
     double *slot(int i) const { return c->world > 1 ? c->d_cell.as<double>() + off[(size_t)i] : nullptr; }
-    void run()
+    void run() { gather(); sum(); }
+    void gather()
     {
         if (c->world <= 1 || epis.empty()) return;
         NK(g_nccl.AllGather(c->d_cell.p, c->d_cellg.p, total, ncclFloat64_, c->comm, S(c)));
+    }
+    void sum()
+    {
+        if (c->world <= 1 || epis.empty()) return;
         for (size_t i = 0; i < epis.size(); ++i) {
             sqlp_epi *e = epis[i];
             const int width = NX * ((int)e->n1 + 2);
@@ -599,6 +604,58 @@ struct CellGather {
         }
     }
 };
+
+// ---- one host thread, several GPUs (sqlp_ctx_create_multi) -----------------------------------------------
+// Shard s of a handle: s = 0 the leader's own, s >= 1 the replica on rank s.
+int n_shards(const sqlp_ctx *c) { return 1 + (int)c->peers.size(); }
+sqlp_ctx *shard(sqlp_ctx *c, int s) { return s == 0 ? c : c->peers[(size_t)s - 1]; }
+sqlp_pool *shard(sqlp_pool *p, int s) { return s == 0 ? p : p->peers[(size_t)s - 1]; }
+sqlp_epi *shard(sqlp_epi *e, int s) { return s == 0 ? e : e->peers[(size_t)s - 1]; }
+
+sqlp_epi *bias_twin(int i, sqlp_epi *const *epi);
+
+// The cuts of a cell at NX points on every GPU of the context: each GPU's chain is enqueued on its own stream (so
+// the GPUs work side by side), then ONE grouped all-gather, then the rank-ordered sums -- every GPU ends with the
+// same bits in d_out / d_flags, the leader's are what the caller reads.  x2[i] = the points of epigraph i (host).
+void cell_cuts_all_shards(sqlp_ctx *c, int NX, int n_epi, sqlp_epi *const *epi, const std::vector<std::vector<double>> &x2)
+{
+    const int ns = n_shards(c);
+    std::vector<std::vector<sqlp_epi *>> es((size_t)ns);
+    std::vector<std::unique_ptr<CellGather>> cg;
+    for (int s = 0; s < ns; ++s) {
+        sqlp_ctx *cs = shard(c, s);
+        cs->bind();
+        for (int i = 0; i < n_epi; ++i) {
+            es[(size_t)s].push_back(shard(epi[i], s));
+            es[(size_t)s].back()->cur_bias = nullptr;
+        }
+        cg.emplace_back(new CellGather(cs, NX, n_epi, es[(size_t)s].data()));
+        for (int i = 0; i < n_epi; ++i)
+            epi_cuts_enqueue(es[(size_t)s][(size_t)i], NX, x2[(size_t)i].data(), nullptr, true,
+                             bias_twin(i, es[(size_t)s].data()), cg.back()->slot(i));
+    }
+    if (ns > 1) {
+        NK(g_nccl.GroupStart());          // one thread, several communicators: the collective is issued as a group
+        for (int s = 0; s < ns; ++s) { shard(c, s)->bind(); cg[(size_t)s]->gather(); }
+        NK(g_nccl.GroupEnd());
+        for (int s = 0; s < ns; ++s) { shard(c, s)->bind(); cg[(size_t)s]->sum(); }
+    } else {
+        cg[0]->run();
+    }
+    c->bind();
+}
+
+// Drain every GPU of the context; pools of the peers learn their size.
+void sync_all_shards(sqlp_ctx *c, sqlp_pool *p)
+{
+    for (int s = 1; s < n_shards(c); ++s) {
+        sqlp_ctx *cs = shard(c, s);
+        cs->bind();
+        if (p) pool_confirm(shard(p, s));
+        CK(cudaStreamSynchronize(S(cs)));
+    }
+    c->bind();
+}
 
 // Among the epigraphs of one call: the first earlier one whose bias vectors this one can reuse.
 sqlp_epi *bias_twin(int i, sqlp_epi *const *epi)

@@ -47,13 +47,16 @@ void pool_push_enqueue(sqlp_pool *p, int64_t n, const double *v_host, const doub
     const double *src = v_dev;
     if (!v_dev || c->world > 1) {
         p->d_vnew.ensure((size_t)n * p->m2 * 8, 0, S(c));
-        if (v_host && (c->world == 1 || c->rank == 0))
+        // one process per GPU: rank 0's vectors count and are broadcast.  One process for all GPUs
+        // (sqlp_ctx_create_multi): the host hands the same vectors to every GPU, no collective needed.
+        const bool mine = c->world == 1 || c->rank == 0 || c->one_process;
+        if (v_host && mine)
             CK(cudaMemcpyAsync(p->d_vnew.p, v_host, (size_t)n * p->m2 * 8, cudaMemcpyHostToDevice, S(c)));
-        else if (v_dev && (c->world == 1 || c->rank == 0))
+        else if (v_dev && mine)
             CK(cudaMemcpyAsync(p->d_vnew.p, v_dev, (size_t)n * p->m2 * 8, cudaMemcpyDeviceToDevice, S(c)));
         else
             REQUIRE(c->world > 1 && c->rank != 0, SQLP_E_INVALID, "push: null vector");
-        if (c->world > 1)   // each new dual vertex is broadcast from rank 0 over NCCL/NVLink
+        if (c->world > 1 && !c->one_process)   // each new dual vertex is broadcast from rank 0 over NCCL/NVLink
             NK(g_nccl.Broadcast(p->d_vnew.p, p->d_vnew.p, (size_t)n * p->m2, ncclFloat64_, 0,
                                 c->comm, S(c)));
         src = p->d_vnew.as<double>();

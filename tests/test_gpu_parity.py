@@ -549,7 +549,9 @@ def test_device_profiler_classes(T, oracle):
     prof = ctx.profile_classes(reset=True)
     ctx.profile(False)
     K, s = len(z["pool"]), P.s
-    assert prof["contract"][1] == 1 and prof["contract"][2] == 2.0 * s * K * N
+    cols, _ = epi.view_columns()                 # flops are counted with the columns the launch swept: one per class
+    assert cols <= K                             # of score-equivalent vertices (92 of these 94 harvested duals)
+    assert prof["contract"][1] == 1 and prof["contract"][2] == 2.0 * s * cols * N
     assert prof["delta"][1] == 1 and prof["delta"][2] == 16.0 * s * N
     assert prof["reduce"][1] == 1 and prof["pool"][1] == 1 and prof["bias"][1] == 1
     assert all(prof[k][0] > 0 for k in ("contract", "delta", "reduce", "pool", "bias"))
