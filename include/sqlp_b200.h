@@ -66,6 +66,17 @@ SQLP_API int32_t sqlp_ctx_create(int32_t device, sqlp_ctx **out);
 SQLP_API int32_t sqlp_nccl_unique_id(void *out128);
 SQLP_API int32_t sqlp_ctx_create_dist(int32_t device, int32_t rank, int32_t world,
                                       const void *nccl_id, sqlp_ctx **out);
+/* ONE host thread driving n GPUs -- what a single-threaded host such as the reference's sd_iteration!
+ * (algorithm.jl:39-115) needs to reach every GPU of the box without becoming an SPMD job.  devices = NULL
+ * means 0 .. n-1.  The returned context is used exactly like a single-GPU one: every handle created on it is
+ * replicated (pools) or sharded (epigraphs: scenario g on GPU (g / 128) % n) behind the scenes, each call drives
+ * all GPUs side by side on their own streams, the host hands pushed vertices to every GPU itself (no broadcast),
+ * the per-epigraph partials of a call travel in one grouped ncclAllGather (ncclCommInitAll communicators) and
+ * are summed in rank order on every GPU -- the same kernels and the same bits as one process per GPU.
+ * sqlp_epi_argmax returns all scenarios in GLOBAL order.  Calls taking device pointers (`_dev`) are single-GPU
+ * only and return SQLP_E_UNSUPPORTED here; the cut list (sqlp_epi_cuts_*), sqlp_epi_delta, sqlp_eval_dual and
+ * the profiling calls act on the first GPU. */
+SQLP_API int32_t sqlp_ctx_create_multi(int32_t n_gpus, const int32_t *devices, sqlp_ctx **out);
 SQLP_API int32_t sqlp_ctx_destroy(sqlp_ctx *ctx);
 
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the

@@ -39,15 +39,37 @@ def sources():
     return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [HEADER]
 
 
+def source_id() -> str:
+    """Content hash of every source of the library and of the compile flags: the binary carries it
+    (``sqlp_version()``), so a stale .so is recognised whatever its timestamps say."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sources():
+        with open(p, "rb") as fh:
+            h.update(os.path.basename(p).encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def built_id(path: str = None) -> str | None:
+    """The source id compiled into an existing binary (read from the file, no CUDA needed)."""
+    path = path or SO_PATH
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as fh:
+        blob = fh.read()
+    i = blob.find(b"sqlp-build-id:")
+    return blob[i + 14:i + 30].decode("ascii", "replace") if i >= 0 else None
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> sqlp_b200/libsqlp_b200.so"""
-    newest = max(os.path.getmtime(p) for p in sources())
-    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= newest:
+    sid = source_id()
+    if not force and built_id() == sid:
         return SO_PATH
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", SO_PATH, SRC, "-ldl"]
+    cmd = [nvcc, *NVCC_FLAGS, f"-DSQLP_BUILD_ID=\"{sid}\"", "-o", SO_PATH, SRC, "-ldl"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -64,6 +86,7 @@ SIGNATURES = {
     "sqlp_ctx_create": [_i32, _P(_vp)],
     "sqlp_nccl_unique_id": [_vp],
     "sqlp_ctx_create_dist": [_i32, _i32, _i32, _vp, _P(_vp)],
+    "sqlp_ctx_create_multi": [_i32, _vp, _P(_vp)],
     "sqlp_ctx_destroy": [_vp],
     "sqlp_ctx_set_stream": [_vp, _vp],
     "sqlp_ctx_synchronize": [_vp],
@@ -132,6 +155,9 @@ def lib():
         if not os.path.exists(SO_PATH):
             raise SqlpError(E_CUDA, f"{SO_PATH} is missing: run `python -c 'import "
                                     "__graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        if not os.environ.get("SQLP_B200_LIB") and built_id() != source_id():
+            raise SqlpError(E_CUDA, f"{SO_PATH} was built from other sources (binary {built_id()}, tree "
+                                    f"{source_id()}): rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
         L = C.CDLL(SO_PATH)
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)

@@ -52,7 +52,11 @@
 // ================================================================ C ABI =================
 extern "C" {
 
-const char *sqlp_version(void) { return "sqlp_b200 0.1 (sm_100a)"; }
+#ifndef SQLP_BUILD_ID
+#define SQLP_BUILD_ID "unidentified..."
+#endif
+// "sqlp-build-id:<hash of the sources>" is searched for in the binary by sqlp_b200/_lib.py: a stale .so is refused
+const char *sqlp_version(void) { return "sqlp_b200 0.2 (sm_100a) sqlp-build-id:" SQLP_BUILD_ID; }
 const char *sqlp_last_error(void) { return g_err.c_str(); }
 
 static void ctx_init(sqlp_ctx *c, int32_t device)
@@ -136,8 +140,47 @@ int32_t sqlp_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const 
     });
 }
 
+int32_t sqlp_ctx_create_multi(int32_t n_gpus, const int32_t *devices, sqlp_ctx **out)
+{
+    return guard([&] {
+        REQUIRE(out && n_gpus >= 1 && n_gpus <= 64, SQLP_E_INVALID, "bad argument");
+        std::vector<int> dev((size_t)n_gpus);
+        for (int i = 0; i < n_gpus; ++i) {
+            dev[(size_t)i] = devices ? devices[i] : i;
+            for (int j = 0; j < i; ++j) REQUIRE(dev[(size_t)j] != dev[(size_t)i], SQLP_E_INVALID, "device listed twice");
+        }
+        std::vector<sqlp_ctx *> cs;
+        try {
+            for (int i = 0; i < n_gpus; ++i) {
+                cs.push_back(new sqlp_ctx());
+                ctx_init(cs.back(), dev[(size_t)i]);
+                cs.back()->rank = i;
+                cs.back()->world = n_gpus;
+                cs.back()->one_process = true;
+            }
+            if (n_gpus > 1) {
+                load_nccl();
+                std::vector<ncclComm_t> comms((size_t)n_gpus);
+                NK(g_nccl.CommInitAll(comms.data(), n_gpus, dev.data()));
+                for (int i = 0; i < n_gpus; ++i) cs[(size_t)i]->comm = comms[(size_t)i];
+            }
+        } catch (...) {
+            for (sqlp_ctx *c : cs) delete c;
+            throw;
+        }
+        cs[0]->peers.assign(cs.begin() + 1, cs.end());
+        cs[0]->bind();
+        *out = cs[0];
+    });
+}
+
 int32_t sqlp_ctx_destroy(sqlp_ctx *c)
 {
+    if (c && !c->peers.empty()) {
+        std::vector<sqlp_ctx *> peers;
+        peers.swap(c->peers);
+        for (sqlp_ctx *q : peers) sqlp_ctx_destroy(q);
+    }
     return guard([&] {
         if (!c) return;
         cudaSetDevice(c->device);
@@ -166,8 +209,10 @@ int32_t sqlp_ctx_synchronize(sqlp_ctx *c)
 {
     return guard([&] {
         REQUIRE(c, SQLP_E_INVALID, "null ctx");
-        c->bind();
-        CK(cudaStreamSynchronize(c->stream));
+        for (int s = n_shards(c) - 1; s >= 0; --s) {
+            shard(c, s)->bind();
+            CK(cudaStreamSynchronize(shard(c, s)->stream));
+        }
     });
 }
 
@@ -215,7 +260,7 @@ int32_t sqlp_ctx_set_screen(sqlp_ctx *c, int32_t mode)
     return guard([&] {
         REQUIRE(c, SQLP_E_INVALID, "null ctx");
         REQUIRE(mode >= 0 && mode <= 2, SQLP_E_INVALID, "screen mode must be 0 (off), 1 (automatic) or 2 (always)");
-        c->screen_mode = mode;
+        for (int s = 0; s < n_shards(c); ++s) shard(c, s)->screen_mode = mode;
     });
 }
 
@@ -282,7 +327,7 @@ int32_t sqlp_ctx_profile_read(sqlp_ctx *c, int32_t reset, double *ms, int64_t *l
 // ---------------------------------------------------------------- pool -------------------
 int32_t sqlp_pool_create(sqlp_ctx *c, int64_t m2, sqlp_pool **out)
 {
-    return guard([&] {
+    int32_t st = guard([&] {
         REQUIRE(c && out, SQLP_E_INVALID, "null argument");
         REQUIRE(m2 >= 1 && m2 < (1 << 24), SQLP_E_INVALID, "bad m2");
         c->bind();
@@ -303,10 +348,24 @@ int32_t sqlp_pool_create(sqlp_ctx *c, int64_t m2, sqlp_pool **out)
         } catch (...) { delete p; throw; }
         *out = p;
     });
+    if (st != SQLP_OK || c->peers.empty()) return st;
+    for (sqlp_ctx *q : c->peers) {   // a multi-GPU context: the replicas of the pool on the other GPUs
+        sqlp_pool *pp = nullptr;
+        st = sqlp_pool_create(q, m2, &pp);
+        if (st != SQLP_OK) return st;
+        (*out)->peers.push_back(pp);
+    }
+    cudaSetDevice(c->device);
+    return SQLP_OK;
 }
 
 int32_t sqlp_pool_destroy(sqlp_pool *p)
 {
+    if (p && !p->peers.empty() && p->epis.empty()) {
+        std::vector<sqlp_pool *> peers;
+        peers.swap(p->peers);
+        for (sqlp_pool *q : peers) sqlp_pool_destroy(q);
+    }
     return guard([&] {
         if (!p) return;
         // an epigraph keeps pointers into its pool (vertex rows, views): it has to go first
@@ -326,12 +385,17 @@ int32_t sqlp_pool_push_batch(sqlp_pool *p, int64_t n, const double *v, int32_t *
         if (n == 0) return;
         sqlp_ctx *c = p->ctx;
         REQUIRE(v || (c->world > 1 && c->rank != 0), SQLP_E_INVALID, "null vector");
+        for (int s = n_shards(c) - 1; s >= 1; --s) {   // multi-GPU context: the same vectors to every GPU's replica
+            shard(c, s)->bind();
+            pool_push_enqueue(shard(p, s), n, v, nullptr);
+        }
         c->bind();
         pool_push_enqueue(p, n, v, nullptr);
         std::vector<PushResult> res((size_t)n);
         CK(cudaMemcpyAsync(res.data(), p->d_results.p, (size_t)n * sizeof(PushResult),
                            cudaMemcpyDeviceToHost, S(c)));
         pool_confirm(p);
+        sync_all_shards(c, p);
         for (int64_t i = 0; i < n; ++i) {
             if (inserted) inserted[i] = res[i].inserted;
             if (index) index[i] = res[i].index;
@@ -351,6 +415,7 @@ int32_t sqlp_pool_push_dev(sqlp_pool *p, int64_t n, const double *d_v)
         REQUIRE(n >= 0, SQLP_E_INVALID, "negative count");
         if (n == 0) return;
         REQUIRE(d_v || (p->ctx->world > 1 && p->ctx->rank != 0), SQLP_E_INVALID, "null vector");
+        REQUIRE(p->ctx->peers.empty(), SQLP_E_UNSUPPORTED, "device pointers belong to one GPU: use the host variants with a multi-GPU context");
         p->ctx->bind();
         pool_push_enqueue(p, n, nullptr, d_v);
     });
@@ -403,7 +468,7 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
                         const int64_t *T_rowval, const double *T_nzval, int64_t s,
                         const int32_t *pos_row, const int32_t *pos_col, sqlp_epi **out)
 {
-    return guard([&] {
+    int32_t st = guard([&] {
         REQUIRE(c && p && out, SQLP_E_INVALID, "null argument");
         REQUIRE(p->ctx == c, SQLP_E_INVALID, "pool belongs to another context");
         REQUIRE(m2 == p->m2, SQLP_E_INVALID, "m2 differs from the pool's vertex length");
@@ -561,10 +626,25 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
         } catch (...) { delete e; throw; }
         *out = e;
     });
+    if (st != SQLP_OK || c->peers.empty()) return st;
+    for (size_t q = 0; q < c->peers.size(); ++q) {   // a multi-GPU context: this epigraph's shards on the other GPUs
+        sqlp_epi *pe = nullptr;
+        st = sqlp_epi_create(c->peers[q], p->peers[q], m2, n1, r_nnz, r_idx, r_val, T_colptr, T_rowval, T_nzval, s,
+                             pos_row, pos_col, &pe);
+        if (st != SQLP_OK) return st;
+        (*out)->peers.push_back(pe);
+    }
+    cudaSetDevice(c->device);
+    return SQLP_OK;
 }
 
 int32_t sqlp_epi_destroy(sqlp_epi *e)
 {
+    if (e && !e->peers.empty()) {
+        std::vector<sqlp_epi *> peers;
+        peers.swap(e->peers);
+        for (sqlp_epi *q : peers) sqlp_epi_destroy(q);
+    }
     return guard([&] {
         if (!e) return;
         cudaSetDevice(e->ctx->device);
@@ -578,6 +658,10 @@ int32_t sqlp_epi_destroy(sqlp_epi *e)
 
 int32_t sqlp_epi_add_scenarios(sqlp_epi *e, int64_t n_new, const double *values, const double *weights)
 {
+    if (e) for (sqlp_epi *q : e->peers) {   // multi-GPU context: every shard
+        int32_t st = sqlp_epi_add_scenarios(q, n_new, values, weights);
+        if (st != SQLP_OK) return st;
+    }
     return guard([&] {
         REQUIRE(e, SQLP_E_INVALID, "null epigraph");
         REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
@@ -595,6 +679,7 @@ int32_t sqlp_epi_add_scenarios_dev(sqlp_epi *e, int64_t n_new, const double *d_v
         REQUIRE(e, SQLP_E_INVALID, "null epigraph");
         REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
         REQUIRE(d_values || n_new == 0 || e->s == 0, SQLP_E_INVALID, "null values");
+        REQUIRE(e->peers.empty(), SQLP_E_UNSUPPORTED, "device pointers belong to one GPU: use sqlp_epi_add_scenarios with a multi-GPU context");
         e->ctx->bind();
         epi_add(e, n_new, nullptr, d_values, weights_host, false, 0, 0);
     });
@@ -603,6 +688,10 @@ int32_t sqlp_epi_add_scenarios_dev(sqlp_epi *e, int64_t n_new, const double *d_v
 int32_t sqlp_epi_set_outcomes(sqlp_epi *e, int64_t mo, const double *vals, const double *cdf,
                               const int32_t *cnt)
 {
+    if (e) for (sqlp_epi *q : e->peers) {   // multi-GPU context: every shard
+        int32_t st = sqlp_epi_set_outcomes(q, mo, vals, cdf, cnt);
+        if (st != SQLP_OK) return st;
+    }
     return guard([&] {
         REQUIRE(e && vals && cdf && cnt, SQLP_E_INVALID, "null argument");
         REQUIRE(mo >= 1, SQLP_E_INVALID, "max_outcomes < 1");
@@ -626,6 +715,10 @@ int32_t sqlp_epi_set_outcomes(sqlp_epi *e, int64_t mo, const double *vals, const
 int32_t sqlp_epi_set_distributions(sqlp_epi *e, const int32_t *kind, const double *par_a,
                                    const double *par_b)
 {
+    if (e) for (sqlp_epi *q : e->peers) {   // multi-GPU context: every shard
+        int32_t st = sqlp_epi_set_distributions(q, kind, par_a, par_b);
+        if (st != SQLP_OK) return st;
+    }
     return guard([&] {
         REQUIRE(e && kind && par_a && par_b, SQLP_E_INVALID, "null argument");
         sqlp_ctx *c = e->ctx;
@@ -649,6 +742,10 @@ int32_t sqlp_epi_set_distributions(sqlp_epi *e, const int32_t *kind, const doubl
 
 int32_t sqlp_epi_sample_scenarios(sqlp_epi *e, int64_t n_new, uint64_t seed, uint64_t weight_seed)
 {
+    if (e) for (sqlp_epi *q : e->peers) {   // multi-GPU context: every shard
+        int32_t st = sqlp_epi_sample_scenarios(q, n_new, seed, weight_seed);
+        if (st != SQLP_OK) return st;
+    }
     return guard([&] {
         REQUIRE(e, SQLP_E_INVALID, "null epigraph");
         REQUIRE(n_new >= 0, SQLP_E_INVALID, "negative count");
@@ -664,7 +761,7 @@ int32_t sqlp_epi_counts(sqlp_epi *e, int64_t *n_global, int64_t *n_local, double
     return guard([&] {
         REQUIRE(e, SQLP_E_INVALID, "null epigraph");
         if (n_global) *n_global = e->n_global;
-        if (n_local) *n_local = e->n_local;
+        if (n_local) *n_local = e->peers.empty() ? e->n_local : e->n_global;   // one process, all GPUs: everything is local
         if (total_weight) *total_weight = e->total_weight;
     });
 }
@@ -723,6 +820,41 @@ int32_t sqlp_epi_argmax(sqlp_epi *e, const double *x, int32_t sense, double *max
         check_sense(sense);
         sqlp_ctx *c = e->ctx;
         c->bind();
+        if (!e->peers.empty()) {
+            // one process, all GPUs: every shard sweeps its scenarios; results come back in GLOBAL scenario order
+            REQUIRE(e->n_global == 0 || (max_val && max_idx), SQLP_E_INVALID, "null output");
+            const int ns = n_shards(c);
+            std::vector<std::vector<double>> hv((size_t)ns);
+            std::vector<std::vector<int>> hi((size_t)ns);
+            for (int s = 0; s < ns; ++s) {
+                sqlp_epi *es = shard(e, s);
+                sqlp_ctx *cs = es->ctx;
+                cs->bind();
+                if (es->n_local == 0) continue;
+                es->cur_bias = nullptr;
+                epi_cuts_enqueue(es, 1, x, nullptr, false);
+                if (es->view->twins)
+                    LAUNCH(cs, k_unmap_idx, (int)std::min<int64_t>((es->n_local + 255) / 256, 4 * cs->sm_count), 256, 0,
+                           es->d_best_idx.as<int>(), (long long)es->n_local, es->view->act());
+                hv[(size_t)s].resize((size_t)es->n_local);
+                hi[(size_t)s].resize((size_t)es->n_local);
+                CK(cudaMemcpyAsync(hv[(size_t)s].data(), es->d_best_val.p, (size_t)es->n_local * 8, cudaMemcpyDeviceToHost, S(cs)));
+                CK(cudaMemcpyAsync(hi[(size_t)s].data(), es->d_best_idx.p, (size_t)es->n_local * 4, cudaMemcpyDeviceToHost, S(cs)));
+            }
+            for (int s = 0; s < ns; ++s) {
+                sqlp_epi *es = shard(e, s);
+                es->ctx->bind();
+                pool_confirm(es->pool);
+                CK(cudaStreamSynchronize(S(es->ctx)));
+                for (int64_t l = 0; l < es->n_local; ++l) {
+                    const int64_t g = ((l / SQLP_TILE) * ns + s) * SQLP_TILE + l % SQLP_TILE;   // inverse of local_of
+                    max_val[g] = hv[(size_t)s][(size_t)l];
+                    max_idx[g] = hi[(size_t)s][(size_t)l];
+                }
+            }
+            c->bind();
+            return;
+        }
         if (e->n_local == 0) return;
         REQUIRE(max_val && max_idx, SQLP_E_INVALID, "null output");
         e->cur_bias = nullptr;
@@ -760,14 +892,20 @@ int32_t sqlp_epi_build_cut(sqlp_epi *e, const double *x, double *alpha, double *
         REQUIRE(e && alpha && (beta || e->n1 == 0) && (x || e->n1 == 0), SQLP_E_INVALID, "null argument");
         sqlp_ctx *c = e->ctx;
         c->bind();
-        e->cur_bias = nullptr;
-        CellGather cg(c, 1, 1, &e);
-        epi_cuts_enqueue(e, 1, x, nullptr, true, nullptr, cg.slot(0));
-        cg.run();
+        if (!c->peers.empty()) {
+            std::vector<std::vector<double>> xs(1, std::vector<double>(x, x + e->n1));
+            cell_cuts_all_shards(c, 1, 1, &e, xs);
+        } else {
+            e->cur_bias = nullptr;
+            CellGather cg(c, 1, 1, &e);
+            epi_cuts_enqueue(e, 1, x, nullptr, true, nullptr, cg.slot(0));
+            cg.run();
+        }
         CutHost h;
         epi_cuts_fetch(e, 1, h);
         pool_confirm(e->pool);
         CK(cudaStreamSynchronize(S(c)));
+        sync_all_shards(c, e->pool);
         finish_cut(e, 1, h, alpha, beta, weight_mark, val);
     });
 }
@@ -788,18 +926,30 @@ int32_t sqlp_cell_build_cuts2(int32_t n_epi, sqlp_epi *const *epi, const double 
             REQUIRE(epi[i] && epi[i]->ctx == c, SQLP_E_INVALID, "epigraphs must share one context");
             epi[i]->cur_bias = nullptr;
         }
-        CellGather cg(c, 2, n_epi, epi);
-        for (int i = 0; i < n_epi; ++i) {
-            sqlp_epi *e = epi[i];
-            REQUIRE((x_cand && x_inc && beta) || e->n1 == 0, SQLP_E_INVALID, "null argument");
-            x2.assign((size_t)2 * e->n1, 0.0);
-            for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
-            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true, bias_twin(i, epi), cg.slot(i));   // x2 is pageable: staged now
+        if (!c->peers.empty()) {
+            std::vector<std::vector<double>> xs((size_t)n_epi);
+            for (int i = 0; i < n_epi; ++i) {
+                sqlp_epi *e = epi[i];
+                REQUIRE((x_cand && x_inc && beta) || e->n1 == 0, SQLP_E_INVALID, "null argument");
+                xs[(size_t)i].assign((size_t)2 * e->n1, 0.0);
+                for (int64_t j = 0; j < e->n1; ++j) { xs[(size_t)i][(size_t)j] = x_cand[j]; xs[(size_t)i][(size_t)(e->n1 + j)] = x_inc[j]; }
+            }
+            cell_cuts_all_shards(c, 2, n_epi, epi, xs);
+        } else {
+            CellGather cg(c, 2, n_epi, epi);
+            for (int i = 0; i < n_epi; ++i) {
+                sqlp_epi *e = epi[i];
+                REQUIRE((x_cand && x_inc && beta) || e->n1 == 0, SQLP_E_INVALID, "null argument");
+                x2.assign((size_t)2 * e->n1, 0.0);
+                for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
+                epi_cuts_enqueue(e, 2, x2.data(), nullptr, true, bias_twin(i, epi), cg.slot(i));   // x2 is pageable: staged now
+            }
+            cg.run();
         }
-        cg.run();
         for (int i = 0; i < n_epi; ++i) epi_cuts_fetch(epi[i], 2, h[(size_t)i]);
         for (int i = 0; i < n_epi; ++i) pool_confirm(epi[i]->pool);
         CK(cudaStreamSynchronize(S(c)));
+        sync_all_shards(c, epi[0]->pool);
         int64_t boff = 0;
         for (int i = 0; i < n_epi; ++i) {
             sqlp_epi *e = epi[i];
@@ -834,14 +984,20 @@ int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const double *val
         REQUIRE(values || n_values == 0, SQLP_E_INVALID, "null values");
         // the drained stream of the previous call makes the two reusable buffers free
         c->h_step.ensure(((size_t)n_vertices * sizeof(PushResult) / 8 + n_out + 1) * 8);
-        c->d_step.ensure(std::max<size_t>(n_values, 1) * 8, 0, S(c), false);
-        if (n_values)
-            CK(cudaMemcpyAsync(c->d_step.p, values, n_values * 8, cudaMemcpyHostToDevice, S(c)));
-        // algorithm.jl:45-46  add_scenario!(epi, scenario, weight) for every epigraph
-        size_t voff = 0;
-        for (int i = 0; i < n_epi; ++i) {
-            epi_add(epi[i], 1, nullptr, c->d_step.as<double>() + voff, weights ? weights + i : nullptr, false, 0, 0);
-            voff += (size_t)epi[i]->s;
+        // algorithm.jl:45-46  add_scenario!(epi, scenario, weight) for every epigraph -- on every GPU of a multi-GPU
+        // context (each keeps the scenarios it owns), the leader last so that it stays the bound device
+        for (int sh = n_shards(c) - 1; sh >= 0; --sh) {
+            sqlp_ctx *cs = shard(c, sh);
+            cs->bind();
+            cs->d_step.ensure(std::max<size_t>(n_values, 1) * 8, 0, S(cs), false);
+            if (n_values)
+                CK(cudaMemcpyAsync(cs->d_step.p, values, n_values * 8, cudaMemcpyHostToDevice, S(cs)));
+            size_t voff = 0;
+            for (int i = 0; i < n_epi; ++i) {
+                epi_add(shard(epi[i], sh), 1, nullptr, cs->d_step.as<double>() + voff, weights ? weights + i : nullptr, false, 0, 0);
+                voff += (size_t)epi[i]->s;
+            }
+            if (sh > 0 && n_vertices) pool_push_enqueue(shard(p, sh), n_vertices, vertices, nullptr);
         }
         // algorithm.jl:50,54  push!(dual_vertices, dual) for the vertices found at the candidate and the incumbent
         PushResult *h_res = c->h_step.as<PushResult>();
@@ -855,14 +1011,23 @@ int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const double *val
         std::vector<double> x2;
         size_t ooff = 0;
         for (int i = 0; i < n_epi; ++i) epi[i]->cur_bias = nullptr;
-        CellGather cg(c, 2, n_epi, epi);
-        for (int i = 0; i < n_epi; ++i) {
-            sqlp_epi *e = epi[i];
-            x2.assign((size_t)2 * e->n1, 0.0);
-            for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
-            epi_cuts_enqueue(e, 2, x2.data(), nullptr, true, bias_twin(i, epi), cg.slot(i));   // x2 is pageable: staged now
+        if (!c->peers.empty()) {
+            std::vector<std::vector<double>> xs((size_t)n_epi);
+            for (int i = 0; i < n_epi; ++i) {
+                xs[(size_t)i].assign((size_t)2 * epi[i]->n1, 0.0);
+                for (int64_t j = 0; j < epi[i]->n1; ++j) { xs[(size_t)i][(size_t)j] = x_cand[j]; xs[(size_t)i][(size_t)(epi[i]->n1 + j)] = x_inc[j]; }
+            }
+            cell_cuts_all_shards(c, 2, n_epi, epi, xs);           // every GPU's chain side by side, one grouped all-gather
+        } else {
+            CellGather cg(c, 2, n_epi, epi);
+            for (int i = 0; i < n_epi; ++i) {
+                sqlp_epi *e = epi[i];
+                x2.assign((size_t)2 * e->n1, 0.0);
+                for (int64_t j = 0; j < e->n1; ++j) { x2[(size_t)j] = x_cand[j]; x2[(size_t)(e->n1 + j)] = x_inc[j]; }
+                epi_cuts_enqueue(e, 2, x2.data(), nullptr, true, bias_twin(i, epi), cg.slot(i));   // x2 is pageable: staged now
+            }
+            cg.run();                                             // sharded job: one all-gather for the whole cell
         }
-        cg.run();                                                 // sharded job: one all-gather for the whole cell
         for (int i = 0; i < n_epi; ++i) {
             sqlp_epi *e = epi[i];
             const size_t NC = (size_t)e->n1 + 2;
@@ -871,9 +1036,10 @@ int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const double *val
             ooff += 2 * NC + 1;
         }
         CK(cudaMemcpyAsync(h_K, p->d_K.p, 8, cudaMemcpyDeviceToHost, S(c)));
-        CK(cudaStreamSynchronize(S(c)));                          // the step's only synchronisation
+        CK(cudaStreamSynchronize(S(c)));                          // the step's only synchronisation (per GPU)
         p->K = *h_K;
         p->pending = 0;
+        sync_all_shards(c, p);
         for (int64_t v = 0; v < n_vertices; ++v) {
             if (inserted) inserted[v] = h_res[v].inserted;
             if (index) index[v] = h_res[v].index;
@@ -919,6 +1085,10 @@ int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *e, const double *d_x2, double *d_out)
 // ---------------------------------------------------------------- cut list (N1 / N3) ----
 int32_t sqlp_epi_set_weights(sqlp_epi *e, double objective_weight, double lower_bound)
 {
+    if (e) for (sqlp_epi *q : e->peers) {   // multi-GPU context: every shard
+        int32_t st = sqlp_epi_set_weights(q, objective_weight, lower_bound);
+        if (st != SQLP_OK) return st;
+    }
     return guard([&] {
         REQUIRE(e, SQLP_E_INVALID, "null epigraph");
         e->objective_weight = objective_weight;

@@ -45,11 +45,18 @@ def _ptr(a):
 class Context:
     """One GPU (and, in a scenario-sharded job, this process's rank)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None):
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None,
+                 devices=None):
         self._h = C.c_void_p()
         self.device, self.rank, self.world = device, rank, world
         L = _lib.lib()
-        if world > 1:
+        if devices is not None:
+            # ONE process (this thread) driving several GPUs: ``sqlp_ctx_create_multi``
+            dv = np.ascontiguousarray(list(devices), dtype=np.int32)
+            self.device, self.rank, self.world = int(dv[0]), 0, 1
+            self.n_gpus = len(dv)
+            check(L.sqlp_ctx_create_multi(len(dv), _ptr(dv), C.byref(self._h)))
+        elif world > 1:
             if nccl_id is None or len(nccl_id) != 128:
                 raise ValueError("a 128-byte ncclUniqueId is required when world > 1")
             buf = C.create_string_buffer(nccl_id, 128)

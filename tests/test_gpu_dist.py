@@ -137,3 +137,54 @@ def test_sharded_cuts(world):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert all(r[2] == res[0][2] for r in res)        # fixed rank-order sum: identical bits on every rank
+    # ONE process driving the same GPUs (sqlp_ctx_create_multi) forms the same cuts, bit for bit
+    assert _one_process_cuts(world) == res[0][2]
+
+
+def _one_process_cuts(world):
+    from oracle import oracle as O
+    from sqlp_b200 import twosd as T
+    from tests.helpers import check_argmax_parity, load_instance, sample_instance_values
+    ctx = T.Context(devices=range(world))
+    P, z = load_instance("storm")
+    N = 1500
+    vals = sample_instance_values(z, N)
+    w = 0.5 + O.u01(4, np.arange(N))
+    pool = z["pool"]
+    coef = T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
+    dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+    ins, idx = dvs.push_many(np.vstack([pool, pool[:3]]))
+    assert ins.sum() == len(pool) and len(dvs) == len(pool)
+    epi = T.sdEpigraph(coef, 1.0, 0.0, dvs)
+    epi.add_scenarios(vals, w)
+    assert epi.counts()[:2] == (N, N)                  # one process: every scenario is "local"
+    xs = (z["x_ev"], z["x_alt"])
+    (cand, inc), val = epi.build_cuts2(*xs, with_val=True)
+    for x, cut in zip(xs, (cand, inc)):
+        mv, mi = epi.argmax(x)                          # GLOBAL scenario order
+        check_argmax_parity(P, vals, x, pool, mv, mi)
+        ref = O.build_sasa_cut(P, vals, w, x, pool, forced_idx=mi)
+        assert abs(cut.alpha - ref["alpha"]) <= 1e-10 * abs(ref["alpha"])
+        assert np.allclose(cut.beta, ref["beta"], rtol=1e-10, atol=1e-6)
+    # the whole iteration in one call, as sd_iteration! would issue it
+    E = 2
+    epis = [T.sdEpigraph(coef, 0.5, 0.0, dvs) for _ in range(E)]
+    for e in range(E):
+        epis[e].add_scenarios(vals[e::E][:-1], w[e::E][:-1])
+    new_v = pool[:2] * 1.5
+    ins2, idx2, cuts = T.sd_step(epis, [vals[e::E][-1] for e in range(E)], [w[e::E][-1] for e in range(E)],
+                                 np.vstack([new_v[0], pool[5], new_v[1], pool[7]]), *xs)
+    assert list(ins2) == [True, False, True, False] and list(idx2) == [len(pool), 5, len(pool) + 1, 7]
+    pool2 = np.vstack([pool, new_v])
+    for e in range(E):
+        for xi, x in enumerate(xs):
+            mv, mi = epis[e].argmax(x)
+            ref = O.build_sasa_cut(P, vals[e::E], w[e::E], x, pool2, forced_idx=mi)
+            assert abs(cuts[e][xi].alpha - ref["alpha"]) <= 1e-10 * abs(ref["alpha"])
+            assert np.allclose(cuts[e][xi].beta, ref["beta"], rtol=1e-10, atol=1e-6)
+    out = np.concatenate([[cand.alpha, inc.alpha], cand.beta, inc.beta]).tobytes()
+    for h in epis + [epi]:
+        h.close()
+    dvs.close()
+    ctx.close()
+    return out
