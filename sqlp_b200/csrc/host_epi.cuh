@@ -346,7 +346,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     c->d_cnt.ensure(nslots * 4, 0, S(c), false);
     c->d_lfin.ensure(nslots * 4, 0, S(c), false);
     // more overflowing lists than this and the pass gives up: each one costs a full sweep of its scenario
-    const unsigned ovf_limit = (unsigned)std::min<int64_t>(e->n_local / 64 + 16, 1 << 20);
+    const unsigned ovf_limit = (unsigned)std::min<int64_t>(e->n_local / 16 + 16, 1 << 20);
     LAUNCH(c, k_screen_prep<NX>, 1, 1024, 0, e->cur_bias, (long long)e->cur_bias_stride, v->d_pn.as<float>(),
            v->d_pnmax.as<float>(), e->d_dnall.as<float>(), v->d_vbad.as<int>(), e->d_ebad.as<int>(),
            v->d_Kv(p), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>());

@@ -52,7 +52,7 @@ namespace sqlp {
 #define SCR_STAGE_BYTES 16384      // one K-step of a chunk: [hi, lo][2 slabs][256][8] bf16
 #define SCR_MAX_STAGES 8
 #define SCR_BIAS_BUFS 4
-#define SCR_CAP 32                 // candidate list entries per (scenario, point, K-range, column half)
+#define SCR_CAP 64                 // candidate list entries per (scenario, point, K-range, column half)
 #define SCR_DEAD (-3.0e38f)        // shifted bias of a vertex that can never win (or does not exist)
 
 template <int NX>
@@ -572,7 +572,18 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             const double *Prow = a.PiS + (size_t)(kk >> 7) * tile_doubles +
                                  ((((size_t)(cv >> 4)) * 32 + (cv & 7) * 4 + (lane & 3)) << 1) + ((cv >> 3) & 1);
             double acc0 = 0.0, acc1 = 0.0;
-            for (int g = 0; g < ng; ++g) {
+            int g = 0;
+            for (; g + 6 <= ng; g += 6) {                            // twelve loads in flight, then the ordered chain
+                double av[6], bv[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) { av[u] = Drow[(size_t)(g + u) * 512]; bv[u] = Prow[(size_t)(g + u) * 512]; }
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc0), "+d"(acc1)
+                                 : "d"(av[u]), "d"(bv[u]));
+            }
+            for (; g < ng; ++g) {
                 const double av = Drow[(size_t)g * 512], bv = Prow[(size_t)g * 512];
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                              : "+d"(acc0), "+d"(acc1)
@@ -634,14 +645,16 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
                 for (int s = 0; s < 2 * a.R; ++s) {
                     if ((s >> 1) * cpr >= nch) continue;
                     const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
-                    const int n = a.cnt[slot];
-                    int2 e = make_int2(0, 0);
-                    if (lane < n) e = a.cand[slot * SCR_CAP + lane];
-                    unsigned pass = __ballot_sync(0xffffffffu, lane < n && __int_as_float(e.y) >= LB[x]);
-                    while (pass) {
-                        const int src = __ffs(pass) - 1;
-                        pass &= pass - 1;
-                        push(__shfl_sync(0xffffffffu, e.x, src), x);
+                    const int n = min(a.cnt[slot], SCR_CAP);
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        int2 e = make_int2(0, 0);
+                        if (b0 + lane < n) e = a.cand[slot * SCR_CAP + b0 + lane];
+                        unsigned pass = __ballot_sync(0xffffffffu, b0 + lane < n && __int_as_float(e.y) >= LB[x]);
+                        while (pass) {
+                            const int src = __ffs(pass) - 1;
+                            pass &= pass - 1;
+                            push(__shfl_sync(0xffffffffu, e.x, src), x);
+                        }
                     }
                 }
             }

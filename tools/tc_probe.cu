@@ -38,6 +38,30 @@ static double bf16_from_double(double x)
     return ldexp(r, e - 8);
 }
 
+// Is mma.sync.m8n8k4.f64 the chain d = fma(a3, b3, fma(a2, b2, fma(a1, b1, fma(a0, b0, c))))?  One warp per sample:
+// a chain of `ng` k-groups on random operands, element (0, 0) against the FMA chain of lane 0's view of the data.
+__global__ void k_dmma_vs_fma(const double *__restrict__ A, const double *__restrict__ B, int ng, int nsamp,
+                              unsigned long long *__restrict__ mismatches, double *__restrict__ worst)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= nsamp) return;
+    const double *a = A + (size_t)w * ng * 4, *b = B + (size_t)w * ng * 4;
+    double acc0 = 0.0, acc1 = 0.0, f = 0.0;
+    for (int g = 0; g < ng; ++g) {
+        // row r of A = a[4g + k] for every r; column c of B = b[4g + k] for every c  ->  every D element = same dot
+        const double av = a[4 * g + (lane & 3)], bv = b[4 * g + (lane & 3)];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(acc0), "+d"(acc1) : "d"(av), "d"(bv));
+        for (int k = 0; k < 4; ++k) f = fma(a[4 * g + k], b[4 * g + k], f);
+    }
+    if (lane == 0 && __double_as_longlong(acc0) != __double_as_longlong(f)) {
+        atomicAdd(mismatches, 1ull);
+        *worst = fabs(acc0 - f);
+    }
+    if (lane == 5 && __double_as_longlong(acc1) != __double_as_longlong(f)) atomicAdd(mismatches + 1, 1ull);
+}
+
 int main(int argc, char **argv)
 {
     long long K = argc > 1 ? atoll(argv[1]) : 4096;
@@ -119,7 +143,9 @@ int main(int argc, char **argv)
     printf("device %s, %d SMs, smem optin %zu\n", prop.name, sms, (size_t)prop.sharedMemPerBlockOptin);
 
     // ---- operand builders + prep ---------------------------------------------------------------
-    k_screen_view_sync<<<2 * sms, 256>>>(d_pi, n_rows, d_srows, n_rows, sp, d_PiB, d_pn, d_pnmax, d_bad, 0, d_K);
+    long long *d_mark;
+    CK(cudaMalloc(&d_mark, 8)); CK(cudaMemset(d_mark, 0, 8));
+    k_screen_view_sync<<<2 * sms, 256>>>(d_pi, n_rows, d_srows, n_rows, sp, d_PiB, d_pn, d_pnmax, d_bad, d_mark, d_K, nullptr);
     k_screen_scen_sync<<<8 * sms, 256>>>(d_D, s_pad, sp, d_DB, d_dnu, d_dnall, d_bad + 1, 0, N);
     k_screen_prep<NX><<<1, 1024>>>(d_bias, kpad, d_pn, d_pnmax, d_dnall, d_bad, d_bad + 1, d_K, sp, (unsigned)(N / 64 + 16),
                                    d_b32c, d_ctl);
@@ -222,6 +248,29 @@ int main(int argc, char **argv)
                 if (fabs(best - bv2[x * npad + i]) > 1e-9 * (fabs(best) + 1.0)) ++hm;
             }
         printf("check 3 (full sweep value vs host fp64, %lld scenarios): %lld beyond 1e-9 -> %s\n", Nh, hm, hm ? "FAIL" : "ok");
+    }
+
+    // ---- is DMMA a chain of FMAs in k order? ------------------------------------------------------
+    {
+        const int ng = s_pad / 4, nsamp = 1 << 18;
+        std::vector<double> ha((size_t)nsamp * ng * 4), hb((size_t)nsamp * ng * 4);
+        for (size_t q = 0; q < ha.size(); ++q) {
+            const double ua = u01(21, q), ub = u01(22, q);
+            ha[q] = (2.0 * ua - 1.0) * exp2(floor(40.0 * u01(23, q)) - 20.0);      // wide dynamic range, cancellation
+            hb[q] = (2.0 * ub - 1.0) * exp2(floor(40.0 * u01(24, q)) - 20.0);
+        }
+        double *dA, *dB, *dw;
+        unsigned long long *dm;
+        CK(cudaMalloc(&dA, ha.size() * 8)); CK(cudaMalloc(&dB, hb.size() * 8)); CK(cudaMalloc(&dm, 16)); CK(cudaMalloc(&dw, 8));
+        CK(cudaMemcpy(dA, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dm, 0, 16)); CK(cudaMemset(dw, 0, 8));
+        k_dmma_vs_fma<<<nsamp / 8, 256>>>(dA, dB, ng, nsamp, dm, dw);
+        CK(cudaDeviceSynchronize());
+        unsigned long long mm[2]; double ww;
+        CK(cudaMemcpy(mm, dm, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&ww, dw, 8, cudaMemcpyDeviceToHost));
+        printf("check 4 (DMMA m8n8k4 chain == FMA chain in k order, %d samples x %d k-groups): %llu / %llu mismatches (last |diff| %.3g)\n",
+               nsamp, ng, mm[0], mm[1], ww);
     }
 
     // ---- timing ----------------------------------------------------------------------------------
