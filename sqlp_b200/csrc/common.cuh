@@ -30,6 +30,12 @@ __device__ __forceinline__ void griddep_sync()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves apart, for kernels whose grid runs in SEVERAL WAVES: a dependent kernel whose blocks need a whole
+// SM (the FP64 sweep, the screening kernel) would otherwise take the SMs the first wave frees and sit there at
+// its own `wait`, leaving the remaining waves of this kernel fewer SMs (measured: 8 x on k_screen_resolve).  Such
+// kernels wait at their start and release their dependents when a block has done its work.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Fragment-major tile layout shared by the scenario store D and the pool view PiS.
 // A tile holds 128 columns (scenarios or vertices) x s_pad row slots.  Slots are grouped by

@@ -198,6 +198,9 @@ struct sqlp_ctx {
     // screening pass (kernels_screen.cuh): 0 = off, 1 = automatic (default), 2 = whenever the shape allows it
     int screen_mode = 1;
     bool screen_smem_set[3] = {false, false, false};
+    bool resolve_fma = false;     // exact decision by DFMA lanes (set when the device check DMMA == DFMA chain passed)
+    int reduce_mode = 0;          // cut reduction: 0 automatic, 1 per-scenario gather only, 2 per-vertex weight sums whenever possible
+    bool hist_smem_set[3] = {false, false, false};
     DevBuf d_cand, d_cnt, d_lfin; // candidate lists of the running pass (shared by the context's epigraphs: stream order)
     DevBuf d_cell, d_cellg;       // sharded job: the rows of a call's epigraphs back to back, and their all-gather
     DevBuf d_step;                // sqlp_cell_sd_step: the step's scenario values on the device
@@ -305,6 +308,7 @@ struct sqlp_epi {
     DevBuf d_rt;
     int64_t rt_cap = 0, rt_synced_lo = 0;
     // work buffers
+    DevBuf d_cpart, d_spart;              // k_cut_hist: per-block weight sums per view column, and scalar sums
     DevBuf d_x2, d_base, d_bias, d_best_val, d_best_idx, d_partial, d_partial2, d_out, d_gather,
         d_flags, d_stage, d_scratch;
     int64_t bias_stride = 0, out_stride = 0;

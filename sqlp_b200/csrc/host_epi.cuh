@@ -402,7 +402,8 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     {
         ProfScope prof(c, SQLP_PROF_RESOLVE, (double)NX * (double)e->n_local);
         const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + 7) / 8, 1), 8 * c->sm_count);
-        LAUNCH(c, k_screen_resolve<NX>, rgrid, 256, 0, ra);
+        if (c->resolve_fma) LAUNCH(c, (k_screen_resolve<NX, 1>), rgrid, 256, 0, ra);
+        else LAUNCH(c, (k_screen_resolve<NX, 0>), rgrid, 256, 0, ra);
     }
     // the control block goes back to the host asynchronously; screen_learn() reads it at a later call
     if (!e->ctl_event) CK(cudaEventCreateWithFlags(&e->ctl_event, cudaEventDisableTiming));
@@ -550,16 +551,55 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         const int nsub = (size_t)8 * width * 8 <= 48 * 1024 ? 8 : 1;
         const size_t sub_smem = nsub > 1 ? (size_t)nsub * width * 8 : 0;
         r.nsub = nsub;
-        if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, sub_smem, r);
-        else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, sub_smem, r);
-        const int group = 64;
-        int64_t ng = (ntiles + group - 1) / group;
-        e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
         // sharded job: the row and its flag word go straight into the cell's gather buffer
         double *fin = cell_slot ? cell_slot : e->d_out.as<double>();
-        LAUNCH(c, k_sum_groups, (int)ng, 256, sub_smem, e->d_partial.as<double>(), (long long)ntiles, group, nsub,
-               width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), fin,
-               (const int *)e->d_flags.as<int>(), cell_slot != nullptr);
+        const int group = 64;
+        // many scenarios, no random element in Tbar: regroup by the selected vertex (k_cut_hist / k_cut_fold) so that
+        // the (rho, tau) table is read once instead of one row per scenario and point
+        const int64_t kc = round_up(std::max<int64_t>(ku, 1), 32);
+        const size_t hist_smem = (size_t)kc * 8 + (size_t)SQLP_HIST_SUB * 12;
+        if (e->n_T == 0 && c->reduce_mode != 1 && (c->reduce_mode == 2 || e->n_local >= 16384) &&
+            hist_smem <= (size_t)c->smem_optin) {
+            const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, (e->n_local + 4095) / 4096));
+            HistArgs h;
+            h.w = r.w; h.rt = r.rt; h.act = r.act; h.bias = r.bias; h.bias_stride = r.bias_stride;
+            h.best_val = r.best_val; h.best_idx = r.best_idx; h.out_stride = r.out_stride; h.n_local = r.n_local;
+            h.seg = round_up((e->n_local + nblk - 1) / nblk, SQLP_TILE);
+            h.d_Kv = e->view->d_Kv(p);
+            h.kc = (int)kc; h.n1 = n1; h.total_weight = r.total_weight;
+            h.D = r.D; h.PiS = r.PiS; h.s_pad = r.s_pad; h.flags = r.flags;
+            e->d_cpart.ensure((size_t)nblk * NX * kc * 8, 0, S(c), false);
+            e->d_spart.ensure((size_t)nblk * NX * 2 * 8, 0, S(c), false);
+            h.cpart = e->d_cpart.as<double>();
+            h.spart = e->d_spart.as<double>();
+            const int nchunk = (int)((kc + SQLP_FOLD_COLS - 1) / SQLP_FOLD_COLS);
+            e->d_partial.ensure((size_t)nchunk * width * 8, 0, S(c), false);
+            if (!c->hist_smem_set[NX]) {
+                if (NX == 2) CK(cudaFuncSetAttribute(k_cut_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+                else CK(cudaFuncSetAttribute(k_cut_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+                c->hist_smem_set[NX] = true;
+            }
+            if (NX == 2) {
+                LAUNCH(c, k_cut_hist<2>, (int)nblk, SQLP_HIST_THREADS, hist_smem, h);
+                LAUNCH(c, k_cut_fold<2>, nchunk, 256, 0, h, (int)nblk, e->d_partial.as<double>());
+            } else {
+                LAUNCH(c, k_cut_hist<1>, (int)nblk, SQLP_HIST_THREADS, hist_smem, h);
+                LAUNCH(c, k_cut_fold<1>, nchunk, 256, 0, h, (int)nblk, e->d_partial.as<double>());
+            }
+            const int64_t ng = (nchunk + group - 1) / group;
+            e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
+            LAUNCH(c, k_sum_groups, (int)ng, 256, sub_smem, e->d_partial.as<double>(), (long long)nchunk, group, nsub,
+                   width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), fin,
+                   (const int *)e->d_flags.as<int>(), cell_slot != nullptr);
+        } else {
+            if (NX == 2) LAUNCH(c, k_cut_partial<2>, (int)ntiles, 256, sub_smem, r);
+            else LAUNCH(c, k_cut_partial<1>, (int)ntiles, 256, sub_smem, r);
+            int64_t ng = (ntiles + group - 1) / group;
+            e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
+            LAUNCH(c, k_sum_groups, (int)ng, 256, sub_smem, e->d_partial.as<double>(), (long long)ntiles, group, nsub,
+                   width, e->d_partial2.as<double>(), (unsigned int *)(e->d_flags.as<int>() + 1), fin,
+                   (const int *)e->d_flags.as<int>(), cell_slot != nullptr);
+        }
         prof_red.stop();
     } else if (cell_slot) {
         CK(cudaMemsetAsync(cell_slot, 0, (size_t)(width + 1) * 8, S(c)));   // this rank holds no scenario

@@ -281,6 +281,174 @@ __global__ void __launch_bounds__(256) k_sum_groups(const double *__restrict__ i
     if (threadIdx.x == 0) *counter = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cut reduction through per-vertex weight sums (delta_T == 0; k_cut_partial above stays for delta_T != 0 and
+// for very small N).  build_sasa_cut (epigraph.jl:134-143) regrouped by the selected vertex:
+//   c_k    = sum_{i : k*(i) = k} p_i
+//   alpha  = sum_k c_k rho_k  + sum_i p_i (PiS[k*(i)] . delta_rhs_i)
+//   beta   = - sum_k c_k tau_k
+//   val    = sum_i p_i max_val_i
+// k_cut_partial gathers one (rho, tau) row per scenario and point -- 2 N (n1 + 1) loads, 488 MB of L2 traffic
+// at the bench shape for 44 MB of algorithmic bytes.  Here the table is read ONCE (K (n1 + 1) doubles).
+// Deterministic without floating-point atomics:
+//   k_cut_hist  block b owns a contiguous segment of scenarios and a private c[] in shared memory; warp w owns
+//               the columns k = w (mod 32); every warp walks the segment in index order and adds, through ONE
+//               lane, the weights of the scenarios whose winner it owns -- so c_b[k] is the index-ordered sum
+//               over the segment, whatever the timing.  The segment's two scalar sums are a fixed tree.
+//   k_cut_fold  c[k] = sum_b c_b[k] in block order; chunk of 256 columns -> sum_k c_k (rho_k, tau_k) in column
+//               order; chunk 0 adds the scalar sums in block order.  k_sum_groups (above) adds the chunks.
+#define SQLP_HIST_THREADS 1024
+#define SQLP_HIST_SUB 2048          // scenarios staged in shared memory at a time
+#define SQLP_FOLD_COLS 256
+
+struct HistArgs {
+    const double *w;          // [n_local]
+    const double *rt;         // [K][n1 + 1] by pool slot
+    const int *act;           // view column -> pool slot, or null
+    const double *bias;       // [NX][bias_stride]
+    long long bias_stride;
+    const double *best_val;   // [NX][out_stride]
+    const int *best_idx;      // [NX][out_stride] view columns
+    long long out_stride;
+    long long n_local;
+    long long seg;            // scenarios per block (multiple of 128)
+    const long long *d_Kv;    // columns of the view
+    int kc;                   // columns the shared-memory histogram holds (>= *d_Kv, host upper bound)
+    int n1;
+    double total_weight;
+    // recomputing the winning dot when the score - bias shortcut is too coarse (see k_cut_partial)
+    const double *D, *PiS;
+    int s_pad;
+    double *cpart;            // [nblk][NX][kc]
+    double *spart;            // [nblk][NX][2]   (sum p dot, sum p score)
+    int *flags;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(SQLP_HIST_THREADS, 1) k_cut_hist(HistArgs a)
+{
+    griddep_sync();
+    extern __shared__ __align__(16) unsigned char hist_raw[];
+    double *c = reinterpret_cast<double *>(hist_raw);                    // [kc]
+    double *ps = c + a.kc;                                               // [SUB] weights p_i
+    int *ks = reinterpret_cast<int *>(ps + SQLP_HIST_SUB);               // [SUB] winning columns
+    __shared__ double red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long i0 = (long long)blockIdx.x * a.seg, i1 = min(a.n_local, i0 + a.seg);
+    const long long RT = a.n1 + 1;
+    for (int x = 0; x < NX; ++x) {
+        for (int k = tid; k < a.kc; k += blockDim.x) c[k] = 0.0;
+        double sdot = 0.0, sval = 0.0;                                   // this thread's scenarios, index order
+        __syncthreads();
+        for (long long b0 = i0; b0 < i1; b0 += SQLP_HIST_SUB) {
+            const int cnt = (int)min((long long)SQLP_HIST_SUB, i1 - b0);
+            for (int q = tid; q < cnt; q += blockDim.x) {
+                const long long i = b0 + q;
+                const int k = a.best_idx[x * a.out_stride + i];
+                double p = 0.0;
+                if (k < 0) {
+                    atomicOr(a.flags, 1);
+                } else {
+                    p = a.w[i] / a.total_weight;                         // epigraph.jl:138
+                    const double sc = a.best_val[x * a.out_stride + i];
+                    double acc = __dsub_rn(sc, a.bias[x * a.bias_stride + k]);
+                    if (fabs(sc) > 8192.0 * fmax(fabs(a.rt[(long long)(a.act ? a.act[k] : k) * RT]), fabs(acc))) {
+                        const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE + tile_off(k & 127, 0);
+                        const double *Dc = a.D + (i >> 7) * (long long)a.s_pad * SQLP_TILE + tile_off((int)(i & 127), 0);
+                        acc = 0.0;
+                        for (int g = 0; g < a.s_pad / 4; ++g, P += 512, Dc += 512)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) acc = fma(P[u * 2], Dc[u * 2], acc);
+                    }
+                    sdot = fma(p, acc, sdot);                            // :140 (the part that is not rho)
+                    sval = fma(p, sc, sval);                             // :142
+                }
+                ks[q] = k;
+                ps[q] = p;
+            }
+            __syncthreads();
+            // warp w adds the weights of the winners k = w (mod 32), in scenario order, through lane 0
+            for (int g = 0; g < cnt; g += 32) {
+                const int q = g + lane;
+                const int k = q < cnt ? ks[q] : -1;
+                const double p = q < cnt ? ps[q] : 0.0;
+                unsigned own = __ballot_sync(0xffffffffu, k >= 0 && (k & 31) == warp);
+                while (own) {
+                    const int src = __ffs(own) - 1;
+                    own &= own - 1;
+                    const int kk = __shfl_sync(0xffffffffu, k, src);
+                    const double pp = __shfl_sync(0xffffffffu, p, src);
+                    if (lane == 0) c[kk] += pp;
+                }
+            }
+            __syncthreads();
+        }
+        // the block's scalar sums: lanes, then warps, in a fixed tree
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, off);
+            sval += __shfl_xor_sync(0xffffffffu, sval, off);
+        }
+        if (lane == 0) { red[0][warp] = sdot; red[1][warp] = sval; }
+        __syncthreads();
+        if (warp == 0) {
+            double u = red[0][lane], v = red[1][lane];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                u += __shfl_xor_sync(0xffffffffu, u, off);
+                v += __shfl_xor_sync(0xffffffffu, v, off);
+            }
+            if (lane == 0) {
+                a.spart[((long long)blockIdx.x * NX + x) * 2] = u;
+                a.spart[((long long)blockIdx.x * NX + x) * 2 + 1] = v;
+            }
+        }
+        double *dst = a.cpart + ((long long)blockIdx.x * NX + x) * a.kc;
+        for (int k = tid; k < a.kc; k += blockDim.x) dst[k] = c[k];
+        __syncthreads();
+    }
+}
+
+// part[chunk][x][col]: col 0 = sum_k c_k rho_k (+ the blocks' sum p dot on chunk 0), 1..n1 = -sum_k c_k tau_kj,
+// n1 + 1 = the blocks' sum p score (chunk 0 only).  One block per chunk of 256 columns.
+template <int NX>
+__global__ void __launch_bounds__(256) k_cut_fold(HistArgs a, int nblk, double *__restrict__ part)
+{
+    griddep_sync();
+    __shared__ double ck[NX][SQLP_FOLD_COLS];
+    __shared__ int kp[SQLP_FOLD_COLS];
+    const long long Kv = *a.d_Kv;
+    const int k0 = blockIdx.x * SQLP_FOLD_COLS;
+    const int NC = a.n1 + 2;
+    const long long RT = a.n1 + 1;
+    for (int q = threadIdx.x; q < NX * SQLP_FOLD_COLS; q += blockDim.x) {
+        const int x = q / SQLP_FOLD_COLS, k = k0 + q % SQLP_FOLD_COLS;
+        double s = 0.0;
+        if (k < Kv && k < a.kc)
+            for (int b = 0; b < nblk; ++b) s += a.cpart[((long long)b * NX + x) * a.kc + k];   // block order
+        ck[x][q % SQLP_FOLD_COLS] = s;
+        if (x == 0) kp[q % SQLP_FOLD_COLS] = k < Kv ? (a.act ? a.act[k] : k) : -1;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < NX * NC; q += blockDim.x) {
+        const int x = q / NC, col = q % NC;
+        double s = 0.0;
+        if (col <= a.n1) {
+            for (int u = 0; u < SQLP_FOLD_COLS; ++u) {
+                const int k = kp[u];
+                if (k >= 0 && ck[x][u] != 0.0) s = fma(ck[x][u], a.rt[(long long)k * RT + col], s);   // column order
+            }
+            if (col > 0) s = -s;                                                                  // :141
+        }
+        if (blockIdx.x == 0 && (col == 0 || col == NC - 1)) {
+            double t = 0.0;
+            for (int b = 0; b < nblk; ++b) t += a.spart[((long long)b * NX + x) * 2 + (col == 0 ? 0 : 1)];
+            s += t;
+        }
+        part[(long long)blockIdx.x * NX * NC + q] = s;
+    }
+}
+
 // eval_dual, subprob.jl:128-131, in the reference's operation order (single thread):
 //   dot(dual, (rbar + delta_rhs) - (Tbar + delta_T) * x)
 struct EvalArgs {

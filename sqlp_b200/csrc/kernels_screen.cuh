@@ -541,30 +541,36 @@ struct ResolveArgs {
     int force_full;             // tests: sweep every vertex for every scenario with this kernel's arithmetic
 };
 
-template <int NX>
+// FMA (0 / 1): the chain as mma.sync.m8n8k4.f64 (eight candidates per chain, one of the eight rows used), or as plain
+// DFMA in the SAME order -- k-groups ascending, the four products of a group in k order from the running sum, which
+// is what the DMMA computes bit for bit (checked on the device at context creation, sqlp_api.cu:ctx_selftest; the
+// library uses the lanes variant only if that check passes): 32 candidates per chain, one per lane.
+template <int NX, int FMA>
 __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
 {
-    griddep_sync();
+    griddep_wait();
     if (!a.force_full && screen_falls_back(a.ctl)) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     const long long K = *a.d_K;
     const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
     const int cpr = (nch + a.R - 1) / max(a.R, 1);
     const int ng = a.s_pad / 4;
     const size_t tile_doubles = (size_t)a.s_pad * SQLP_TILE;
+    __shared__ int sq[8][32];                 // the warp's queue of candidates: vertex | point << 30  (lanes variant)
     unsigned long long evald = 0;
-    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.n_local; i += nw) {
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + wib; i < a.n_local; i += nw) {
         double best[NX];
         int bidx[NX];
 #pragma unroll
         for (int x = 0; x < NX; ++x) { best[x] = -INFINITY; bidx[x] = -1; }
         const int ci = (int)(i & 127);
-        const double *Drow = a.D + (size_t)(i >> 7) * tile_doubles +
-                             ((((size_t)(ci >> 4)) * 32 + (ci & 7) * 4 + (lane & 3)) << 1) + ((ci >> 3) & 1);
+        const double *Dtile = a.D + (size_t)(i >> 7) * tile_doubles;
         int qk = 0, qx = 0, qn = 0;
-        auto flush = [&]() {
+        // ---- DMMA variant: up to 8 queued (vertex, point) pairs, one chain ------------------------------------
+        auto flush8 = [&]() {
             if (qn == 0) return;
+            const double *Drow = Dtile + ((((size_t)(ci >> 4)) * 32 + (ci & 7) * 4 + (lane & 3)) << 1) + ((ci >> 3) & 1);
             const int kfirst = __shfl_sync(0xffffffffu, qk, 0);
             int kk = __shfl_sync(0xffffffffu, qk, lane >> 2);
             if ((lane >> 2) >= qn) kk = kfirst;                      // unused columns repeat a valid vertex
@@ -607,9 +613,58 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             evald += qn;
             qn = 0;
         };
+        // ---- lanes variant: lane l scores queued pair l with the DFMA chain; then a warp argmax per point -----
+        auto flush32 = [&]() {
+            if (qn == 0) return;
+            const int e = lane < qn ? sq[wib][lane] : sq[wib][0];
+            const int kk = e & 0x3FFFFFFF, xq = (e >> 30) & 3;           // xq = 2: every point (full sweeps)
+            const int cv = kk & 127;
+            const double *Pc = a.PiS + (size_t)(kk >> 7) * tile_doubles + ((((size_t)(cv >> 4)) * 32 + (cv & 7) * 4) << 1) + ((cv >> 3) & 1);
+            const double *Dc = Dtile + ((((size_t)(ci >> 4)) * 32 + (ci & 7) * 4) << 1) + ((ci >> 3) & 1);
+            double acc = 0.0;
+            int g = 0;
+            for (; g + 4 <= ng; g += 4) {
+                double pv[16], dv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    pv[u] = Pc[(size_t)(g + (u >> 2)) * 512 + (u & 3) * 2];
+                    dv[u] = Dc[(size_t)(g + (u >> 2)) * 512 + (u & 3) * 2];
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc = fma(dv[u], pv[u], acc);
+            }
+            for (; g < ng; ++g)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc = fma(Dc[(size_t)g * 512 + u * 2], Pc[(size_t)g * 512 + u * 2], acc);
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                double v = -INFINITY;
+                int kv = -1;
+                if (lane < qn && kk < K && (xq == 2 || xq == x)) {
+                    const double t = acc + a.bias[x * a.bias_stride + kk];
+                    if (t > -INFINITY) { v = t; kv = kk; }               // NaN and -Inf never win (subprob.jl:151-156)
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, kv, off);
+                    if (oi >= 0 && (kv < 0 || ov > v || (ov == v && oi < kv))) { v = ov; kv = oi; }
+                }
+                if (kv >= 0 && (v > best[x] || (v == best[x] && bidx[x] >= 0 && kv < bidx[x]))) { best[x] = v; bidx[x] = kv; }
+            }
+            evald += qn;
+            qn = 0;
+            __syncwarp();
+        };
         auto push = [&](int k, int x) {
-            if (lane == qn) { qk = k; qx = x; }
-            if (++qn == 8) flush();
+            if (FMA) {
+                if (lane == 0) sq[wib][qn] = k | (x << 30);
+                __syncwarp();
+                if (++qn == 32) flush32();
+            } else {
+                if (lane == qn) { qk = k; qx = x; }
+                if (++qn == 8) flush8();
+            }
         };
         // final lower bounds and overflow over the thread lists of this scenario
         float LB[NX];
@@ -634,10 +689,19 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             full = full || ovf;
         }
         if (full) {
-            for (long long k0 = 0; k0 < K; k0 += 8) {              // qx = -1: the dot serves every point
-                if (lane < 8) { qk = (int)min(k0 + lane, K - 1); qx = -1; }
-                qn = (int)min((long long)8, K - k0);
-                flush();
+            if (FMA) {
+                for (long long k0 = 0; k0 < K; k0 += 32) {          // xq = 2: the dot serves every point
+                    if (k0 + lane < K) sq[wib][lane] = (int)(k0 + lane) | (2 << 30);
+                    __syncwarp();
+                    qn = (int)min((long long)32, K - k0);
+                    flush32();
+                }
+            } else {
+                for (long long k0 = 0; k0 < K; k0 += 8) {           // qx = -1: the dot serves every point
+                    if (lane < 8) { qk = (int)min(k0 + lane, K - 1); qx = -1; }
+                    qn = (int)min((long long)8, K - k0);
+                    flush8();
+                }
             }
         } else {
 #pragma unroll
@@ -650,15 +714,30 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
                         int2 e = make_int2(0, 0);
                         if (b0 + lane < n) e = a.cand[slot * SCR_CAP + b0 + lane];
                         unsigned pass = __ballot_sync(0xffffffffu, b0 + lane < n && __int_as_float(e.y) >= LB[x]);
-                        while (pass) {
-                            const int src = __ffs(pass) - 1;
-                            pass &= pass - 1;
-                            push(__shfl_sync(0xffffffffu, e.x, src), x);
+                        if (FMA) {
+                            // the passing entries go to the queue in list order, 32 at most per flush
+                            while (pass) {
+                                const int room = 32 - qn, npass = __popc(pass);
+                                const int rank = __popc(pass & ((1u << lane) - 1u));
+                                const bool mine = ((pass >> lane) & 1u) && rank < room;
+                                if (mine) sq[wib][qn + rank] = e.x | (x << 30);
+                                const unsigned took = __ballot_sync(0xffffffffu, mine);
+                                __syncwarp();
+                                qn += min(room, npass);
+                                pass &= ~took;
+                                if (qn == 32) flush32();
+                            }
+                        } else {
+                            while (pass) {
+                                const int src = __ffs(pass) - 1;
+                                pass &= pass - 1;
+                                push(__shfl_sync(0xffffffffu, e.x, src), x);
+                            }
                         }
                     }
                 }
             }
-            flush();
+            if (FMA) flush32(); else flush8();
         }
         if (lane == 0) {
 #pragma unroll
@@ -669,6 +748,33 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
         }
     }
     if (lane == 0 && evald) atomicAdd(&a.ctl->n_eval, evald);
+    griddep_launch();
+}
+
+// Device check behind the lanes variant: on `n` random chains of `ng` k-groups, is mma.sync.m8n8k4.f64 the DFMA
+// chain in k order, bit for bit?  *bad counts the chains where it is not.
+__global__ void k_dmma_is_fma_chain(int ng, int n, unsigned int *__restrict__ bad)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    double acc0 = 0.0, acc1 = 0.0, f = 0.0;
+    for (int g = 0; g < ng; ++g) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {      // wide dynamic range and signs: cancellation, so that the order matters
+            const unsigned long long q = ((unsigned long long)w * ng + g) * 4 + k;
+            av[k] = (2.0 * u01(21, q) - 1.0) * exp2(floor(40.0 * u01(23, q)) - 20.0);
+            bv[k] = (2.0 * u01(22, q) - 1.0) * exp2(floor(40.0 * u01(24, q)) - 20.0);
+        }
+        const double a1 = av[lane & 3], b1 = bv[lane & 3];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(acc0), "+d"(acc1) : "d"(a1), "d"(b1));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f = fma(av[k], bv[k], f);
+    }
+    const bool differ = __double_as_longlong(acc0) != __double_as_longlong(f) || __double_as_longlong(acc1) != __double_as_longlong(f);
+    if (__any_sync(0xffffffffu, differ) && lane == 0) atomicAdd(bad, 1u);
 }
 
 }  // namespace sqlp

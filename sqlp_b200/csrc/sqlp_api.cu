@@ -82,6 +82,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     if (const char *g = getenv("SQLP_PDL")) c->pdl = atoi(g) != 0;
     if (const char *g = getenv("SQLP_SCREEN")) c->screen_mode = std::max(0, std::min(2, atoi(g)));
     if (const char *g = getenv("SQLP_TWINS")) c->twins = atoi(g) != 0;
+    if (const char *g = getenv("SQLP_REDUCE")) c->reduce_mode = std::max(0, std::min(2, atoi(g)));
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_PREFETCH")) c->contract_prefetch = atoi(g);
     if (const char *g = getenv("SQLP_CONTRACT_LAG_NS")) c->contract_lag_ns = atoi(g);
@@ -95,6 +96,20 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     c->stream = c->own_stream;
     CK(cudaEventCreate(&c->t0));
     CK(cudaEventCreate(&c->t1));
+    {   // may the exact decision score candidates with plain DFMA chains?  Only if, on THIS device, the DMMA of the
+        // FP64 sweep is that chain bit for bit (it is on sm_100a; checked, not assumed).  SQLP_RESOLVE=dmma keeps DMMA.
+        const char *g = getenv("SQLP_RESOLVE");
+        if (!g || strcmp(g, "dmma")) {
+            unsigned int *d_bad = nullptr, h_bad = 1;
+            CK(cudaMalloc(&d_bad, 4));
+            CK(cudaMemsetAsync(d_bad, 0, 4, c->stream));
+            k_dmma_is_fma_chain<<<2048 / 8, 256, 0, c->stream>>>(32, 2048, d_bad);
+            CK(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaFree(d_bad));
+            c->resolve_fma = (h_bad == 0);
+        }
+    }
 }
 
 int32_t sqlp_ctx_create(int32_t device, sqlp_ctx **out)

@@ -197,3 +197,36 @@ def test_score_minus_bias_shortcut_is_guarded(T, oracle):
         cut, v = epi2.build_cut(x, with_val=True)
         mv, mi = epi2.argmax(x)
         cut_vs_forced(oracle, P, vals, w, x, pool2, mi, cut, v)
+
+
+@pytest.mark.parametrize("name,K,N", [("storm", 3000, 5000), ("ssn", 1200, 700), ("baa99-20", 1024, 130)])
+def test_cut_reduction_by_vertex_weights(T, oracle, monkeypatch, name, K, N):
+    """The two cut reductions -- one (rho, tau) row gathered per scenario (k_cut_partial) and per-vertex weight sums
+    (k_cut_hist / k_cut_fold: the table is read once) -- regroup the same sum (epigraph.jl:134-143): both within
+    1e-10 of the oracle on the same selection, each bitwise reproducible from run to run."""
+    P, z = load_instance(name)
+    pool = load_pool(name, {"storm": 16384, "ssn": 5000, "baa99-20": 1024}[name])[:K]
+    vals = sampled_values_at(z, 5, np.arange(N))
+    w = 0.5 + oracle.u01(9, np.arange(N))
+    xs = (z["x_ev"], z["x_alt"])
+    got = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("SQLP_REDUCE", mode)
+        ctx = T.Context(0)
+        dvs = T.sdDualVertexSet(ctx=ctx, m2=P.m2)
+        dvs.push_many(pool)
+        epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+        epi.add_scenarios(vals, w)
+        (c0, c1), val = epi.build_cuts2(*xs, with_val=True)
+        (d0, d1), val2 = epi.build_cuts2(*xs, with_val=True)
+        assert c0.alpha == d0.alpha and np.array_equal(c1.beta, d1.beta) and np.array_equal(val, val2)
+        for x, cut, v in zip(xs, (c0, c1), val):
+            mv, mi = epi.argmax(x)
+            cut_vs_forced(oracle, P, vals, w, x, pool, mi, cut, v)
+        one = epi.build_cut(xs[1], with_val=True)            # the single-point form
+        assert abs(one[0].alpha - c1.alpha) <= 1e-12 * abs(c1.alpha)
+        got[mode] = (c0, c1)
+        epi.close(); dvs.close(); ctx.close()
+    for a, b in zip(got["1"], got["2"]):
+        assert abs(a.alpha - b.alpha) <= 1e-12 * abs(a.alpha)
+        assert np.allclose(a.beta, b.beta, rtol=1e-11, atol=1e-9 * np.abs(a.beta).max())

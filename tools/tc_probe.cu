@@ -208,16 +208,36 @@ int main(int argc, char **argv)
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaMemset(d_bi, 0xff, (size_t)NX * npad * 4));
     CK(cudaEventRecord(e0));
-    k_screen_resolve<NX><<<8 * sms, 256>>>(ra);
+    k_screen_resolve<NX, 0><<<8 * sms, 256>>>(ra);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms_res = 0;
     CK(cudaEventElapsedTime(&ms_res, e0, e1));
+    {   // the lanes variant (DFMA chains, 32 candidates per pass) must give the same bits
+        std::vector<double> v0((size_t)NX * npad), v1((size_t)NX * npad);
+        std::vector<int> i0((size_t)NX * npad), i1((size_t)NX * npad);
+        CK(cudaMemcpy(v0.data(), d_bv, v0.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(i0.data(), d_bi, i0.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(d_bi, 0xff, (size_t)NX * npad * 4));
+        CK(cudaEventRecord(e0));
+        k_screen_resolve<NX, 1><<<8 * sms, 256>>>(ra);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms1 = 0;
+        CK(cudaEventElapsedTime(&ms1, e0, e1));
+        CK(cudaMemcpy(v1.data(), d_bv, v1.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(i1.data(), d_bi, i1.size() * 4, cudaMemcpyDeviceToHost));
+        long long mm = 0;
+        for (int x = 0; x < NX; ++x)
+            for (long long i = 0; i < N; ++i)
+                if (i0[x * npad + i] != i1[x * npad + i] || memcmp(&v0[x * npad + i], &v1[x * npad + i], 8)) ++mm;
+        printf("check 5 (DFMA-lanes resolve == DMMA resolve, %lld scenarios x %d points): %lld mismatches; %.3f ms vs %.3f ms\n", N, NX, mm, ms1, ms_res);
+    }
     CK(cudaMemcpy(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     printf("resolve: %.3f ms, %llu exact evaluations (%.2f per scenario-point)\n", ms_res, ctl.n_eval, (double)ctl.n_eval / (double)(N * NX));
     const long long Nfull = std::min<long long>(N, 4096);      // the full sweep with this kernel is slow: a prefix
     ra.n_local = Nfull; ra.best_val = d_bv2; ra.best_idx = d_bi2; ra.force_full = 1;
-    k_screen_resolve<NX><<<8 * sms, 256>>>(ra);
+    k_screen_resolve<NX, 1><<<8 * sms, 256>>>(ra);
     CK(cudaDeviceSynchronize());
     std::vector<double> bv((size_t)NX * npad), bv2((size_t)NX * npad);
     std::vector<int> bi((size_t)NX * npad), bi2((size_t)NX * npad);
