@@ -559,7 +559,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         const int64_t kc = round_up(std::max<int64_t>(ku, 1), 32);
         const size_t hist_smem = (size_t)kc * 8 + (size_t)SQLP_HIST_SUB * 12;
         if (e->n_T == 0 && c->reduce_mode != 1 && (c->reduce_mode == 2 || e->n_local >= 16384) &&
-            hist_smem <= (size_t)c->smem_optin) {
+            hist_smem + 1024 <= (size_t)c->smem_optin) {
             const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, (e->n_local + 4095) / 4096));
             HistArgs h;
             h.w = r.w; h.rt = r.rt; h.act = r.act; h.bias = r.bias; h.bias_stride = r.bias_stride;
@@ -575,8 +575,9 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
             const int nchunk = (int)((kc + SQLP_FOLD_COLS - 1) / SQLP_FOLD_COLS);
             e->d_partial.ensure((size_t)nchunk * width * 8, 0, S(c), false);
             if (!c->hist_smem_set[NX]) {
-                if (NX == 2) CK(cudaFuncSetAttribute(k_cut_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-                else CK(cudaFuncSetAttribute(k_cut_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+                // (the kernel also has 512 B of static shared memory: the dynamic part cannot be the whole opt-in size)
+                if (NX == 2) CK(cudaFuncSetAttribute(k_cut_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
+                else CK(cudaFuncSetAttribute(k_cut_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
                 c->hist_smem_set[NX] = true;
             }
             if (NX == 2) {

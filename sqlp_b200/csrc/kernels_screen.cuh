@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
         const int ci = (int)(i & 127);
         const double *Dtile = a.D + (size_t)(i >> 7) * tile_doubles;
         int qk = 0, qx = 0, qn = 0;
-        // ---- DMMA variant: up to 8 queued (vertex, point) pairs, one chain ------------------------------------
+        // ---- DMMA chain: up to 8 (vertex, point) pairs held by lanes 0..7 (qk, qx), qn of them ------------------
         auto flush8 = [&]() {
             if (qn == 0) return;
             const double *Drow = Dtile + ((((size_t)(ci >> 4)) * 32 + (ci & 7) * 4 + (lane & 3)) << 1) + ((ci >> 3) & 1);
@@ -616,6 +616,23 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
         // ---- lanes variant: lane l scores queued pair l with the DFMA chain; then a warp argmax per point -----
         auto flush32 = [&]() {
             if (qn == 0) return;
+            if (!FMA || qn <= 8) {
+                // few candidates (the usual case on pools with clear winners): DMMA chains of eight are quicker
+                const int total = qn;
+                for (int b0 = 0; b0 < total; b0 += 8) {
+                    const int m = min(8, total - b0);
+                    if (lane < m) {
+                        const int e8 = sq[wib][b0 + lane];
+                        qk = e8 & 0x3FFFFFFF;
+                        qx = ((e8 >> 30) & 3) == 2 ? -1 : ((e8 >> 30) & 3);
+                    }
+                    qn = m;
+                    flush8();
+                }
+                qn = 0;
+                __syncwarp();
+                return;
+            }
             const int e = lane < qn ? sq[wib][lane] : sq[wib][0];
             const int kk = e & 0x3FFFFFFF, xq = (e >> 30) & 3;           // xq = 2: every point (full sweeps)
             const int cv = kk & 127;
@@ -656,16 +673,6 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             qn = 0;
             __syncwarp();
         };
-        auto push = [&](int k, int x) {
-            if (FMA) {
-                if (lane == 0) sq[wib][qn] = k | (x << 30);
-                __syncwarp();
-                if (++qn == 32) flush32();
-            } else {
-                if (lane == qn) { qk = k; qx = x; }
-                if (++qn == 8) flush8();
-            }
-        };
         // final lower bounds and overflow over the thread lists of this scenario
         float LB[NX];
         bool full = a.force_full != 0;
@@ -689,19 +696,11 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             full = full || ovf;
         }
         if (full) {
-            if (FMA) {
-                for (long long k0 = 0; k0 < K; k0 += 32) {          // xq = 2: the dot serves every point
-                    if (k0 + lane < K) sq[wib][lane] = (int)(k0 + lane) | (2 << 30);
-                    __syncwarp();
-                    qn = (int)min((long long)32, K - k0);
-                    flush32();
-                }
-            } else {
-                for (long long k0 = 0; k0 < K; k0 += 8) {           // qx = -1: the dot serves every point
-                    if (lane < 8) { qk = (int)min(k0 + lane, K - 1); qx = -1; }
-                    qn = (int)min((long long)8, K - k0);
-                    flush8();
-                }
+            for (long long k0 = 0; k0 < K; k0 += 32) {              // point code 2: the dot serves every point
+                if (k0 + lane < K) sq[wib][lane] = (int)(k0 + lane) | (2 << 30);
+                __syncwarp();
+                qn = (int)min((long long)32, K - k0);
+                flush32();
             }
         } else {
 #pragma unroll
@@ -714,30 +713,22 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
                         int2 e = make_int2(0, 0);
                         if (b0 + lane < n) e = a.cand[slot * SCR_CAP + b0 + lane];
                         unsigned pass = __ballot_sync(0xffffffffu, b0 + lane < n && __int_as_float(e.y) >= LB[x]);
-                        if (FMA) {
-                            // the passing entries go to the queue in list order, 32 at most per flush
-                            while (pass) {
-                                const int room = 32 - qn, npass = __popc(pass);
-                                const int rank = __popc(pass & ((1u << lane) - 1u));
-                                const bool mine = ((pass >> lane) & 1u) && rank < room;
-                                if (mine) sq[wib][qn + rank] = e.x | (x << 30);
-                                const unsigned took = __ballot_sync(0xffffffffu, mine);
-                                __syncwarp();
-                                qn += min(room, npass);
-                                pass &= ~took;
-                                if (qn == 32) flush32();
-                            }
-                        } else {
-                            while (pass) {
-                                const int src = __ffs(pass) - 1;
-                                pass &= pass - 1;
-                                push(__shfl_sync(0xffffffffu, e.x, src), x);
-                            }
+                        // the passing entries go to the warp's queue in list order, 32 at most per flush
+                        while (pass) {
+                            const int room = 32 - qn, npass = __popc(pass);
+                            const int rank = __popc(pass & ((1u << lane) - 1u));
+                            const bool mine = ((pass >> lane) & 1u) && rank < room;
+                            if (mine) sq[wib][qn + rank] = e.x | (x << 30);
+                            const unsigned took = __ballot_sync(0xffffffffu, mine);
+                            __syncwarp();
+                            qn += min(room, npass);
+                            pass &= ~took;
+                            if (qn == 32) flush32();
                         }
                     }
                 }
             }
-            if (FMA) flush32(); else flush8();
+            flush32();
         }
         if (lane == 0) {
 #pragma unroll
