@@ -49,12 +49,21 @@ end
 function context()
     if CTX[] == C_NULL
         out = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:sqlp_ctx_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), Int32(DEVICE[]), out))
+        if N_GPUS[] > 1
+            # this one Julia thread drives every GPU of the box (SURVEY.md 8(b)): pools replicated, epigraphs
+            # sharded, one grouped all-gather per call -- nothing else in this file changes
+            devs = Int32.(DEVICE[]:DEVICE[]+N_GPUS[]-1)
+            check(ccall((:sqlp_ctx_create_multi, LIB[]), Int32, (Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+                        Int32(N_GPUS[]), devs, out))
+        else
+            check(ccall((:sqlp_ctx_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), Int32(DEVICE[]), out))
+        end
         CTX[] = out[]
     end
     return CTX[]
 end
 const DEVICE = Ref{Int}(0)
+const N_GPUS = Ref{Int}(1)
 
 function new_pool(m2::Int)
     out = Ref{Ptr{Cvoid}}(C_NULL)
@@ -91,8 +100,8 @@ function position_table(T, coef, sto)
     return order, rows, cols
 end
 
-function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, sto = nothing)
-    LIB[] = lib; DEVICE[] = device
+function enable!(T::Module; lib::String = "libsqlp_b200.so", device::Int = 0, n_gpus::Int = 1, sto = nothing)
+    LIB[] = lib; DEVICE[] = device; N_GPUS[] = n_gpus
     sto === nothing && error("pass the spStoType so the position table can be resolved once")
 
     # --- the device half of an sdEpigraph, created at the first call that names the dual-vertex set ----

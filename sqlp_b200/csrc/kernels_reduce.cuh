@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_sum_groups(const double *__restrict__ i
 //               order; chunk 0 adds the scalar sums in block order.  k_sum_groups (above) adds the chunks.
 #define SQLP_HIST_THREADS 1024
 #define SQLP_HIST_SUB 2048          // scenarios staged in shared memory at a time
-#define SQLP_FOLD_COLS 256
+#define SQLP_FOLD_COLS 64
 
 struct HistArgs {
     const double *w;          // [n_local]
@@ -424,8 +424,17 @@ __global__ void __launch_bounds__(256) k_cut_fold(HistArgs a, int nblk, double *
     for (int q = threadIdx.x; q < NX * SQLP_FOLD_COLS; q += blockDim.x) {
         const int x = q / SQLP_FOLD_COLS, k = k0 + q % SQLP_FOLD_COLS;
         double s = 0.0;
-        if (k < Kv && k < a.kc)
-            for (int b = 0; b < nblk; ++b) s += a.cpart[((long long)b * NX + x) * a.kc + k];   // block order
+        if (k < Kv && k < a.kc) {
+            const double *src = a.cpart + (long long)x * a.kc + k;
+            const long long bs = (long long)NX * a.kc;
+            for (int b = 0; b < nblk; b += 8) {              // block order; eight loads in flight
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = b + u < nblk ? src[(b + u) * bs] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];       // + 0.0 changes nothing (s starts at +0)
+            }
+        }
         ck[x][q % SQLP_FOLD_COLS] = s;
         if (x == 0) kp[q % SQLP_FOLD_COLS] = k < Kv ? (a.act ? a.act[k] : k) : -1;
     }
@@ -434,9 +443,19 @@ __global__ void __launch_bounds__(256) k_cut_fold(HistArgs a, int nblk, double *
         const int x = q / NC, col = q % NC;
         double s = 0.0;
         if (col <= a.n1) {
-            for (int u = 0; u < SQLP_FOLD_COLS; ++u) {
-                const int k = kp[u];
-                if (k >= 0 && ck[x][u] != 0.0) s = fma(ck[x][u], a.rt[(long long)k * RT + col], s);   // column order
+            // column order.  The table row of a vertex nobody selected is loaded (from a valid address) but not
+            // used: its entries may be Inf / NaN, and 0 * Inf is not 0.
+            for (int u0 = 0; u0 < SQLP_FOLD_COLS; u0 += 8) {
+                double tv[8], cw[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = kp[u0 + u];
+                    cw[u] = ck[x][u0 + u];
+                    const double t = a.rt[(long long)max(k, 0) * RT + col];
+                    tv[u] = (k >= 0 && cw[u] != 0.0) ? t : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s = fma(cw[u], tv[u], s);
             }
             if (col > 0) s = -s;                                                                  // :141
         }

@@ -673,27 +673,101 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             qn = 0;
             __syncwarp();
         };
+        // the passing entries of a batch of 32 go to the warp's queue in list order, 32 at most per flush
+        auto enqueue = [&](unsigned pass, int k, int x) {
+            while (pass) {
+                const int room = 32 - qn, npass = __popc(pass);
+                const int rank = __popc(pass & ((1u << lane) - 1u));
+                const bool mine = ((pass >> lane) & 1u) && rank < room;
+                if (mine) sq[wib][qn + rank] = k | (x << 30);
+                const unsigned took = __ballot_sync(0xffffffffu, mine);
+                __syncwarp();
+                qn += min(room, npass);
+                pass &= ~took;
+                if (qn == 32) flush32();
+            }
+        };
         // final lower bounds and overflow over the thread lists of this scenario
         float LB[NX];
         bool full = a.force_full != 0;
+        if (a.R == 1) {
+            // the usual case (enough scenarios to fill the GPU): 2 NX lists.  Lane l < 2 NX reads the count and the
+            // bound of list l; then every entry of every list is requested before any is looked at, so the scenario
+            // costs three dependent memory round trips (counts, entries, operands) whatever the number of lists.
+            constexpr int L = 2 * NX;
+            int myn = 0;
+            float mylb = -INFINITY;
+            if (lane < L && nch > 0) {
+                const long long slot = (long long)lane * a.npad + i;       // ((x * 1 + 0) * 2 + h) = lane
+                myn = a.cnt[slot];
+                mylb = a.lfin[slot];
+            }
+            int nl[L];
 #pragma unroll
-        for (int x = 0; x < NX; ++x) {
-            float lb = -INFINITY;
-            int ovf = 0;
-            for (int s = lane; s < 2 * a.R; s += 32) {
-                const int r = s >> 1;
-                if (r * cpr >= nch) continue;                         // empty K-range: nothing was written
-                const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
-                lb = fmaxf(lb, a.lfin[slot]);
-                ovf |= a.cnt[slot] > SCR_CAP;
+            for (int l = 0; l < L; ++l) {
+                nl[l] = __shfl_sync(0xffffffffu, myn, l);
+                full = full || nl[l] > SCR_CAP;
             }
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, off));
-                ovf |= __shfl_xor_sync(0xffffffffu, ovf, off);
+            for (int x = 0; x < NX; ++x)
+                LB[x] = fmaxf(__shfl_sync(0xffffffffu, mylb, 2 * x), __shfl_sync(0xffffffffu, mylb, 2 * x + 1));
+            if (!full) {
+                int2 ent[L][SCR_CAP / 32];
+#pragma unroll
+                for (int l = 0; l < L; ++l)
+#pragma unroll
+                    for (int b = 0; b < SCR_CAP / 32; ++b) {
+                        ent[l][b] = make_int2(0, 0);
+                        if (b * 32 + lane < nl[l]) ent[l][b] = a.cand[((long long)l * a.npad + i) * SCR_CAP + b * 32 + lane];
+                    }
+#pragma unroll
+                for (int l = 0; l < L; ++l)
+#pragma unroll
+                    for (int b = 0; b < SCR_CAP / 32; ++b) {
+                        if (b * 32 >= nl[l]) continue;
+                        const unsigned pass = __ballot_sync(0xffffffffu, b * 32 + lane < nl[l] &&
+                                                                         __int_as_float(ent[l][b].y) >= LB[l >> 1]);
+                        enqueue(pass, ent[l][b].x, l >> 1);
+                    }
+                flush32();
             }
-            LB[x] = lb;
-            full = full || ovf;
+        } else {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                float lb = -INFINITY;
+                int ovf = 0;
+                for (int s = lane; s < 2 * a.R; s += 32) {
+                    const int r = s >> 1;
+                    if (r * cpr >= nch) continue;                         // empty K-range: nothing was written
+                    const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
+                    lb = fmaxf(lb, a.lfin[slot]);
+                    ovf |= a.cnt[slot] > SCR_CAP;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, off));
+                    ovf |= __shfl_xor_sync(0xffffffffu, ovf, off);
+                }
+                LB[x] = lb;
+                full = full || ovf;
+            }
+            if (!full) {
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    for (int s = 0; s < 2 * a.R; ++s) {
+                        if ((s >> 1) * cpr >= nch) continue;
+                        const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
+                        const int n = min(a.cnt[slot], SCR_CAP);
+                        for (int b0 = 0; b0 < n; b0 += 32) {
+                            int2 e = make_int2(0, 0);
+                            if (b0 + lane < n) e = a.cand[slot * SCR_CAP + b0 + lane];
+                            const unsigned pass = __ballot_sync(0xffffffffu, b0 + lane < n && __int_as_float(e.y) >= LB[x]);
+                            enqueue(pass, e.x, x);
+                        }
+                    }
+                }
+                flush32();
+            }
         }
         if (full) {
             for (long long k0 = 0; k0 < K; k0 += 32) {              // point code 2: the dot serves every point
@@ -702,33 +776,6 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
                 qn = (int)min((long long)32, K - k0);
                 flush32();
             }
-        } else {
-#pragma unroll
-            for (int x = 0; x < NX; ++x) {
-                for (int s = 0; s < 2 * a.R; ++s) {
-                    if ((s >> 1) * cpr >= nch) continue;
-                    const long long slot = ((long long)(x * a.R) * 2 + s) * a.npad + i;
-                    const int n = min(a.cnt[slot], SCR_CAP);
-                    for (int b0 = 0; b0 < n; b0 += 32) {
-                        int2 e = make_int2(0, 0);
-                        if (b0 + lane < n) e = a.cand[slot * SCR_CAP + b0 + lane];
-                        unsigned pass = __ballot_sync(0xffffffffu, b0 + lane < n && __int_as_float(e.y) >= LB[x]);
-                        // the passing entries go to the warp's queue in list order, 32 at most per flush
-                        while (pass) {
-                            const int room = 32 - qn, npass = __popc(pass);
-                            const int rank = __popc(pass & ((1u << lane) - 1u));
-                            const bool mine = ((pass >> lane) & 1u) && rank < room;
-                            if (mine) sq[wib][qn + rank] = e.x | (x << 30);
-                            const unsigned took = __ballot_sync(0xffffffffu, mine);
-                            __syncwarp();
-                            qn += min(room, npass);
-                            pass &= ~took;
-                            if (qn == 32) flush32();
-                        }
-                    }
-                }
-            }
-            flush32();
         }
         if (lane == 0) {
 #pragma unroll
