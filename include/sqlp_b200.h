@@ -233,7 +233,9 @@ SQLP_API int32_t sqlp_cell_sd_step(int32_t n_epi, sqlp_epi *const *epi, const do
                                    double *weight_mark, double *val /*or NULL*/);
 /* Screening statistics of an epigraph (synchronises): out[0] passes seen by the host, [1] of which fell back to
  * the FP64 sweep, and for the last pass seen: [2] candidates emitted, [3] exact evaluations, [4] overflowed
- * candidate lists, [5] non-finite / out-of-range operands, [6..7] vertices that could win at each point. */
+ * candidate lists, [5] bit 0: non-finite / out-of-range operands, >> 1: passes that succeeded but needed more than
+ * eight exact evaluations per scenario-point (the automatic mode then leaves the pass out for a while: the FP64
+ * sweep is quicker on such pools), [6..7] vertices that could win at each point. */
 SQLP_API int32_t sqlp_epi_screen_stats(sqlp_epi *epi, int64_t *out /*[8]*/);
 /* Enqueue only: d_x2 = [x_cand | x_inc] on the device, d_out = [2][n1 + 2] on the device
  * holding (alpha, beta[n1], val) per x.  Errors such as a missing argmax surface at the

@@ -328,7 +328,8 @@ struct sqlp_epi {
     cudaEvent_t ctl_event = nullptr;
     bool ctl_pending = false;
     int scr_skip = 0, scr_backoff = 0;   // calls to leave the pass out after it fell back (doubles up to 1024)
-    int64_t scr_runs = 0, scr_fallbacks = 0;
+    int64_t scr_runs = 0, scr_fallbacks = 0, scr_unprofitable = 0;
+    int scr_nx = 0;                // points of the pass whose control block is on its way back
     ScreenCtl scr_last = {};       // statistics of the last pass the host has seen
 };
 

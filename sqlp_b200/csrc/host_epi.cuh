@@ -249,7 +249,13 @@ void screen_learn(sqlp_epi *e)
     const ScreenCtl &h = *e->h_ctl.as<ScreenCtl>();
     e->scr_last = h;
     ++e->scr_runs;
-    if (h.bad != 0 || h.overflow > h.ovf_limit) {
+    // A pass that succeeded may still not have paid: every exact evaluation is a gather of two operand rows
+    // (measured on B200: the cost of ~50 pairs of the FP64 sweep), and a pool of near-ties -- storm's real duals
+    // leave ~23 candidates per scenario and point among 3 600 classes -- makes the pass as slow as the sweep it
+    // stands in for.  Past eight evaluations per scenario-point the sweep is the better plan.
+    const bool unprofitable = (double)h.n_eval > 8.0 * (double)e->n_local * (double)std::max(1, e->scr_nx);
+    if (unprofitable) ++e->scr_unprofitable;
+    if (h.bad != 0 || h.overflow > h.ovf_limit || unprofitable) {
         // it fell back to the FP64 sweep (non-finite operands, or candidate lists overflowing: a pool of
         // near-ties such as storm's real duals): leave the pass out for a while, longer every time
         ++e->scr_fallbacks;
@@ -405,6 +411,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
         if (c->resolve_fma) LAUNCH(c, (k_screen_resolve<NX, 1>), rgrid, 256, 0, ra);
         else LAUNCH(c, (k_screen_resolve<NX, 0>), rgrid, 256, 0, ra);
     }
+    e->scr_nx = NX;
     // the control block goes back to the host asynchronously; screen_learn() reads it at a later call
     if (!e->ctl_event) CK(cudaEventCreateWithFlags(&e->ctl_event, cudaEventDisableTiming));
     if (!e->ctl_pending) {

@@ -292,7 +292,7 @@ int32_t sqlp_epi_screen_stats(sqlp_epi *e, int64_t *out /*[8]*/)
         out[2] = (int64_t)h.n_emit;
         out[3] = (int64_t)h.n_eval;
         out[4] = (int64_t)h.overflow;
-        out[5] = h.bad;
+        out[5] = h.bad + 2 * e->scr_unprofitable;   // bit 0: bad operands; the rest: passes judged unprofitable
         out[6] = h.live[0];
         out[7] = h.live[1];
     });

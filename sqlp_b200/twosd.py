@@ -538,7 +538,10 @@ class sdEpigraph:
         out = np.zeros(8, dtype=np.int64)
         check(_lib.lib().sqlp_epi_screen_stats(self._h, _ptr(out)))
         keys = ("passes", "fallbacks", "emitted", "evaluated", "overflowed_lists", "bad_operands", "live_0", "live_1")
-        return {k: int(v) for k, v in zip(keys, out)}
+        d = {k: int(v) for k, v in zip(keys, out)}
+        d["unprofitable_passes"] = d["bad_operands"] // 2       # succeeded, but slower than the FP64 sweep would be
+        d["bad_operands"] &= 1
+        return d
 
     def eval_dual(self, local_scen, vertex, x):
         x = _f64(x)

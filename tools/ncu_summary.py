@@ -17,7 +17,14 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        # 5th-generation tensor cores (tcgen05): pipe activity, bf16 -> fp32 operations, tensor memory traffic
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.per_second",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 STALL = "smsp__average_warps_issue_stalled_"
 
 def main():
