@@ -372,13 +372,21 @@ __global__ void __launch_bounds__(SQLP_HIST_THREADS, 1) k_cut_hist(HistArgs a)
                 const int q = g + lane;
                 const int k = q < cnt ? ks[q] : -1;
                 const double p = q < cnt ? ps[q] : 0.0;
-                unsigned own = __ballot_sync(0xffffffffu, k >= 0 && (k & 31) == warp);
+                const bool mine = k >= 0 && (k & 31) == warp;
+                unsigned own = __ballot_sync(0xffffffffu, mine);
                 while (own) {
-                    const int src = __ffs(own) - 1;
-                    own &= own - 1;
-                    const int kk = __shfl_sync(0xffffffffu, k, src);
-                    const double pp = __shfl_sync(0xffffffffu, p, src);
-                    if (lane == 0) c[kk] += pp;
+                    // the owned scenarios of this group that chose the same column are added up first (in lane
+                    // order, in a register) and reach shared memory as ONE update: when the winners concentrate on
+                    // a few vertices, a chain of dependent shared-memory updates would serialise the block
+                    const int kk = __shfl_sync(0xffffffffu, k, __ffs(own) - 1);
+                    unsigned same = __ballot_sync(0xffffffffu, mine && k == kk);
+                    own &= ~same;
+                    double sum = 0.0;
+                    while (same) {
+                        sum += __shfl_sync(0xffffffffu, p, __ffs(same) - 1);
+                        same &= same - 1;
+                    }
+                    if (lane == 0) c[kk] += sum;
                 }
             }
             __syncthreads();
