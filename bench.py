@@ -399,14 +399,15 @@ def run_ours(args):
             staged.append((torch.from_numpy(scen).to(dev), torch.from_numpy(verts).to(dev)))
         torch.cuda.synchronize()
 
+        cell_handles = (C.c_void_p * Ecell)(*[e._h for e in cell.epis])
+
         def dev_step(t):
             scen_d, verts_d = staged[t]
             for e, epi in enumerate(cell.epis):
                 _lib.check(L.sqlp_epi_add_scenarios_dev(epi._h, 1, C.c_void_p(scen_d[e].data_ptr()), None))
             _lib.check(L.sqlp_pool_push_dev(cell.dvs._h, 2 * Ecell, C.c_void_p(verts_d.data_ptr())))
-            for e, epi in enumerate(cell.epis):
-                _lib.check(L.sqlp_epi_build_cuts2_dev(epi._h, C.c_void_p(x2_dev.data_ptr()),
-                                                      C.c_void_p(out_dev[e].data_ptr())))
+            _lib.check(L.sqlp_cell_build_cuts2_dev(Ecell, cell_handles, C.c_void_p(x2_dev.data_ptr()),
+                                                   C.c_void_p(out_dev.data_ptr())))
 
         # warm-up steps: after the first one every kernel class is bracketed by events (roofline_other); the timed
         # steps bracket only the argmax kernels, so the instrumentation costs two event records per launch
@@ -437,7 +438,15 @@ def run_ours(args):
         if cuprof:
             torch.cuda.cudart().cudaProfilerStop()
         clocks = sampler.finish()
-        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        ms_mine = ev0.elapsed_time(ev1)
+        ms = max_over_ranks(ms_mine)
+        per_rank = None
+        if world > 1:     # which GPU was the slow one, and at what clock (8 GPUs share a box's power budget)
+            mine = torch.tensor([ms_mine, clocks["sm_mhz"] or 0.0, float(len(clocks["reasons"]))], dtype=torch.float64, device=dev)
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = {"ms": [round(float(a[0]), 3) for a in allr], "sm_mhz": [float(a[1]) for a in allr],
+                        "throttle_reasons_seen": [int(a[2]) for a in allr]}
         launches = ctx.launch_count() - launches0
         prof = ctx.profile_classes(reset=True)
         ctx.profile(False)
@@ -448,7 +457,7 @@ def run_ours(args):
         cols, nrel = cell.epis[0].view_columns()
         return {"ms": ms, "ms_per_step": ms / max(1, steps), "value": evals / (ms * 1e-3), "launches": launches,
                 "prof": prof, "prof_warm": prof_warm, "clocks": clocks, "out": out_dev.cpu().numpy(),
-                "screen": cell.epis[0].screen_stats(),
+                "screen": cell.epis[0].screen_stats(), "per_rank": per_rank,
                 "sweep": {"pool_vertices": K_after, "columns_swept": cols, "relevant_rows": nrel, "rows": m2,
                           "note": "evaluations are counted as the reference performs them (2 points x K x N per "
                                   "iteration); vertices equal on every relevant row have bit-identical scores and "
@@ -535,7 +544,8 @@ def run_ours(args):
     assert np.isfinite(cut_check).all()
 
     # ---- parity of the bench's OWN state against the oracle -----------------------------------
-    parity = parity_sample(args, T, dist if world > 1 else None, cell, world, rank, alpha, beta, x_c, x_i, pool_all)
+    parity = (parity_sample(args, T, dist if world > 1 else None, cell, world, rank, alpha, beta, x_c, x_i, pool_all)
+              if args.parity_n > 0 else {"n": 0, "skipped": "--parity-n 0"})
 
     # ---- the other pool, and the strong-scaled form of the job, in the same run -----------------
     other = strong = None
@@ -613,6 +623,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / max(1, args.steps)},
             "gpu_launches": launches, "setup_s": t_setup, "screening": leg["screen"], "sweep": leg["sweep"],
+            "per_rank": leg["per_rank"],
             "parity_sample": parity}
     if other:
         line["other_pool"] = other
@@ -630,7 +641,8 @@ def run_ours(args):
 def leg_summary(leg, kind, cell):
     r = rooflines(leg, None)
     return {"pool": kind, "ms_per_step": leg["ms_per_step"], "value": leg["value"], "unit": UNIT,
-            "gpu_launches": leg["launches"], "screening": leg["screen"], "sweep": leg["sweep"], "roofline": r["dominant"],
+            "gpu_launches": leg["launches"], "screening": leg["screen"], "sweep": leg["sweep"], "per_rank": leg["per_rank"],
+            "roofline": r["dominant"],
             "roofline_kernels": r["all"],
             "share_of_step": r["dominant"]["share_of_step"] if r["dominant"] else None, "clocks": leg["clocks"]}
 
@@ -744,7 +756,9 @@ def parity_sample(args, T, dist, cell, world, rank, alpha, beta, x_c, x_i, pool_
             idx_glob[xi_] = full
         else:
             idx_glob[xi_] = mi
-    if rank == 0:
+    if rank == 0 and n_glob > 1_500_000:
+        res["cut_check"] = f"skipped: {n_glob} scenarios in epigraph 0 (the host copy of their values would not fit)"
+    elif rank == 0:
         g = np.arange(n_glob, dtype=np.uint64)
         vals = np.empty((n_glob, P.s))
         for a in range(0, n_glob, 32768):

@@ -241,6 +241,10 @@ SQLP_API int32_t sqlp_epi_screen_stats(sqlp_epi *epi, int64_t *out /*[8]*/);
  * holding (alpha, beta[n1], val) per x.  Errors such as a missing argmax surface at the
  * next blocking call. */
 SQLP_API int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *epi, const double *d_x2, double *d_out);
+/* The same for every epigraph of a cell in one call: d_out = [n_epi][2][n1 + 2].  Epigraphs with the same
+ * template share their bias vectors; in a sharded job the whole cell costs ONE all-gather. */
+SQLP_API int32_t sqlp_cell_build_cuts2_dev(int32_t n_epi, sqlp_epi *const *epi, const double *d_x2,
+                                           double *d_out);
 
 /* ---------------------------------------------------------------- cut list (next rows N1, N3) --- */
 

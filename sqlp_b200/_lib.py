@@ -99,6 +99,7 @@ SIGNATURES = {
     "sqlp_ctx_profile_classes": [_vp, _i32, _vp, _vp, _vp],
     "sqlp_ctx_set_screen": [_vp, _i32],
     "sqlp_epi_screen_stats": [_vp, _vp],
+    "sqlp_cell_build_cuts2_dev": [_i32, _vp, _vp, _vp],
     "sqlp_epi_view_columns": [_vp, _P(_i64), _P(_i64)],
     "sqlp_pool_create": [_vp, _i64, _P(_vp)],
     "sqlp_pool_destroy": [_vp],

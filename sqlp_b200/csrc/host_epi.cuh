@@ -565,7 +565,7 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         // the (rho, tau) table is read once instead of one row per scenario and point
         const int64_t kc = round_up(std::max<int64_t>(ku, 1), 32);
         const size_t hist_smem = (size_t)kc * 8 + (size_t)SQLP_HIST_SUB * 12;
-        if (e->n_T == 0 && c->reduce_mode != 1 && (c->reduce_mode == 2 || e->n_local >= 16384) &&
+        if (e->n_T == 0 && c->reduce_mode != 1 && (c->reduce_mode == 2 || e->n_local >= 131072) &&
             hist_smem + 1024 <= (size_t)c->smem_optin) {
             const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, (e->n_local + 4095) / 4096));
             HistArgs h;

@@ -1097,6 +1097,29 @@ int32_t sqlp_epi_build_cuts2_dev(sqlp_epi *e, const double *d_x2, double *d_out)
     });
 }
 
+int32_t sqlp_cell_build_cuts2_dev(int32_t n_epi, sqlp_epi *const *epi, const double *d_x2, double *d_out)
+{
+    return guard([&] {
+        REQUIRE(n_epi >= 1 && epi && epi[0] && d_out, SQLP_E_INVALID, "bad argument");
+        sqlp_ctx *c = epi[0]->ctx;
+        REQUIRE(c->peers.empty(), SQLP_E_UNSUPPORTED, "device pointers belong to one GPU: use sqlp_cell_build_cuts2 with a multi-GPU context");
+        c->bind();
+        for (int i = 0; i < n_epi; ++i) {
+            REQUIRE(epi[i] && epi[i]->ctx == c && epi[i]->n1 == epi[0]->n1, SQLP_E_INVALID,
+                    "the epigraphs of a cell share a context and a first stage");
+            REQUIRE(d_x2 || epi[i]->n1 == 0, SQLP_E_INVALID, "null points");
+            epi[i]->cur_bias = nullptr;
+        }
+        CellGather cg(c, 2, n_epi, epi);
+        for (int i = 0; i < n_epi; ++i)
+            epi_cuts_enqueue(epi[i], 2, nullptr, d_x2, true, bias_twin(i, epi), cg.slot(i));
+        cg.run();                                       // sharded job: one all-gather for the whole cell
+        const size_t row = (size_t)2 * ((size_t)epi[0]->n1 + 2);
+        for (int i = 0; i < n_epi; ++i)
+            CK(cudaMemcpyAsync(d_out + (size_t)i * row, epi[i]->d_out.p, row * 8, cudaMemcpyDeviceToDevice, S(c)));
+    });
+}
+
 // ---------------------------------------------------------------- cut list (N1 / N3) ----
 int32_t sqlp_epi_set_weights(sqlp_epi *e, double objective_weight, double lower_bound)
 {
