@@ -476,18 +476,29 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         e->cur_bias = e->d_bias.as<double>();
         e->cur_bias_stride = e->bias_stride;
         ProfScope prof_bias(c, SQLP_PROF_BIAS, 8.0 * (double)ku * m2 + 8.0 * NX * (double)ku);
-        LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
-               e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
-               e->d_x2.as<double>(), e->d_base.as<double>(), e->d_flags.as<int>());
-        int bgrid = (int)((kpad + 7) / 8);
-        if (NX == 2)
-            LAUNCH(c, k_bias<2>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
-                   e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(),
-                   (long long)e->bias_stride, e->view->act());
-        else
-            LAUNCH(c, k_bias<1>, bgrid, 256, 0, p->d_pi.as<double>(), m2, e->d_base.as<double>(),
-                   e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(),
-                   (long long)e->bias_stride, e->view->act());
+        BaseArgs ba{e->d_rbar.as<double>(), e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
+                    e->d_x2.as<double>(), n1, e->d_flags.as<int>()};
+        const int bgrid = (int)((kpad + 7) / 8);
+        const size_t base_smem = (size_t)NX * m2 * 8;
+        if (base_smem <= 40 * 1024) {
+            // base_x = rbar - Tbar x is rebuilt by every block of k_bias in shared memory: one launch less
+            if (NX == 2)
+                LAUNCH(c, (k_bias<2, true>), bgrid, 256, base_smem, p->d_pi.as<double>(), m2, (const double *)nullptr,
+                       e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(), (long long)e->bias_stride, e->view->act(), ba);
+            else
+                LAUNCH(c, (k_bias<1, true>), bgrid, 256, base_smem, p->d_pi.as<double>(), m2, (const double *)nullptr,
+                       e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(), (long long)e->bias_stride, e->view->act(), ba);
+        } else {
+            LAUNCH(c, k_base, dim3((m2 + 127) / 128, NX), 128, 0, e->d_rbar.as<double>(), m2, n1,
+                   e->d_rptr.as<int>(), e->d_rcol.as<int>(), e->d_rval.as<double>(),
+                   e->d_x2.as<double>(), e->d_base.as<double>(), e->d_flags.as<int>());
+            if (NX == 2)
+                LAUNCH(c, (k_bias<2, false>), bgrid, 256, 0, p->d_pi.as<double>(), m2, (const double *)e->d_base.as<double>(),
+                       e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(), (long long)e->bias_stride, e->view->act(), ba);
+            else
+                LAUNCH(c, (k_bias<1, false>), bgrid, 256, 0, p->d_pi.as<double>(), m2, (const double *)e->d_base.as<double>(),
+                       e->view->d_Kv(p), (long long)kpad, e->d_bias.as<double>(), (long long)e->bias_stride, e->view->act(), ba);
+        }
 
         prof_bias.stop();
     }

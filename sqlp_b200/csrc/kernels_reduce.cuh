@@ -40,12 +40,37 @@ __global__ void k_base(const double *__restrict__ rbar, int m2, int n1,
 // lanes stride the row, fixed shuffle tree.  Slots K..kpad-1 get -inf so padded vertices
 // of the last chunk can never win.
 // With twins (kernels_pool.cuh) k runs over the view's columns and act[k] is the pool slot of the class's first vertex.
-template <int NX>
+// FUSED: every block first builds base_x = rbar - Tbar x for its NX points in shared memory (one thread per row, the
+// row's entries in column order -- the arithmetic of k_base, which is then not launched) and block 0 clears the
+// call's "no argmax" bit; one launch less per cut formation, which is what small shapes are made of.
+struct BaseArgs {
+    const double *rbar;       // [m2]
+    const int *R_ptr, *R_col; // CSR copy of Tbar, columns ascending within a row
+    const double *R_val;
+    const double *x2;         // [NX][n1]
+    int n1;
+    int *flags;
+};
+
+template <int NX, bool FUSED>
 __global__ void k_bias(const double *__restrict__ pi, int m2, const double *__restrict__ base,
                        const long long *__restrict__ d_K, long long kpad, double *__restrict__ bias,
-                       long long bias_stride, const int *__restrict__ act)
+                       long long bias_stride, const int *__restrict__ act, BaseArgs b)
 {
     griddep_sync();
+    extern __shared__ double sbase[];            // [NX][m2] when FUSED
+    if (FUSED) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *b.flags = 0;
+        for (int q = threadIdx.x; q < NX * m2; q += blockDim.x) {
+            const int x = q / m2, j = q % m2;
+            const double *xx = b.x2 + (long long)x * b.n1;
+            double y = 0.0;
+            for (int t = b.R_ptr[j]; t < b.R_ptr[j + 1]; ++t) y = __dadd_rn(y, __dmul_rn(b.R_val[t], xx[b.R_col[t]]));
+            sbase[q] = __dsub_rn(b.rbar[j], y);
+        }
+        __syncthreads();
+        base = sbase;
+    }
     const long long K = *d_K;
     const int lane = threadIdx.x & 31;
     const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -382,9 +407,15 @@ __global__ void __launch_bounds__(SQLP_HIST_THREADS, 1) k_cut_hist(HistArgs a)
                     unsigned same = __ballot_sync(0xffffffffu, mine && k == kk);
                     own &= ~same;
                     double sum = 0.0;
-                    while (same) {
-                        sum += __shfl_sync(0xffffffffu, p, __ffs(same) - 1);
-                        same &= same - 1;
+                    if (__popc(same) <= 4) {                 // a few: one after the other, in lane order
+                        while (same) {
+                            sum += __shfl_sync(0xffffffffu, p, __ffs(same) - 1);
+                            same &= same - 1;
+                        }
+                    } else {                                 // many: the fixed butterfly over the 32 lanes (non-members add +0)
+                        sum = ((same >> lane) & 1u) ? p : 0.0;
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
                     }
                     if (lane == 0) c[kk] += sum;
                 }
