@@ -54,6 +54,12 @@ enum { SQLP_MIN_SENSE = 0, SQLP_MAX_SENSE = 1 }; /* MOI.OptimizationSense */
 SQLP_API const char *sqlp_version(void);
 SQLP_API const char *sqlp_last_error(void);
 
+/* Memory-safety check without a sanitizer (compute-sanitizer is closed on the GPU pool this was developed on): with
+ * SQLP_GUARD=1 in the environment every device buffer of the library carries 512 bytes of a known pattern in front
+ * of it and behind it; this call synchronises the device, reads all of them back and returns how many guarded
+ * buffers are alive and how many guard zones were written to.  tests/test_gpu_guards.py. */
+SQLP_API int32_t sqlp_guard_check(int64_t *buffers, int64_t *damaged);
+
 /* ---------------------------------------------------------------- context ---------- */
 
 /* One context per GPU.  `device` is the CUDA ordinal. */

@@ -83,6 +83,7 @@ _P = C.POINTER
 
 # name -> argtypes; every function returns int32 unless listed in _RESTYPE
 SIGNATURES = {
+    "sqlp_guard_check": [_P(_i64), _P(_i64)],
     "sqlp_ctx_create": [_i32, _P(_vp)],
     "sqlp_nccl_unique_id": [_vp],
     "sqlp_ctx_create_dist": [_i32, _i32, _i32, _vp, _P(_vp)],

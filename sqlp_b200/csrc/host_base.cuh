@@ -100,10 +100,34 @@ void load_nccl()
     } while (0)
 
 // ---------------------------------------------------------------- device buffers -------
+// Guard zones (SQLP_GUARD=1 in the environment, read once): compute-sanitizer is closed on this GPU pool, so an
+// out-of-bounds WRITE has to be caught by the library itself.  With guards on, every device buffer is allocated
+// with 512 bytes of 0xA5 in front of it and behind it; sqlp_guard_check() reads all of them back and counts the
+// zones that no longer hold the pattern (tests/test_gpu_guards.py runs the smallest case of every kernel under it).
+constexpr size_t SQLP_GUARD_BYTES = 512;
+inline bool guards_on()
+{
+    static const int on = [] { const char *g = getenv("SQLP_GUARD"); return g && atoi(g) != 0 ? 1 : 0; }();
+    return on != 0;
+}
+struct DevBuf;
+inline std::vector<DevBuf *> &live_bufs()
+{
+    static std::vector<DevBuf *> v;
+    return v;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    bool guarded = false;
+    void *base() const { return guarded ? (char *)p - SQLP_GUARD_BYTES : p; }
+    ~DevBuf()
+    {
+        if (p) cudaFree(base());
+        auto &v = live_bufs();
+        v.erase(std::remove(v.begin(), v.end(), this), v.end());
+    }
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -117,16 +141,26 @@ struct DevBuf {
         // (N and K grow every SD iteration) neither synchronises the host with the device nor stalls the
         // device the way cudaMalloc / cudaFree do; the old block goes back to the pool once the work queued
         // before this point has finished with it
-        void *np = nullptr;
-        cudaError_t e = cudaMallocAsync(&np, nb, st);
+        const bool g = guards_on();
+        const size_t pad = g ? SQLP_GUARD_BYTES : 0;
+        nb = (nb + 15) / 16 * 16;
+        void *nbase = nullptr;
+        cudaError_t e = cudaMallocAsync(&nbase, nb + 2 * pad, st);
         if (e != cudaSuccess)
             throw Error(SQLP_E_NOMEM, std::string("cudaMallocAsync(") + std::to_string(nb) +
                                           "): " + cudaGetErrorString(e));
+        void *np = (char *)nbase + pad;
+        if (g) {
+            CK(cudaMemsetAsync(nbase, 0xA5, pad, st));
+            CK(cudaMemsetAsync((char *)np + nb, 0xA5, pad, st));
+        }
         if (keep) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
         if (zero && nb > keep) CK(cudaMemsetAsync((char *)np + keep, 0, nb - keep, st));
-        if (p) CK(cudaFreeAsync(p, st));
+        if (p) CK(cudaFreeAsync(base(), st));
+        else live_bufs().push_back(this);
         p = np;
         bytes = nb;
+        guarded = g;
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };

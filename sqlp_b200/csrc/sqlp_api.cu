@@ -112,6 +112,33 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     }
 }
 
+int32_t sqlp_guard_check(int64_t *buffers, int64_t *damaged)
+{
+    return guard([&] {
+        REQUIRE(buffers && damaged, SQLP_E_INVALID, "null argument");
+        *buffers = 0;
+        *damaged = 0;
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned char> h(SQLP_GUARD_BYTES);
+        for (DevBuf *b : live_bufs()) {
+            if (!b->p || !b->guarded) continue;
+            ++*buffers;
+            for (int side = 0; side < 2; ++side) {
+                const void *src = side == 0 ? b->base() : (const void *)((const char *)b->p + b->bytes);
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, src) != cudaSuccess) { cudaGetLastError(); continue; }
+                int cur = 0;
+                CK(cudaGetDevice(&cur));
+                if (at.device != cur) CK(cudaSetDevice(at.device));
+                CK(cudaMemcpy(h.data(), src, SQLP_GUARD_BYTES, cudaMemcpyDeviceToHost));
+                if (at.device != cur) CK(cudaSetDevice(cur));
+                for (unsigned char c : h)
+                    if (c != 0xA5) { ++*damaged; break; }
+            }
+        }
+    });
+}
+
 int32_t sqlp_ctx_create(int32_t device, sqlp_ctx **out)
 {
     return guard([&] {
