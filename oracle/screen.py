@@ -1,5 +1,5 @@
-"""CPU restatement of the SCREENING pass proposed in DESIGN.md section 10 -- the oracle of a kernel that does
-not exist yet.  Test infrastructure like the rest of ``oracle/``: nothing in the product imports it.
+"""CPU restatement of the SCREENING pass (kernel: ``csrc/kernels_screen.cuh``).  Test
+infrastructure like the rest of ``oracle/``: nothing in the product imports it.
 
 The argmax of subprob.jl:141-169 only needs the exact FP64 score of the vertices that can still win.  The
 screening pass computes every score approximately with bf16 operands (each fp64 operand split into two bf16
@@ -17,6 +17,14 @@ Error budget for one dot of length s (u_b = 2**-8, bf16 round to nearest: 8 sign
   With Cauchy-Schwarz, sum_j |pi_j| |d_j| <= ||pi|| ||d||, so
       |approx - exact| <= EPS(s) * ||pi_k|_S|| * ||d_i||,   EPS(s) = 1.01 * (4 u_b**2 + (3 s + 2) * 2 u_s).
   Both norms are one cheap pass each (K + N values), rounded UP.
+
+Centred operands (``centre=True``): for any fixed vectors c and dbar,
+      bias_k + pi_k . d_i = [bias_k + pi_k . dbar] + (pi_k - c) . (d_i - dbar) + c . (d_i - dbar),
+  and the last term does not depend on k, so the argmax over k is that of the first two.  The pass multiplies the
+  centred operands; every term of the bound is then relative to ||pi_k - c|| ||d_i - dbar||, which on real pools
+  (clouds around a common point) is an order of magnitude below ||pi_k|| ||d_i||.  The FP64 roundings of the
+  subtractions, of pi_k . dbar and of the exact scores themselves are bounded on the UNcentred magnitudes
+  (``eabs``).
 """
 from __future__ import annotations
 
@@ -61,15 +69,31 @@ def up(x):
     return np.nextafter(x, np.inf)
 
 
-def screen(bias: np.ndarray, PiS: np.ndarray, D: np.ndarray):
+CENTRE_COLS, CENTRE_SCEN = 1024, 256          # kernels_screen.cuh SCR_CENTRE_COLS / SCR_CENTRE_SCEN
+
+
+def screen(bias: np.ndarray, PiS: np.ndarray, D: np.ndarray, centre: bool = True):
     """Candidate mask [N, K]: vertex k stays for scenario i iff its upper bound reaches the best lower bound.
     bias[k] is exact (fp64).  NaN / -Inf biases (which never win, subprob.jl:156) are never candidates unless
     nothing else is."""
     s = PiS.shape[1]
+    eabs = 0.0
+    if centre and len(PiS) and len(D):
+        with np.errstate(all="ignore"):
+            c = np.nan_to_num(PiS[:CENTRE_COLS].mean(axis=0), nan=0.0, posinf=0.0, neginf=0.0)
+            dbar = np.nan_to_num(D[:CENTRE_SCEN].mean(axis=0), nan=0.0, posinf=0.0, neginf=0.0)
+            bias = bias + PiS @ dbar
+            raw_p = np.sqrt((PiS * PiS).sum(axis=1))
+            raw_d = np.sqrt((D * D).sum(axis=1))
+            fin = np.isfinite(bias)
+            eabs = (s + 8) * 2.0 ** -52 * ((np.abs(bias[fin]).max() if fin.any() else 0.0) +
+                                           np.nanmax(raw_p[np.isfinite(raw_p)], initial=0.0) *
+                                           np.nanmax(raw_d, initial=0.0) * 2.0)
+        PiS, D = PiS - c, D - dbar
     approx = approx_dots(PiS, D)
     pn = up(np.sqrt(up((PiS * PiS).sum(axis=1))))
     dn = up(np.sqrt(up((D * D).sum(axis=1))))
-    bound = up(eps(s) * np.outer(dn, pn))
+    bound = up(eps(s) * np.outer(dn, pn)) + eabs
     sc = bias[None, :] + approx
     finite = np.isfinite(sc)
     lower = np.where(finite, sc - bound, -np.inf).max(axis=1)
@@ -77,7 +101,7 @@ def screen(bias: np.ndarray, PiS: np.ndarray, D: np.ndarray):
     return finite & (sc + bound + slack >= (lower - np.abs(lower) * 2.0 ** -50)[:, None])
 
 
-def argmax_screened(P, values, x, pool):
+def argmax_screened(P, values, x, pool, centre: bool = True):
     """max_val, max_idx as ``oracle.argmax_procedure`` -- exact arithmetic on the candidates only -- plus the
     candidate counts per scenario."""
     from . import oracle as O
@@ -89,7 +113,7 @@ def argmax_screened(P, values, x, pool):
     base = P.rbar - P.T_dense() @ np.asarray(x, dtype=np.float64)
     bias = pool @ base
     D = values - P.rbar[S][None, :]
-    mask = screen(bias, pool[:, S], D)
+    mask = screen(bias, pool[:, S], D, centre)
     mv, mi = np.full(N, -np.inf), np.full(N, -1, dtype=np.int64)
     for i in range(N):
         cand = np.nonzero(mask[i])[0]

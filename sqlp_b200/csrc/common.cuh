@@ -124,6 +124,7 @@ struct ScreenCtl {                 // written by k_screen_prep, read by every ke
     unsigned long long n_emit;     // statistics: candidates emitted / evaluated exactly
     unsigned long long n_eval;
     int live[2];                   // vertices that may win at point x
+    float eabs[2];                 // absolute part of E: FP64 roundings on the uncentred magnitudes (k_screen_prep)
 };
 
 __device__ __forceinline__ bool screen_falls_back(const ScreenCtl *ctl)

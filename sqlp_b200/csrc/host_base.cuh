@@ -232,6 +232,7 @@ struct sqlp_ctx {
     // screening pass (kernels_screen.cuh): 0 = off, 1 = automatic (default), 2 = whenever the shape allows it
     int screen_mode = 1;
     bool screen_smem_set[3] = {false, false, false};
+    bool screen_centre = true;    // bf16 operands relative to the centre of the pool / of the scenarios (SQLP_CENTRE=0: raw)
     bool resolve_fma = false;     // exact decision by DFMA lanes (set when the device check DMMA == DFMA chain passed)
     int reduce_mode = 0;          // cut reduction: 0 automatic, 1 per-scenario gather only, 2 per-vertex weight sums whenever possible
     bool hist_smem_set[3] = {false, false, false};
@@ -273,6 +274,7 @@ struct PoolView {   // the pool restricted to one set of stochastic rows, in til
     std::vector<int> rows;
     int n_rows = 0, s_pad = 0;
     DevBuf d_rows, d_piS;
+    DevBuf d_piR;            // the same view row-major [column][s_pad]: what the exact decision gathers (one contiguous row per candidate)
     int64_t synced_lo = 0;   // vertices < synced_lo are final in d_piS
     // score-equivalent vertices (kernels_pool.cuh, "twins"): with rows that can never enter a score the view holds
     // one column per CLASS of vertices equal on the relevant rows; d_act[v] = pool slot of the first vertex of class v
@@ -287,6 +289,8 @@ struct PoolView {   // the pool restricted to one set of stochastic rows, in til
     // the same rows as bf16 hi / lo operands of the screening pass, built on first use
     int sp = 0;              // row slots padded to a multiple of 16
     DevBuf d_piB, d_pn, d_pnmax, d_vbad, d_scr_lo;
+    DevBuf d_ctr;                             // centre the bf16 operands are taken relative to (sp values + its norm)
+    int64_t ctr_cols = 0;                     // columns it was the mean of (0: none yet)
     int64_t scr_synced_lo = 0, scr_cap = 0;   // vertices final in d_piB / capacity (multiple of 256)
 };
 
@@ -357,6 +361,8 @@ struct sqlp_epi {
     int last_nx = 0;   // points of the last cut formation whose result is still in d_out
     // screening pass: bf16 scenario operands, per-call control block, what the host has learnt
     DevBuf d_DB, d_dnu, d_dnall, d_ebad, d_b32c, d_ctl;
+    DevBuf d_dbar, d_pdb;                     // centre of the scenarios (sp values + norm); P_k . dbar per view column
+    int64_t dbar_n = 0;                       // scenarios dbar was the mean of
     int64_t scr_synced = 0, scr_units_cap = 0;
     PinnedBuf h_ctl;               // the control block of the last pass, copied back without a synchronisation
     cudaEvent_t ctl_event = nullptr;

@@ -300,13 +300,26 @@ void screen_sync_operands(sqlp_epi *e)
         v->d_pnmax.ensure((size_t)(ncap / SCR_NB) * 4, (size_t)(v->scr_cap / SCR_NB) * 4, S(c));
         v->scr_cap = ncap;
     }
+    v->d_scr_lo.ensure(16, 0, S(c));         // device-side mark: view columns below it are final in d_piB
+    v->d_ctr.ensure((size_t)(v->sp + 1) * 8, 0, S(c));
+    // The centre (kernels_screen.cuh, "Centred operands"): mean of the first <= 1 024 columns, taken again -- and
+    // every column split again -- when four times as many are there.  Any centre is a correct one.
+    const int64_t ctr_want = std::min<int64_t>(hi, SCR_CENTRE_COLS);
+    if (c->screen_centre && ctr_want > 0 && ctr_want >= 4 * v->ctr_cols && v->ctr_cols < SCR_CENTRE_COLS) {
+        LAUNCH(c, k_screen_centre, 1, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(), v->n_rows, v->sp,
+               v->act(), v->d_Kv(p), (long long)ctr_want, v->d_ctr.as<double>());
+        CK(cudaMemsetAsync(v->d_scr_lo.p, 0, 8, S(c)));
+        CK(cudaMemsetAsync(v->d_pnmax.p, 0, (size_t)(v->scr_cap / SCR_NB) * 4, S(c)));
+        v->ctr_cols = ctr_want;
+        v->scr_synced_lo = 0;
+        v->scr_epoch = -1;
+    }
     if (v->scr_epoch != p->push_epoch && hi > 0) {
         const int64_t work = std::max<int64_t>(1, hi - std::min(v->scr_synced_lo, hi));
         const int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 8 * c->sm_count);
-        v->d_scr_lo.ensure(16, 0, S(c));     // device-side mark: view columns below it are final in d_piB
         LAUNCH(c, k_screen_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(), v->n_rows, v->sp,
                v->d_piB.as<__nv_bfloat16>(), v->d_pn.as<float>(), v->d_pnmax.as<float>(), v->d_vbad.as<int>(),
-               v->d_scr_lo.as<long long>(), v->d_Kv(p), v->act());
+               v->d_scr_lo.as<long long>(), v->d_Kv(p), v->act(), (const double *)v->d_ctr.as<double>());
         LAUNCH(c, k_screen_mark, 1, 32, 0, v->d_scr_lo.as<long long>(), v->d_Kv(p));
     }
     v->scr_synced_lo = p->K;                // confirmed vertices: a lower bound of the device's mark (in pool slots)
@@ -320,12 +333,22 @@ void screen_sync_operands(sqlp_epi *e)
         e->d_ebad.ensure(16, 0, S(c));
         e->scr_units_cap = ncap;
     }
+    e->d_dbar.ensure((size_t)(v->sp + 1) * 8, 0, S(c));
+    const int64_t dbar_want = std::min<int64_t>(e->n_local, SCR_CENTRE_SCEN);
+    if (c->screen_centre && dbar_want >= 4 * e->dbar_n && e->dbar_n < SCR_CENTRE_SCEN) {     // as for the view's centre
+        LAUNCH(c, k_screen_dbar, 1, 256, 0, e->d_D.as<double>(), v->s_pad, v->sp, (long long)dbar_want,
+               e->d_dbar.as<double>());
+        CK(cudaMemsetAsync(e->d_dnu.p, 0, (size_t)e->scr_units_cap * 4, S(c)));
+        CK(cudaMemsetAsync(e->d_dnall.p, 0, 4, S(c)));
+        e->dbar_n = dbar_want;
+        e->scr_synced = 0;
+    }
     if (e->n_local > e->scr_synced) {
         const int64_t work = e->n_local - e->scr_synced;
         const int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 16 * c->sm_count);
         LAUNCH(c, k_screen_scen_sync, grid, 256, 0, e->d_D.as<double>(), v->s_pad, v->sp, e->d_DB.as<__nv_bfloat16>(),
                e->d_dnu.as<float>(), e->d_dnall.as<float>(), e->d_ebad.as<int>(), (long long)e->scr_synced,
-               (long long)e->n_local);
+               (long long)e->n_local, (const double *)e->d_dbar.as<double>());
         e->scr_synced = e->n_local;
     }
 }
@@ -353,9 +376,15 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     c->d_lfin.ensure(nslots * 4, 0, S(c), false);
     // more overflowing lists than this and the pass gives up: each one costs a full sweep of its scenario
     const unsigned ovf_limit = (unsigned)std::min<int64_t>(e->n_local / 16 + 16, 1 << 20);
+    e->d_pdb.ensure((size_t)std::max<int64_t>(nch, 1) * SCR_NB * 8, 0, S(c), false);
+    LAUNCH(c, k_screen_pdbar, (int)std::min<int64_t>(std::max<int64_t>((ku + 7) / 8, 1), 8 * c->sm_count), 256, 0,
+           (const double *)v->d_piR.as<double>(), v->s_pad, (const double *)e->d_dbar.as<double>(), v->d_Kv(p),
+           e->d_pdb.as<double>());
     LAUNCH(c, k_screen_prep<NX>, 1, 1024, 0, e->cur_bias, (long long)e->cur_bias_stride, v->d_pn.as<float>(),
            v->d_pnmax.as<float>(), e->d_dnall.as<float>(), v->d_vbad.as<int>(), e->d_ebad.as<int>(),
-           v->d_Kv(p), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>());
+           v->d_Kv(p), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>(),
+           (const double *)e->d_pdb.as<double>(), (const double *)v->d_ctr.as<double>(),
+           (const double *)e->d_dbar.as<double>());
     int nstages = SCR_MAX_STAGES;
     while (nstages > 3 && scr_smem_bytes(v->sp, nstages, NX) > (size_t)c->smem_optin) --nstages;
     const size_t smem = scr_smem_bytes(v->sp, nstages, NX);
@@ -390,6 +419,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     ResolveArgs ra;
     ra.D = e->d_D.as<double>();
     ra.PiS = v->d_piS.as<double>();
+    ra.PiR = v->d_piR.as<double>();
     ra.bias = e->cur_bias;
     ra.bias_stride = e->cur_bias_stride;
     ra.s_pad = v->s_pad;

@@ -16,6 +16,8 @@ void pool_reserve(sqlp_pool *p, int64_t need)
         size_t per_chunk = (size_t)v->s_pad * SQLP_TILE * 8;
         v->d_piS.ensure((size_t)(ncap / SQLP_TILE) * per_chunk,
                         (size_t)((used + SQLP_TILE - 1) / SQLP_TILE) * per_chunk, S(c));
+        v->d_piR.ensure((size_t)(ncap / SQLP_TILE) * per_chunk,
+                        (size_t)((used + SQLP_TILE - 1) / SQLP_TILE) * per_chunk, S(c));
     }
     for (sqlp_epi *e : p->epis) {
         e->d_rt.ensure((size_t)ncap * (e->n1 + 1) * 8, (size_t)used * (e->n1 + 1) * 8, S(c));
@@ -122,7 +124,7 @@ void view_sync(sqlp_pool *p, PoolView *v)
             const int64_t fwork = work * v->n_rows;
             const int fgrid = (int)std::min<int64_t>(std::max<int64_t>((fwork + 255) / 256, 1), 8 * c->sm_count);
             LAUNCH(c, k_view_fill, fgrid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(), v->n_rows, v->s_pad,
-                   v->d_piS.as<double>(), (const TwinState *)st, (const int *)v->d_act.as<int>());
+                   v->d_piS.as<double>(), v->d_piR.as<double>(), (const TwinState *)st, (const int *)v->d_act.as<int>());
         }
         v->synced_lo = p->K;                // confirmed vertices: a lower bound of the device's mark
         v->twin_epoch = p->push_epoch;
@@ -132,7 +134,7 @@ void view_sync(sqlp_pool *p, PoolView *v)
         int64_t work = (hi - v->synced_lo) * v->n_rows;
         int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 8 * c->sm_count);
         LAUNCH(c, k_view_sync, grid, 256, 0, p->d_pi.as<double>(), (int)p->m2, v->d_rows.as<int>(),
-               v->n_rows, v->s_pad, v->d_piS.as<double>(), (long long)v->synced_lo,
+               v->n_rows, v->s_pad, v->d_piS.as<double>(), v->d_piR.as<double>(), (long long)v->synced_lo,
                p->d_K.as<long long>());
     }
     v->synced_lo = p->K;   // only confirmed vertices are final

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) k_pool_push(double *__restrict__ pi, unsi
 // (common.cuh tile_off): vertex k is column k % 128 of tile k / 128, slot j < s_pad.
 // Idempotent; run over [k_lo, *d_K) after pushes.
 __global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows,
-                            int n_rows, int s_pad, double *__restrict__ piS, long long k_lo,
+                            int n_rows, int s_pad, double *__restrict__ piS, double *__restrict__ piR, long long k_lo,
                             const long long *__restrict__ d_K)
 {
     griddep_sync();
@@ -173,7 +173,9 @@ __global__ void k_view_sync(const double *__restrict__ pi, int m2, const int *__
          t += (long long)gridDim.x * blockDim.x) {
         long long k = k_lo + t / n_rows;
         int j = (int)(t % n_rows);
-        piS[(k >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(k & 127), j)] = pi[k * m2 + s_rows[j]];
+        const double val = pi[k * m2 + s_rows[j]];
+        piS[(k >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(k & 127), j)] = val;
+        piR[k * (long long)s_pad + j] = val;             // row-major copy for the exact decision's gathers
     }
 }
 
@@ -360,7 +362,8 @@ __global__ void __launch_bounds__(1024) k_twin_compact(const long long *__restri
 
 // View columns [Kv_prev, Kv) from the pool rows of their representatives (same tile layout as k_view_sync).
 __global__ void k_view_fill(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows, int n_rows, int s_pad,
-                            double *__restrict__ piS, const TwinState *__restrict__ st, const int *__restrict__ act)
+                            double *__restrict__ piS, double *__restrict__ piR, const TwinState *__restrict__ st,
+                            const int *__restrict__ act)
 {
     griddep_sync();
     const long long v0 = st->Kv_prev, v1 = st->Kv;
@@ -368,7 +371,9 @@ __global__ void k_view_fill(const double *__restrict__ pi, int m2, const int *__
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long v = v0 + t / n_rows;
         const int j = (int)(t % n_rows);
-        piS[(v >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(v & 127), j)] = pi[(long long)act[v] * m2 + s_rows[j]];
+        const double val = pi[(long long)act[v] * m2 + s_rows[j]];
+        piS[(v >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(v & 127), j)] = val;
+        piR[v * (long long)s_pad + j] = val;
     }
 }
 

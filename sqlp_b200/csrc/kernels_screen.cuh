@@ -53,6 +53,8 @@ namespace sqlp {
 #define SCR_MAX_STAGES 8
 #define SCR_BIAS_BUFS 4
 #define SCR_CAP 64                 // candidate list entries per (scenario, point, K-range, column half)
+#define SCR_CENTRE_COLS 1024       // the view's centre is the mean of at most this many columns,
+#define SCR_CENTRE_SCEN 256        // an epigraph's of at most this many scenarios
 #define SCR_DEAD (-3.0e38f)        // shifted bias of a vertex that can never win (or does not exist)
 
 template <int NX>
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
         const float coef_q = a.ctl->coef_q;
         float cb[NX];
 #pragma unroll
-        for (int x = 0; x < NX; ++x) cb[x] = __fmaf_ru(a.ctl->coef_b, a.ctl->bmax[x], 1e-30f);
+        for (int x = 0; x < NX; ++x) cb[x] = __fmaf_ru(a.ctl->coef_b, a.ctl->bmax[x], a.ctl->eabs[x]);
         unsigned t = 0, bb = 0, bph = 0;
         unsigned long long emitted = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x) {
@@ -332,14 +334,99 @@ __device__ __forceinline__ void atomic_max_pos(float *addr, float v)   // v >= 0
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
 }
 
-// Pool view for screening: vertices [k_lo, K) restricted to the stochastic rows, split in bf16 hi / lo,
-// plus ||PiS[k]||_2 (rounded up) and its maximum per chunk of 256.  One warp per vertex.
+// Centred operands.  The argmax over k of  bias_k + P_k . d_i  does not change when a term that depends on i
+// alone is taken away, and
+//     bias_k + P_k . d_i  =  [bias_k + P_k . dbar]  +  (P_k - ctr) . (d_i - dbar)  +  ctr . (d_i - dbar)
+// for ANY fixed vectors ctr and dbar: the pass multiplies the centred operands, adds P_k . dbar (FP64, once per call,
+// k_screen_pdbar) to the bias and never forms the last term.  Every term of the error bound is proportional to
+// ||P_k - ctr|| ||d_i - dbar||; real pools are clouds around a common point (storm: ||P|| ~ 8 300 but
+// ||P - mean|| ~ 2 000, ||d|| ~ 1 080 but ||d - mean|| ~ 340), so the bound shrinks tenfold and the candidate lists
+// with it.  ctr = mean of the view's first columns, dbar = mean of the epigraph's first scenarios; both are frozen
+// between (rare, geometric) re-centrings that rebuild the bf16 operands.  Layout: sp values, then the 2-norm.
+__global__ void k_screen_centre(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows, int n_rows, int sp,
+                                const int *__restrict__ act, const long long *__restrict__ d_K, long long n_max,
+                                double *__restrict__ ctr)
+{
+    griddep_sync();
+    __shared__ double red[32];
+    const long long n = min(*d_K, n_max);
+    double ss = 0.0;
+    for (int j = threadIdx.x; j < sp; j += blockDim.x) {
+        double m = 0.0;
+        if (j < n_rows && n > 0) {
+            const int r = s_rows[j];
+            for (long long k = 0; k < n; ++k) m += pi[(act ? (long long)act[k] : k) * m2 + r];
+            m /= (double)n;
+            if (!isfinite(m)) m = 0.0;
+        }
+        ctr[j] = m;
+        ss = fma(m, m, ss);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        ctr[sp] = sqrt(t) * (1.0 + 0x1p-40);
+    }
+}
+
+// The same for the scenarios of an epigraph: mean of the first n local scenarios (FP64 tiles), slot by slot.
+__global__ void k_screen_dbar(const double *__restrict__ D, int s_pad, int sp, long long n, double *__restrict__ dbar)
+{
+    griddep_sync();
+    __shared__ double red[32];
+    double ss = 0.0;
+    for (int j = threadIdx.x; j < sp; j += blockDim.x) {
+        double m = 0.0;
+        if (j < s_pad && n > 0) {
+            for (long long i = 0; i < n; ++i) m += D[(i >> 7) * (long long)s_pad * SQLP_TILE + tile_off((int)(i & 127), j)];
+            m /= (double)n;
+            if (!isfinite(m)) m = 0.0;
+        }
+        dbar[j] = m;
+        ss = fma(m, m, ss);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        dbar[sp] = sqrt(t) * (1.0 + 0x1p-40);
+    }
+}
+
+// pdb[k] = P_k . dbar for every column of the view (row-major copy: one warp reads one contiguous row).
+__global__ void k_screen_pdbar(const double *__restrict__ PiR, int s_pad, const double *__restrict__ dbar,
+                               const long long *__restrict__ d_K, double *__restrict__ pdb)
+{
+    griddep_sync();
+    const long long K = *d_K;
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nw) {
+        const double *row = PiR + k * (long long)s_pad;
+        double acc = 0.0;
+        for (int j = lane; j < s_pad; j += 32) acc = fma(row[j], dbar[j], acc);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) pdb[k] = acc;
+    }
+}
+
+// Pool view for screening: vertices [k_lo, K) restricted to the stochastic rows, minus the centre, split in bf16
+// hi / lo, plus ||PiS[k] - ctr||_2 (rounded up) and its maximum per chunk of 256.  One warp per vertex.
 // k runs over the view's columns [*mark, K); act (twins, kernels_pool.cuh) maps a column to its pool slot.  The
 // mark is advanced by k_screen_mark, the next kernel of the stream.
 __global__ void k_screen_view_sync(const double *__restrict__ pi, int m2, const int *__restrict__ s_rows, int n_rows,
                                    int sp, __nv_bfloat16 *__restrict__ PiB, float *__restrict__ pn,
                                    float *__restrict__ pnmax, int *__restrict__ bad, long long *__restrict__ mark,
-                                   const long long *__restrict__ d_K, const int *__restrict__ act)
+                                   const long long *__restrict__ d_K, const int *__restrict__ act,
+                                   const double *__restrict__ ctr)
 {
     griddep_sync();
     const long long K = *d_K, k_lo = *mark;
@@ -352,7 +439,7 @@ __global__ void k_screen_view_sync(const double *__restrict__ pi, int m2, const 
         const long long kp = act ? (long long)act[k] : k;
         double ss = 0.0;
         for (int j = lane; j < sp; j += 32) {
-            const double p = j < n_rows ? pi[kp * m2 + s_rows[j]] : 0.0;
+            const double p = j < n_rows ? pi[kp * m2 + s_rows[j]] - (ctr ? ctr[j] : 0.0) : 0.0;
             __nv_bfloat16 hi, lo;
             split_bf16(p, hi, lo);
             const size_t off = ((size_t)(c * J + j / 16) * 2) * (2 * SCR_NB * 8) + (size_t)((j % 16) / 8) * (SCR_NB * 8) +
@@ -378,11 +465,12 @@ __global__ void k_screen_mark(long long *__restrict__ mark, const long long *__r
     if (threadIdx.x == 0 && blockIdx.x == 0) *mark = *d_K;
 }
 
-// Scenario store for screening: local scenarios [lo, n_local) from the FP64 tiles, split in bf16 hi / lo,
-// plus the largest ||d_i||_2 per unit of 128 and overall.  One warp per scenario.
+// Scenario store for screening: local scenarios [lo, n_local) from the FP64 tiles, minus dbar, split in bf16
+// hi / lo, plus the largest ||d_i - dbar||_2 per unit of 128 and overall.  One warp per scenario.
 __global__ void k_screen_scen_sync(const double *__restrict__ D, int s_pad, int sp, __nv_bfloat16 *__restrict__ DB,
                                    float *__restrict__ dnmax_unit, float *__restrict__ dnmax_all,
-                                   int *__restrict__ bad, long long lo, long long n_local)
+                                   int *__restrict__ bad, long long lo, long long n_local,
+                                   const double *__restrict__ dbar)
 {
     griddep_sync();
     const int lane = threadIdx.x & 31;
@@ -393,7 +481,7 @@ __global__ void k_screen_scen_sync(const double *__restrict__ D, int s_pad, int 
         const double *Dt = D + (i >> 7) * (long long)s_pad * SQLP_TILE;
         double ss = 0.0;
         for (int j = lane; j < sp; j += 32) {
-            const double d = j < s_pad ? Dt[tile_off((int)(i & 127), j)] : 0.0;
+            const double d = j < s_pad ? Dt[tile_off((int)(i & 127), j)] - (dbar ? dbar[j] : 0.0) : 0.0;
             __nv_bfloat16 hi, lw;
             split_bf16(d, hi, lw);
             const size_t off = (size_t)u * (2 * sp * SCR_UNIT) + (size_t)(j / 8) * (SCR_UNIT * 8) + (size_t)row * 8 + (j % 8);
@@ -424,11 +512,13 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
                                                       const float *__restrict__ dnmax_all, const int *__restrict__ view_bad,
                                                       const int *__restrict__ epi_bad, const long long *__restrict__ d_K,
                                                       int sp, unsigned int ovf_limit, float *__restrict__ b32c,
-                                                      ScreenCtl *__restrict__ ctl)
+                                                      ScreenCtl *__restrict__ ctl, const double *__restrict__ pdb,
+                                                      const double *__restrict__ ctr, const double *__restrict__ dbar)
 {
     griddep_sync();
     __shared__ double red[32];
     __shared__ double lbg[NX];
+    __shared__ double babs[NX];
     __shared__ float fmx[NX];
     __shared__ int nlive[NX];
     __shared__ int sbad;
@@ -441,22 +531,36 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
     if (tid < NX) { fmx[tid] = 0.f; nlive[tid] = 0; }
     __syncthreads();
     for (int x = 0; x < NX; ++x) {
-        double m = -INFINITY;
+        double m = -INFINITY, ma = 0.0;
         bool pinf = false;
         for (long long k = tid; k < K; k += blockDim.x) {
-            const double b = bias[x * bias_stride + k];
+            const double b = bias[x * bias_stride + k] + (pdb ? pdb[k] : 0.0);
             if (b == INFINITY) pinf = true;
-            if (isfinite(b)) m = fmax(m, b - (double)pn[k] * dn);
+            if (isfinite(b)) {
+                m = fmax(m, b - (double)pn[k] * dn);
+                ma = fmax(ma, fabs(b));
+            }
         }
         if (pinf) sbad = 1;                                        // a +Inf score wins everywhere: leave it to the FP64 sweep
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        for (int off = 16; off >= 1; off >>= 1) {
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+            ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+        }
         if (lane == 0) red[warp] = m;
         __syncthreads();
         if (tid == 0) {
             double mm = -INFINITY;
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
             lbg[x] = mm;
+        }
+        __syncthreads();
+        if (lane == 0) red[warp] = ma;
+        __syncthreads();
+        if (tid == 0) {
+            double mm = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
+            babs[x] = mm;
         }
         __syncthreads();
     }
@@ -467,7 +571,7 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
         for (long long k = tid; k < (long long)nch * SCR_NB; k += blockDim.x) {
             float out = SCR_DEAD;
             if (k < K) {
-                const double b = bias[x * bias_stride + k];
+                const double b = bias[x * bias_stride + k] + (pdb ? pdb[k] : 0.0);
                 const double q = (double)pn[k] * dn;
                 if (isfinite(b) && isfinite(lb) && b + q + 1e-9 * (fabs(lb) + q) >= lb) {
                     out = __double2float_rn(b - lb);
@@ -498,16 +602,28 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
         pmx = fmaxf(pmx, p);
     }
     if ((double)pmx * dn > 1.0e30) sbad = 1;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) pmx = fmaxf(pmx, __shfl_xor_sync(0xffffffffu, pmx, off));
+    __syncthreads();
+    if (lane == 0) red[warp] = (double)pmx;
     __syncthreads();
     if (tid == 0) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) pmx = fmaxf(pmx, (float)red[w]);
         const double cq = (3.0 * 0x1p-16 * (1.0 + 0x1p-7) + (3.0 * sp + 8.0) * 0x1p-22 * 1.02 + 1.02 * 0x1p-23 + 0x1p-40) *
                           (1.0 + 0x1p-10);
         ctl->coef_q = __double2float_ru(cq);
         ctl->coef_b = __double2float_ru((0x1p-23 + 0x1p-40) * (1.0 + 0x1p-10));
+        // What the FP64 arithmetic on the UNcentred operands may lose -- the sweep's chain of s_pad fused
+        // multiply-adds and its bias add, the s_pad terms of P_k . dbar, the subtractions of ctr and dbar -- against
+        // the magnitudes before centring: (sp + 8) 2^-52 (max |bias'_k| + (max||P'|| + ||ctr||) (max||d'|| + ||dbar||)).
+        const double raw = ((double)pmx * (1.0 + 0x1p-20) + (ctr ? ctr[sp] : 0.0)) * (dn + (dbar ? dbar[sp] : 0.0));
         for (int x = 0; x < NX; ++x) {
             ctl->shift[x] = lbg[x];
             ctl->bmax[x] = fmx[x];
             ctl->live[x] = nlive[x];
+            const double ea = (sp + 8.0) * 0x1p-52 * (babs[x] + raw) * (1.0 + 0x1p-10) + 1e-30;
+            ctl->eabs[x] = ea < 1.0e30 ? __double2float_ru(ea) : 1.0e30f;
+            if (!(ea < 1.0e30)) sbad = 1;
         }
         ctl->bad = sbad;
         ctl->overflow = 0u;
@@ -524,7 +640,8 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
 // compared on (value desc, index asc).  A scenario whose list overflowed is swept over all K vertices.
 struct ResolveArgs {
     const double *D;            // FP64 scenario tiles (fragment-major)
-    const double *PiS;          // FP64 pool view (fragment-major)
+    const double *PiS;          // FP64 pool view (fragment-major): what the sweep multiplies
+    const double *PiR;          // the same values row-major [column][s_pad]: one contiguous row per candidate
     const double *bias;         // [NX][bias_stride]
     long long bias_stride;
     int s_pad;
@@ -574,15 +691,15 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             const int kfirst = __shfl_sync(0xffffffffu, qk, 0);
             int kk = __shfl_sync(0xffffffffu, qk, lane >> 2);
             if ((lane >> 2) >= qn) kk = kfirst;                      // unused columns repeat a valid vertex
-            const int cv = kk & 127;
-            const double *Prow = a.PiS + (size_t)(kk >> 7) * tile_doubles +
-                                 ((((size_t)(cv >> 4)) * 32 + (cv & 7) * 4 + (lane & 3)) << 1) + ((cv >> 3) & 1);
+            // B fragment of lane t: vertex kk (column t / 4 of the chain), slot 4 g + t % 4 -- four lanes read one
+            // 32-byte sector of the vertex's row
+            const double *Prow = a.PiR + (size_t)kk * a.s_pad + (lane & 3);
             double acc0 = 0.0, acc1 = 0.0;
             int g = 0;
             for (; g + 6 <= ng; g += 6) {                            // twelve loads in flight, then the ordered chain
                 double av[6], bv[6];
 #pragma unroll
-                for (int u = 0; u < 6; ++u) { av[u] = Drow[(size_t)(g + u) * 512]; bv[u] = Prow[(size_t)(g + u) * 512]; }
+                for (int u = 0; u < 6; ++u) { av[u] = Drow[(size_t)(g + u) * 512]; bv[u] = Prow[(size_t)(g + u) * 4]; }
 #pragma unroll
                 for (int u = 0; u < 6; ++u)
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -590,7 +707,7 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
                                  : "d"(av[u]), "d"(bv[u]));
             }
             for (; g < ng; ++g) {
-                const double av = Drow[(size_t)g * 512], bv = Prow[(size_t)g * 512];
+                const double av = Drow[(size_t)g * 512], bv = Prow[(size_t)g * 4];
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                              : "+d"(acc0), "+d"(acc1)
                              : "d"(av), "d"(bv));
@@ -635,24 +752,31 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             }
             const int e = lane < qn ? sq[wib][lane] : sq[wib][0];
             const int kk = e & 0x3FFFFFFF, xq = (e >> 30) & 3;           // xq = 2: every point (full sweeps)
-            const int cv = kk & 127;
-            const double *Pc = a.PiS + (size_t)(kk >> 7) * tile_doubles + ((((size_t)(cv >> 4)) * 32 + (cv & 7) * 4) << 1) + ((cv >> 3) & 1);
+            // the candidate's row is contiguous (s_pad doubles, 64-byte aligned): 16-byte loads, every sector used
+            const double2 *Pc = reinterpret_cast<const double2 *>(a.PiR + (size_t)kk * a.s_pad);
             const double *Dc = Dtile + ((((size_t)(ci >> 4)) * 32 + (ci & 7) * 4) << 1) + ((ci >> 3) & 1);
             double acc = 0.0;
             int g = 0;
             for (; g + 4 <= ng; g += 4) {
-                double pv[16], dv[16];
+                double2 pv[8];
+                double dv[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    pv[u] = Pc[(size_t)(g + (u >> 2)) * 512 + (u & 3) * 2];
-                    dv[u] = Dc[(size_t)(g + (u >> 2)) * 512 + (u & 3) * 2];
+                for (int u = 0; u < 8; ++u) pv[u] = Pc[(size_t)g * 2 + u];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) dv[u] = Dc[(size_t)(g + (u >> 2)) * 512 + (u & 3) * 2];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {                        // slots in order: the chain of the sweep's DMMA
+                    acc = fma(dv[2 * u], pv[u].x, acc);
+                    acc = fma(dv[2 * u + 1], pv[u].y, acc);
                 }
-#pragma unroll
-                for (int u = 0; u < 16; ++u) acc = fma(dv[u], pv[u], acc);
             }
-            for (; g < ng; ++g)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) acc = fma(Dc[(size_t)g * 512 + u * 2], Pc[(size_t)g * 512 + u * 2], acc);
+            for (; g < ng; ++g) {
+                const double2 p0 = Pc[(size_t)g * 2], p1 = Pc[(size_t)g * 2 + 1];
+                acc = fma(Dc[(size_t)g * 512], p0.x, acc);
+                acc = fma(Dc[(size_t)g * 512 + 2], p0.y, acc);
+                acc = fma(Dc[(size_t)g * 512 + 4], p1.x, acc);
+                acc = fma(Dc[(size_t)g * 512 + 6], p1.y, acc);
+            }
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
                 double v = -INFINITY;

@@ -81,6 +81,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     }
     if (const char *g = getenv("SQLP_PDL")) c->pdl = atoi(g) != 0;
     if (const char *g = getenv("SQLP_SCREEN")) c->screen_mode = std::max(0, std::min(2, atoi(g)));
+    if (const char *g = getenv("SQLP_CENTRE")) c->screen_centre = atoi(g) != 0;
     if (const char *g = getenv("SQLP_TWINS")) c->twins = atoi(g) != 0;
     if (const char *g = getenv("SQLP_REDUCE")) c->reduce_mode = std::max(0, std::min(2, atoi(g)));
     if (const char *g = getenv("SQLP_CONTRACT_GRID")) c->contract_grid = atoi(g);
@@ -579,6 +580,7 @@ int32_t sqlp_epi_create(sqlp_ctx *c, sqlp_pool *p, int64_t m2, int64_t n1, int64
                 upload(v->d_rows, rows, S(c));
                 size_t per_chunk = (size_t)v->s_pad * SQLP_TILE * 8;
                 v->d_piS.ensure((size_t)(p->cap / SQLP_TILE) * per_chunk, 0, S(c));
+                v->d_piR.ensure((size_t)(p->cap / SQLP_TILE) * per_chunk, 0, S(c));
                 p->views.push_back(v);
                 e->view = v;
             }

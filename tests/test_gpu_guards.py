@@ -61,7 +61,7 @@ SCRIPT = textwrap.dedent('''
             epi.master_rows()
             epi.eval_dual(0, 0, x)
             epi.delta(0)
-            T.sd_step([epi], [vals[0]], [1.0], np.vstack([pool[0] * 1.5, pool[1]]), x, x + 1.0)
+            T.sd_step([epi], [vals[0]], [1.0], np.vstack([pool[0] * 1.5, pool[K - 1]]), x, x + 1.0)
             check_guards()
             epi.close(); dvs.close()
     # real instance: sampled scenarios, classes, both reductions at a size where the weight-sum path runs

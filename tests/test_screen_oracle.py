@@ -2,12 +2,13 @@
 three products, fp32 accumulation, a Cauchy-Schwarz error bound -- and the exact arithmetic deciding among the
 survivors.  The claim under test: the survivors always contain the vertex the full FP64 sweep selects, so the
 screened argmax IS the oracle's argmax (same index, same value), while only a handful of vertices per scenario
-need the exact score.  CPU only; no kernel exists for this yet."""
+need the exact score.  CPU only; the kernel's own tests are in ``test_gpu_screen.py``."""
 import numpy as np
 import pytest
 
 from oracle import screen as S
-from tests.helpers import load_instance, sample_instance_values, synthetic_pool, synthetic_problem, synthetic_values
+from tests.helpers import (load_instance, load_pool, sample_instance_values, synthetic_pool, synthetic_problem,
+                           synthetic_values)
 
 
 def test_bf16_split_error_budget():
@@ -40,7 +41,23 @@ def test_screened_argmax_is_the_oracle_argmax_on_real_instances(oracle, name, ma
             assert ncand.mean() <= max_mean, ncand.mean()
 
 
-def test_screened_argmax_with_ties_near_ties_and_dominant_bias(oracle):
+def test_centred_operands_keep_the_argmax_and_shrink_the_lists_on_storms_real_pool(oracle):
+    """Real LP duals of storm are a cloud around a common point: relative to its centre (and the scenarios relative
+    to theirs) the error bound is ~10x smaller.  Same argmax either way; far fewer exact evaluations."""
+    P, z = load_instance("storm")
+    pool = load_pool("storm", 2048)
+    vals = sample_instance_values(z, 200, seed=5)
+    ov, oi = oracle.argmax_procedure(P, vals, z["x_alt"], pool)
+    counts = {}
+    for centre in (False, True):
+        mv, mi, ncand = S.argmax_screened(P, vals, z["x_alt"], pool, centre=centre)
+        assert np.array_equal(mi, oi) and np.array_equal(mv, ov)
+        counts[centre] = ncand.mean()
+    assert counts[True] < 0.5 * counts[False], counts
+
+
+@pytest.mark.parametrize("centre", [False, True])
+def test_screened_argmax_with_ties_near_ties_and_dominant_bias(oracle, centre):
     """Adversarial pool: exact duplicates of the winner's stochastic part (first index must win), vertices one
     ulp-scale step away, a bias six orders above the dots, a NaN vertex, an all-zero scenario."""
     P = synthetic_problem(m2=90, n1=10, s=40)
@@ -55,7 +72,7 @@ def test_screened_argmax_with_ties_near_ties_and_dominant_bias(oracle):
     pool[200, 3] = np.nan                                    # never wins (subprob.jl:156)
     x = 10.0 * oracle.u01(3, np.arange(P.n1))
     ov, oi = oracle.argmax_procedure(P, vals, x, pool)
-    mv, mi, ncand = S.argmax_screened(P, vals, x, pool)
+    mv, mi, ncand = S.argmax_screened(P, vals, x, pool, centre=centre)
     assert np.array_equal(mi, oi) and np.array_equal(mv, ov)
     assert not (mi == 200).any() and not (mi == 50).any()
     assert ncand.max() < K

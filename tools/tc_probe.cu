@@ -101,6 +101,9 @@ int main(int argc, char **argv)
         for (int j = 0; j < n_rows; ++j) Dt[(i >> 7) * (size_t)s_pad * 128 + tile_off((int)(i & 127), j)] = d[i * n_rows + j];
     for (long long k = 0; k < K; ++k)
         for (int j = 0; j < n_rows; ++j) PiS[(k >> 7) * (size_t)s_pad * 128 + tile_off((int)(k & 127), j)] = pi[k * n_rows + j];
+    std::vector<double> PiR((size_t)kpad * s_pad, 0.0);
+    for (long long k = 0; k < K; ++k)
+        for (int j = 0; j < n_rows; ++j) PiR[(size_t)k * s_pad + j] = pi[k * n_rows + j];
     std::vector<int> srows(n_rows);
     for (int j = 0; j < n_rows; ++j) srows[j] = j;
 
@@ -116,6 +119,8 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&d_pi, pi.size() * 8)); CK(cudaMemcpy(d_pi, pi.data(), pi.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_D, Dt.size() * 8)); CK(cudaMemcpy(d_D, Dt.data(), Dt.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_PiS, PiS.size() * 8)); CK(cudaMemcpy(d_PiS, PiS.data(), PiS.size() * 8, cudaMemcpyHostToDevice));
+    double *d_PiR;
+    CK(cudaMalloc(&d_PiR, PiR.size() * 8)); CK(cudaMemcpy(d_PiR, PiR.data(), PiR.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_bias, bias.size() * 8)); CK(cudaMemcpy(d_bias, bias.data(), bias.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_srows, n_rows * 4)); CK(cudaMemcpy(d_srows, srows.data(), n_rows * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_K, 8)); CK(cudaMemcpy(d_K, &K, 8, cudaMemcpyHostToDevice));
@@ -145,10 +150,10 @@ int main(int argc, char **argv)
     // ---- operand builders + prep ---------------------------------------------------------------
     long long *d_mark;
     CK(cudaMalloc(&d_mark, 8)); CK(cudaMemset(d_mark, 0, 8));
-    k_screen_view_sync<<<2 * sms, 256>>>(d_pi, n_rows, d_srows, n_rows, sp, d_PiB, d_pn, d_pnmax, d_bad, d_mark, d_K, nullptr);
-    k_screen_scen_sync<<<8 * sms, 256>>>(d_D, s_pad, sp, d_DB, d_dnu, d_dnall, d_bad + 1, 0, N);
+    k_screen_view_sync<<<2 * sms, 256>>>(d_pi, n_rows, d_srows, n_rows, sp, d_PiB, d_pn, d_pnmax, d_bad, d_mark, d_K, nullptr, nullptr);
+    k_screen_scen_sync<<<8 * sms, 256>>>(d_D, s_pad, sp, d_DB, d_dnu, d_dnall, d_bad + 1, 0, N, nullptr);
     k_screen_prep<NX><<<1, 1024>>>(d_bias, kpad, d_pn, d_pnmax, d_dnall, d_bad, d_bad + 1, d_K, sp, (unsigned)(N / 64 + 16),
-                                   d_b32c, d_ctl);
+                                   d_b32c, d_ctl, nullptr, nullptr, nullptr);
     CK(cudaDeviceSynchronize());
     ScreenCtl ctl;
     CK(cudaMemcpy(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
@@ -201,7 +206,7 @@ int main(int argc, char **argv)
 
     // ---- resolve: screened and full ------------------------------------------------------------
     ResolveArgs ra;
-    ra.D = d_D; ra.PiS = d_PiS; ra.bias = d_bias; ra.bias_stride = kpad; ra.s_pad = s_pad; ra.d_K = d_K;
+    ra.D = d_D; ra.PiS = d_PiS; ra.PiR = d_PiR; ra.bias = d_bias; ra.bias_stride = kpad; ra.s_pad = s_pad; ra.d_K = d_K;
     ra.n_local = N; ra.npad = npad; ra.R = R; ra.cand = d_cand; ra.cnt = d_cnt; ra.lfin = d_lfin;
     ra.best_val = d_bv; ra.best_idx = d_bi; ra.out_stride = npad; ra.ctl = d_ctl; ra.force_full = 0;
     cudaEvent_t e0, e1;
@@ -296,7 +301,7 @@ int main(int argc, char **argv)
     // ---- timing ----------------------------------------------------------------------------------
     sa.dbg = nullptr;
     for (int rep = 0; rep < 3; ++rep) {
-        k_screen_prep<NX><<<1, 1024>>>(d_bias, kpad, d_pn, d_pnmax, d_dnall, d_bad, d_bad + 1, d_K, sp, (unsigned)(N / 64 + 16), d_b32c, d_ctl);
+        k_screen_prep<NX><<<1, 1024>>>(d_bias, kpad, d_pn, d_pnmax, d_dnall, d_bad, d_bad + 1, d_K, sp, (unsigned)(N / 64 + 16), d_b32c, d_ctl, nullptr, nullptr, nullptr);
         CK(cudaEventRecord(e0));
         k_screen<NX><<<grid, SCR_THREADS, smem>>>(sa);
         CK(cudaEventRecord(e1));
