@@ -286,7 +286,8 @@ def workload_config(args, z, world):
             "instance": args.instance, "s": int(len(z["pos_row"])), "m2": int(z["m2"]), "n1": int(z["n1"]),
             "K_vertices": args.vertices, "N_scenarios_per_gpu": args.scen_per_gpu,
             "N_scenarios_total": args.scen_per_gpu * world, "epigraphs": args.epigraphs,
-            "weights": "0.5+u", "points_per_step": 2, "parallelism": f"scenario-shard x{world}",
+            "weights": "0.5+u", "points_per_step": 2,
+            "points": "new candidate every iteration (<= 5 % step + 1 % jitter), incumbent replaced every 4th", "parallelism": f"scenario-shard x{world}",
             "l2": "inputs larger than L2 (scenario store 8*s_pad*N bytes per GPU)"}
 
 
@@ -367,8 +368,18 @@ def run_ours(args):
     total_steps = 2 * n_steps + 2            # device-resident leg + e2e leg (+ slack)
     kind = pool_kind(args)
     pool_all = make_pool(z, K0, E * total_steps, kind, args.instance)
-    x_c = np.ascontiguousarray(z["x_ev"])
-    x_i = np.ascontiguousarray(z["x_alt"])
+    x_ev = np.ascontiguousarray(z["x_ev"])
+    x_alt = np.ascontiguousarray(z["x_alt"])
+
+    def points_of(t):
+        """Candidate and incumbent of SD iteration t.  As in an SD run the candidate is a new point every iteration
+        (here: a step of up to 5 % of the way from the EV solution towards the alternative point plus a 1 % jitter of
+        every coordinate) and the incumbent is replaced by an earlier candidate every fourth iteration -- nothing
+        in the timed region sees the same pair of points twice."""
+        def cand(k):
+            return x_ev + 0.05 * float(u01(11, k)) * (x_alt - x_ev) + 0.01 * np.abs(x_ev) * (u01(13 + k, np.arange(n1)) - 0.5)
+        k_inc = (t // 4) * 4 - 1
+        return np.ascontiguousarray(cand(t)), np.ascontiguousarray(x_alt if k_inc < 0 else cand(k_inc))
     coef = T.sdSubprobCoefficients.from_tables(z["rbar"], z["T_colptr"], z["T_rowval"], z["T_nzval"],
                                                z["pos_row"], z["pos_col"])
 
@@ -384,7 +395,6 @@ def run_ours(args):
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return float(tns.item())
 
-    x2_dev = torch.from_numpy(np.concatenate([x_c, x_i])).to(dev)
 
     def device_leg(cell, warmup, steps, want_profiles):
         """`warmup` untimed + `steps` timed SD iterations with every input already resident in HBM and no host
@@ -396,13 +406,14 @@ def run_ours(args):
         staged = []
         for t in range(warmup + steps):
             scen, verts = cell.step_inputs(t0 + t)
-            staged.append((torch.from_numpy(scen).to(dev), torch.from_numpy(verts).to(dev)))
+            staged.append((torch.from_numpy(scen).to(dev), torch.from_numpy(verts).to(dev),
+                           torch.from_numpy(np.concatenate(points_of(t0 + t))).to(dev)))
         torch.cuda.synchronize()
 
         cell_handles = (C.c_void_p * Ecell)(*[e._h for e in cell.epis])
 
         def dev_step(t):
-            scen_d, verts_d = staged[t]
+            scen_d, verts_d, x2_dev = staged[t]
             for e, epi in enumerate(cell.epis):
                 _lib.check(L.sqlp_epi_add_scenarios_dev(epi._h, 1, C.c_void_p(scen_d[e].data_ptr()), None))
             _lib.check(L.sqlp_pool_push_dev(cell.dvs._h, 2 * Ecell, C.c_void_p(verts_d.data_ptr())))
@@ -503,8 +514,9 @@ def run_ours(args):
     host_in = []
     for t in range(n_steps):
         scen, verts = cell.step_inputs(base_t + t)
-        host_in.append((torch.from_numpy(scen).pin_memory(), torch.from_numpy(verts).pin_memory()))
-    xc_p, xi_p = torch.from_numpy(x_c).pin_memory(), torch.from_numpy(x_i).pin_memory()
+        host_in.append((torch.from_numpy(scen).pin_memory(), torch.from_numpy(verts).pin_memory(),
+                        [torch.from_numpy(x).pin_memory() for x in points_of(base_t + t)]))
+    x_c, x_i = points_of(base_t + n_steps - 1)          # the last iteration's points: what the checks below use
     alpha = np.zeros((E, 2)); beta = np.zeros((E, 2, n1)); wm = np.zeros(E); val = np.zeros((E, 2))
     handles = (C.c_void_p * E)(*[e._h for e in cell.epis])
     ins = np.zeros(2 * E, dtype=np.int32); idx = np.zeros(2 * E, dtype=np.int64)
@@ -512,7 +524,7 @@ def run_ours(args):
     def e2e_step(t):
         # the call a host makes once per SD iteration: scenarios, the iteration's dual vertices and both
         # points in (host buffers), dedup decisions and both cuts of every epigraph out
-        scen_p, verts_p = host_in[t]
+        scen_p, verts_p, (xc_p, xi_p) = host_in[t]
         _lib.check(L.sqlp_cell_sd_step(E, handles, C.c_void_p(scen_p.data_ptr()), None, 2 * E,
                                        C.c_void_p(verts_p.data_ptr()), ins.ctypes.data_as(C.c_void_p),
                                        idx.ctypes.data_as(C.c_void_p), C.c_void_p(xc_p.data_ptr()),

@@ -232,10 +232,12 @@ struct sqlp_ctx {
     // screening pass (kernels_screen.cuh): 0 = off, 1 = automatic (default), 2 = whenever the shape allows it
     int screen_mode = 1;
     bool screen_smem_set[3] = {false, false, false};
+    bool screen_seed = true;      // start the scan from the previous winners' scores (SQLP_SEED=0: from -Inf)
     bool screen_centre = true;    // bf16 operands relative to the centre of the pool / of the scenarios (SQLP_CENTRE=0: raw)
     bool resolve_fma = false;     // exact decision by DFMA lanes (set when the device check DMMA == DFMA chain passed)
     int reduce_mode = 0;          // cut reduction: 0 automatic, 1 per-scenario gather only, 2 per-vertex weight sums whenever possible
     bool hist_smem_set[3] = {false, false, false};
+    DevBuf d_lseed;               // [NX][npad] warm-start bounds of the running pass
     DevBuf d_cand, d_cnt, d_lfin; // candidate lists of the running pass (shared by the context's epigraphs: stream order)
     DevBuf d_cell, d_cellg;       // sharded job: the rows of a call's epigraphs back to back, and their all-gather
     DevBuf d_step;                // sqlp_cell_sd_step: the step's scenario values on the device
@@ -361,6 +363,9 @@ struct sqlp_epi {
     int last_nx = 0;   // points of the last cut formation whose result is still in d_out
     // screening pass: bf16 scenario operands, per-call control block, what the host has learnt
     DevBuf d_DB, d_dnu, d_dnall, d_ebad, d_b32c, d_ctl;
+    DevBuf d_prev;                            // [n_local][2]: 1 + view column selected at the previous pass, per point
+    int64_t prev_cap = 0;
+    bool prev_valid = false;
     DevBuf d_dbar, d_pdb;                     // centre of the scenarios (sp values + norm); P_k . dbar per view column
     int64_t dbar_n = 0;                       // scenarios dbar was the mean of
     int64_t scr_synced = 0, scr_units_cap = 0;

@@ -385,6 +385,35 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
            v->d_Kv(p), v->sp, ovf_limit, e->d_b32c.as<float>(), e->d_ctl.as<ScreenCtl>(),
            (const double *)e->d_pdb.as<double>(), (const double *)v->d_ctr.as<double>(),
            (const double *)e->d_dbar.as<double>());
+    // warm start of the scan from the winners of the previous pass (k_screen_seed)
+    const float *lseed = nullptr;
+    if (c->screen_seed) {
+        if (npad > e->prev_cap) {
+            const int64_t ncap = std::max<int64_t>(npad, e->prev_cap * 2);
+            e->d_prev.ensure((size_t)ncap * 8, (size_t)e->prev_cap * 8, S(c));
+            e->prev_cap = ncap;
+        }
+        if (e->prev_valid) {
+            c->d_lseed.ensure((size_t)NX * npad * 4, 0, S(c), false);
+            SeedArgs sd;
+            sd.D = e->d_D.as<double>();
+            sd.PiR = v->d_piR.as<double>();
+            sd.bias = e->cur_bias;
+            sd.bias_stride = e->cur_bias_stride;
+            sd.pdb = e->d_pdb.as<double>();
+            sd.ctr = v->d_ctr.as<double>();
+            sd.dbar = e->d_dbar.as<double>();
+            sd.prev = e->d_prev.as<int>();
+            sd.d_K = v->d_Kv(p);
+            sd.ctl = e->d_ctl.as<ScreenCtl>();
+            sd.s_pad = v->s_pad;
+            sd.n_local = e->n_local;
+            sd.npad = npad;
+            sd.lseed = c->d_lseed.as<float>();
+            LAUNCH(c, k_screen_seed<NX>, (int)std::min<int64_t>(nunits, 16 * c->sm_count), 128, (size_t)2 * v->s_pad * 8, sd);
+            lseed = c->d_lseed.as<float>();
+        }
+    }
     int nstages = SCR_MAX_STAGES;
     while (nstages > 3 && scr_smem_bytes(v->sp, nstages, NX) > (size_t)c->smem_optin) --nstages;
     const size_t smem = scr_smem_bytes(v->sp, nstages, NX);
@@ -408,6 +437,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     sa.cand = c->d_cand.as<int2>();
     sa.cnt = c->d_cnt.as<int>();
     sa.lfin = c->d_lfin.as<float>();
+    sa.lseed = lseed;
     sa.dbg = nullptr;
     sa.desc_mode = 0;
     const int grid = (int)std::min<int64_t>(c->sm_count, nunits * R);
@@ -435,6 +465,8 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     ra.out_stride = e->out_stride;
     ra.ctl = e->d_ctl.as<ScreenCtl>();
     ra.force_full = 0;
+    ra.prev = c->screen_seed ? e->d_prev.as<int>() : nullptr;
+    e->prev_valid = c->screen_seed;
     {
         ProfScope prof(c, SQLP_PROF_RESOLVE, (double)NX * (double)e->n_local);
         const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + 7) / 8, 1), 8 * c->sm_count);

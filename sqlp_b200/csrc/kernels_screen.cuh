@@ -76,6 +76,7 @@ struct ScreenArgs {
     int2 *cand;                    // [((x * R + r) * 2 + h) * npad + i][SCR_CAP]  (vertex, upper bound bits)
     int *cnt;                      // [((x * R + r) * 2 + h) * npad + i]
     float *lfin;                   // same shape: the thread's final lower bound of the best score
+    const float *lseed;            // optional [NX][npad]: a lower bound of the scenario's best score known beforehand
     float *dbg;                    // optional [128][256] raw accumulators of the first tile of block 0
     int desc_mode;                 // 0: LBO = K-direction, SBO = row-group direction (tc05.cuh); 1: swapped (probe only)
 };
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
             long long slot[NX];
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
-                L[x] = -INFINITY;
+                L[x] = (a.lseed && valid) ? a.lseed[(long long)x * a.npad + i] : -INFINITY;
                 n[x] = 0;
                 slot[x] = ((long long)(x * a.R + r) * 2 + h) * a.npad + i;
             }
@@ -634,6 +635,90 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warm start.  The epilogue of k_screen keeps every vertex that could still win when it is seen, so a list also
+// holds the "record breakers" of the scan -- about (candidates) x ln K entries, most of them stale at the end --
+// and the warp takes its slow path whenever one of its 32 scenarios meets one.  An SD iteration moves the candidate
+// point a little and the incumbent rarely: the vertex that won a scenario at the previous call is almost always a
+// near-winner now.  Its score at the new point is a lower bound of the scenario's best score that is valid whatever
+// the history (ANY vertex gives one), so the scan starts from it instead of from -Inf.  Per scenario: the winners of
+// the previous call at both points (a, b), the centred dots P'_a . d'_i and P'_b . d'_i in FP64 (they do not depend
+// on the point), and per point the larger of the two scores, minus what the FP64 operations may have lost, rounded
+// down to fp32.  One thread per scenario, one block per FP64 tile: the block reads the tile contiguously.
+struct SeedArgs {
+    const double *D;            // FP64 scenario tiles (fragment-major)
+    const double *PiR;          // FP64 view, row-major
+    const double *bias;         // [NX][bias_stride]
+    long long bias_stride;
+    const double *pdb;          // P_k . dbar
+    const double *ctr, *dbar;   // the centres (sp values each)
+    const int *prev;            // [n][2]: 1 + view column, 0 = none
+    const long long *d_K;
+    const ScreenCtl *ctl;
+    int s_pad;
+    long long n_local, npad;
+    float *lseed;               // [NX][npad]
+};
+
+template <int NX>
+__global__ void __launch_bounds__(128) k_screen_seed(SeedArgs a)
+{
+    griddep_sync();
+    extern __shared__ double seed_sh[];
+    double *cs = seed_sh, *ds = seed_sh + a.s_pad;
+    for (int j = threadIdx.x; j < a.s_pad; j += blockDim.x) { cs[j] = a.ctr[j]; ds[j] = a.dbar[j]; }
+    __syncthreads();
+    const long long K = *a.d_K;
+    const int c = threadIdx.x, ng = a.s_pad / 4;
+    double shift[NX], slack[NX];
+#pragma unroll
+    for (int x = 0; x < NX; ++x) { shift[x] = a.ctl->shift[x]; slack[x] = 2.0 * (double)a.ctl->eabs[x]; }
+    for (long long tile = blockIdx.x; tile * SQLP_TILE < a.npad; tile += gridDim.x) {
+        const long long i = tile * SQLP_TILE + c;
+        const bool valid = i < a.n_local;
+        int ka = -1, kb = -1;
+        if (valid) {
+            const int2 pc = reinterpret_cast<const int2 *>(a.prev)[i];
+            ka = pc.x - 1;
+            kb = pc.y - 1;
+        }
+        if (ka >= K) ka = -1;
+        if (kb >= K || kb == ka) kb = -1;
+        if (ka < 0) { ka = kb; kb = -1; }
+        double da = 0.0, db = 0.0;
+        if (ka >= 0) {
+            const double *Dc = a.D + (size_t)tile * a.s_pad * SQLP_TILE + ((((size_t)(c >> 4)) * 32 + (c & 7) * 4) << 1) + ((c >> 3) & 1);
+            const double2 *Pa = reinterpret_cast<const double2 *>(a.PiR + (size_t)ka * a.s_pad);
+            const double2 *Pb = reinterpret_cast<const double2 *>(a.PiR + (size_t)(kb >= 0 ? kb : ka) * a.s_pad);
+#pragma unroll 2
+            for (int g = 0; g < ng; ++g) {
+                const double2 a0 = Pa[2 * g], a1 = Pa[2 * g + 1], b0 = Pb[2 * g], b1 = Pb[2 * g + 1];
+                const double d0 = Dc[(size_t)g * 512] - ds[4 * g], d1 = Dc[(size_t)g * 512 + 2] - ds[4 * g + 1];
+                const double d2 = Dc[(size_t)g * 512 + 4] - ds[4 * g + 2], d3 = Dc[(size_t)g * 512 + 6] - ds[4 * g + 3];
+                const double c0 = cs[4 * g], c1 = cs[4 * g + 1], c2 = cs[4 * g + 2], c3 = cs[4 * g + 3];
+                da = fma(a0.x - c0, d0, da); da = fma(a0.y - c1, d1, da); da = fma(a1.x - c2, d2, da); da = fma(a1.y - c3, d3, da);
+                db = fma(b0.x - c0, d0, db); db = fma(b0.y - c1, d1, db); db = fma(b1.x - c2, d2, db); db = fma(b1.y - c3, d3, db);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            double best = -INFINITY;
+            if (ka >= 0) {
+                const double v = a.bias[x * a.bias_stride + ka] + a.pdb[ka] - shift[x] + da;
+                if (isfinite(v)) best = v;
+            }
+            if (kb >= 0) {
+                const double v = a.bias[x * a.bias_stride + kb] + a.pdb[kb] - shift[x] + db;
+                if (isfinite(v)) best = fmax(best, v);
+            }
+            best -= slack[x] + 0x1p-40 * fabs(best);
+            float out = -INFINITY;
+            if (best > -1.0e37 && best < 1.0e37) out = __double2float_rd(best);
+            a.lseed[(long long)x * a.npad + i] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The exact decision.  One warp per scenario: the candidates that survive the final lower bound are scored
 // with the FP64 sweep's own arithmetic -- mma.sync.m8n8k4.f64 over the k-groups in ascending order from a
 // zero accumulator, then + bias -- eight vertices per chain (the eight rows of A all hold the scenario), and
@@ -656,6 +741,7 @@ struct ResolveArgs {
     long long out_stride;
     ScreenCtl *ctl;
     int force_full;             // tests: sweep every vertex for every scenario with this kernel's arithmetic
+    int *prev;                  // optional [n][2]: 1 + the view column selected for (scenario, point), for k_screen_seed
 };
 
 // FMA (0 / 1): the chain as mma.sync.m8n8k4.f64 (eight candidates per chain, one of the eight rows used), or as plain
@@ -906,6 +992,7 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             for (int x = 0; x < NX; ++x) {
                 a.best_val[x * a.out_stride + i] = best[x];
                 a.best_idx[x * a.out_stride + i] = bidx[x];
+                if (a.prev) a.prev[2 * i + x] = bidx[x] + 1;
             }
         }
     }

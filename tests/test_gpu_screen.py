@@ -160,6 +160,45 @@ def test_growing_pool_and_scenarios(T, ctx):
     assert epi.screen_stats()["passes"] >= 6
 
 
+def test_warm_start_from_previous_winners(T, ctx):
+    """From the second pass on the scan of a scenario starts from the score of the vertices that won it at the
+    previous pass (k_screen_seed) instead of from -Inf.  An SD-like run on storm's real pool -- the candidate moves
+    every iteration (a little, or across the whole box), the incumbent now and then, vertices and scenarios arrive --
+    must stay bit-identical to the FP64 sweep, and the lists must get shorter."""
+    P, z = load_instance("storm")
+    pool = load_pool("storm", 16384)
+    dvs = T.sdDualVertexSet(m2=P.m2)
+    dvs.push_many(pool[:5000])
+    epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+    vals = sampled_values_at(z, 9, np.arange(6000))
+    epi.add_scenarios(vals[:5000], 0.5 + np.arange(5000) % 3)
+    x0, x1 = z["x_ev"], z["x_alt"]
+    inc = x0
+    emitted = []
+    for it in range(9):
+        dvs.push_many(pool[5000 + 30 * it: 5000 + 30 * (it + 1)])
+        epi.add_scenarios(vals[5000 + 100 * it: 5000 + 100 * (it + 1)], None)
+        lam = [0.0, 0.02, 0.05, 1.0, 0.97, 0.5, 0.48, -0.3, 0.1][it]           # small steps and jumps
+        cand = x0 + lam * (x1 - x0)
+        if it % 4 == 3:
+            inc = x0 + [0.0, 0.02, 0.05][it // 4] * (x1 - x0)                  # the incumbent becomes an earlier candidate
+        res = {}
+        for mode in (0, 2):
+            ctx.set_screen(mode)
+            cuts, val = epi.build_cuts2(cand, inc, with_val=True)
+            if mode == 2:
+                emitted.append(epi.screen_stats()["emitted"])      # of the two-point pass just run
+            mv, mi = epi.argmax(cand)
+            res[mode] = (np.array([cuts[0].alpha, cuts[1].alpha]), np.stack([cuts[0].beta, cuts[1].beta]), val, mv, mi)
+        for u, v in zip(res[0], res[2]):
+            u, v = np.asarray(u), np.asarray(v)
+            assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), it
+    st = epi.screen_stats()
+    assert st["fallbacks"] == 0 and st["passes"] >= 18, st
+    print("emitted per pass:", emitted)
+    assert emitted[2] < emitted[0]          # a small step of the candidate: far fewer stale entries than the cold scan
+
+
 # ---- score-equivalent vertices ("twins", csrc/kernels_pool.cuh) ---------------------------------------------
 
 def test_twins_leave_results_bit_identical(T, monkeypatch):

@@ -168,7 +168,7 @@ int main(int argc, char **argv)
     ScreenArgs sa;
     sa.DB = d_DB; sa.PiB = d_PiB; sa.b32c = d_b32c; sa.dnmax_unit = d_dnu; sa.ctl = d_ctl; sa.d_K = d_K;
     sa.sp = sp; sa.nunits = (int)nunits; sa.R = R; sa.nstages = nstages; sa.n_local = N; sa.npad = npad;
-    sa.cand = d_cand; sa.cnt = d_cnt; sa.lfin = d_lfin; sa.dbg = d_dbg; sa.desc_mode = desc_mode;
+    sa.cand = d_cand; sa.cnt = d_cnt; sa.lfin = d_lfin; sa.dbg = d_dbg; sa.desc_mode = desc_mode; sa.lseed = nullptr;
     const int grid = (int)std::min<long long>(sms, nunits * R);
     printf("k_screen: grid %d, %d threads, %zu B smem, %d stages\n", grid, SCR_THREADS, smem, nstages);
     k_screen<NX><<<grid, SCR_THREADS, smem>>>(sa);
@@ -208,7 +208,7 @@ int main(int argc, char **argv)
     ResolveArgs ra;
     ra.D = d_D; ra.PiS = d_PiS; ra.PiR = d_PiR; ra.bias = d_bias; ra.bias_stride = kpad; ra.s_pad = s_pad; ra.d_K = d_K;
     ra.n_local = N; ra.npad = npad; ra.R = R; ra.cand = d_cand; ra.cnt = d_cnt; ra.lfin = d_lfin;
-    ra.best_val = d_bv; ra.best_idx = d_bi; ra.out_stride = npad; ra.ctl = d_ctl; ra.force_full = 0;
+    ra.best_val = d_bv; ra.best_idx = d_bi; ra.out_stride = npad; ra.ctl = d_ctl; ra.force_full = 0; ra.prev = nullptr;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaMemset(d_bi, 0xff, (size_t)NX * npad * 4));
