@@ -234,6 +234,8 @@ struct sqlp_ctx {
     bool screen_smem_set[3] = {false, false, false};
     bool screen_seed = true;      // start the scan from the previous winners' scores (SQLP_SEED=0: from -Inf)
     bool screen_centre = true;    // bf16 operands relative to the centre of the pool / of the scenarios (SQLP_CENTRE=0: raw)
+    bool resolve_rows = true;     // exact decision moves whole rows through shared memory (SQLP_RESOLVE=lanes: a lane per row)
+    size_t decide_smem_set[3] = {0, 0, 0};
     bool resolve_fma = false;     // exact decision by DFMA lanes (set when the device check DMMA == DFMA chain passed)
     int reduce_mode = 0;          // cut reduction: 0 automatic, 1 per-scenario gather only, 2 per-vertex weight sums whenever possible
     bool hist_smem_set[3] = {false, false, false};
@@ -344,6 +346,7 @@ struct sqlp_epi {
     int64_t n_global = 0, n_local = 0, cap_tiles = 0;
     double total_weight = 0.0;
     DevBuf d_D, d_dT, d_w, d_Dx;
+    DevBuf d_DR;                              // d_D row-major [scenario][s_pad] (epigraphs without random T entries)
     // per-vertex tables (rho, tau)
     DevBuf d_rt;
     int64_t rt_cap = 0, rt_synced_lo = 0;

@@ -32,6 +32,7 @@ void epi_reserve_scenarios(sqlp_epi *e, int64_t n_local_new)
     int64_t used_tiles = (e->n_local + SQLP_TILE - 1) / SQLP_TILE;
     size_t per_tile = (size_t)e->view->s_pad * SQLP_TILE * 8;
     e->d_D.ensure(ncap * per_tile, used_tiles * per_tile, S(c));
+    if (!e->n_T) e->d_DR.ensure(ncap * per_tile, used_tiles * per_tile, S(c));
     e->d_w.ensure((size_t)ncap * SQLP_TILE * 8, (size_t)used_tiles * SQLP_TILE * 8, S(c));
     if (e->n_T)
         e->d_dT.ensure((size_t)ncap * SQLP_TILE * e->n_T * 8,
@@ -100,11 +101,11 @@ void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_d
             LAUNCH(c, k_delta_build<true>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
                    (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
                    e->d_dT.as<double>(), e->d_w.as<double>(), wts, (unsigned long long)seed,
-                   (unsigned long long)wseed);
+                   (unsigned long long)wseed, e->d_DR.as<double>());
         else
             LAUNCH(c, k_delta_build<false>, blocks, SQLP_DELTA_THREADS, dsmem, tb, vals, (long long)gs,
                    (long long)cnt, c->rank, c->world, e->view->s_pad, e->d_D.as<double>(),
-                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, 0ull, 0ull);
+                   e->d_dT.as<double>(), e->d_w.as<double>(), wts, 0ull, 0ull, e->d_DR.as<double>());
         if (!sample && !v_dev) CK(cudaStreamSynchronize(S(c)));   // staging buffer is reused
         off = end;
     }
@@ -387,7 +388,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
            (const double *)e->d_dbar.as<double>());
     // warm start of the scan from the winners of the previous pass (k_screen_seed)
     const float *lseed = nullptr;
-    if (c->screen_seed) {
+    if (c->screen_seed && e->d_DR.p) {
         if (npad > e->prev_cap) {
             const int64_t ncap = std::max<int64_t>(npad, e->prev_cap * 2);
             e->d_prev.ensure((size_t)ncap * 8, (size_t)e->prev_cap * 8, S(c));
@@ -396,7 +397,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
         if (e->prev_valid) {
             c->d_lseed.ensure((size_t)NX * npad * 4, 0, S(c), false);
             SeedArgs sd;
-            sd.D = e->d_D.as<double>();
+            sd.DR = e->d_DR.as<double>();
             sd.PiR = v->d_piR.as<double>();
             sd.bias = e->cur_bias;
             sd.bias_stride = e->cur_bias_stride;
@@ -410,7 +411,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
             sd.n_local = e->n_local;
             sd.npad = npad;
             sd.lseed = c->d_lseed.as<float>();
-            LAUNCH(c, k_screen_seed<NX>, (int)std::min<int64_t>(nunits, 16 * c->sm_count), 128, (size_t)2 * v->s_pad * 8, sd);
+            LAUNCH(c, k_screen_seed<NX>, (int)std::min<int64_t>((npad + 7) / 8, 32 * c->sm_count), 256, (size_t)2 * v->s_pad * 8, sd);
             lseed = c->d_lseed.as<float>();
         }
     }
@@ -465,13 +466,26 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     ra.out_stride = e->out_stride;
     ra.ctl = e->d_ctl.as<ScreenCtl>();
     ra.force_full = 0;
-    ra.prev = c->screen_seed ? e->d_prev.as<int>() : nullptr;
-    e->prev_valid = c->screen_seed;
+    ra.DR = e->d_DR.as<double>();
+    ra.prev = (c->screen_seed && e->d_DR.p) ? e->d_prev.as<int>() : nullptr;
+    e->prev_valid = ra.prev != nullptr;
     {
         ProfScope prof(c, SQLP_PROF_RESOLVE, (double)NX * (double)e->n_local);
-        const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + 7) / 8, 1), 8 * c->sm_count);
-        if (c->resolve_fma) LAUNCH(c, (k_screen_resolve<NX, 1>), rgrid, 256, 0, ra);
-        else LAUNCH(c, (k_screen_resolve<NX, 0>), rgrid, 256, 0, ra);
+        const size_t dsmem = scr_decide_smem(v->s_pad);
+        if (c->resolve_fma && c->resolve_rows && R == 1 && e->d_DR.p && dsmem <= (size_t)c->smem_optin) {
+            // whole rows through shared memory (k_screen_decide)
+            if (dsmem > c->decide_smem_set[NX]) {
+                CK(cudaFuncSetAttribute(k_screen_decide<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+                c->decide_smem_set[NX] = dsmem;
+            }
+            const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + SCR_DEC_WARPS - 1) / SCR_DEC_WARPS, 1),
+                                                     20 * c->sm_count);
+            LAUNCH(c, k_screen_decide<NX>, rgrid, 32 * SCR_DEC_WARPS, dsmem, ra);
+        } else {
+            const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + 7) / 8, 1), 8 * c->sm_count);
+            if (c->resolve_fma) LAUNCH(c, (k_screen_resolve<NX, 1>), rgrid, 256, 0, ra);
+            else LAUNCH(c, (k_screen_resolve<NX, 0>), rgrid, 256, 0, ra);
+        }
     }
     e->scr_nx = NX;
     // the control block goes back to the host asynchronously; screen_learn() reads it at a later call

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(SQLP_DELTA_THREADS, 2)
 k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, long long n_new,
               int rank, int world, int s_pad, double *__restrict__ D, double *__restrict__ dT,
               double *__restrict__ w, const double *__restrict__ w_batch, unsigned long long seed,
-              unsigned long long wseed)
+              unsigned long long wseed, double *__restrict__ DR)
 {
     griddep_sync();
     extern __shared__ __align__(16) double sh[];   // [SQLP_DELTA_COLS][stride]
@@ -185,6 +185,13 @@ k_delta_build(DeltaTables tb, const double *__restrict__ values, long long g0, l
             } else {
                 if (c >= c0 && c < c1) dst[0] = src[0];
                 if (c + 8 >= c0 && c + 8 < c1) dst[1] = src[8 * stride];
+            }
+        }
+        // the same values row-major [scenario][s_pad]: what the exact decision of the screening pass gathers
+        if (DR) {
+            for (int q = threadIdx.x; q < (c1 - c0) * jn; q += blockDim.x) {
+                const int c = c0 + q / jn, jj = q - (c - c0) * jn;
+                DR[(ltile * SQLP_TILE + c) * (long long)s_pad + j0 + jj] = sh[(c - cb) * stride + jj];
             }
         }
         __syncthreads();

@@ -250,38 +250,51 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
 #pragma unroll
                         for (int e = 0; e < 32; ++e) a.dbg[row * SCR_NB + h * 128 + g * 32 + e] = __uint_as_float(v[e]);
                     }
+                    // the eight (group of 8 columns, point) maxima of these 32 columns first, branch-free -- eight
+                    // independent add / max trees the scheduler can interleave -- and ONE test whether any of them
+                    // reaches its threshold; only then the groups are looked at one by one, in the order and with the
+                    // running threshold of a column-by-column scan (thr only moves inside the slow path, so the pre-test
+                    // with the thresholds at the start of the 32 columns can only err towards "look")
+                    float gmx[4][NX];
+                    bool any = false;
 #pragma unroll
                     for (int s8 = 0; s8 < 4; ++s8) {
 #pragma unroll
                         for (int x = 0; x < NX; ++x) {
                             const float4 b0 = *reinterpret_cast<const float4 *>(bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8);
                             const float4 b1 = *reinterpret_cast<const float4 *>(bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8 + 4);
-                            float tt[8];
-                            tt[0] = __uint_as_float(v[s8 * 8 + 0]) + b0.x;
-                            tt[1] = __uint_as_float(v[s8 * 8 + 1]) + b0.y;
-                            tt[2] = __uint_as_float(v[s8 * 8 + 2]) + b0.z;
-                            tt[3] = __uint_as_float(v[s8 * 8 + 3]) + b0.w;
-                            tt[4] = __uint_as_float(v[s8 * 8 + 4]) + b1.x;
-                            tt[5] = __uint_as_float(v[s8 * 8 + 5]) + b1.y;
-                            tt[6] = __uint_as_float(v[s8 * 8 + 6]) + b1.z;
-                            tt[7] = __uint_as_float(v[s8 * 8 + 7]) + b1.w;
-                            const float gm = fmaxf(fmaxf(fmaxf(tt[0], tt[1]), fmaxf(tt[2], tt[3])),
-                                                   fmaxf(fmaxf(tt[4], tt[5]), fmaxf(tt[6], tt[7])));
-                            if (gm >= thr[x]) {
-                                // rare: some of the eight may still win.  Dead / padded vertices (SCR_DEAD) and
-                                // rows beyond the epigraph's scenarios never enter a list.
-                                const int kb = c * SCR_NB + h * 128 + g * 32 + s8 * 8;
+                            const float t0 = __uint_as_float(v[s8 * 8 + 0]) + b0.x, t1 = __uint_as_float(v[s8 * 8 + 1]) + b0.y;
+                            const float t2 = __uint_as_float(v[s8 * 8 + 2]) + b0.z, t3 = __uint_as_float(v[s8 * 8 + 3]) + b0.w;
+                            const float t4 = __uint_as_float(v[s8 * 8 + 4]) + b1.x, t5 = __uint_as_float(v[s8 * 8 + 5]) + b1.y;
+                            const float t6 = __uint_as_float(v[s8 * 8 + 6]) + b1.z, t7 = __uint_as_float(v[s8 * 8 + 7]) + b1.w;
+                            gmx[s8][x] = fmaxf(fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)), fmaxf(fmaxf(t4, t5), fmaxf(t6, t7)));
+                            any = any || gmx[s8][x] >= thr[x];
+                        }
+                    }
+                    if (any) {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    if (tt[e] >= thr[x] && tt[e] > -1.0e38f && valid) {
-                                        if (n[x] < SCR_CAP)
-                                            a.cand[slot[x] * SCR_CAP + n[x]] =
-                                                make_int2(kb + e, __float_as_int(__fadd_ru(tt[e], E[x])));
-                                        ++n[x];
-                                        ++emitted;
+                        for (int s8 = 0; s8 < 4; ++s8) {
+#pragma unroll
+                            for (int x = 0; x < NX; ++x) {
+                                const float gm = gmx[s8][x];
+                                if (gm >= thr[x]) {
+                                    // rare: some of the eight may still win.  Dead / padded vertices (SCR_DEAD) and
+                                    // rows beyond the epigraph's scenarios never enter a list.
+                                    const int kb = c * SCR_NB + h * 128 + g * 32 + s8 * 8;
+                                    const float *bx = bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8;
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float te = __uint_as_float(v[s8 * 8 + e]) + bx[e];   // the same add as above
+                                        if (te >= thr[x] && te > -1.0e38f && valid) {
+                                            if (n[x] < SCR_CAP)
+                                                a.cand[slot[x] * SCR_CAP + n[x]] =
+                                                    make_int2(kb + e, __float_as_int(__fadd_ru(te, E[x])));
+                                            ++n[x];
+                                            ++emitted;
+                                        }
                                     }
+                                    thr[x] = fmaxf(thr[x], __fadd_rd(gm, -E2[x]));
                                 }
-                                thr[x] = fmaxf(thr[x], __fadd_rd(gm, -E2[x]));
                             }
                         }
                     }
@@ -643,9 +656,11 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
 // the history (ANY vertex gives one), so the scan starts from it instead of from -Inf.  Per scenario: the winners of
 // the previous call at both points (a, b), the centred dots P'_a . d'_i and P'_b . d'_i in FP64 (they do not depend
 // on the point), and per point the larger of the two scores, minus what the FP64 operations may have lost, rounded
-// down to fp32.  One thread per scenario, one block per FP64 tile: the block reads the tile contiguously.
+// down to fp32.  One warp per scenario: the three rows (scenario, two vertices; row-major copies) are read as
+// contiguous 16-byte pieces, lanes along the row -- a thread per scenario walking its own rows costs one L1 tag
+// look-up per 32 bytes and was bound by exactly that (profiles/r02_decide_notes.md).
 struct SeedArgs {
-    const double *D;            // FP64 scenario tiles (fragment-major)
+    const double *DR;           // FP64 scenarios, row-major [i][s_pad]
     const double *PiR;          // FP64 view, row-major
     const double *bias;         // [NX][bias_stride]
     long long bias_stride;
@@ -660,23 +675,22 @@ struct SeedArgs {
 };
 
 template <int NX>
-__global__ void __launch_bounds__(128) k_screen_seed(SeedArgs a)
+__global__ void __launch_bounds__(256) k_screen_seed(SeedArgs a)
 {
     griddep_sync();
-    extern __shared__ double seed_sh[];
-    double *cs = seed_sh, *ds = seed_sh + a.s_pad;
-    for (int j = threadIdx.x; j < a.s_pad; j += blockDim.x) { cs[j] = a.ctr[j]; ds[j] = a.dbar[j]; }
+    extern __shared__ __align__(16) double seed_sh[];
+    double2 *cs = reinterpret_cast<double2 *>(seed_sh), *ds = cs + a.s_pad / 2;
+    for (int j = threadIdx.x; j < a.s_pad; j += blockDim.x) { seed_sh[j] = a.ctr[j]; seed_sh[a.s_pad + j] = a.dbar[j]; }
     __syncthreads();
     const long long K = *a.d_K;
-    const int c = threadIdx.x, ng = a.s_pad / 4;
+    const int lane = threadIdx.x & 31, sp2 = a.s_pad / 2;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     double shift[NX], slack[NX];
 #pragma unroll
     for (int x = 0; x < NX; ++x) { shift[x] = a.ctl->shift[x]; slack[x] = 2.0 * (double)a.ctl->eabs[x]; }
-    for (long long tile = blockIdx.x; tile * SQLP_TILE < a.npad; tile += gridDim.x) {
-        const long long i = tile * SQLP_TILE + c;
-        const bool valid = i < a.n_local;
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.npad; i += nw) {
         int ka = -1, kb = -1;
-        if (valid) {
+        if (i < a.n_local) {
             const int2 pc = reinterpret_cast<const int2 *>(a.prev)[i];
             ka = pc.x - 1;
             kb = pc.y - 1;
@@ -686,21 +700,26 @@ __global__ void __launch_bounds__(128) k_screen_seed(SeedArgs a)
         if (ka < 0) { ka = kb; kb = -1; }
         double da = 0.0, db = 0.0;
         if (ka >= 0) {
-            const double *Dc = a.D + (size_t)tile * a.s_pad * SQLP_TILE + ((((size_t)(c >> 4)) * 32 + (c & 7) * 4) << 1) + ((c >> 3) & 1);
+            const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad);
             const double2 *Pa = reinterpret_cast<const double2 *>(a.PiR + (size_t)ka * a.s_pad);
             const double2 *Pb = reinterpret_cast<const double2 *>(a.PiR + (size_t)(kb >= 0 ? kb : ka) * a.s_pad);
-#pragma unroll 2
-            for (int g = 0; g < ng; ++g) {
-                const double2 a0 = Pa[2 * g], a1 = Pa[2 * g + 1], b0 = Pb[2 * g], b1 = Pb[2 * g + 1];
-                const double d0 = Dc[(size_t)g * 512] - ds[4 * g], d1 = Dc[(size_t)g * 512 + 2] - ds[4 * g + 1];
-                const double d2 = Dc[(size_t)g * 512 + 4] - ds[4 * g + 2], d3 = Dc[(size_t)g * 512 + 6] - ds[4 * g + 3];
-                const double c0 = cs[4 * g], c1 = cs[4 * g + 1], c2 = cs[4 * g + 2], c3 = cs[4 * g + 3];
-                da = fma(a0.x - c0, d0, da); da = fma(a0.y - c1, d1, da); da = fma(a1.x - c2, d2, da); da = fma(a1.y - c3, d3, da);
-                db = fma(b0.x - c0, d0, db); db = fma(b0.y - c1, d1, db); db = fma(b1.x - c2, d2, db); db = fma(b1.y - c3, d3, db);
+            for (int q = lane; q < sp2; q += 32) {
+                const double2 d = Dr[q], pa = Pa[q], pb = Pb[q], c = cs[q], m = ds[q];
+                const double dx = d.x - m.x, dy = d.y - m.y;
+                da = fma(pa.x - c.x, dx, da);
+                da = fma(pa.y - c.y, dy, da);
+                db = fma(pb.x - c.x, dx, db);
+                db = fma(pb.y - c.y, dy, db);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                da += __shfl_xor_sync(0xffffffffu, da, off);
+                db += __shfl_xor_sync(0xffffffffu, db, off);
             }
         }
 #pragma unroll
         for (int x = 0; x < NX; ++x) {
+            if (lane != x) continue;
             double best = -INFINITY;
             if (ka >= 0) {
                 const double v = a.bias[x * a.bias_stride + ka] + a.pdb[ka] - shift[x] + da;
@@ -727,6 +746,7 @@ struct ResolveArgs {
     const double *D;            // FP64 scenario tiles (fragment-major)
     const double *PiS;          // FP64 pool view (fragment-major): what the sweep multiplies
     const double *PiR;          // the same values row-major [column][s_pad]: one contiguous row per candidate
+    const double *DR;           // the scenarios row-major [i][s_pad] (k_screen_decide)
     const double *bias;         // [NX][bias_stride]
     long long bias_stride;
     int s_pad;
@@ -995,6 +1015,225 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
                 if (a.prev) a.prev[2 * i + x] = bidx[x] + 1;
             }
         }
+    }
+    if (lane == 0 && evald) atomicAdd(&a.ctl->n_eval, evald);
+    griddep_launch();
+}
+
+// The exact decision, second form (the one used when the DMMA == DFMA-chain check passed and the sweep was not split
+// in K-ranges).  k_screen_resolve gives every candidate a lane that walks the candidate's row by itself: five
+// active lanes, five cache lines per load instruction for 80 useful bytes, and the kernel is bound by L1 tag
+// look-ups and by the latency of ~70 dependent loads per scenario (ncu: 16 of 64 warps resident, issue slots 28 %
+// busy).  Here the warp moves whole rows: the scenario's row and up to eight candidate rows (row-major copies,
+// 16-byte pieces, lanes along the row: one instruction = 512 contiguous bytes, all loads of a batch in flight
+// together) go to the warp's shared memory, and lane c then runs the chain of candidate c from there -- the same
+// DFMA chain in the same order (slot 0, 1, 2, ... from a zero accumulator, then + bias), so the same bits.  A
+// vertex that is a candidate at both points is scored once: the dot does not depend on the point, and scoring a
+// vertex at a point where it was no candidate is what the full sweep does anyway.
+#define SCR_DEC_WARPS 4
+#define SCR_DEC_ROWS 8
+#define SCR_DEC_QUEUE 256            // 2 points x 2 column halves x SCR_CAP entries
+__host__ __device__ inline size_t scr_decide_smem(int s_pad)
+{
+    return (size_t)SCR_DEC_WARPS * ((size_t)(SCR_DEC_ROWS + 1) * (s_pad + 2) * 8 + SCR_DEC_QUEUE * 4);
+}
+
+template <int NX>
+__global__ void __launch_bounds__(32 * SCR_DEC_WARPS, 5) k_screen_decide(ResolveArgs a)
+{
+    griddep_wait();
+    if (screen_falls_back(a.ctl)) return;
+    static_assert(2 * NX * SCR_CAP <= SCR_DEC_QUEUE, "queue too small");
+    extern __shared__ __align__(16) unsigned char dec_sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int rs = a.s_pad + 2;               // row stride: 8 s_pad + 16 bytes -- the eight chains' 16-byte reads hit eight different bank groups
+    const int sp2 = a.s_pad / 2;
+    double *rows = reinterpret_cast<double *>(dec_sm) + (size_t)wib * (SCR_DEC_ROWS + 1) * rs;
+    int *wq = reinterpret_cast<int *>(reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * (SCR_DEC_ROWS + 1) * rs) +
+              wib * SCR_DEC_QUEUE;
+    const long long nw = (long long)gridDim.x * SCR_DEC_WARPS;
+    const long long K = *a.d_K;
+    const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
+    unsigned long long evald = 0;
+    for (long long i = (long long)blockIdx.x * SCR_DEC_WARPS + wib; i < a.n_local; i += nw) {
+        double best[NX];
+        int bidx[NX];
+#pragma unroll
+        for (int x = 0; x < NX; ++x) { best[x] = -INFINITY; bidx[x] = -1; }
+        // the scenario's row: requested first, stored after the lists have been requested too
+        const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad);
+        double2 d0 = make_double2(0.0, 0.0), d1 = d0;
+        if (lane < sp2) d0 = Dr[lane];
+        if (lane + 32 < sp2) d1 = Dr[lane + 32];
+        constexpr int L = 2 * NX;
+        int myn = 0;
+        float mylb = -INFINITY;
+        if (lane < L && nch > 0) {
+            const long long slot = (long long)lane * a.npad + i;           // list (x, h) = lane 2 x + h
+            myn = a.cnt[slot];
+            mylb = a.lfin[slot];
+        }
+        int nl[L];
+        bool full = false;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            nl[l] = __shfl_sync(0xffffffffu, myn, l);
+            full = full || nl[l] > SCR_CAP;
+        }
+        float LB[NX];
+#pragma unroll
+        for (int x = 0; x < NX; ++x)
+            LB[x] = fmaxf(__shfl_sync(0xffffffffu, mylb, 2 * x), __shfl_sync(0xffffffffu, mylb, 2 * x + 1));
+        int n = 0;
+        if (!full) {
+            int2 ent[L][SCR_CAP / 32];
+#pragma unroll
+            for (int l = 0; l < L; ++l)
+#pragma unroll
+                for (int b = 0; b < SCR_CAP / 32; ++b) {
+                    ent[l][b] = make_int2(0, 0);
+                    if (b * 32 + lane < nl[l]) ent[l][b] = a.cand[((long long)l * a.npad + i) * SCR_CAP + b * 32 + lane];
+                }
+#pragma unroll
+            for (int l = 0; l < L; ++l)
+#pragma unroll
+                for (int b = 0; b < SCR_CAP / 32; ++b) {
+                    if (b * 32 >= nl[l]) continue;
+                    const bool ok = b * 32 + lane < nl[l] && __int_as_float(ent[l][b].y) >= LB[l >> 1];
+                    const unsigned pass = __ballot_sync(0xffffffffu, ok);
+                    if (ok) wq[n + __popc(pass & ((1u << lane) - 1u))] = ent[l][b].x;
+                    n += __popc(pass);
+                }
+            __syncwarp();
+            // one chain per vertex: the later copies of a column (the other point's list) are struck out
+            if (NX > 1 && n > 1) {
+                const int n0 = n;
+                unsigned dupm[SCR_DEC_QUEUE / 32];
+#pragma unroll
+                for (int cb = 0; cb < SCR_DEC_QUEUE / 32; ++cb) {
+                    dupm[cb] = 0u;
+                    if (cb * 32 >= n0) continue;
+                    const int t = cb * 32 + lane;
+                    bool dup = false;
+                    if (t < n0) {
+                        const int e = wq[t];
+                        for (int m = 0; m < t; ++m) dup = dup || wq[m] == e;
+                    }
+                    dupm[cb] = __ballot_sync(0xffffffffu, dup);
+                }
+                __syncwarp();
+                n = 0;
+#pragma unroll
+                for (int cb = 0; cb < SCR_DEC_QUEUE / 32; ++cb) {
+                    if (cb * 32 >= n0) continue;
+                    const int t = cb * 32 + lane;
+                    const int e = t < n0 ? wq[t] : 0;
+                    const unsigned keep = __ballot_sync(0xffffffffu, t < n0) & ~dupm[cb];
+                    __syncwarp();
+                    if ((keep >> lane) & 1u) wq[n + __popc(keep & ((1u << lane) - 1u))] = e;
+                    n += __popc(keep);
+                    __syncwarp();
+                }
+            }
+        }
+        // the scenario's row to shared memory
+        {
+            double2 *r2 = reinterpret_cast<double2 *>(rows);
+            if (lane < sp2) r2[lane] = d0;
+            if (lane + 32 < sp2) r2[lane + 32] = d1;
+            for (int q = lane + 64; q < sp2; q += 32) r2[q] = Dr[q];
+        }
+        // the queue's vertices, eight at a time
+        auto run_queue = [&](int cnt) {
+            for (int base = 0; base < cnt; base += SCR_DEC_ROWS) {
+                const int nb = min(SCR_DEC_ROWS, cnt - base);
+                double2 v0[SCR_DEC_ROWS], v1[SCR_DEC_ROWS];
+#pragma unroll
+                for (int r = 0; r < SCR_DEC_ROWS; ++r) {
+                    v0[r] = make_double2(0.0, 0.0);
+                    v1[r] = v0[r];
+                    if (r < nb) {
+                        const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad);
+                        if (lane < sp2) v0[r] = P[lane];
+                        if (lane + 32 < sp2) v1[r] = P[lane + 32];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < SCR_DEC_ROWS; ++r) {
+                    if (r < nb) {
+                        double2 *r2 = reinterpret_cast<double2 *>(rows + (size_t)(1 + r) * rs);
+                        if (lane < sp2) r2[lane] = v0[r];
+                        if (lane + 32 < sp2) r2[lane + 32] = v1[r];
+                        if (sp2 > 64) {
+                            const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad);
+                            for (int q = lane + 64; q < sp2; q += 32) r2[q] = P[q];
+                        }
+                    }
+                }
+                __syncwarp();
+                double acc = 0.0;
+                int kk = -1;
+                if (lane < nb) {
+                    kk = wq[base + lane];
+                    const double2 *pr = reinterpret_cast<const double2 *>(rows + (size_t)(1 + lane) * rs);
+                    const double2 *dr = reinterpret_cast<const double2 *>(rows);
+                    int q = 0;
+                    for (; q + 4 <= sp2; q += 4) {
+                        double2 pv[4], dv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { pv[u] = pr[q + u]; dv[u] = dr[q + u]; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {                // slots in order: the chain of the sweep's DMMA
+                            acc = fma(dv[u].x, pv[u].x, acc);
+                            acc = fma(dv[u].y, pv[u].y, acc);
+                        }
+                    }
+                    for (; q < sp2; ++q) {
+                        const double2 pv = pr[q], dv = dr[q];
+                        acc = fma(dv.x, pv.x, acc);
+                        acc = fma(dv.y, pv.y, acc);
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    double v = -INFINITY;
+                    int kv = -1;
+                    if (kk >= 0 && kk < K) {
+                        const double t = acc + a.bias[x * a.bias_stride + kk];
+                        if (t > -INFINITY) { v = t; kv = kk; }               // NaN and -Inf never win (subprob.jl:151-156)
+                    }
+#pragma unroll
+                    for (int off = SCR_DEC_ROWS / 2; off >= 1; off >>= 1) {  // lanes 0..7 hold the batch
+                        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, kv, off);
+                        if (oi >= 0 && (kv < 0 || ov > v || (ov == v && oi < kv))) { v = ov; kv = oi; }
+                    }
+                    // (meaningful on lane 0, which writes the result)
+                    if (kv >= 0 && (v > best[x] || (v == best[x] && bidx[x] >= 0 && kv < bidx[x]))) { best[x] = v; bidx[x] = kv; }
+                }
+                evald += nb;
+                __syncwarp();
+            }
+        };
+        if (!full) {
+            run_queue(n);
+        } else {
+            for (long long k0 = 0; k0 < K; k0 += SCR_DEC_QUEUE) {    // a list overflowed: every vertex, for every point
+                const int cnt = (int)min((long long)SCR_DEC_QUEUE, K - k0);
+                for (int t = lane; t < cnt; t += 32) wq[t] = (int)(k0 + t);
+                __syncwarp();
+                run_queue(cnt);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                a.best_val[x * a.out_stride + i] = best[x];
+                a.best_idx[x * a.out_stride + i] = bidx[x];
+                if (a.prev) a.prev[2 * i + x] = bidx[x] + 1;
+            }
+        }
+        __syncwarp();
     }
     if (lane == 0 && evald) atomicAdd(&a.ctl->n_eval, evald);
     griddep_launch();

@@ -101,6 +101,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     {   // may the exact decision score candidates with plain DFMA chains?  Only if, on THIS device, the DMMA of the
         // FP64 sweep is that chain bit for bit (it is on sm_100a; checked, not assumed).  SQLP_RESOLVE=dmma keeps DMMA.
         const char *g = getenv("SQLP_RESOLVE");
+        if (g && !strcmp(g, "lanes")) c->resolve_rows = false;
         if (!g || strcmp(g, "dmma")) {
             unsigned int *d_bad = nullptr, h_bad = 1;
             CK(cudaMalloc(&d_bad, 4));

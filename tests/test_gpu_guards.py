@@ -81,7 +81,7 @@ SCRIPT = textwrap.dedent('''
 
 
 @pytest.mark.parametrize("env", [{}, {"SQLP_CONTRACT": "stream"}, {"SQLP_CONTRACT": "resident", "SQLP_CONTRACT_GRID": "7"},
-                                 {"SQLP_REDUCE": "2", "SQLP_RESOLVE": "dmma"}, {"SQLP_TWINS": "0", "SQLP_REDUCE": "1"}])
+                                 {"SQLP_REDUCE": "2", "SQLP_RESOLVE": "dmma"}, {"SQLP_TWINS": "0", "SQLP_REDUCE": "1"}, {"SQLP_RESOLVE": "lanes", "SQLP_SEED": "0"}])
 def test_no_guard_zone_is_written(env):
     e = dict(os.environ, SQLP_GUARD="1", **env)
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=e, capture_output=True, text=True, timeout=600)

@@ -199,6 +199,54 @@ def test_warm_start_from_previous_winners(T, ctx):
     assert emitted[2] < emitted[0]          # a small step of the candidate: far fewer stale entries than the cold scan
 
 
+SWITCH_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+from sqlp_b200 import twosd as T
+from tests.helpers import load_instance, load_pool, sampled_values_at
+P, z = load_instance("storm")
+pool = load_pool("storm", 16384)[:3000]
+ctx = T.default_context()
+dvs = T.sdDualVertexSet(m2=P.m2)
+dvs.push_many(pool[:2500])
+coef = T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
+epi = T.sdEpigraph(coef, 1.0, 0.0, dvs)
+vals = sampled_values_at(z, 4, np.arange(2600))
+epi.add_scenarios(vals[:2500], 0.5 + np.arange(2500) %% 4)
+for it in range(4):
+    dvs.push_many(pool[2500 + 100 * it: 2600 + 100 * it])
+    epi.add_scenarios(vals[2500 + 25 * it: 2525 + 25 * it], None)
+    x = z["x_ev"] + 0.3 * it * (z["x_alt"] - z["x_ev"])
+    out = {}
+    for mode in (0, 2):
+        ctx.set_screen(mode)
+        cuts, val = epi.build_cuts2(x, z["x_alt"], with_val=True)
+        mv, mi = epi.argmax(x)
+        out[mode] = [np.array([cuts[0].alpha, cuts[1].alpha]), np.stack([cuts[0].beta, cuts[1].beta]), np.asarray(val), mv, mi]
+    for u, v in zip(out[0], out[2]):
+        assert np.array_equal(np.asarray(u).view(np.uint8), np.asarray(v).view(np.uint8)), it
+st = epi.screen_stats()
+assert st["passes"] >= 8 and st["overflowed_lists"] == 0 and st["bad_operands"] == 0, st
+print("SWITCH OK", st)
+"""
+
+
+@pytest.mark.parametrize("env", [{"SQLP_RESOLVE": "lanes"}, {"SQLP_RESOLVE": "dmma"}, {"SQLP_SEED": "0"},
+                                 {"SQLP_CENTRE": "0"}, {"SQLP_CENTRE": "0", "SQLP_SEED": "0", "SQLP_RESOLVE": "lanes"},
+                                 {"SQLP_TWINS": "0"}])
+def test_every_variant_of_the_pass_is_bit_identical(env):
+    """The switches that select an older form of a step of the pass (a lane per candidate row, DMMA chains, cold scan,
+    uncentred operands, every vertex a column) are kept for measurements; each must give the FP64 sweep's bits too."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", SWITCH_SCRIPT % {"root": root}], env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SWITCH OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
 # ---- score-equivalent vertices ("twins", csrc/kernels_pool.cuh) ---------------------------------------------
 
 def test_twins_leave_results_bit_identical(T, monkeypatch):
