@@ -125,6 +125,7 @@ struct ScreenCtl {                 // written by k_screen_prep, read by every ke
     unsigned long long n_eval;
     int live[2];                   // vertices that may win at point x
     float eabs[2];                 // absolute part of E: FP64 roundings on the uncentred magnitudes (k_screen_prep)
+    double cdb;                    // ctr . dbar (k_screen_seed)
 };
 
 __device__ __forceinline__ bool screen_falls_back(const ScreenCtl *ctl)

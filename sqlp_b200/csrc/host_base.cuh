@@ -295,6 +295,7 @@ struct PoolView {   // the pool restricted to one set of stochastic rows, in til
     DevBuf d_piB, d_pn, d_pnmax, d_vbad, d_scr_lo;
     DevBuf d_ctr;                             // centre the bf16 operands are taken relative to (sp values + its norm)
     int64_t ctr_cols = 0;                     // columns it was the mean of (0: none yet)
+    int64_t ctr_epoch = 0;                    // counts the re-centrings (an epigraph's ctr . d_i follow it)
     int64_t scr_synced_lo = 0, scr_cap = 0;   // vertices final in d_piB / capacity (multiple of 256)
 };
 
@@ -367,7 +368,8 @@ struct sqlp_epi {
     // screening pass: bf16 scenario operands, per-call control block, what the host has learnt
     DevBuf d_DB, d_dnu, d_dnall, d_ebad, d_b32c, d_ctl;
     DevBuf d_prev;                            // [n_local][2]: 1 + view column selected at the previous pass, per point
-    int64_t prev_cap = 0;
+    DevBuf d_prevdot, d_cd;                   // [n_local][2] the dots P_k . d_i of those columns; [n_local] ctr . d_i
+    int64_t prev_cap = 0, cd_synced = 0, cd_epoch = -1;
     bool prev_valid = false;
     DevBuf d_dbar, d_pdb;                     // centre of the scenarios (sp values + norm); P_k . dbar per view column
     int64_t dbar_n = 0;                       // scenarios dbar was the mean of

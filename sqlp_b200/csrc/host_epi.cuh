@@ -312,6 +312,7 @@ void screen_sync_operands(sqlp_epi *e)
         CK(cudaMemsetAsync(v->d_scr_lo.p, 0, 8, S(c)));
         CK(cudaMemsetAsync(v->d_pnmax.p, 0, (size_t)(v->scr_cap / SCR_NB) * 4, S(c)));
         v->ctr_cols = ctr_want;
+        ++v->ctr_epoch;
         v->scr_synced_lo = 0;
         v->scr_epoch = -1;
     }
@@ -388,30 +389,38 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
            (const double *)e->d_dbar.as<double>());
     // warm start of the scan from the winners of the previous pass (k_screen_seed)
     const float *lseed = nullptr;
-    if (c->screen_seed && e->d_DR.p) {
+    const bool rows_decide = c->resolve_rows && e->d_DR.p && scr_decide_smem(v->s_pad) <= (size_t)c->smem_optin;
+    const bool seeding = c->screen_seed && rows_decide;
+    if (seeding) {
         if (npad > e->prev_cap) {
             const int64_t ncap = std::max<int64_t>(npad, e->prev_cap * 2);
             e->d_prev.ensure((size_t)ncap * 8, (size_t)e->prev_cap * 8, S(c));
+            e->d_prevdot.ensure((size_t)ncap * 16, (size_t)e->prev_cap * 16, S(c));
+            e->d_cd.ensure((size_t)ncap * 8, (size_t)e->prev_cap * 8, S(c));
             e->prev_cap = ncap;
+        }
+        if (e->cd_epoch != v->ctr_epoch) { e->cd_synced = 0; e->cd_epoch = v->ctr_epoch; }
+        if (e->n_local > e->cd_synced) {
+            const int64_t work = e->n_local - e->cd_synced;
+            LAUNCH(c, k_screen_cd, (int)std::min<int64_t>((work + 7) / 8, 16 * c->sm_count), 256, 0,
+                   (const double *)e->d_DR.as<double>(), v->s_pad, (const double *)v->d_ctr.as<double>(),
+                   (long long)e->cd_synced, (long long)e->n_local, e->d_cd.as<double>());
+            e->cd_synced = e->n_local;
         }
         if (e->prev_valid) {
             c->d_lseed.ensure((size_t)NX * npad * 4, 0, S(c), false);
             SeedArgs sd;
-            sd.DR = e->d_DR.as<double>();
-            sd.PiR = v->d_piR.as<double>();
             sd.bias = e->cur_bias;
             sd.bias_stride = e->cur_bias_stride;
-            sd.pdb = e->d_pdb.as<double>();
-            sd.ctr = v->d_ctr.as<double>();
-            sd.dbar = e->d_dbar.as<double>();
             sd.prev = e->d_prev.as<int>();
+            sd.prevdot = e->d_prevdot.as<double>();
+            sd.cd = e->d_cd.as<double>();
             sd.d_K = v->d_Kv(p);
             sd.ctl = e->d_ctl.as<ScreenCtl>();
-            sd.s_pad = v->s_pad;
             sd.n_local = e->n_local;
             sd.npad = npad;
             sd.lseed = c->d_lseed.as<float>();
-            LAUNCH(c, k_screen_seed<NX>, (int)std::min<int64_t>((npad + 7) / 8, 32 * c->sm_count), 256, (size_t)2 * v->s_pad * 8, sd);
+            LAUNCH(c, k_screen_seed<NX>, (int)std::min<int64_t>((npad + 255) / 256, 8 * c->sm_count), 256, 0, sd);
             lseed = c->d_lseed.as<float>();
         }
     }
@@ -467,16 +476,21 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     ra.ctl = e->d_ctl.as<ScreenCtl>();
     ra.force_full = 0;
     ra.DR = e->d_DR.as<double>();
-    ra.prev = (c->screen_seed && e->d_DR.p) ? e->d_prev.as<int>() : nullptr;
-    e->prev_valid = ra.prev != nullptr;
+    ra.prev = nullptr;
+    ra.prevdot = nullptr;
     {
         ProfScope prof(c, SQLP_PROF_RESOLVE, (double)NX * (double)e->n_local);
-        const size_t dsmem = scr_decide_smem(v->s_pad);
-        if (c->resolve_fma && c->resolve_rows && R == 1 && e->d_DR.p && dsmem <= (size_t)c->smem_optin) {
-            // whole rows through shared memory (k_screen_decide)
+        if (rows_decide && R == 1) {
+            // whole rows through shared memory (k_screen_decide); it also leaves the winners for the next warm start
+            const size_t dsmem = scr_decide_smem(v->s_pad);
             if (dsmem > c->decide_smem_set[NX]) {
                 CK(cudaFuncSetAttribute(k_screen_decide<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
                 c->decide_smem_set[NX] = dsmem;
+            }
+            if (seeding) {
+                ra.prev = e->d_prev.as<int>();
+                ra.prevdot = e->d_prevdot.as<double>();
+                e->prev_valid = true;
             }
             const int rgrid = (int)std::min<int64_t>(std::max<int64_t>((e->n_local + SCR_DEC_WARPS - 1) / SCR_DEC_WARPS, 1),
                                                      20 * c->sm_count);

@@ -639,6 +639,10 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
             ctl->eabs[x] = ea < 1.0e30 ? __double2float_ru(ea) : 1.0e30f;
             if (!(ea < 1.0e30)) sbad = 1;
         }
+        double cdb = 0.0;
+        if (ctr && dbar)
+            for (int j = 0; j < sp; ++j) cdb = fma(ctr[j], dbar[j], cdb);
+        ctl->cdb = cdb;
         ctl->bad = sbad;
         ctl->overflow = 0u;
         ctl->ovf_limit = ovf_limit;
@@ -653,23 +657,21 @@ __global__ void __launch_bounds__(1024) k_screen_prep(const double *__restrict__
 // and the warp takes its slow path whenever one of its 32 scenarios meets one.  An SD iteration moves the candidate
 // point a little and the incumbent rarely: the vertex that won a scenario at the previous call is almost always a
 // near-winner now.  Its score at the new point is a lower bound of the scenario's best score that is valid whatever
-// the history (ANY vertex gives one), so the scan starts from it instead of from -Inf.  Per scenario: the winners of
-// the previous call at both points (a, b), the centred dots P'_a . d'_i and P'_b . d'_i in FP64 (they do not depend
-// on the point), and per point the larger of the two scores, minus what the FP64 operations may have lost, rounded
-// down to fp32.  One warp per scenario: the three rows (scenario, two vertices; row-major copies) are read as
-// contiguous 16-byte pieces, lanes along the row -- a thread per scenario walking its own rows costs one L1 tag
-// look-up per 32 bytes and was bound by exactly that (profiles/r02_decide_notes.md).
+// the history (ANY vertex gives one), so the scan starts from it instead of from -Inf.
+// It costs no dot product: the exact decision already computed P_a . d_i for the winner a (it does not depend on
+// the point, nor on time: vertices and scenarios never change), and in the pass's centred and shifted scale
+//     s_a(i) = bias_a - shift + P_a . d_i - ctr . d_i + ctr . dbar,
+// with ctr . d_i kept per scenario (k_screen_cd) and ctr . dbar per call (k_screen_prep).  Per scenario and point:
+// the larger of the scores of the previous winners at both points, minus what the FP64 operations may have lost
+// (the cancellation is on the uncentred magnitudes: that is what eabs bounds), rounded down to fp32.
 struct SeedArgs {
-    const double *DR;           // FP64 scenarios, row-major [i][s_pad]
-    const double *PiR;          // FP64 view, row-major
     const double *bias;         // [NX][bias_stride]
     long long bias_stride;
-    const double *pdb;          // P_k . dbar
-    const double *ctr, *dbar;   // the centres (sp values each)
     const int *prev;            // [n][2]: 1 + view column, 0 = none
+    const double *prevdot;      // [n][2]: P_k . d_i of that column
+    const double *cd;           // [n]: ctr . d_i
     const long long *d_K;
     const ScreenCtl *ctl;
-    int s_pad;
     long long n_local, npad;
     float *lseed;               // [NX][npad]
 };
@@ -678,62 +680,54 @@ template <int NX>
 __global__ void __launch_bounds__(256) k_screen_seed(SeedArgs a)
 {
     griddep_sync();
-    extern __shared__ __align__(16) double seed_sh[];
-    double2 *cs = reinterpret_cast<double2 *>(seed_sh), *ds = cs + a.s_pad / 2;
-    for (int j = threadIdx.x; j < a.s_pad; j += blockDim.x) { seed_sh[j] = a.ctr[j]; seed_sh[a.s_pad + j] = a.dbar[j]; }
-    __syncthreads();
     const long long K = *a.d_K;
-    const int lane = threadIdx.x & 31, sp2 = a.s_pad / 2;
-    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
-    double shift[NX], slack[NX];
-#pragma unroll
-    for (int x = 0; x < NX; ++x) { shift[x] = a.ctl->shift[x]; slack[x] = 2.0 * (double)a.ctl->eabs[x]; }
-    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.npad; i += nw) {
+    const double cdb = a.ctl->cdb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.npad; i += (long long)gridDim.x * blockDim.x) {
         int ka = -1, kb = -1;
+        double da = 0.0, db = 0.0;
         if (i < a.n_local) {
             const int2 pc = reinterpret_cast<const int2 *>(a.prev)[i];
+            const double2 pd = reinterpret_cast<const double2 *>(a.prevdot)[i];
+            const double off = cdb - a.cd[i];
             ka = pc.x - 1;
             kb = pc.y - 1;
+            da = pd.x + off;
+            db = pd.y + off;
         }
         if (ka >= K) ka = -1;
         if (kb >= K || kb == ka) kb = -1;
-        if (ka < 0) { ka = kb; kb = -1; }
-        double da = 0.0, db = 0.0;
-        if (ka >= 0) {
-            const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad);
-            const double2 *Pa = reinterpret_cast<const double2 *>(a.PiR + (size_t)ka * a.s_pad);
-            const double2 *Pb = reinterpret_cast<const double2 *>(a.PiR + (size_t)(kb >= 0 ? kb : ka) * a.s_pad);
-            for (int q = lane; q < sp2; q += 32) {
-                const double2 d = Dr[q], pa = Pa[q], pb = Pb[q], c = cs[q], m = ds[q];
-                const double dx = d.x - m.x, dy = d.y - m.y;
-                da = fma(pa.x - c.x, dx, da);
-                da = fma(pa.y - c.y, dy, da);
-                db = fma(pb.x - c.x, dx, db);
-                db = fma(pb.y - c.y, dy, db);
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                da += __shfl_xor_sync(0xffffffffu, da, off);
-                db += __shfl_xor_sync(0xffffffffu, db, off);
-            }
-        }
 #pragma unroll
         for (int x = 0; x < NX; ++x) {
-            if (lane != x) continue;
             double best = -INFINITY;
             if (ka >= 0) {
-                const double v = a.bias[x * a.bias_stride + ka] + a.pdb[ka] - shift[x] + da;
+                const double v = a.bias[x * a.bias_stride + ka] - a.ctl->shift[x] + da;
                 if (isfinite(v)) best = v;
             }
             if (kb >= 0) {
-                const double v = a.bias[x * a.bias_stride + kb] + a.pdb[kb] - shift[x] + db;
+                const double v = a.bias[x * a.bias_stride + kb] - a.ctl->shift[x] + db;
                 if (isfinite(v)) best = fmax(best, v);
             }
-            best -= slack[x] + 0x1p-40 * fabs(best);
+            best -= 2.0 * (double)a.ctl->eabs[x] + 0x1p-40 * fabs(best);
             float out = -INFINITY;
             if (best > -1.0e37 && best < 1.0e37) out = __double2float_rd(best);
             a.lseed[(long long)x * a.npad + i] = out;
         }
+    }
+}
+
+// cd[i] = ctr . d_i for the local scenarios [lo, n): one warp per scenario over the row-major store.
+__global__ void k_screen_cd(const double *__restrict__ DR, int s_pad, const double *__restrict__ ctr, long long lo,
+                            long long n, double *__restrict__ cd)
+{
+    griddep_sync();
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) {
+        double acc = 0.0;
+        for (int j = lane; j < s_pad; j += 32) acc = fma(ctr[j], DR[i * (long long)s_pad + j], acc);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) cd[i] = acc;
     }
 }
 
@@ -762,6 +756,7 @@ struct ResolveArgs {
     ScreenCtl *ctl;
     int force_full;             // tests: sweep every vertex for every scenario with this kernel's arithmetic
     int *prev;                  // optional [n][2]: 1 + the view column selected for (scenario, point), for k_screen_seed
+    double *prevdot;            // with prev: the selected vertex's dot P_k . d_i
 };
 
 // FMA (0 / 1): the chain as mma.sync.m8n8k4.f64 (eight candidates per chain, one of the eight rows used), or as plain
@@ -1012,7 +1007,6 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
             for (int x = 0; x < NX; ++x) {
                 a.best_val[x * a.out_stride + i] = best[x];
                 a.best_idx[x * a.out_stride + i] = bidx[x];
-                if (a.prev) a.prev[2 * i + x] = bidx[x] + 1;
             }
         }
     }
@@ -1020,51 +1014,64 @@ __global__ void __launch_bounds__(256) k_screen_resolve(ResolveArgs a)
     griddep_launch();
 }
 
-// The exact decision, second form (the one used when the DMMA == DFMA-chain check passed and the sweep was not split
-// in K-ranges).  k_screen_resolve gives every candidate a lane that walks the candidate's row by itself: five
-// active lanes, five cache lines per load instruction for 80 useful bytes, and the kernel is bound by L1 tag
-// look-ups and by the latency of ~70 dependent loads per scenario (ncu: 16 of 64 warps resident, issue slots 28 %
-// busy).  Here the warp moves whole rows: the scenario's row and up to eight candidate rows (row-major copies,
-// 16-byte pieces, lanes along the row: one instruction = 512 contiguous bytes, all loads of a batch in flight
-// together) go to the warp's shared memory, and lane c then runs the chain of candidate c from there -- the same
-// DFMA chain in the same order (slot 0, 1, 2, ... from a zero accumulator, then + bias), so the same bits.  A
-// vertex that is a candidate at both points is scored once: the dot does not depend on the point, and scoring a
-// vertex at a point where it was no candidate is what the full sweep does anyway.
+// The exact decision, second form (used when the sweep was not split in K-ranges).  k_screen_resolve gives every
+// candidate a lane that walks the candidate's row by itself: five active lanes, five cache lines per load
+// instruction for 80 useful bytes, ~760 instructions and ~70 dependent loads per scenario (ncu: 16 of 64 warps
+// resident, issue slots 28 % busy).  Here the warp moves whole rows: the scenario's row and up to eight candidate
+// rows (row-major copies) go to the warp's shared memory as 16-byte asynchronous copies -- one instruction = 512
+// contiguous bytes, no registers, every copy of a batch in flight together -- and the chain is the sweep's own
+// instruction, mma.sync.m8n8k4.f64 over the k-groups in ascending order from a zero accumulator with the eight
+// candidates as the eight columns of B and the scenario in every row of A, then + bias: 30 dependent DMMAs for eight
+// exact scores, bit for bit those of the sweep.  A vertex that is a candidate at both points is scored once: the
+// dot does not depend on the point, and scoring a vertex at a point where it was no candidate is what the full
+// sweep does anyway.
 #define SCR_DEC_WARPS 4
 #define SCR_DEC_ROWS 8
 #define SCR_DEC_QUEUE 256            // 2 points x 2 column halves x SCR_CAP entries
+__host__ __device__ inline int scr_decide_stride(int s_pad)    // doubles per staged row: 4 or 12 (mod 16), so that the
+{                                                                  // B fragments of four rows fall in four bank groups
+    return s_pad + (((s_pad & 15) == 0 || (s_pad & 15) == 8) ? 4 : 0);
+}
 __host__ __device__ inline size_t scr_decide_smem(int s_pad)
 {
-    return (size_t)SCR_DEC_WARPS * ((size_t)(SCR_DEC_ROWS + 1) * (s_pad + 2) * 8 + SCR_DEC_QUEUE * 4);
+    return (size_t)SCR_DEC_WARPS * ((size_t)(SCR_DEC_ROWS + 1) * scr_decide_stride(s_pad) * 8 + SCR_DEC_ROWS * 8 + SCR_DEC_QUEUE * 4);
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
 template <int NX>
-__global__ void __launch_bounds__(32 * SCR_DEC_WARPS, 5) k_screen_decide(ResolveArgs a)
+__global__ void __launch_bounds__(32 * SCR_DEC_WARPS) k_screen_decide(ResolveArgs a)
 {
     griddep_wait();
     if (screen_falls_back(a.ctl)) return;
     static_assert(2 * NX * SCR_CAP <= SCR_DEC_QUEUE, "queue too small");
     extern __shared__ __align__(16) unsigned char dec_sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int rs = a.s_pad + 2;               // row stride: 8 s_pad + 16 bytes -- the eight chains' 16-byte reads hit eight different bank groups
-    const int sp2 = a.s_pad / 2;
+    const int rs = scr_decide_stride(a.s_pad);
+    const int sp2 = a.s_pad / 2, ng = a.s_pad / 4;
     double *rows = reinterpret_cast<double *>(dec_sm) + (size_t)wib * (SCR_DEC_ROWS + 1) * rs;
-    int *wq = reinterpret_cast<int *>(reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * (SCR_DEC_ROWS + 1) * rs) +
+    double *dots = reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * (SCR_DEC_ROWS + 1) * rs + wib * SCR_DEC_ROWS;
+    int *wq = reinterpret_cast<int *>(reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * ((SCR_DEC_ROWS + 1) * rs + SCR_DEC_ROWS)) +
               wib * SCR_DEC_QUEUE;
     const long long nw = (long long)gridDim.x * SCR_DEC_WARPS;
     const long long K = *a.d_K;
     const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
     unsigned long long evald = 0;
     for (long long i = (long long)blockIdx.x * SCR_DEC_WARPS + wib; i < a.n_local; i += nw) {
-        double best[NX];
-        int bidx[NX];
-#pragma unroll
-        for (int x = 0; x < NX; ++x) { best[x] = -INFINITY; bidx[x] = -1; }
-        // the scenario's row: requested first, stored after the lists have been requested too
-        const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad);
-        double2 d0 = make_double2(0.0, 0.0), d1 = d0;
-        if (lane < sp2) d0 = Dr[lane];
-        if (lane + 32 < sp2) d1 = Dr[lane + 32];
+        double best = -INFINITY, bdot = 0.0;      // of point x = lane (lanes < NX)
+        int bidx = -1;
+        // the scenario's row is requested first; it is waited for together with the first batch of candidate rows
+        {
+            const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad);
+            double2 *r2 = reinterpret_cast<double2 *>(rows);
+            for (int q = lane; q < sp2; q += 32) cp_async16(r2 + q, Dr + q);
+        }
         constexpr int L = 2 * NX;
         int myn = 0;
         float mylb = -INFINITY;
@@ -1105,111 +1112,71 @@ __global__ void __launch_bounds__(32 * SCR_DEC_WARPS, 5) k_screen_decide(Resolve
                     n += __popc(pass);
                 }
             __syncwarp();
-            // one chain per vertex: the later copies of a column (the other point's list) are struck out
-            if (NX > 1 && n > 1) {
-                const int n0 = n;
-                unsigned dupm[SCR_DEC_QUEUE / 32];
-#pragma unroll
-                for (int cb = 0; cb < SCR_DEC_QUEUE / 32; ++cb) {
-                    dupm[cb] = 0u;
-                    if (cb * 32 >= n0) continue;
-                    const int t = cb * 32 + lane;
-                    bool dup = false;
-                    if (t < n0) {
-                        const int e = wq[t];
-                        for (int m = 0; m < t; ++m) dup = dup || wq[m] == e;
-                    }
-                    dupm[cb] = __ballot_sync(0xffffffffu, dup);
-                }
+            // one chain per vertex: the second copy of a column (the other point's list) is struck out.  Queues of
+            // more than 32 are left as they are -- a vertex scored twice is only work
+            if (NX > 1 && n > 1 && n <= 32) {
+                const int e = lane < n ? wq[lane] : -1 - lane;
+                const unsigned same = __match_any_sync(0xffffffffu, e);
+                const bool keep = lane < n && (__ffs(same) - 1) == lane;
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
                 __syncwarp();
-                n = 0;
-#pragma unroll
-                for (int cb = 0; cb < SCR_DEC_QUEUE / 32; ++cb) {
-                    if (cb * 32 >= n0) continue;
-                    const int t = cb * 32 + lane;
-                    const int e = t < n0 ? wq[t] : 0;
-                    const unsigned keep = __ballot_sync(0xffffffffu, t < n0) & ~dupm[cb];
-                    __syncwarp();
-                    if ((keep >> lane) & 1u) wq[n + __popc(keep & ((1u << lane) - 1u))] = e;
-                    n += __popc(keep);
-                    __syncwarp();
-                }
+                if (keep) wq[__popc(km & ((1u << lane) - 1u))] = e;
+                n = __popc(km);
+                __syncwarp();
             }
-        }
-        // the scenario's row to shared memory
-        {
-            double2 *r2 = reinterpret_cast<double2 *>(rows);
-            if (lane < sp2) r2[lane] = d0;
-            if (lane + 32 < sp2) r2[lane + 32] = d1;
-            for (int q = lane + 64; q < sp2; q += 32) r2[q] = Dr[q];
         }
         // the queue's vertices, eight at a time
         auto run_queue = [&](int cnt) {
             for (int base = 0; base < cnt; base += SCR_DEC_ROWS) {
                 const int nb = min(SCR_DEC_ROWS, cnt - base);
-                double2 v0[SCR_DEC_ROWS], v1[SCR_DEC_ROWS];
-#pragma unroll
-                for (int r = 0; r < SCR_DEC_ROWS; ++r) {
-                    v0[r] = make_double2(0.0, 0.0);
-                    v1[r] = v0[r];
-                    if (r < nb) {
-                        const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad);
-                        if (lane < sp2) v0[r] = P[lane];
-                        if (lane + 32 < sp2) v1[r] = P[lane + 32];
-                    }
+                for (int r = 0; r < nb; ++r) {
+                    const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad) + lane;
+                    double2 *r2 = reinterpret_cast<double2 *>(rows + (size_t)(1 + r) * rs) + lane;
+                    if (lane < sp2) cp_async16(r2, P);
+                    if (lane + 32 < sp2) cp_async16(r2 + 32, P + 32);
+                    for (int q = 64; q + lane < sp2; q += 32) cp_async16(r2 + q, P + q);
                 }
+                cp_async_wait_all();
+                __syncwarp();
+                // A: the scenario in every row (lane t: slot 4 g + t % 4); B: column t / 4 = staged row t / 4.  Columns
+                // beyond nb read whatever the rows hold: a column's result depends on that column alone
+                const double *ap = rows + (lane & 3);
+                const double *bp = rows + (size_t)(1 + (lane >> 2)) * rs + (lane & 3);
+                double acc0 = 0.0, acc1 = 0.0;
+                int g = 0;
+                for (; g + 6 <= ng; g += 6) {
+                    double av[6], bv[6];
 #pragma unroll
-                for (int r = 0; r < SCR_DEC_ROWS; ++r) {
-                    if (r < nb) {
-                        double2 *r2 = reinterpret_cast<double2 *>(rows + (size_t)(1 + r) * rs);
-                        if (lane < sp2) r2[lane] = v0[r];
-                        if (lane + 32 < sp2) r2[lane + 32] = v1[r];
-                        if (sp2 > 64) {
-                            const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad);
-                            for (int q = lane + 64; q < sp2; q += 32) r2[q] = P[q];
-                        }
-                    }
+                    for (int u = 0; u < 6; ++u) { av[u] = ap[(g + u) * 4]; bv[u] = bp[(g + u) * 4]; }
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(acc0), "+d"(acc1)
+                                     : "d"(av[u]), "d"(bv[u]));
+                }
+                for (; g < ng; ++g) {
+                    const double av = ap[g * 4], bv = bp[g * 4];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc0), "+d"(acc1)
+                                 : "d"(av), "d"(bv));
+                }
+                // row 0 of C: lane l < 4 holds the dots of columns 2 l and 2 l + 1.  They go to the warp's scratch and
+                // lane x < NX walks the batch for point x, keeping that point's best in its own registers
+                if (lane < 4) {
+                    dots[2 * lane] = acc0;
+                    dots[2 * lane + 1] = acc1;
                 }
                 __syncwarp();
-                double acc = 0.0;
-                int kk = -1;
-                if (lane < nb) {
-                    kk = wq[base + lane];
-                    const double2 *pr = reinterpret_cast<const double2 *>(rows + (size_t)(1 + lane) * rs);
-                    const double2 *dr = reinterpret_cast<const double2 *>(rows);
-                    int q = 0;
-                    for (; q + 4 <= sp2; q += 4) {
-                        double2 pv[4], dv[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) { pv[u] = pr[q + u]; dv[u] = dr[q + u]; }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {                // slots in order: the chain of the sweep's DMMA
-                            acc = fma(dv[u].x, pv[u].x, acc);
-                            acc = fma(dv[u].y, pv[u].y, acc);
-                        }
+                if (lane < NX) {
+                    const double *bx = a.bias + (size_t)lane * a.bias_stride;
+                    for (int cidx = 0; cidx < nb; ++cidx) {
+                        const int kj = wq[base + cidx];
+                        if (kj >= K) continue;
+                        const double dj = dots[cidx];
+                        const double t = dj + bx[kj];                               // the sweep's epilogue: acc + bias
+                        // NaN and -Inf never win (subprob.jl:151-156); equal scores: the smaller index
+                        if (t > best || (t == best && bidx >= 0 && kj < bidx)) { best = t; bdot = dj; bidx = kj; }
                     }
-                    for (; q < sp2; ++q) {
-                        const double2 pv = pr[q], dv = dr[q];
-                        acc = fma(dv.x, pv.x, acc);
-                        acc = fma(dv.y, pv.y, acc);
-                    }
-                }
-#pragma unroll
-                for (int x = 0; x < NX; ++x) {
-                    double v = -INFINITY;
-                    int kv = -1;
-                    if (kk >= 0 && kk < K) {
-                        const double t = acc + a.bias[x * a.bias_stride + kk];
-                        if (t > -INFINITY) { v = t; kv = kk; }               // NaN and -Inf never win (subprob.jl:151-156)
-                    }
-#pragma unroll
-                    for (int off = SCR_DEC_ROWS / 2; off >= 1; off >>= 1) {  // lanes 0..7 hold the batch
-                        const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-                        const int oi = __shfl_xor_sync(0xffffffffu, kv, off);
-                        if (oi >= 0 && (kv < 0 || ov > v || (ov == v && oi < kv))) { v = ov; kv = oi; }
-                    }
-                    // (meaningful on lane 0, which writes the result)
-                    if (kv >= 0 && (v > best[x] || (v == best[x] && bidx[x] >= 0 && kv < bidx[x]))) { best[x] = v; bidx[x] = kv; }
                 }
                 evald += nb;
                 __syncwarp();
@@ -1225,12 +1192,13 @@ __global__ void __launch_bounds__(32 * SCR_DEC_WARPS, 5) k_screen_decide(Resolve
                 run_queue(cnt);
             }
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int x = 0; x < NX; ++x) {
-                a.best_val[x * a.out_stride + i] = best[x];
-                a.best_idx[x * a.out_stride + i] = bidx[x];
-                if (a.prev) a.prev[2 * i + x] = bidx[x] + 1;
+        cp_async_wait_all();                                          // (a scenario without candidates: its row is still on its way)
+        if (lane < NX) {
+            a.best_val[lane * a.out_stride + i] = best;
+            a.best_idx[lane * a.out_stride + i] = bidx;
+            if (a.prev) {
+                a.prev[2 * i + lane] = bidx + 1;
+                a.prevdot[2 * i + lane] = bdot;                      // the winner's dot P_k . d_i, as the chain gave it
             }
         }
         __syncwarp();

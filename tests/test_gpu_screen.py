@@ -170,14 +170,15 @@ def test_warm_start_from_previous_winners(T, ctx):
     dvs = T.sdDualVertexSet(m2=P.m2)
     dvs.push_many(pool[:5000])
     epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
-    vals = sampled_values_at(z, 9, np.arange(6000))
-    epi.add_scenarios(vals[:5000], 0.5 + np.arange(5000) % 3)
+    N0 = 40000            # enough units of 128 scenarios to fill the GPU without K-ranges: the row-staging decision runs
+    vals = sampled_values_at(z, 9, np.arange(N0 + 1000))
+    epi.add_scenarios(vals[:N0], 0.5 + np.arange(N0) % 3)
     x0, x1 = z["x_ev"], z["x_alt"]
     inc = x0
     emitted = []
     for it in range(9):
         dvs.push_many(pool[5000 + 30 * it: 5000 + 30 * (it + 1)])
-        epi.add_scenarios(vals[5000 + 100 * it: 5000 + 100 * (it + 1)], None)
+        epi.add_scenarios(vals[N0 + 100 * it: N0 + 100 * (it + 1)], None)
         lam = [0.0, 0.02, 0.05, 1.0, 0.97, 0.5, 0.48, -0.3, 0.1][it]           # small steps and jumps
         cand = x0 + lam * (x1 - x0)
         if it % 4 == 3:

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU: screening tests, device legs on both pools, then ncu of the chain (launch list + full capture).
 mkdir -p gpurun_out
-T=${1:-u}
+T=${1:-v}
 (timeout 900 python -m pytest tests/test_gpu_screen.py tests/test_gpu_guards.py -m gpu -q -x 2>&1 | tail -6) > gpurun_out/r02${T}_tests.log 2>&1
 : > gpurun_out/r02${T}_legs.jsonl
 run() { echo "# $*" >> gpurun_out/r02${T}_legs.err; echo "# $*" >> gpurun_out/r02${T}_legs.jsonl; env "$1" timeout 300 python bench.py --dev-only --no-cpu-baseline --no-extra-legs "${@:2}" 2>>gpurun_out/r02${T}_legs.err | grep '^{' | tail -1 >> gpurun_out/r02${T}_legs.jsonl; }

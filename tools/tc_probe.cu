@@ -208,7 +208,7 @@ int main(int argc, char **argv)
     ResolveArgs ra;
     ra.D = d_D; ra.PiS = d_PiS; ra.PiR = d_PiR; ra.bias = d_bias; ra.bias_stride = kpad; ra.s_pad = s_pad; ra.d_K = d_K;
     ra.n_local = N; ra.npad = npad; ra.R = R; ra.cand = d_cand; ra.cnt = d_cnt; ra.lfin = d_lfin;
-    ra.best_val = d_bv; ra.best_idx = d_bi; ra.out_stride = npad; ra.ctl = d_ctl; ra.force_full = 0; ra.prev = nullptr; ra.DR = nullptr;
+    ra.best_val = d_bv; ra.best_idx = d_bi; ra.out_stride = npad; ra.ctl = d_ctl; ra.force_full = 0; ra.prev = nullptr; ra.prevdot = nullptr; ra.DR = nullptr;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaMemset(d_bi, 0xff, (size_t)NX * npad * 4));
