@@ -234,6 +234,9 @@ struct sqlp_ctx {
     bool screen_smem_set[3] = {false, false, false};
     bool screen_seed = true;      // start the scan from the previous winners' scores (SQLP_SEED=0: from -Inf)
     bool screen_centre = true;    // bf16 operands relative to the centre of the pool / of the scenarios (SQLP_CENTRE=0: raw)
+    bool hist_fx = true;          // per-vertex weight sums in fixed point (SQLP_HIST=float: the ordered FP64 sums)
+    bool hist_fx_set[3] = {false, false, false};
+    DevBuf d_hfx;
     bool resolve_rows = true;     // exact decision moves whole rows through shared memory (SQLP_RESOLVE=lanes: a lane per row)
     size_t decide_smem_set[3] = {0, 0, 0};
     bool resolve_fma = false;     // exact decision by DFMA lanes (set when the device check DMMA == DFMA chain passed)
@@ -346,6 +349,7 @@ struct sqlp_epi {
     // scenario store
     int64_t n_global = 0, n_local = 0, cap_tiles = 0;
     double total_weight = 0.0;
+    double w_absmax = 0.0;                    // largest |weight| seen (k_cut_hist_fx scales by it); NaN once a weight was NaN
     DevBuf d_D, d_dT, d_w, d_Dx;
     DevBuf d_DR;                              // d_D row-major [scenario][s_pad] (epigraphs without random T entries)
     // per-vertex tables (rho, tau)

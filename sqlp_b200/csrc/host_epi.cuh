@@ -56,6 +56,7 @@ void epi_add(sqlp_epi *e, int64_t n_new, const double *v_host, const double *v_d
         if (sample) { if (wseed) w = 0.5 + u01(wseed, (uint64_t)(g0 + i)); }
         else if (w_host) w = w_host[i];
         e->total_weight += w;
+        e->w_absmax = (std::isnan(w) || std::isnan(e->w_absmax)) ? NAN : std::max(e->w_absmax, std::fabs(w));
     }
     DeltaTables tb = delta_tables(e);
     // algorithmic bytes: 8 s in + 8 s out per scenario (sampled: out only), this rank's share
@@ -371,7 +372,10 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     e->d_b32c.ensure((size_t)std::max<int64_t>(nch, 1) * BF * 4, 0, S(c), false);
     e->d_ctl.ensure(sizeof(ScreenCtl), 0, S(c));
     // split a unit's sweep into K-ranges when there are too few units to fill the GPU
-    int R = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * c->sm_count + nunits - 1) / nunits), std::max<int64_t>(nch, 1));
+    // (one unit per SM or more: no split -- the row-staging decision and the warm start need whole sweeps, and both
+    // are worth more than the last quarter of a wave)
+    int R = nunits >= c->sm_count ? 1
+            : (int)std::min<int64_t>(std::max<int64_t>(1, (2 * c->sm_count + nunits - 1) / nunits), std::max<int64_t>(nch, 1));
     const size_t nslots = (size_t)NX * R * 2 * npad;
     c->d_cand.ensure(nslots * SCR_CAP * sizeof(int2), 0, S(c), false);
     c->d_cnt.ensure(nslots * 4, 0, S(c), false);
@@ -668,33 +672,61 @@ void epi_cuts_enqueue(sqlp_epi *e, int NX, const double *x_host, const double *x
         const size_t hist_smem = (size_t)kc * 8 + (size_t)SQLP_HIST_SUB * 12;
         if (e->n_T == 0 && c->reduce_mode != 1 && (c->reduce_mode == 2 || e->n_local >= 131072) &&
             hist_smem + 1024 <= (size_t)c->smem_optin) {
-            const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, (e->n_local + 4095) / 4096));
+            // fixed-point weight sums (k_cut_hist_fx) when the scale exists: |p_i| <= max|w| / |total| < 2^eb
+            int sh1 = 0;
+            const size_t fx_cap = (size_t)c->smem_optin - 2048;
+            bool fx = c->hist_fx && (size_t)kc * 12 <= fx_cap;
+            if (fx) {
+                const double pb = e->w_absmax / std::fabs(e->total_weight);
+                fx = std::isfinite(pb) && pb > 0.0;
+                if (fx) {
+                    int eb = 0;
+                    std::frexp(pb, &eb);
+                    sh1 = 60 - eb;
+                    fx = std::abs(sh1) < 900;
+                }
+            }
+            const size_t fx_smem = std::min<size_t>((size_t)NX * kc * 12, fx_cap);
+            const int64_t nblk = fx ? std::max<int64_t>(1, (e->n_local + SQLP_HISTFX_SEG - 1) / SQLP_HISTFX_SEG)
+                                    : std::max<int64_t>(1, std::min<int64_t>(c->sm_count, (e->n_local + 4095) / 4096));
             HistArgs h;
             h.w = r.w; h.rt = r.rt; h.act = r.act; h.bias = r.bias; h.bias_stride = r.bias_stride;
             h.best_val = r.best_val; h.best_idx = r.best_idx; h.out_stride = r.out_stride; h.n_local = r.n_local;
-            h.seg = round_up((e->n_local + nblk - 1) / nblk, SQLP_TILE);
+            h.seg = fx ? SQLP_HISTFX_SEG : round_up((e->n_local + nblk - 1) / nblk, SQLP_TILE);
             h.d_Kv = e->view->d_Kv(p);
             h.kc = (int)kc; h.n1 = n1; h.total_weight = r.total_weight;
             h.D = r.D; h.PiS = r.PiS; h.s_pad = r.s_pad; h.flags = r.flags;
-            e->d_cpart.ensure((size_t)nblk * NX * kc * 8, 0, S(c), false);
+            h.hfx = nullptr;
+            h.sc1 = std::ldexp(1.0, sh1); h.inv1 = std::ldexp(1.0, -sh1);
+            if (!fx) e->d_cpart.ensure((size_t)nblk * NX * kc * 8, 0, S(c), false);
             e->d_spart.ensure((size_t)nblk * NX * 2 * 8, 0, S(c), false);
             h.cpart = e->d_cpart.as<double>();
             h.spart = e->d_spart.as<double>();
             const int nchunk = (int)((kc + SQLP_FOLD_COLS - 1) / SQLP_FOLD_COLS);
             e->d_partial.ensure((size_t)nchunk * width * 8, 0, S(c), false);
-            if (!c->hist_smem_set[NX]) {
-                // (the kernel also has 512 B of static shared memory: the dynamic part cannot be the whole opt-in size)
-                if (NX == 2) CK(cudaFuncSetAttribute(k_cut_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
-                else CK(cudaFuncSetAttribute(k_cut_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
-                c->hist_smem_set[NX] = true;
-            }
-            if (NX == 2) {
-                LAUNCH(c, k_cut_hist<2>, (int)nblk, SQLP_HIST_THREADS, hist_smem, h);
-                LAUNCH(c, k_cut_fold<2>, nchunk, 256, 0, h, (int)nblk, e->d_partial.as<double>());
+            if (fx) {
+                c->d_hfx.ensure((size_t)2 * kc * 24, 0, S(c), false);
+                CK(cudaMemsetAsync(c->d_hfx.p, 0, (size_t)NX * kc * 24, S(c)));
+                h.hfx = c->d_hfx.as<long long>();
+                if (!c->hist_fx_set[NX]) {
+                    if (NX == 2) CK(cudaFuncSetAttribute(k_cut_hist_fx<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
+                    else CK(cudaFuncSetAttribute(k_cut_hist_fx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
+                    c->hist_fx_set[NX] = true;
+                }
+                if (NX == 2) LAUNCH(c, k_cut_hist_fx<2>, (int)nblk, SQLP_HIST_THREADS, fx_smem, h, (int)fx_smem);
+                else LAUNCH(c, k_cut_hist_fx<1>, (int)nblk, SQLP_HIST_THREADS, fx_smem, h, (int)fx_smem);
             } else {
-                LAUNCH(c, k_cut_hist<1>, (int)nblk, SQLP_HIST_THREADS, hist_smem, h);
-                LAUNCH(c, k_cut_fold<1>, nchunk, 256, 0, h, (int)nblk, e->d_partial.as<double>());
+                if (!c->hist_smem_set[NX]) {
+                    // (the kernel also has 512 B of static shared memory: the dynamic part cannot be the whole opt-in size)
+                    if (NX == 2) CK(cudaFuncSetAttribute(k_cut_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
+                    else CK(cudaFuncSetAttribute(k_cut_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024));
+                    c->hist_smem_set[NX] = true;
+                }
+                if (NX == 2) LAUNCH(c, k_cut_hist<2>, (int)nblk, SQLP_HIST_THREADS, hist_smem, h);
+                else LAUNCH(c, k_cut_hist<1>, (int)nblk, SQLP_HIST_THREADS, hist_smem, h);
             }
+            if (NX == 2) LAUNCH(c, k_cut_fold<2>, nchunk, 256, 0, h, (int)nblk, e->d_partial.as<double>());
+            else LAUNCH(c, k_cut_fold<1>, nchunk, 256, 0, h, (int)nblk, e->d_partial.as<double>());
             const int64_t ng = (nchunk + group - 1) / group;
             e->d_partial2.ensure((size_t)ng * width * 8, 0, S(c), false);
             LAUNCH(c, k_sum_groups, (int)ng, 256, sub_smem, e->d_partial.as<double>(), (long long)nchunk, group, nsub,

@@ -347,6 +347,9 @@ struct HistArgs {
     double *cpart;            // [nblk][NX][kc]
     double *spart;            // [nblk][NX][2]   (sum p dot, sum p score)
     int *flags;
+    // k_cut_hist_fx: the weight sums as integers (see there)
+    long long *hfx;           // [NX][kc][3] limb sums, zero before the launch; null: cpart holds the sums
+    double sc1, inv1;         // 2^(60 - eb) and its inverse
 };
 
 template <int NX>
@@ -448,6 +451,107 @@ __global__ void __launch_bounds__(SQLP_HIST_THREADS, 1) k_cut_hist(HistArgs a)
     }
 }
 
+// The weight sums in fixed point.  k_cut_hist keeps the sums deterministic by giving every column to one warp that
+// adds its scenarios in order -- every warp reads every staged scenario, 32 x the work, and the kernel ran at 4 % of
+// what its bytes allow.  Integers add in any order to the same bits, so here every thread handles its own scenario
+// and the sums are atomic integer adds.  With |p_i| <= max|w| / |total| < 2^eb (both known on the host) and
+// f_i = rint(p_i 2^(60 - eb)), |f_i| < 2^60, a weight is three signed limbs of 20 bits, f = a 2^40 + b 2^20 + c: a
+// block of at most 2 047 scenarios adds limbs into 32-bit words of its shared-memory table (native atomics, no
+// overflow: 2 047 x 2^20 < 2^31), its non-zero words go to 64-bit global sums, and the fold forms
+// c_k = (A_k 2^40 + B_k 2^20 + C_k) 2^(eb - 60): every weight to 2^-60 of the largest one (the reference's sequential
+// FP64 sum carries 2^-53 of the running sum), the same bits whatever the block partition and the order of the adds.
+// The table holds the columns the view really has (*d_Kv): both points at once if they fit the launch's shared
+// memory, else one point per pass.  The scalar sums stay as in k_cut_hist (fixed tree per block, blocks in order).
+#define SQLP_HISTFX_SEG 1792          // scenarios per block: 14 tiles, < 2 048
+template <int NX>
+__global__ void __launch_bounds__(SQLP_HIST_THREADS, 1) k_cut_hist_fx(HistArgs a, int smem_bytes)
+{
+    griddep_sync();
+    extern __shared__ __align__(16) unsigned char hist_raw[];
+    int *H = reinterpret_cast<int *>(hist_raw);                                   // [xp][Kv][3]
+    __shared__ double red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long i0 = (long long)blockIdx.x * a.seg, i1 = min(a.n_local, i0 + a.seg);
+    const long long RT = a.n1 + 1;
+    const int Kv = (int)min(*a.d_Kv, (long long)a.kc);
+    const int xp = ((long long)NX * Kv * 12 <= smem_bytes) ? NX : 1;               // points per pass
+    for (int x0 = 0; x0 < NX; x0 += xp) {
+        for (int t = tid; t < xp * Kv * 3; t += blockDim.x) H[t] = 0;
+        double sdot[NX], sval[NX];
+#pragma unroll
+        for (int x = 0; x < NX; ++x) { sdot[x] = 0.0; sval[x] = 0.0; }
+        __syncthreads();
+        for (long long i = i0 + tid; i < i1; i += blockDim.x) {              // this thread's scenarios, index order
+            const double p = a.w[i] / a.total_weight;                            // epigraph.jl:138
+            const long long f = __double2ll_rn(p * a.sc1);
+            const long long m = f < 0 ? -f : f;
+            const int sg = f < 0 ? -1 : 1;
+            const int la = sg * (int)(m >> 40), lb = sg * (int)((m >> 20) & 0xFFFFF), lc = sg * (int)(m & 0xFFFFF);
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                if (x < x0 || x >= x0 + xp) continue;
+                const int k = a.best_idx[x * a.out_stride + i];
+                if (k < 0 || k >= Kv) {
+                    atomicOr(a.flags, 1);
+                    continue;
+                }
+                const double sc = a.best_val[x * a.out_stride + i];
+                double acc = __dsub_rn(sc, a.bias[x * a.bias_stride + k]);
+                if (fabs(sc) > 8192.0 * fmax(fabs(a.rt[(long long)(a.act ? a.act[k] : k) * RT]), fabs(acc))) {
+                    const double *P = a.PiS + ((long long)(k >> 7) * a.s_pad) * SQLP_TILE + tile_off(k & 127, 0);
+                    const double *Dc = a.D + (i >> 7) * (long long)a.s_pad * SQLP_TILE + tile_off((int)(i & 127), 0);
+                    acc = 0.0;
+                    for (int g = 0; g < a.s_pad / 4; ++g, P += 512, Dc += 512)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc = fma(P[u * 2], Dc[u * 2], acc);
+                }
+                sdot[x] = fma(p, acc, sdot[x]);                                  // :140 (the part that is not rho)
+                sval[x] = fma(p, sc, sval[x]);                                   // :142
+                int *h = H + ((size_t)(x - x0) * Kv + k) * 3;
+                if (la) atomicAdd(h, la);
+                if (lb) atomicAdd(h + 1, lb);
+                if (lc) atomicAdd(h + 2, lc);
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < xp * Kv * 3; t += blockDim.x) {
+            const int v = H[t];
+            if (v) {
+                const int xx = t / (Kv * 3), rem = t - xx * (Kv * 3);
+                atomicAdd(reinterpret_cast<unsigned long long *>(a.hfx) + ((size_t)(x0 + xx) * a.kc) * 3 + rem,
+                          (unsigned long long)(long long)v);
+            }
+        }
+        // the block's scalar sums: lanes, then warps, in a fixed tree
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            if (x < x0 || x >= x0 + xp) continue;
+            double u = sdot[x], v = sval[x];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                u += __shfl_xor_sync(0xffffffffu, u, off);
+                v += __shfl_xor_sync(0xffffffffu, v, off);
+            }
+            if (lane == 0) { red[0][warp] = u; red[1][warp] = v; }
+            __syncthreads();
+            if (warp == 0) {
+                u = red[0][lane];
+                v = red[1][lane];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    u += __shfl_xor_sync(0xffffffffu, u, off);
+                    v += __shfl_xor_sync(0xffffffffu, v, off);
+                }
+                if (lane == 0) {
+                    a.spart[((long long)blockIdx.x * NX + x) * 2] = u;
+                    a.spart[((long long)blockIdx.x * NX + x) * 2 + 1] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // part[chunk][x][col]: col 0 = sum_k c_k rho_k (+ the blocks' sum p dot on chunk 0), 1..n1 = -sum_k c_k tau_kj,
 // n1 + 1 = the blocks' sum p score (chunk 0 only).  One block per chunk of 256 columns.
 template <int NX>
@@ -463,7 +567,10 @@ __global__ void __launch_bounds__(256) k_cut_fold(HistArgs a, int nblk, double *
     for (int q = threadIdx.x; q < NX * SQLP_FOLD_COLS; q += blockDim.x) {
         const int x = q / SQLP_FOLD_COLS, k = k0 + q % SQLP_FOLD_COLS;
         double s = 0.0;
-        if (k < Kv && k < a.kc) {
+        if (k < Kv && k < a.kc && a.hfx) {
+            const long long *hh = a.hfx + ((long long)x * a.kc + k) * 3;       // limb sums: exact as doubles (< 2^53)
+            s = ((double)hh[0] * 0x1p40 + (double)hh[1] * 0x1p20 + (double)hh[2]) * a.inv1;
+        } else if (k < Kv && k < a.kc) {
             const double *src = a.cpart + (long long)x * a.kc + k;
             const long long bs = (long long)NX * a.kc;
             for (int b = 0; b < nblk; b += 8) {              // block order; eight loads in flight
