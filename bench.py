@@ -184,7 +184,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.004)        # a timed region is a few tens of ms: several samples inside it
 
     def finish(self):
         self._halt.set()
@@ -437,6 +437,8 @@ def run_ours(args):
         launches0 = ctx.launch_count()
         sampler = ClockSampler(local)
         sampler.start()
+        barrier()           # again: starting the clock sampler costs a rank a few ms of host time, and a rank that
+        #                     enters the timed region early only waits for the others at the first exchange
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cuprof = os.environ.get("SQLP_BENCH_CUPROF") == "1"     # ncu --profile-from-start off: the timed steps only
         if cuprof:
