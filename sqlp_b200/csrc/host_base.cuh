@@ -232,6 +232,8 @@ struct sqlp_ctx {
     // screening pass (kernels_screen.cuh): 0 = off, 1 = automatic (default), 2 = whenever the shape allows it
     int screen_mode = 1;
     bool screen_smem_set[3] = {false, false, false};
+    bool screen_fadd2 = false;    // SQLP_FADD2=1: the epilogue adds two scores per instruction (add.f32x2).  Measured on one box,
+                                  // three rounds each: +2 % on the round-1 pool (fast path), -2.5 % on storm's real pool (166 registers)
     bool screen_seed = true;      // start the scan from the previous winners' scores (SQLP_SEED=0: from -Inf)
     bool screen_centre = true;    // bf16 operands relative to the centre of the pool / of the scenarios (SQLP_CENTRE=0: raw)
     bool hist_fx = true;          // per-vertex weight sums in fixed point (SQLP_HIST=float: the ordered FP64 sums)

@@ -432,7 +432,8 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     while (nstages > 3 && scr_smem_bytes(v->sp, nstages, NX) > (size_t)c->smem_optin) --nstages;
     const size_t smem = scr_smem_bytes(v->sp, nstages, NX);
     if (!c->screen_smem_set[NX]) {
-        CK(cudaFuncSetAttribute(k_screen<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        CK(cudaFuncSetAttribute((k_screen<NX, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        CK(cudaFuncSetAttribute((k_screen<NX, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         c->screen_smem_set[NX] = true;
     }
     ScreenArgs sa;
@@ -458,7 +459,8 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     {
         // executed bf16 flops: three products over sp slots for every (vertex of a whole chunk, scenario of a whole unit)
         ProfScope prof(c, SQLP_PROF_SCREEN, 6.0 * v->sp * (double)npad, p, SCR_NB, v);
-        LAUNCH(c, k_screen<NX>, grid, SCR_THREADS, smem, sa);
+        if (c->screen_fadd2) LAUNCH(c, (k_screen<NX, 1>), grid, SCR_THREADS, smem, sa);
+        else LAUNCH(c, (k_screen<NX, 0>), grid, SCR_THREADS, smem, sa);
     }
     ResolveArgs ra;
     ra.D = e->d_D.as<double>();

@@ -88,7 +88,18 @@ __host__ __device__ inline size_t scr_smem_bytes(int sp, int nstages, int nx)
            (size_t)SCR_BIAS_BUFS * (nx * SCR_NB + 4) * 4;   // alignment slack + barrier block + A + ring + biases
 }
 
-template <int NX>
+// Two fp32 additions in one instruction (add.rn.f32x2, SASS FADD2: sm_100 packs a pair of fp32 lanes per register
+// pair): round to nearest each, the same bits as two FADDs.
+__device__ __forceinline__ void add2(float &r0, float &r1, uint32_t a0, uint32_t a1, float b0, float b1)
+{
+    unsigned long long x, y, z;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(z));
+}
+
+template <int NX, int PK = 1>
 __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
 {
     griddep_sync();
@@ -263,10 +274,18 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
                         for (int x = 0; x < NX; ++x) {
                             const float4 b0 = *reinterpret_cast<const float4 *>(bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8);
                             const float4 b1 = *reinterpret_cast<const float4 *>(bs + x * SCR_NB + h * 128 + g * 32 + s8 * 8 + 4);
-                            const float t0 = __uint_as_float(v[s8 * 8 + 0]) + b0.x, t1 = __uint_as_float(v[s8 * 8 + 1]) + b0.y;
-                            const float t2 = __uint_as_float(v[s8 * 8 + 2]) + b0.z, t3 = __uint_as_float(v[s8 * 8 + 3]) + b0.w;
-                            const float t4 = __uint_as_float(v[s8 * 8 + 4]) + b1.x, t5 = __uint_as_float(v[s8 * 8 + 5]) + b1.y;
-                            const float t6 = __uint_as_float(v[s8 * 8 + 6]) + b1.z, t7 = __uint_as_float(v[s8 * 8 + 7]) + b1.w;
+                            float t0, t1, t2, t3, t4, t5, t6, t7;                 // score = accumulator + bias
+                            if (PK) {                                             // two per FADD2
+                                add2(t0, t1, v[s8 * 8 + 0], v[s8 * 8 + 1], b0.x, b0.y);
+                                add2(t2, t3, v[s8 * 8 + 2], v[s8 * 8 + 3], b0.z, b0.w);
+                                add2(t4, t5, v[s8 * 8 + 4], v[s8 * 8 + 5], b1.x, b1.y);
+                                add2(t6, t7, v[s8 * 8 + 6], v[s8 * 8 + 7], b1.z, b1.w);
+                            } else {
+                                t0 = __uint_as_float(v[s8 * 8 + 0]) + b0.x; t1 = __uint_as_float(v[s8 * 8 + 1]) + b0.y;
+                                t2 = __uint_as_float(v[s8 * 8 + 2]) + b0.z; t3 = __uint_as_float(v[s8 * 8 + 3]) + b0.w;
+                                t4 = __uint_as_float(v[s8 * 8 + 4]) + b1.x; t5 = __uint_as_float(v[s8 * 8 + 5]) + b1.y;
+                                t6 = __uint_as_float(v[s8 * 8 + 6]) + b1.z; t7 = __uint_as_float(v[s8 * 8 + 7]) + b1.w;
+                            }
                             gmx[s8][x] = fmaxf(fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)), fmaxf(fmaxf(t4, t5), fmaxf(t6, t7)));
                             any = any || gmx[s8][x] >= thr[x];
                         }

@@ -83,6 +83,7 @@ static void ctx_init(sqlp_ctx *c, int32_t device)
     if (const char *g = getenv("SQLP_SCREEN")) c->screen_mode = std::max(0, std::min(2, atoi(g)));
     if (const char *g = getenv("SQLP_CENTRE")) c->screen_centre = atoi(g) != 0;
     if (const char *g = getenv("SQLP_SEED")) c->screen_seed = atoi(g) != 0;
+    if (const char *g = getenv("SQLP_FADD2")) c->screen_fadd2 = atoi(g) != 0;
     if (const char *g = getenv("SQLP_HIST")) c->hist_fx = strcmp(g, "float") != 0;
     if (const char *g = getenv("SQLP_TWINS")) c->twins = atoi(g) != 0;
     if (const char *g = getenv("SQLP_REDUCE")) c->reduce_mode = std::max(0, std::min(2, atoi(g)));
