@@ -578,7 +578,7 @@ def run_ours(args):
             # C4 as BASELINE.json names it: N = scen_per_gpu scenarios IN TOTAL, sharded over the GPUs
             scell = Cell(T, ctx, z, coef, pool_all, K0, E, args.scen_per_gpu // E)
             sleg = device_leg(scell, args.warmup, args.steps, False)
-            strong = leg_summary(sleg, kind, scell)
+            strong = leg_summary(sleg, kind, scell, traffic_shape=False)
             strong["N_total"] = args.scen_per_gpu
             # the weak-scaled step of this run does, per GPU, exactly the work of the 1-GPU form of this job
             strong["efficiency_vs_n1"] = (leg["ms_per_step"] / world) / sleg["ms_per_step"]
@@ -652,8 +652,8 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def leg_summary(leg, kind, cell):
-    r = rooflines(leg, None)
+def leg_summary(leg, kind, cell, traffic_shape=True):
+    r = rooflines(leg, None, kind if traffic_shape else "-")
     return {"pool": kind, "ms_per_step": leg["ms_per_step"], "value": leg["value"], "unit": UNIT,
             "gpu_launches": leg["launches"], "screening": leg["screen"], "sweep": leg["sweep"], "per_rank": leg["per_rank"],
             "roofline": r["dominant"],
@@ -661,7 +661,7 @@ def leg_summary(leg, kind, cell):
             "share_of_step": r["dominant"]["share_of_step"] if r["dominant"] else None, "clocks": leg["clocks"]}
 
 
-def rooflines(leg, args):
+def rooflines(leg, args, kind=None):
     """One entry per argmax kernel class that ran in the timed steps; `dominant` = the one with the most device time.
     achieved = work of the launches (flops counted with the pool size each launch saw) / their CUDA-event time."""
     prof, ms_dev = leg["prof"], leg["ms"]
@@ -687,7 +687,10 @@ def rooflines(leg, args):
         if n == 0 or ms <= 0 or work <= 0:
             return
         tf = work / (ms * 1e-3) * 1e-12
-        tj = traffic.get(tkey) if isinstance(traffic.get(tkey), dict) else (traffic if tkey == "fp64" and "dram_bytes_read" in traffic else None)
+        # (captured at the default bench shape only: storm, K = 16 384, 250k scenarios per epigraph)
+        at_shape = args is None or (args.instance == "storm" and args.vertices == 16384 and args.scen_per_gpu == 1_000_000 and args.epigraphs == 4)
+        tj = traffic.get(f"{tkey}_{kind or pool_kind(args)}" if tkey == "screen" else tkey) if at_shape else None
+        tj = tj if isinstance(tj, dict) else None
         out.append({"bound": "tensor", "pipe": pipe, "kernel": kernel, "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                     "frac": tf / peak if peak else None,
                     "traffic": (tj["dram_bytes_read"] + tj["dram_bytes_write"]) if tj else None,
