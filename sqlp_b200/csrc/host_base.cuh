@@ -372,7 +372,7 @@ struct sqlp_epi {
     bool has_inc = false, has_prev_inc = false;
     int last_nx = 0;   // points of the last cut formation whose result is still in d_out
     // screening pass: bf16 scenario operands, per-call control block, what the host has learnt
-    DevBuf d_DB, d_dnu, d_dnall, d_ebad, d_b32c, d_ctl;
+    DevBuf d_DB, d_dnu, d_dn, d_dnall, d_ebad, d_b32c, d_ctl;
     DevBuf d_prev;                            // [n_local][2]: 1 + view column selected at the previous pass, per point
     DevBuf d_prevdot, d_cd;                   // [n_local][2] the dots P_k . d_i of those columns; [n_local] ctr . d_i
     int64_t prev_cap = 0, cd_synced = 0, cd_epoch = -1;

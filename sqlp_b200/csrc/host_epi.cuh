@@ -332,6 +332,7 @@ void screen_sync_operands(sqlp_epi *e)
         const int64_t ncap = std::max<int64_t>(units, std::max<int64_t>(8, e->scr_units_cap * 2));
         e->d_DB.ensure((size_t)ncap * 512 * v->sp, (size_t)e->scr_units_cap * 512 * v->sp, S(c));
         e->d_dnu.ensure((size_t)ncap * 4, (size_t)e->scr_units_cap * 4, S(c));
+        e->d_dn.ensure((size_t)ncap * SCR_UNIT * 4, (size_t)e->scr_units_cap * SCR_UNIT * 4, S(c));
         e->d_dnall.ensure(16, 0, S(c));
         e->d_ebad.ensure(16, 0, S(c));
         e->scr_units_cap = ncap;
@@ -351,7 +352,7 @@ void screen_sync_operands(sqlp_epi *e)
         const int grid = (int)std::min<int64_t>(std::max<int64_t>((work + 7) / 8, 1), 16 * c->sm_count);
         LAUNCH(c, k_screen_scen_sync, grid, 256, 0, e->d_D.as<double>(), v->s_pad, v->sp, e->d_DB.as<__nv_bfloat16>(),
                e->d_dnu.as<float>(), e->d_dnall.as<float>(), e->d_ebad.as<int>(), (long long)e->scr_synced,
-               (long long)e->n_local, (const double *)e->d_dbar.as<double>());
+               (long long)e->n_local, (const double *)e->d_dbar.as<double>(), e->d_dn.as<float>());
         e->scr_synced = e->n_local;
     }
 }
@@ -441,6 +442,7 @@ const ScreenCtl *screen_enqueue(sqlp_epi *e)
     sa.PiB = v->d_piB.as<__nv_bfloat16>();
     sa.b32c = e->d_b32c.as<float>();
     sa.dnmax_unit = e->d_dnu.as<float>();
+    sa.dn = e->d_dn.as<float>();
     sa.ctl = e->d_ctl.as<ScreenCtl>();
     sa.d_K = v->d_Kv(p);
     sa.sp = v->sp;

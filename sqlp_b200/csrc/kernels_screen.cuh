@@ -65,6 +65,7 @@ struct ScreenArgs {
     const __nv_bfloat16 *PiB;      // [nchunks][sp / 16][2][2][256][8]
     const float *b32c;             // [nchunks][NX * 256 + 4]
     const float *dnmax_unit;       // [nunits] largest ||d_i|| of the unit, rounded up
+    const float *dn;               // [npad] ||d_i - dbar|| per scenario, rounded up (the epilogue thread owns ONE scenario)
     ScreenCtl *ctl;
     const long long *d_K;
     int sp;                        // row slots padded to a multiple of 16
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(ScreenArgs a)
             if (c0 >= c1) continue;
             const long long i = (long long)u * SCR_UNIT + row;
             const bool valid = i < a.n_local;
-            const float dnu = a.dnmax_unit[u];
+            // the bound of THIS thread's scenario: its own norm, not the unit's largest (E is per (vertex, scenario))
+            const float dnu = a.dn ? (valid ? a.dn[i] : 0.f) : a.dnmax_unit[u];
             const float eq = __fmul_ru(coef_q, dnu);
             float L[NX];
             int n[NX];
@@ -503,7 +505,7 @@ __global__ void k_screen_mark(long long *__restrict__ mark, const long long *__r
 __global__ void k_screen_scen_sync(const double *__restrict__ D, int s_pad, int sp, __nv_bfloat16 *__restrict__ DB,
                                    float *__restrict__ dnmax_unit, float *__restrict__ dnmax_all,
                                    int *__restrict__ bad, long long lo, long long n_local,
-                                   const double *__restrict__ dbar)
+                                   const double *__restrict__ dbar, float *__restrict__ dn_out)
 {
     griddep_sync();
     const int lane = threadIdx.x & 31;
@@ -526,6 +528,7 @@ __global__ void k_screen_scen_sync(const double *__restrict__ D, int s_pad, int 
         for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
         if (lane == 0) {
             const float nrm = norm_up(ss);
+            if (dn_out) dn_out[i] = nrm;
             if (nrm < 1.0e18f) {
                 atomic_max_pos(dnmax_unit + u, nrm);
                 atomic_max_pos(dnmax_all, nrm);
@@ -1053,7 +1056,7 @@ __host__ __device__ inline int scr_decide_stride(int s_pad)    // doubles per st
 }
 __host__ __device__ inline size_t scr_decide_smem(int s_pad)
 {
-    return (size_t)SCR_DEC_WARPS * ((size_t)(SCR_DEC_ROWS + 1) * scr_decide_stride(s_pad) * 8 + SCR_DEC_ROWS * 8 + SCR_DEC_QUEUE * 4);
+    return (size_t)SCR_DEC_WARPS * ((size_t)(SCR_DEC_ROWS + 2) * scr_decide_stride(s_pad) * 8 + SCR_DEC_ROWS * 8 + SCR_DEC_QUEUE * 4);
 }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -1062,6 +1065,14 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_but_last()     // every group but the most recent one has landed
+{
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
 }
 
 template <int NX>
@@ -1074,31 +1085,48 @@ __global__ void __launch_bounds__(32 * SCR_DEC_WARPS) k_screen_decide(ResolveArg
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int rs = scr_decide_stride(a.s_pad);
     const int sp2 = a.s_pad / 2, ng = a.s_pad / 4;
-    double *rows = reinterpret_cast<double *>(dec_sm) + (size_t)wib * (SCR_DEC_ROWS + 1) * rs;
-    double *dots = reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * (SCR_DEC_ROWS + 1) * rs + wib * SCR_DEC_ROWS;
-    int *wq = reinterpret_cast<int *>(reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * ((SCR_DEC_ROWS + 1) * rs + SCR_DEC_ROWS)) +
+    // per warp: two scenario rows (this scenario's and the next one's, on its way), eight candidate rows
+    double *drow = reinterpret_cast<double *>(dec_sm) + (size_t)wib * (SCR_DEC_ROWS + 2) * rs;
+    double *rows = drow + 2 * rs;
+    double *dots = reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * (SCR_DEC_ROWS + 2) * rs + wib * SCR_DEC_ROWS;
+    int *wq = reinterpret_cast<int *>(reinterpret_cast<double *>(dec_sm) + (size_t)SCR_DEC_WARPS * ((SCR_DEC_ROWS + 2) * rs + SCR_DEC_ROWS)) +
               wib * SCR_DEC_QUEUE;
     const long long nw = (long long)gridDim.x * SCR_DEC_WARPS;
     const long long K = *a.d_K;
     const int nch = (int)((K + SCR_NB - 1) / SCR_NB);
+    constexpr int L = 2 * NX;                 // lists of a scenario: (point, column half)
+    constexpr int HEAD = 32 / L;              // entries of every list that ONE load instruction fetches (lane = list * HEAD + entry)
     unsigned long long evald = 0;
-    for (long long i = (long long)blockIdx.x * SCR_DEC_WARPS + wib; i < a.n_local; i += nw) {
+    // The head of a scenario -- counts and bounds of its lists (lanes < L), the first HEAD entries of every list, its
+    // row -- is requested one scenario ahead, before the rows of the current one: of the three dependent round trips
+    // (counts, entries, operand rows) only the last is waited for.  (Entries beyond a list's count are read and ignored.)
+    auto request = [&](long long i, int par, int &myn, float &mylb, int2 &e8) {
+        myn = 0;
+        mylb = -INFINITY;
+        e8 = make_int2(0, 0);
+        if (nch > 0) {
+            if (lane < L) {
+                const long long slot = (long long)lane * a.npad + i;       // list (x, h) = lane 2 x + h
+                myn = a.cnt[slot];
+                mylb = a.lfin[slot];
+            }
+            e8 = a.cand[((long long)(lane / HEAD) * a.npad + i) * SCR_CAP + (lane % HEAD)];
+        }
+        const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad) + lane;
+        double2 *r2 = reinterpret_cast<double2 *>(drow + (size_t)par * rs) + lane;
+        if (lane < sp2) cp_async16(r2, Dr);
+        if (lane + 32 < sp2) cp_async16(r2 + 32, Dr + 32);
+        for (int q = 64; q + lane < sp2; q += 32) cp_async16(r2 + q, Dr + q);
+    };
+    long long i = (long long)blockIdx.x * SCR_DEC_WARPS + wib;
+    int par = 0, myn = 0;
+    float mylb = -INFINITY;
+    int2 e8 = make_int2(0, 0);
+    if (i < a.n_local) request(i, par, myn, mylb, e8);
+    cp_async_commit();
+    for (; i < a.n_local; i += nw, par ^= 1) {
         double best = -INFINITY, bdot = 0.0;      // of point x = lane (lanes < NX)
         int bidx = -1;
-        // the scenario's row is requested first; it is waited for together with the first batch of candidate rows
-        {
-            const double2 *Dr = reinterpret_cast<const double2 *>(a.DR + (size_t)i * a.s_pad);
-            double2 *r2 = reinterpret_cast<double2 *>(rows);
-            for (int q = lane; q < sp2; q += 32) cp_async16(r2 + q, Dr + q);
-        }
-        constexpr int L = 2 * NX;
-        int myn = 0;
-        float mylb = -INFINITY;
-        if (lane < L && nch > 0) {
-            const long long slot = (long long)lane * a.npad + i;           // list (x, h) = lane 2 x + h
-            myn = a.cnt[slot];
-            mylb = a.lfin[slot];
-        }
         int nl[L];
         bool full = false;
 #pragma unroll
@@ -1112,24 +1140,30 @@ __global__ void __launch_bounds__(32 * SCR_DEC_WARPS) k_screen_decide(ResolveArg
             LB[x] = fmaxf(__shfl_sync(0xffffffffu, mylb, 2 * x), __shfl_sync(0xffffffffu, mylb, 2 * x + 1));
         int n = 0;
         if (!full) {
-            int2 ent[L][SCR_CAP / 32];
+            // the heads of all lists in one ballot
+            int mycnt = 0;
+            float mylbx = INFINITY;
 #pragma unroll
             for (int l = 0; l < L; ++l)
+                if (lane / HEAD == l) { mycnt = nl[l]; mylbx = LB[l >> 1]; }
+            {
+                const bool ok = (lane % HEAD) < mycnt && __int_as_float(e8.y) >= mylbx;
+                const unsigned pass = __ballot_sync(0xffffffffu, ok);
+                if (ok) wq[__popc(pass & ((1u << lane) - 1u))] = e8.x;
+                n = __popc(pass);
+            }
+            // the rest of a long list (rare once the scan is warm-started)
 #pragma unroll
-                for (int b = 0; b < SCR_CAP / 32; ++b) {
-                    ent[l][b] = make_int2(0, 0);
-                    if (b * 32 + lane < nl[l]) ent[l][b] = a.cand[((long long)l * a.npad + i) * SCR_CAP + b * 32 + lane];
-                }
-#pragma unroll
-            for (int l = 0; l < L; ++l)
-#pragma unroll
-                for (int b = 0; b < SCR_CAP / 32; ++b) {
-                    if (b * 32 >= nl[l]) continue;
-                    const bool ok = b * 32 + lane < nl[l] && __int_as_float(ent[l][b].y) >= LB[l >> 1];
+            for (int l = 0; l < L; ++l) {
+                for (int b0 = HEAD; b0 < nl[l]; b0 += 32) {
+                    int2 e = make_int2(0, 0);
+                    if (b0 + lane < nl[l]) e = a.cand[((long long)l * a.npad + i) * SCR_CAP + b0 + lane];
+                    const bool ok = b0 + lane < nl[l] && __int_as_float(e.y) >= LB[l >> 1];
                     const unsigned pass = __ballot_sync(0xffffffffu, ok);
-                    if (ok) wq[n + __popc(pass & ((1u << lane) - 1u))] = ent[l][b].x;
+                    if (ok) wq[n + __popc(pass & ((1u << lane) - 1u))] = e.x;
                     n += __popc(pass);
                 }
+            }
             __syncwarp();
             // one chain per vertex: the second copy of a column (the other point's list) is struck out.  Queues of
             // more than 32 are left as they are -- a vertex scored twice is only work
@@ -1144,74 +1178,94 @@ __global__ void __launch_bounds__(32 * SCR_DEC_WARPS) k_screen_decide(ResolveArg
                 __syncwarp();
             }
         }
-        // the queue's vertices, eight at a time
-        auto run_queue = [&](int cnt) {
-            for (int base = 0; base < cnt; base += SCR_DEC_ROWS) {
-                const int nb = min(SCR_DEC_ROWS, cnt - base);
-                for (int r = 0; r < nb; ++r) {
-                    const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad) + lane;
-                    double2 *r2 = reinterpret_cast<double2 *>(rows + (size_t)(1 + r) * rs) + lane;
-                    if (lane < sp2) cp_async16(r2, P);
-                    if (lane + 32 < sp2) cp_async16(r2 + 32, P + 32);
-                    for (int q = 64; q + lane < sp2; q += 32) cp_async16(r2 + q, P + q);
-                }
-                cp_async_wait_all();
-                __syncwarp();
-                // A: the scenario in every row (lane t: slot 4 g + t % 4); B: column t / 4 = staged row t / 4.  Columns
-                // beyond nb read whatever the rows hold: a column's result depends on that column alone
-                const double *ap = rows + (lane & 3);
-                const double *bp = rows + (size_t)(1 + (lane >> 2)) * rs + (lane & 3);
-                double acc0 = 0.0, acc1 = 0.0;
-                int g = 0;
-                for (; g + 6 <= ng; g += 6) {
-                    double av[6], bv[6];
-#pragma unroll
-                    for (int u = 0; u < 6; ++u) { av[u] = ap[(g + u) * 4]; bv[u] = bp[(g + u) * 4]; }
-#pragma unroll
-                    for (int u = 0; u < 6; ++u)
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                                     : "+d"(acc0), "+d"(acc1)
-                                     : "d"(av[u]), "d"(bv[u]));
-                }
-                for (; g < ng; ++g) {
-                    const double av = ap[g * 4], bv = bp[g * 4];
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                                 : "+d"(acc0), "+d"(acc1)
-                                 : "d"(av), "d"(bv));
-                }
-                // row 0 of C: lane l < 4 holds the dots of columns 2 l and 2 l + 1.  They go to the warp's scratch and
-                // lane x < NX walks the batch for point x, keeping that point's best in its own registers
-                if (lane < 4) {
-                    dots[2 * lane] = acc0;
-                    dots[2 * lane + 1] = acc1;
-                }
-                __syncwarp();
-                if (lane < NX) {
-                    const double *bx = a.bias + (size_t)lane * a.bias_stride;
-                    for (int cidx = 0; cidx < nb; ++cidx) {
-                        const int kj = wq[base + cidx];
-                        if (kj >= K) continue;
-                        const double dj = dots[cidx];
-                        const double t = dj + bx[kj];                               // the sweep's epilogue: acc + bias
-                        // NaN and -Inf never win (subprob.jl:151-156); equal scores: the smaller index
-                        if (t > best || (t == best && bidx >= 0 && kj < bidx)) { best = t; bdot = dj; bidx = kj; }
-                    }
-                }
-                evald += nb;
-                __syncwarp();
+        const double *dcur = drow + (size_t)par * rs;
+        auto stage = [&](int base, int nb) {       // candidate rows of a batch -> the warp's shared memory, asynchronously
+            for (int r = 0; r < nb; ++r) {
+                const double2 *P = reinterpret_cast<const double2 *>(a.PiR + (size_t)wq[base + r] * a.s_pad) + lane;
+                double2 *r2 = reinterpret_cast<double2 *>(rows + (size_t)r * rs) + lane;
+                if (lane < sp2) cp_async16(r2, P);
+                if (lane + 32 < sp2) cp_async16(r2 + 32, P + 32);
+                for (int q = 64; q + lane < sp2; q += 32) cp_async16(r2 + q, P + q);
             }
         };
+        auto chain = [&](int base, int nb) {
+            // A: the scenario in every row (lane t: slot 4 g + t % 4); B: column t / 4 = staged row t / 4.  Columns
+            // beyond nb read whatever the rows hold: a column's result depends on that column alone
+            const double *ap = dcur + (lane & 3);
+            const double *bp = rows + (size_t)(lane >> 2) * rs + (lane & 3);
+            double acc0 = 0.0, acc1 = 0.0;
+            int g = 0;
+            for (; g + 6 <= ng; g += 6) {
+                double av[6], bv[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) { av[u] = ap[(g + u) * 4]; bv[u] = bp[(g + u) * 4]; }
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc0), "+d"(acc1)
+                                 : "d"(av[u]), "d"(bv[u]));
+            }
+            for (; g < ng; ++g) {
+                const double av = ap[g * 4], bv = bp[g * 4];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc0), "+d"(acc1)
+                             : "d"(av), "d"(bv));
+            }
+            // row 0 of C: lane l < 4 holds the dots of columns 2 l and 2 l + 1.  They go to the warp's scratch and
+            // lane x < NX walks the batch for point x, keeping that point's best in its own registers
+            if (lane < 4) {
+                dots[2 * lane] = acc0;
+                dots[2 * lane + 1] = acc1;
+            }
+            __syncwarp();
+            if (lane < NX) {
+                const double *bx = a.bias + (size_t)lane * a.bias_stride;
+                for (int cidx = 0; cidx < nb; ++cidx) {
+                    const int kj = wq[base + cidx];
+                    if (kj >= K) continue;
+                    const double dj = dots[cidx];
+                    const double t = dj + bx[kj];                               // the sweep's epilogue: acc + bias
+                    // NaN and -Inf never win (subprob.jl:151-156); equal scores: the smaller index
+                    if (t > best || (t == best && bidx >= 0 && kj < bidx)) { best = t; bdot = dj; bidx = kj; }
+                }
+            }
+            evald += nb;
+            __syncwarp();
+        };
+        // First batch of rows (group A), THEN the next scenario's head and row (group B): waiting for "all but the
+        // last group" gives this scenario's row (group B of the previous iteration) and its first rows without
+        // waiting for the next scenario's row, which has a trip to DRAM ahead of it.
+        const int nb0 = full ? 0 : min(SCR_DEC_ROWS, n);
+        stage(0, nb0);
+        cp_async_commit();
+        const long long inext = i + nw;
+        if (inext < a.n_local) request(inext, par ^ 1, myn, mylb, e8);
+        cp_async_commit();
+        cp_async_wait_but_last();
+        __syncwarp();
         if (!full) {
-            run_queue(n);
+            if (nb0) chain(0, nb0);
+            for (int base = SCR_DEC_ROWS; base < n; base += SCR_DEC_ROWS) {
+                const int nb = min(SCR_DEC_ROWS, n - base);
+                stage(base, nb);
+                cp_async_wait_all();
+                __syncwarp();
+                chain(base, nb);
+            }
         } else {
             for (long long k0 = 0; k0 < K; k0 += SCR_DEC_QUEUE) {    // a list overflowed: every vertex, for every point
                 const int cnt = (int)min((long long)SCR_DEC_QUEUE, K - k0);
                 for (int t = lane; t < cnt; t += 32) wq[t] = (int)(k0 + t);
                 __syncwarp();
-                run_queue(cnt);
+                for (int base = 0; base < cnt; base += SCR_DEC_ROWS) {
+                    const int nb = min(SCR_DEC_ROWS, cnt - base);
+                    stage(base, nb);
+                    cp_async_wait_all();
+                    __syncwarp();
+                    chain(base, nb);
+                }
             }
         }
-        cp_async_wait_all();                                          // (a scenario without candidates: its row is still on its way)
         if (lane < NX) {
             a.best_val[lane * a.out_stride + i] = best;
             a.best_idx[lane * a.out_stride + i] = bidx;

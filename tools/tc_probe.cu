@@ -151,7 +151,7 @@ int main(int argc, char **argv)
     long long *d_mark;
     CK(cudaMalloc(&d_mark, 8)); CK(cudaMemset(d_mark, 0, 8));
     k_screen_view_sync<<<2 * sms, 256>>>(d_pi, n_rows, d_srows, n_rows, sp, d_PiB, d_pn, d_pnmax, d_bad, d_mark, d_K, nullptr, nullptr);
-    k_screen_scen_sync<<<8 * sms, 256>>>(d_D, s_pad, sp, d_DB, d_dnu, d_dnall, d_bad + 1, 0, N, nullptr);
+    k_screen_scen_sync<<<8 * sms, 256>>>(d_D, s_pad, sp, d_DB, d_dnu, d_dnall, d_bad + 1, 0, N, nullptr, nullptr);
     k_screen_prep<NX><<<1, 1024>>>(d_bias, kpad, d_pn, d_pnmax, d_dnall, d_bad, d_bad + 1, d_K, sp, (unsigned)(N / 64 + 16),
                                    d_b32c, d_ctl, nullptr, nullptr, nullptr);
     CK(cudaDeviceSynchronize());
@@ -168,7 +168,7 @@ int main(int argc, char **argv)
     ScreenArgs sa;
     sa.DB = d_DB; sa.PiB = d_PiB; sa.b32c = d_b32c; sa.dnmax_unit = d_dnu; sa.ctl = d_ctl; sa.d_K = d_K;
     sa.sp = sp; sa.nunits = (int)nunits; sa.R = R; sa.nstages = nstages; sa.n_local = N; sa.npad = npad;
-    sa.cand = d_cand; sa.cnt = d_cnt; sa.lfin = d_lfin; sa.dbg = d_dbg; sa.desc_mode = desc_mode; sa.lseed = nullptr;
+    sa.cand = d_cand; sa.cnt = d_cnt; sa.lfin = d_lfin; sa.dbg = d_dbg; sa.desc_mode = desc_mode; sa.lseed = nullptr; sa.dn = nullptr;
     const int grid = (int)std::min<long long>(sms, nunits * R);
     printf("k_screen: grid %d, %d threads, %zu B smem, %d stages\n", grid, SCR_THREADS, smem, nstages);
     k_screen<NX><<<grid, SCR_THREADS, smem>>>(sa);
