@@ -200,6 +200,38 @@ def test_warm_start_from_previous_winners(T, ctx):
     assert emitted[2] < emitted[0]          # a small step of the candidate: far fewer stale entries than the cold scan
 
 
+def test_recentring_of_both_operands(T, ctx):
+    """The centres of the pool view and of the scenario set are taken again when four times as many columns /
+    scenarios are there (until 1 024 / 256): every bf16 operand, `ctr . d_i` and the warm-start state have to follow.
+    A pool growing 60 -> 4 100 vertices under an epigraph growing 40 -> 20 100 scenarios, the pass forced at every
+    stage, two calls per stage (the second one warm-started where the sweep is not split), against the FP64 sweep."""
+    P, z = load_instance("storm")
+    pool = load_pool("storm", 16384)
+    vals = sampled_values_at(z, 11, np.arange(20100))
+    dvs = T.sdDualVertexSet(m2=P.m2)
+    epi = T.sdEpigraph(coef_of(T, P), 1.0, 0.0, dvs)
+    k_have = n_have = 0
+    x0, x1 = z["x_ev"], z["x_alt"]
+    for stage, (k_to, n_to) in enumerate(((60, 40), (250, 200), (1000, 1000), (4100, 20000), (4100, 20100))):
+        if k_to > k_have:
+            dvs.push_many(pool[k_have:k_to])
+        epi.add_scenarios(vals[n_have:n_to], 0.5 + np.arange(n_to - n_have) % 5)
+        k_have, n_have = k_to, n_to
+        for rep, lam in enumerate((0.1 * stage, 0.1 * stage + 0.03)):
+            cand = x0 + lam * (x1 - x0)
+            res = {}
+            for mode in (0, 2):
+                ctx.set_screen(mode)
+                cuts, val = epi.build_cuts2(cand, x1, with_val=True)
+                mv, mi = epi.argmax(cand)
+                res[mode] = (np.array([cuts[0].alpha, cuts[1].alpha]), np.stack([cuts[0].beta, cuts[1].beta]), val, mv, mi)
+            for u, v in zip(res[0], res[2]):
+                u, v = np.asarray(u), np.asarray(v)
+                assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), (stage, rep)
+    st = epi.screen_stats()
+    assert st["passes"] >= 20 and st["bad_operands"] == 0 and st["overflowed_lists"] == 0, st
+
+
 SWITCH_SCRIPT = """
 import sys
 import numpy as np
