@@ -77,9 +77,10 @@ def test_real_pools_bit_identical(T, ctx, name, K, N):
     print(name, st)
 
 
-def test_storm_real_pool_falls_back(T, ctx):
-    """Storm's real duals tie by the dozen: the candidate lists overflow and the pass hands over to the FP64 sweep
-    on the device (no host round trip) -- same answers."""
+def test_storm_real_pool_full_size(T, ctx):
+    """Storm's real duals tie by the dozen at full K.  (Before the operands were centred the candidate lists
+    overflowed here and the pass handed over to the FP64 sweep; `test_crowd_overflows_and_falls_back` keeps that
+    path under test.)"""
     P, z = load_instance("storm")
     pool = load_pool("storm", 16384)
     N = 4000
@@ -230,6 +231,53 @@ def test_recentring_of_both_operands(T, ctx):
                 assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), (stage, rep)
     st = epi.screen_stats()
     assert st["passes"] >= 20 and st["bad_operands"] == 0 and st["overflowed_lists"] == 0, st
+
+
+CROWD_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+from sqlp_b200 import twosd as T
+from tests.helpers import synthetic_pool, synthetic_problem, synthetic_values
+P = synthetic_problem(m2=80, n1=12, s=30, first_stoch_row=5)
+N, K = 3000, 600
+vals = synthetic_values(P, N, seed=4)
+base_v = synthetic_pool(P.m2, 1, seed=3, scale=300.0)[0]
+rng = np.random.default_rng(5)
+pool = np.tile(base_v, (K, 1)) * (1.0 + 2e-5 * rng.standard_normal((K, P.m2)))
+ctx = T.default_context()
+dvs = T.sdDualVertexSet(m2=P.m2)
+ins, _ = dvs.push_many(pool)
+assert ins.sum() > 400, ins.sum()          # distinct under the dedup rule (16 significant binary digits)
+coef = T.sdSubprobCoefficients.from_tables(P.rbar, P.T_colptr, P.T_rowval, P.T_nzval, P.pos_row, P.pos_col)
+epi = T.sdEpigraph(coef, 1.0, 0.0, dvs)
+epi.add_scenarios(vals, None)
+x = np.ones(P.n1)
+out = {}
+for mode in (0, 2):
+    ctx.set_screen(mode)
+    cuts, val = epi.build_cuts2(x, 0.5 * x, with_val=True)
+    mv, mi = epi.argmax(x)
+    out[mode] = [np.array([cuts[0].alpha, cuts[1].alpha]), np.stack([cuts[0].beta, cuts[1].beta]), np.asarray(val), mv, mi]
+for u, v in zip(out[0], out[2]):
+    assert np.array_equal(np.asarray(u).view(np.uint8), np.asarray(v).view(np.uint8))
+st = epi.screen_stats()
+assert st["fallbacks"] >= 1 and st["overflowed_lists"] > N // 16 + 16, st
+print("CROWD OK", st)
+"""
+
+
+def test_crowd_overflows_and_falls_back():
+    """A crowd of vertices 2e-5 apart: with uncentred operands every one of them is within the bound of the best,
+    the lists (64 entries) overflow for every scenario, and the FP64 sweep queued behind the pass -- gated on the
+    pass's control block, no host round trip -- must run and give the answer."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", CROWD_SCRIPT % {"root": root}], env=dict(os.environ, SQLP_CENTRE="0"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "CROWD OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
 
 
 SWITCH_SCRIPT = """
