@@ -164,10 +164,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     long long t0 = 0;
     for (;;) {
         asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
+            : "r"(bar), "r"(parity), "r"(2000u)    // suspend-time hint (ns): the warp sleeps in the instruction, not in this loop --
+            : "memory");                            // polls of the single-thread producer / MMA warps were 17 % of k_screen's instructions
         if (done) return;
         if (t0 == 0) t0 = clock64();
         else if (clock64() - t0 > 4000000000ll) __trap();
