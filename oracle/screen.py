@@ -101,6 +101,51 @@ def screen(bias: np.ndarray, PiS: np.ndarray, D: np.ndarray, centre: bool = True
     return finite & (sc + bound + slack >= (lower - np.abs(lower) * 2.0 ** -50)[:, None])
 
 
+def screen_scan(bias: np.ndarray, PiS: np.ndarray, D: np.ndarray, prev=None, centre: bool = True):
+    """The scan as the kernel runs it (k_screen's epilogue + k_screen_seed), restated column by column: a scenario's
+    lower bound L starts from the score of its previous winners (`prev[i]` = up to two vertex indices, -1 = none;
+    ANY vertices give a valid bound), a vertex is EMITTED when its upper bound reaches the running L, and the entries
+    that still reach the final L survive.  Returns (survivor mask [N, K], emitted count per scenario)."""
+    s = PiS.shape[1]
+    N, K = len(D), len(PiS)
+    with np.errstate(all="ignore"):
+        if centre and K and N:
+            c = np.nan_to_num(PiS[:CENTRE_COLS].mean(axis=0), nan=0.0, posinf=0.0, neginf=0.0)
+            dbar = np.nan_to_num(D[:CENTRE_SCEN].mean(axis=0), nan=0.0, posinf=0.0, neginf=0.0)
+        else:
+            c, dbar = np.zeros(s), np.zeros(s)
+        b1 = bias + PiS @ dbar
+        raw_p, raw_d = np.sqrt((PiS * PiS).sum(axis=1)), np.sqrt((D * D).sum(axis=1))
+        fin = np.isfinite(b1)
+        eabs = (s + 8) * 2.0 ** -52 * ((np.abs(b1[fin]).max() if fin.any() else 0.0) +
+                                       np.nanmax(raw_p[np.isfinite(raw_p)], initial=0.0) * np.nanmax(raw_d, initial=0.0) * 2.0)
+        P1, D1 = PiS - c, D - dbar
+        approx = approx_dots(P1, D1)
+        pn = up(np.sqrt(up((P1 * P1).sum(axis=1))))
+        dn = up(np.sqrt(up((D1 * D1).sum(axis=1))))
+        E = up(eps(s) * np.outer(dn, pn)) + eabs + 2.0 ** -50 * (np.abs(b1)[None, :] + np.abs(approx))
+        t = b1[None, :] + approx
+        L = np.full(N, -np.inf)
+        if prev is not None:                                   # k_screen_seed: exact centred score of the previous winners
+            prev = np.asarray(prev).reshape(N, -1)
+            for j in range(prev.shape[1]):
+                k = prev[:, j]
+                ok = (k >= 0) & (k < K)
+                kk = np.where(ok, k, 0)
+                sc = b1[kk] + np.einsum("ij,ij->i", P1[kk], D1) - 2.0 * eabs
+                sc = sc - 2.0 ** -40 * np.abs(sc)
+                sc = np.where(ok & np.isfinite(sc), sc.astype(np.float32).astype(np.float64) - np.abs(sc) * 2.0 ** -23, -np.inf)
+                L = np.maximum(L, sc)
+        emitted = np.zeros((N, K), dtype=bool)
+        for k in range(K):                                     # the scan, in column order
+            tk, Ek = t[:, k], E[:, k]
+            good = np.isfinite(tk)
+            emitted[:, k] = good & (tk + Ek >= L)
+            L = np.where(good, np.maximum(L, tk - Ek), L)
+        ub = np.where(np.isfinite(t), t + E, -np.inf)
+    return emitted & (ub >= L[:, None]), emitted.sum(axis=1)
+
+
 def argmax_screened(P, values, x, pool, centre: bool = True):
     """max_val, max_idx as ``oracle.argmax_procedure`` -- exact arithmetic on the candidates only -- plus the
     candidate counts per scenario."""

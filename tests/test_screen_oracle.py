@@ -56,6 +56,31 @@ def test_centred_operands_keep_the_argmax_and_shrink_the_lists_on_storms_real_po
     assert counts[True] < 0.5 * counts[False], counts
 
 
+def test_warm_started_scan_never_loses_the_argmax(oracle):
+    """k_screen_seed restated: the scan of a scenario starts from the score of ANY vertices (here: the winners at
+    another point, random vertices, none) -- the survivors must still contain the oracle's argmax, and with the
+    winners of a nearby point far fewer vertices are emitted than by the cold scan."""
+    P, z = load_instance("storm")
+    pool = load_pool("storm", 2048)
+    vals = sample_instance_values(z, 160, seed=8)
+    Sx = np.asarray(P.pos_row)
+    D = vals - P.rbar[Sx][None, :]
+    x0, x1 = z["x_ev"], z["x_ev"] + 0.03 * (z["x_alt"] - z["x_ev"])
+    _, w0 = oracle.argmax_procedure(P, vals, x0, pool)           # winners at the previous point
+    ov, oi = oracle.argmax_procedure(P, vals, x1, pool)
+    bias = pool @ (P.rbar - P.T_dense() @ x1)
+    rng = np.random.default_rng(3)
+    emitted = {}
+    for name, prev in (("cold", None), ("previous winners", np.stack([w0, w0[::-1]], axis=1)),
+                       ("random vertices", rng.integers(-1, len(pool), size=(len(vals), 2)))):
+        mask, n_emit = S.screen_scan(bias, pool[:, Sx], D, prev)
+        assert mask[np.arange(len(vals)), oi].all(), name       # the argmax survives
+        exact = bias[None, :] + D @ pool[:, Sx].T
+        assert np.array_equal(np.where(mask, exact, -np.inf).argmax(axis=1), exact.argmax(axis=1)), name
+        emitted[name] = n_emit.mean()
+    assert emitted["previous winners"] < 0.5 * emitted["cold"], emitted
+
+
 @pytest.mark.parametrize("centre", [False, True])
 def test_screened_argmax_with_ties_near_ties_and_dominant_bias(oracle, centre):
     """Adversarial pool: exact duplicates of the winner's stochastic part (first index must win), vertices one
