@@ -16,13 +16,21 @@
 // accumulated by the tensor core in fp32 as ONE accumulation of 3 * sp terms (sp = row slots padded to 16):
 //     per K-step of 16 slots:  D += [dh | dl](A, 128 scenarios) x [ph | ph]    (two instructions)
 //                              D += [dh](A)                     x [pl]         (one instruction)
-// Error budget per (k, i), Q = ||PiS[k]||_2 ||d_i||_2 >= sum_j |p_j d_j| (Cauchy-Schwarz):
+// The operands are CENTRED first (see "Centred operands" below): P'_k = PiS[k] - ctr, d'_i = d_i - dbar, and the
+// bias carries P_k . dbar; a term that depends on the scenario alone does not change the argmax.
+// Error budget per (k, i), Q = ||P'_k||_2 ||d'_i||_2 >= sum_j |p'_j d'_j| (Cauchy-Schwarz):
 //     dropped products            <= 3 * 2^-16 * (1 + 2^-8)       Q
 //     fp32 accumulation, any order, truncating adders allowed      <= (3 sp + 8) * 2^-22 * 1.02  Q
 //     bias rounded to fp32 after a common shift, final fp32 add    <= 2^-23 (|b32[k]| + 1.02 Q)
-//     the FP64 sweep's own rounding                                <= 2^-40 (|b32[k]| + Q)
-// E(tile) = coef_q * max_k ||PiS[k]|| (256 vertices) * max_i ||d_i|| (128 scenarios) + coef_b * max |b32|,
+//     FP64 operations on the uncentred operands (the sweep's own chain and bias add, P_k . dbar, the centring)
+//                                                                  <= eabs  (k_screen_prep)
+// E(chunk, i) = coef_q * max_k ||P'_k|| (256 vertices) * ||d'_i|| + coef_b * max |b32| + eabs,
 // all norms rounded up, thresholds rounded towards "more candidates".
+//
+// Chain of a pass (host_epi.cuh:screen_enqueue): operand syncs (k_screen_view_sync, k_screen_scen_sync,
+// k_screen_cd: new columns / scenarios only), k_screen_pdbar, k_screen_prep, k_screen_seed (warm start from the
+// previous winners), k_screen, k_screen_decide (k_screen_resolve when the sweep was split in K-ranges), and the FP64
+// sweep gated on the pass's control block behind it.
 //
 // Data layouts (tc05.cuh): scenario store DB[unit][part hi,lo][slab][128 scenarios][8] bf16, one contiguous
 // block of 512 sp bytes per unit; pool view PiB[chunk of 256 vertices][K-step][hi,lo][slab 2][256][8] bf16,
@@ -31,9 +39,10 @@
 //
 // Kernel k_screen: one persistent CTA per SM, 320 threads:
 //   warps 0-7  epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (one scenario per thread), columns
-//              128 (w / 4) .. +127 of the 128 x 256 accumulator; per score one FADD per point and one FMNMX
-//              per point; every 8 columns one compare against the running threshold; the rare hit appends
-//              (vertex, upper bound) to the thread's own candidate list -- no atomics, no cross-lane traffic.
+//              128 (w / 4) .. +127 of the 128 x 256 accumulator; per score one FADD per point and a share of a
+//              3-input max; every 32 columns ONE test of the eight group maxima against the running thresholds;
+//              a hit appends (vertex, upper bound) to the thread's own candidate list -- no atomics, no cross-lane
+//              traffic.
 //   warp 8     producer: bulk async copies (TMA 1-D) of the unit's scenarios (resident for the whole sweep),
 //              of the biases of a chunk and of the ring stages.
 //   warp 9     one thread issues tcgen05.mma; tcgen05.commit releases ring stages and publishes accumulators.
