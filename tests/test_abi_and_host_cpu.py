@@ -131,3 +131,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "evals/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_bench_roofline_entries_from_a_recorded_profile():
+    """bench.py's roofline arithmetic on a recorded device profile (no GPU): achieved = work / event time of the
+    kernel class, the fraction against the sustained cuBLAS figure (and the burst one beside it), and the DRAM traffic
+    of the captured shape only -- per pool, and not for the strong-scaled leg, whose shape the capture does not have."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(_lib.ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    leg = {"prof": {"contract": [0.0, 0, 0.0], "screen": [15.4, 20, 1.4752e13], "resolve": [5.9, 20, 1.0e7],
+                    "fallback": [0.14, 20, 0.0]}, "ms": 24.55}
+    args = types.SimpleNamespace(instance="storm", vertices=16384, scen_per_gpu=1_000_000, epigraphs=4, pool="real")
+    r = b.rooflines(leg, args)
+    d = r["dominant"]
+    assert d["kernel"].startswith("k_screen") and d["bound"] == "tensor" and d["unit"] == "TFLOP/s"
+    assert abs(d["achieved"] - 1.4752e13 / 15.4e-3 * 1e-12) < 1e-6 and abs(d["frac"] - d["achieved"] / d["peak"]) < 1e-12
+    assert abs(d["share_of_step"] - 15.4 / 24.55) < 1e-12 and d["launches"] == 20
+    assert d["traffic"] and "r02_step_kernels" in d["traffic_source"]
+    if "frac_of_burst" in d:
+        assert d["frac_of_burst"] < d["frac"]
+    assert any(k["kernel"] == "k_screen_resolve" for k in r["all"])
+    assert b.rooflines(leg, None, "synthetic")["dominant"]["traffic"] != d["traffic"]
+    assert b.rooflines(leg, None, "-")["dominant"]["traffic"] is None            # the strong-scaled leg
+    args.scen_per_gpu = 125_000
+    assert b.rooflines(leg, args)["dominant"]["traffic"] is None                  # another shape
