@@ -81,6 +81,27 @@ def test_warm_started_scan_never_loses_the_argmax(oracle):
     assert emitted["previous winners"] < 0.5 * emitted["cold"], emitted
 
 
+def test_scan_bounds_on_random_shapes_and_magnitudes():
+    """The bound and the seed slack, restated: 400 random problems -- 1 to 40 rows, operands as clouds far from the
+    origin or around it, scales from 1e-3 to 1e5, biases up to 1e9 above the dots, exact and 2^-40 / 2^-20 near-ties,
+    random seeds -- and every vertex attaining the FP64 maximum of a scenario survives the scan, cold or seeded."""
+    rng = np.random.default_rng(2026)
+    for _ in range(200):
+        s, K, N = int(rng.integers(1, 41)), int(rng.integers(2, 200)), int(rng.integers(1, 40))
+        sp_, sd_ = 10.0 ** rng.uniform(-3, 5), 10.0 ** rng.uniform(-3, 4)
+        PiS = rng.standard_normal(s) * sp_ * 10.0 ** rng.uniform(-2, 2) + rng.standard_normal((K, s)) * sp_
+        D = rng.standard_normal(s) * sd_ * 10.0 ** rng.uniform(-2, 2) + rng.standard_normal((N, s)) * sd_
+        bias = rng.standard_normal(K) * sp_ * sd_ * 10.0 ** rng.uniform(-2, 6) + 10.0 ** rng.uniform(0, 9) * rng.choice([0, 1, -1])
+        for k in range(0, K - 1, 7):
+            PiS[k + 1] = PiS[k] * (1 + rng.choice([0, 2.0 ** -40, 2.0 ** -20]))
+            bias[k + 1] = bias[k] * (1 + rng.choice([0, 2.0 ** -45]))
+        exact = bias[None, :] + D @ PiS.T
+        ties = exact == exact.max(axis=1, keepdims=True)
+        for prev in (None, rng.integers(-1, K, size=(N, 2))):
+            mask, _ = S.screen_scan(bias, PiS, D, prev)
+            assert (mask | ~ties).all()
+
+
 @pytest.mark.parametrize("centre", [False, True])
 def test_screened_argmax_with_ties_near_ties_and_dominant_bias(oracle, centre):
     """Adversarial pool: exact duplicates of the winner's stochastic part (first index must win), vertices one
